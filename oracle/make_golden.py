@@ -1,0 +1,243 @@
+"""Freeze golden vectors from the REAL reference modules and pin oracle/restate.py against them.
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+Writes tests/golden/golden_v1.pt (a dict of small fp32 tensors + metadata).  TEST INFRASTRUCTURE ONLY.
+
+For every module on the hot path the script
+  1. seeds torch (42, as train.py:49), builds the reference nn.Module and the restated state dict with the same seed,
+     and asserts that keys, shapes and values agree exactly (pins creation order + initialisers);
+  2. runs reference module and restatement on the same synthetic slices and asserts bit-equality (CPU fp32);
+  3. stores inputs seeds, outputs and gradient fingerprints as golden vectors.
+Iteration bodies (the trainers cannot be instantiated) are driven here with the reference's own
+nn.Modules + torch.optim.Adam following the cited trainer lines, and compared with restate.*_step.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import restate as R  # noqa: E402
+from oracle.ref_loader import load_reference  # noqa: E402
+
+torch.set_num_threads(8)
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden", "golden_v1.pt")
+
+
+def seed(s=42):
+    random.seed(s)
+    torch.manual_seed(s)
+
+
+def check_state(ref_module, sd, what):
+    rsd = ref_module.state_dict()
+    assert list(rsd.keys()) == list(sd.keys()), (what, [k for k in rsd if k not in sd][:5], [k for k in sd if k not in rsd][:5])
+    for k in rsd:
+        assert rsd[k].shape == sd[k].shape, (what, k)
+        assert torch.equal(rsd[k], sd[k]), (what, k, (rsd[k] - sd[k]).abs().max())
+    return {k: (tuple(v.shape), float(v.double().sum()), float(v.double().abs().sum())) for k, v in rsd.items()}
+
+
+def grad_fingerprint(params: dict):
+    return {k: (float(p.grad.double().norm()), float(p.grad.double().sum())) for k, p in params.items() if p.grad is not None}
+
+
+def main():
+    ref = load_reference()
+    G = {}
+    S = 64
+
+    # ---------------- Generator ----------------
+    seed(); g_ref = ref.CycleGan.Generator(1, 1)
+    seed(); g_sd = R.init_generator(1, 1)
+    G["generator.state_fp"] = check_state(g_ref, g_sd, "Generator")
+    seed(); g_hd = ref.HdGan.Generator(1, 1)
+    check_state(g_hd, g_sd, "HdGan.Generator")
+    a, b = R.synthetic_pair(1, S, seed=42)
+    y_ref = g_ref(a)
+    leaf = R.leafify(g_sd)
+    y = R.generator_forward(leaf, a)
+    assert torch.equal(y_ref, y), (y_ref - y).abs().max()
+    (y_ref * b).sum().backward()
+    (y * b).sum().backward()
+    for (k, p), (k2, p2) in zip(g_ref.named_parameters(), leaf.items()):
+        assert k == k2 and torch.equal(p.grad, p2.grad), k
+    G["generator.out_64"] = y_ref.detach().clone()
+    G["generator.grad_fp_64"] = grad_fingerprint(leaf)
+    a2, _ = R.synthetic_pair(2, 128, seed=7, phantom=True)
+    G["generator.out_128_phantom_b2"] = g_ref(a2).detach().clone()
+    assert torch.equal(G["generator.out_128_phantom_b2"], R.generator_forward(g_sd, a2))
+
+    # ---------------- Discriminator ----------------
+    for nc in (1, 2):
+        seed(); d_ref = ref.CycleGan.Discriminator(nc)
+        seed(); d_sd = R.init_discriminator(nc)
+        G[f"discriminator{nc}.state_fp"] = check_state(d_ref, d_sd, "Discriminator")
+        x = torch.cat([a, b], 1)[:, :nc]
+        x2 = torch.cat([x, -x], 0)
+        p_ref = d_ref(x2)
+        leaf = R.leafify(d_sd)
+        p = R.discriminator_forward(leaf, x2)
+        assert torch.equal(p_ref, p)
+        l_ref = torch.nn.MSELoss()(p_ref, torch.ones(1, 1)); l_ref.backward()
+        l = R.mse_vs_const(p, 1.0); l.backward()
+        assert torch.equal(l_ref, l)
+        for (k, q), (k2, q2) in zip(d_ref.named_parameters(), leaf.items()):
+            assert k == k2 and torch.allclose(q.grad, q2.grad, rtol=0, atol=0), k
+        G[f"discriminator{nc}.pred_64_b2"] = p_ref.detach().clone()
+        G[f"discriminator{nc}.mse_real"] = l_ref.detach().clone()
+        G[f"discriminator{nc}.grad_fp"] = grad_fingerprint(leaf)
+
+    # ---------------- Discriminator_m + GANLoss ----------------
+    seed(); dm_ref = ref.HdGan.Discriminator_m(1)
+    seed(); dm_sd = R.init_discriminator_m(1)
+    G["discriminator_m.state_fp"] = check_state(dm_ref, dm_sd, "Discriminator_m")
+    feats_ref = dm_ref(a)
+    feats = R.discriminator_m_forward(dm_sd, a)
+    assert len(feats_ref) == 1 and len(feats_ref[0]) == 5
+    for fr, f in zip(feats_ref[0], feats[0]):
+        assert torch.equal(fr, f)
+    gl = ref.HdGan.GANLoss()
+    for flag in (True, False):
+        assert torch.equal(gl(feats_ref, flag), R.gan_loss(feats, flag))
+        G[f"discriminator_m.ganloss_{flag}"] = gl(feats_ref, flag).detach().clone()
+    G["discriminator_m.last_64"] = feats_ref[0][-1].detach().clone()
+    G["discriminator_m.feat_shapes"] = [tuple(f.shape) for f in feats_ref[0]]
+
+    # ---------------- Reg (needs >= 256) ----------------
+    seed(); r_ref = ref.reg.Reg(256, 256, 1, 1)
+    seed(); r_sd = R.init_reg(1, 1)
+    G["reg.state_fp"] = check_state(r_ref, r_sd, "Reg")
+    ra, rb = R.synthetic_pair(1, 256, seed=3, phantom=True)
+    fl_ref = r_ref(ra, rb)
+    leaf = R.leafify(r_sd)
+    fl = R.reg_forward(leaf, ra, rb)
+    assert torch.equal(fl_ref, fl), (fl_ref - fl).abs().max()
+    G["reg.flow_256"] = fl_ref.detach().clone()
+    # make the flow non-trivial for the gradient fingerprint: scale output weights up
+    seed(1); wbig = torch.randn_like(r_sd["offset_map.output.conv2d.weight"]) * 0.05
+    r_ref.offset_map.output.conv2d.weight.data.copy_(wbig)
+    leaf["offset_map.output.conv2d.weight"].data.copy_(wbig)
+    fl_ref = r_ref(ra, rb); fl = R.reg_forward(leaf, ra, rb)
+    assert torch.equal(fl_ref, fl)
+    G["reg.flow_256_bigw"] = fl_ref.detach().clone()
+    ref.utils.smooothing_loss(fl_ref).backward()
+    R.smoothing_loss(fl).backward()
+    for (k, q), (k2, q2) in zip(r_ref.named_parameters(), leaf.items()):
+        assert k == k2 and torch.equal(q.grad, q2.grad), k
+    G["reg.grad_fp_bigw"] = grad_fingerprint(leaf)
+    G["reg.smooth_bigw"] = ref.utils.smooothing_loss(fl_ref).detach().clone()
+
+    # ---------------- warp (Transformer_2D) + smoothness ----------------
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self        # transformer.py:21 hard-codes .cuda()
+    try:
+        tr = ref.transformer.Transformer_2D()
+        for name, (Bn, Hh, Ww, mag) in {"small": (2, 32, 48, 3.0), "sq": (1, 64, 64, 1.5), "tiny_flow": (1, 64, 64, 1e-3),
+                                       "oob": (1, 40, 40, 30.0)}.items():
+            gsrc = torch.Generator().manual_seed(11)
+            src = (torch.rand(Bn, 1, Hh, Ww, generator=gsrc) * 2 - 1).requires_grad_(True)
+            flow = ((torch.rand(Bn, 2, Hh, Ww, generator=gsrc) * 2 - 1) * mag).requires_grad_(True)
+            wt = torch.rand(Bn, 1, Hh, Ww, generator=gsrc)
+            o_ref = tr(src, flow)
+            (o_ref * wt).sum().backward()
+            gs_ref, gf_ref = src.grad.clone(), flow.grad.clone()
+            src.grad = None; flow.grad = None
+            o = R.warp(src, flow)
+            (o * wt).sum().backward()
+            assert torch.equal(o_ref, o) and torch.equal(gs_ref, src.grad) and torch.equal(gf_ref, flow.grad), name
+            G[f"warp.{name}"] = {"src": src.detach().clone(), "flow": flow.detach().clone(), "wt": wt,
+                                 "out": o_ref.detach().clone(), "gsrc": gs_ref, "gflow": gf_ref}
+            sl_ref = ref.utils.smooothing_loss(flow.detach())
+            assert torch.equal(sl_ref, R.smoothing_loss(flow.detach()))
+            G[f"smooth.{name}"] = sl_ref.clone()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+    # ---------------- ReplayBuffer ----------------
+    random.seed(5); rb_ref = ref.utils.ReplayBuffer(max_size=4)
+    picks_ref = [rb_ref.push_and_pop(torch.full((1, 1, 2, 2), float(i))).flatten()[0].item() for i in range(24)]
+    random.seed(5); rb_my = R.ReplayBuffer(max_size=4)
+    picks = [rb_my.push_and_pop(torch.full((1, 1, 2, 2), float(i))).flatten()[0].item() for i in range(24)]
+    assert picks_ref == picks
+    G["replay.picks_seed5_size4"] = picks_ref
+
+    # ---------------- iteration bodies: reference modules driven per the trainer lines ----------------
+    Sx = 64
+    # Cyc (CycTrainer.py:138-197)
+    seed()
+    nets = [ref.CycleGan.Generator(1, 1), ref.CycleGan.Discriminator(1), ref.CycleGan.Generator(1, 1), ref.CycleGan.Discriminator(1)]
+    gA2B, dB, gB2A, dA = nets
+    import itertools
+    oDB = torch.optim.Adam(dB.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    oG = torch.optim.Adam(itertools.chain(gA2B.parameters(), gB2A.parameters()), lr=1e-4, betas=(0.5, 0.999))
+    oDA = torch.optim.Adam(dA.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    mse, l1 = torch.nn.MSELoss(), torch.nn.L1Loss()
+    t1, t0 = torch.ones(1, 1), torch.zeros(1, 1)
+    bufA, bufB = ref.utils.ReplayBuffer(), ref.utils.ReplayBuffer()
+    seed(); st = R.CycState()
+    cyc_losses = []
+    for it in range(2):
+        rA, rB = R.synthetic_pair(1, Sx, seed=100 + it, phantom=True)
+        oG.zero_grad()
+        fB = gA2B(rA); lg1 = 1 * mse(dB(fB), t1)
+        fA = gB2A(rB); lg2 = 1 * mse(dA(fA), t1)
+        lc1 = 10 * l1(gB2A(fB), rA); lc2 = 10 * l1(gA2B(fA), rB)
+        lt = lg1 + lg2 + lc1 + lc2; lt.backward(); oG.step()
+        oDA.zero_grad()
+        lr_ = 1 * mse(dA(rA), t1); fA_ = bufA.push_and_pop(fA); lf_ = 1 * mse(dA(fA_.detach()), t0)
+        lDA = lr_ + lf_; lDA.backward(); oDA.step()
+        oDB.zero_grad()
+        lr_ = 1 * mse(dB(rB), t1); fB_ = bufB.push_and_pop(fB); lf_ = 1 * mse(dB(fB_.detach()), t0)
+        lDB = lr_ + lf_; lDB.backward(); oDB.step()
+        mine = R.cyc_step(st, rA, rB)
+        refl = {"loss_G": float(lt), "loss_D_A": float(lDA), "loss_D_B": float(lDB)}
+        for k, v in refl.items():
+            assert v == mine[k], (it, k, v, mine[k])
+        cyc_losses.append(mine)
+    G["cyc_step.losses_64"] = cyc_losses
+    G["cyc_step.G_A2B_head_w_after2"] = st.G_A2B["model_head.1.weight"].detach().clone()
+    assert torch.equal(gA2B.model_head[1].weight, st.G_A2B["model_head.1.weight"])
+
+    # Reg (RegTrainer.py:170-198) at 256 (Reg's minimum), 3-block generator to keep CPU time low
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        seed()
+        g = ref.CycleGan.Generator(1, 1, n_residual_blocks=3); d = ref.CycleGan.Discriminator(1)
+        oD = torch.optim.Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.999))
+        r = ref.reg.Reg(256, 256, 1, 1); tr = ref.transformer.Transformer_2D()
+        oR = torch.optim.Adam(r.parameters(), lr=1e-4, betas=(0.5, 0.999))
+        oG = torch.optim.Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.999))
+        seed(); st = R.RegState(n_blocks=3)
+        reg_losses = []
+        for it in range(2):
+            rA, rB = R.synthetic_pair(1, 256, seed=200 + it, phantom=True)
+            oR.zero_grad(); oG.zero_grad()
+            fB = g(rA); T = r(fB, rB); sr_ = tr(fB, T)
+            SR = 20 * l1(sr_, rB); adv = 1 * mse(d(fB), t1); SM = 10 * ref.utils.smooothing_loss(T)
+            tot = SM + adv + SR; tot.backward(); oR.step(); oG.step()
+            oD.zero_grad()
+            with torch.no_grad():
+                fB = g(rA)
+            lD = 1 * mse(d(fB), t0) + 1 * mse(d(rB), t1); lD.backward(); oD.step()
+            mine = R.reg_step(st, rA, rB)
+            for k, v in {"SR_loss": float(SR), "adv_loss": float(adv), "SM_loss": float(SM), "loss_D_B": float(lD)}.items():
+                assert v == mine[k], (it, k, v, mine[k])
+            reg_losses.append(mine)
+        G["reg_step.losses_256_nb3"] = reg_losses
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+    G["meta"] = {"torch": torch.__version__, "reference": ref.root, "note": "all tensors fp32 CPU, seed 42 init"}
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    torch.save(G, OUT)
+    print("wrote", OUT, os.path.getsize(OUT) / 1e6, "MB;", len(G), "entries")
+
+
+if __name__ == "__main__":
+    main()
