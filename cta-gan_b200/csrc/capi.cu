@@ -1,0 +1,75 @@
+// C-ABI glue: error state, device checks and engine dispatch for the convolution entry points.
+#include <stdarg.h>
+#include "common.cuh"
+
+int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
+int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
+// tcgen05 engine (conv_tc.cu): return CTAGAN_ERR_UNSUPPORTED when the geometry does not tile
+int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
+int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
+int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g);
+int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g);
+
+static thread_local char g_err[512] = "";
+
+void ctagan_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ctagan_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+extern "C" int ctagan_version(void) { return 100; }
+extern "C" const char *ctagan_last_error(void) { return g_err; }
+
+extern "C" int ctagan_check_device(int dev) {
+  int major = 0, minor = 0;
+  CTAGAN_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CTAGAN_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    ctagan_set_error("libctagan is built for sm_100a only; device %d is sm_%d%d (no fallback path)", dev, major, minor);
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  return CTAGAN_OK;
+}
+
+static int check_geom(const ctagan_conv_geom *g, const char *who) {
+  CTAGAN_REQUIRE(g, "%s: null geometry", who);
+  CTAGAN_REQUIRE(g->N > 0 && g->Hi > 0 && g->Wi > 0 && g->Ci > 0 && g->Ho > 0 && g->Wo > 0 && g->Co > 0, "%s: non-positive extent", who);
+  CTAGAN_REQUIRE(g->KH > 0 && g->KW > 0 && g->stride > 0 && g->dil > 0, "%s: bad kernel/stride/dilation", who);
+  CTAGAN_REQUIRE(g->dtype == CTAGAN_F32 || g->dtype == CTAGAN_BF16, "%s: bad dtype", who);
+  CTAGAN_REQUIRE(g->act >= 0 && g->act <= 3, "%s: bad activation", who);
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, int engine,
+                                  void *stream) {
+  int rc = check_geom(g, "conv_gather");
+  if (rc) return rc;
+  CTAGAN_REQUIRE(x && wp && y, "conv_gather: null pointer");
+  CTAGAN_REQUIRE(engine >= 0 && engine <= 2, "conv_gather: bad engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == 2 || (engine == 0 && ctagan_conv_gather_tc_eligible(g))) return ctagan_conv_gather_tc(g, x, wp, bias, y, st);
+  return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
+}
+
+extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, int engine,
+                                 void *stream) {
+  int rc = check_geom(g, "conv_wgrad");
+  if (rc) return rc;
+  CTAGAN_REQUIRE(gy && gx && dw, "conv_wgrad: null pointer");
+  CTAGAN_REQUIRE(engine >= 0 && engine <= 2, "conv_wgrad: bad engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == 2 || (engine == 0 && ctagan_conv_wgrad_tc_eligible(g))) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, st);
+  return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, st);
+}

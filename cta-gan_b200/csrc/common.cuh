@@ -1,0 +1,127 @@
+// Shared device/host helpers for libctagan (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/ctagan.h"
+
+typedef __nv_bfloat16 bf16;
+
+void ctagan_set_error(const char *fmt, ...);
+
+#define CTAGAN_REQUIRE(cond, ...)                      \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ctagan_set_error(__VA_ARGS__);                   \
+      return CTAGAN_ERR_ARG;                           \
+    }                                                  \
+  } while (0)
+
+#define CTAGAN_CUDA_OK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ctagan_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return CTAGAN_ERR_CUDA;                                                             \
+    }                                                                                     \
+  } while (0)
+
+#define CTAGAN_LAUNCH_OK()                                                                 \
+  do {                                                                                     \
+    cudaError_t e_ = cudaGetLastError();                                                   \
+    if (e_ != cudaSuccess) {                                                               \
+      ctagan_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return CTAGAN_ERR_CUDA;                                                              \
+    }                                                                                      \
+  } while (0)
+
+// dispatch on the runtime activation dtype
+#define CTAGAN_DISPATCH_DTYPE(dtype, T, ...)                               \
+  do {                                                                     \
+    if ((dtype) == CTAGAN_F32) { typedef float T; __VA_ARGS__; }           \
+    else if ((dtype) == CTAGAN_BF16) { typedef bf16 T; __VA_ARGS__; }      \
+    else { ctagan_set_error("bad dtype %d", (int)(dtype)); return CTAGAN_ERR_ARG; } \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// Vector of V elements of T moved with one 16-byte (or smaller) access.
+template <typename T, int V> struct Vec {
+  T v[V];
+};
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T *p, float (&out)[V]) {
+  if constexpr (V == 1) {
+    out[0] = to_f(p[0]);
+  } else if constexpr (sizeof(T) * V == 16) {
+    uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) out[i] = to_f(e[i]);
+  } else if constexpr (sizeof(T) * V == 8) {
+    uint2 raw = *reinterpret_cast<const uint2 *>(p);
+    const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) out[i] = to_f(e[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) out[i] = to_f(p[i]);
+  }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T *p, const float (&in)[V]) {
+  if constexpr (V == 1) {
+    p[0] = from_f<T>(in[0]);
+  } else if constexpr (sizeof(T) * V == 16) {
+    uint4 raw;
+    T *e = reinterpret_cast<T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) e[i] = from_f<T>(in[i]);
+    *reinterpret_cast<uint4 *>(p) = raw;
+  } else if constexpr (sizeof(T) * V == 8) {
+    uint2 raw;
+    T *e = reinterpret_cast<T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) e[i] = from_f<T>(in[i]);
+    *reinterpret_cast<uint2 *>(p) = raw;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = from_f<T>(in[i]);
+  }
+}
+
+// widest vector (in elements) that keeps 16-byte accesses legal for C channels of T
+template <typename T> __host__ __device__ constexpr int max_vec() { return 16 / (int)sizeof(T); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case CTAGAN_ACT_RELU: return v > 0.f ? v : 0.f;
+    case CTAGAN_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
+    case CTAGAN_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// number of SMs (B200: 148); cached
+int ctagan_num_sms();

@@ -1,0 +1,310 @@
+// CUDA-core (FFMA, fp32 accumulate) implicit-GEMM convolution kernels.
+//
+// These are the *validation-mode* engine (fp32 activations, <=1e-4 vs the fp32 oracle: tcgen05 has no IEEE-fp32 MMA) and the
+// engine for shapes that do not tile onto tensor cores (Cin=1 7x7 head, Cout<=2 tails, <=16x16 maps of Reg).
+// One "gather" geometry (ctagan_conv_geom) covers Conv2d fwd/dgrad and ConvTranspose2d fwd/dgrad; see include/ctagan.h.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
+
+struct PixelCoord {
+  int n, oh, ow;
+  bool valid;
+};
+
+__device__ __forceinline__ bool tap_coord(const ctagan_conv_geom &g, int o, int k, int pad, int in_extent, int &i_out) {
+  int num = o * g.stride + k - pad;
+  if (num < 0) return false;
+  if (g.dil > 1) {
+    if (num % g.dil) return false;
+    num /= g.dil;
+  }
+  i_out = num;
+  return num < in_extent;
+}
+
+// y[m, co] = act(bias + sum_k A[m,k] * W[co,k]);  A gathered from x on the fly.
+// FLAT=false requires Ci % 16 == 0 (vector loads, K chunks never straddle taps); FLAT=true handles any Ci.
+template <typename T, bool FLAT>
+__global__ void __launch_bounds__(256) conv_gather_simt_kernel(ctagan_conv_geom g, const T *__restrict__ x,
+                                                               const T *__restrict__ wp, const float *__restrict__ bias,
+                                                               T *__restrict__ y) {
+  __shared__ __align__(16) float As[BK][BM + PADM];
+  __shared__ __align__(16) float Bs[BK][BN + PADM];
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  const long long M = (long long)g.N * g.Ho * g.Wo;
+  const int ntaps = g.KH * g.KW;
+  const int Ktot = ntaps * g.Ci;
+
+  // loader coordinates: row r (pixel for A, cout for B), 4 consecutive k at kseg
+  const int r = t >> 2, kseg = (t & 3) * 4;
+  const long long m = (long long)blockIdx.x * BM + r;
+  PixelCoord pc;
+  pc.valid = m < M;
+  {
+    long long mm = pc.valid ? m : 0;
+    pc.ow = (int)(mm % g.Wo);
+    long long q = mm / g.Wo;
+    pc.oh = (int)(q % g.Ho);
+    pc.n = (int)(q / g.Ho);
+  }
+  const int co_l = blockIdx.y * BN + r;
+  const bool co_ok = co_l < g.Co;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = FLAT ? (Ktot + BK - 1) / BK : ntaps * (g.Ci / BK);
+  const int cchunks = FLAT ? 1 : g.Ci / BK;
+  for (int it = 0; it < nk; ++it) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (!FLAT) {
+      const int tap = it / cchunks, c0 = (it - tap * cchunks) * BK;
+      const int kh = tap / g.KW, kw = tap - kh * g.KW;
+      int ih, iw;
+      if (pc.valid && tap_coord(g, pc.oh, kh, g.pad_h, g.Hi, ih) && tap_coord(g, pc.ow, kw, g.pad_w, g.Wi, iw)) {
+        const T *p = x + (((long long)pc.n * g.Hi + ih) * g.Wi + iw) * g.Ci + c0 + kseg;
+        load_vec<T, 4>(p, a);
+      }
+      if (co_ok) {
+        const T *q = wp + ((long long)co_l * ntaps + tap) * g.Ci + c0 + kseg;
+        load_vec<T, 4>(q, b);
+      }
+    } else {
+      const int k0 = it * BK + kseg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = k0 + j;
+        if (kk < Ktot) {
+          const int tap = kk / g.Ci, ci = kk - tap * g.Ci;
+          const int kh = tap / g.KW, kw = tap - kh * g.KW;
+          int ih, iw;
+          if (pc.valid && tap_coord(g, pc.oh, kh, g.pad_h, g.Hi, ih) && tap_coord(g, pc.ow, kw, g.pad_w, g.Wi, iw))
+            a[j] = to_f(x[(((long long)pc.n * g.Hi + ih) * g.Wi + iw) * g.Ci + ci]);
+          if (co_ok) b[j] = to_f(wp[(long long)co_l * Ktot + kk]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[kseg + j][r] = a[j];
+      Bs[kseg + j][r] = b[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+
+  const int co0 = blockIdx.y * BN + tx * 4;
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (co0 + j < g.Co) bv[j] = bias[co0 + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long mo = (long long)blockIdx.x * BM + ty * 4 + i;
+    if (mo >= M) continue;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = apply_act(acc[i][j] + bv[j], g.act);
+    T *dst = y + mo * g.Co + co0;
+    if ((g.Co & 3) == 0 && co0 + 3 < g.Co) {
+      store_vec<T, 4>(dst, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co0 + j < g.Co) dst[j] = from_f<T>(o[j]);
+    }
+  }
+}
+
+// dw[a, b, kh, kw] (+)= sum_p gy[p, a] * gx[gather(p, kh, kw), b];   tile 64 a x 64 n' (n' = tap*B + b), K = pixels.
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ctagan_conv_geom g, const T *__restrict__ gy,
+                                                              const T *__restrict__ gx, float *__restrict__ dw,
+                                                              float *__restrict__ db, int pixels_per_split, int use_atomics) {
+  __shared__ __align__(16) float As[BK][BM + PADM];
+  __shared__ __align__(16) float Bs[BK][BN + PADM];
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  const int A = g.Co, B = g.Ci;
+  const int ntaps = g.KH * g.KW, NP = ntaps * B;
+  const long long P = (long long)g.N * g.Ho * g.Wo;
+  const long long p_begin = (long long)blockIdx.z * pixels_per_split;
+  const long long p_end = min(P, p_begin + (long long)pixels_per_split);
+
+  const int lp = t >> 4, seg = (t & 15) * 4;  // loader: pixel lp of the chunk, 4 consecutive columns at seg
+  const int a_l = blockIdx.x * BM + seg;
+  const int n_l = blockIdx.y * BN + seg;
+  const bool a_vec = (A & 3) == 0 && a_l + 3 < A;
+  const bool b_vec = (B & 3) == 0 && n_l + 3 < NP;
+  int tapj[4], bj[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int np = n_l + j;
+    tapj[j] = np < NP ? np / B : -1;
+    bj[j] = np < NP ? np - tapj[j] * B : 0;
+  }
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float colsum = 0.f;  // bias gradient partial for a = blockIdx.x*BM + t (t < 64)
+
+  for (long long p0 = p_begin; p0 < p_end; p0 += BK) {
+    const long long p = p0 + lp;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < p_end) {
+      if (a_vec) {
+        load_vec<T, 4>(gy + p * A + a_l, a);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (a_l + j < A) a[j] = to_f(gy[p * A + a_l + j]);
+      }
+      const int ow = (int)(p % g.Wo);
+      const long long q = p / g.Wo;
+      const int oh = (int)(q % g.Ho), n = (int)(q / g.Ho);
+      if (b_vec) {
+        const int kh = tapj[0] / g.KW, kw = tapj[0] - kh * g.KW;
+        int ih, iw;
+        if (tap_coord(g, oh, kh, g.pad_h, g.Hi, ih) && tap_coord(g, ow, kw, g.pad_w, g.Wi, iw))
+          load_vec<T, 4>(gx + (((long long)n * g.Hi + ih) * g.Wi + iw) * B + bj[0], b);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (tapj[j] < 0) continue;
+          const int kh = tapj[j] / g.KW, kw = tapj[j] - kh * g.KW;
+          int ih, iw;
+          if (tap_coord(g, oh, kh, g.pad_h, g.Hi, ih) && tap_coord(g, ow, kw, g.pad_w, g.Wi, iw))
+            b[j] = to_f(gx[(((long long)n * g.Hi + ih) * g.Wi + iw) * B + bj[j]]);
+        }
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4 *>(&As[lp][seg]) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4 *>(&Bs[lp][seg]) = make_float4(b[0], b[1], b[2], b[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    if (db != nullptr && blockIdx.y == 0 && t < BM) {
+#pragma unroll
+      for (int k = 0; k < BK; ++k) colsum += As[k][t];
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = blockIdx.x * BM + ty * 4 + i;
+    if (a >= A) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int np = blockIdx.y * BN + tx * 4 + j;
+      if (np >= NP) continue;
+      const int tap = np / B, bb = np - tap * B;
+      float *dst = dw + ((long long)a * B + bb) * ntaps + tap;
+      if (use_atomics) atomicAdd(dst, acc[i][j]);
+      else *dst = acc[i][j];
+    }
+  }
+  if (db != nullptr && blockIdx.y == 0 && t < BM) {
+    const int a = blockIdx.x * BM + t;
+    if (a < A) atomicAdd(db + a, colsum);
+  }
+}
+
+template <typename T>
+__global__ void pack_weights_kernel(const float *__restrict__ w, T *__restrict__ wp, int O, int I, int KH, int KW, int mode) {
+  const long long total = (long long)O * I * KH * KW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    // idx enumerates the PACKED layout (coalesced writes)
+    long long r = idx;
+    if (mode == 0) {
+      const int i = (int)(r % I); r /= I;
+      const int kw = (int)(r % KW); r /= KW;
+      const int kh = (int)(r % KH); r /= KH;
+      const int o = (int)r;
+      wp[idx] = from_f<T>(w[(((long long)o * I + i) * KH + kh) * KW + kw]);
+    } else {
+      const int o = (int)(r % O); r /= O;
+      const int kw = (int)(r % KW); r /= KW;
+      const int kh = (int)(r % KH); r /= KH;
+      const int i = (int)r;
+      wp[idx] = from_f<T>(w[(((long long)o * I + i) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)]);
+    }
+  }
+}
+
+}  // namespace
+
+int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st) {
+  const long long M = (long long)g->N * g->Ho * g->Wo;
+  dim3 grid(cdiv(M, BM), cdiv(g->Co, BN));
+  const bool flat = (g->Ci % BK) != 0;
+  CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+    if (flat) conv_gather_simt_kernel<T, true><<<grid, 256, 0, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+    else conv_gather_simt_kernel<T, false><<<grid, 256, 0, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st) {
+  const long long P = (long long)g->N * g->Ho * g->Wo;
+  const int ntaps = g->KH * g->KW;
+  const int gx_ = cdiv(g->Co, BM), gy_ = cdiv((long long)ntaps * g->Ci, BN);
+  // split the pixel (K) dimension until the grid covers ~2 waves of the SMs
+  const int target = 2 * ctagan_num_sms();
+  int splits = (int)((target + (long long)gx_ * gy_ - 1) / ((long long)gx_ * gy_));
+  const int max_splits = (int)((P + 255) / 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int pps = (int)((P + splits - 1) / splits);
+  pps = ((pps + BK - 1) / BK) * BK;
+  splits = (int)((P + pps - 1) / pps);
+  const int use_atomics = splits > 1;
+  if (use_atomics) CTAGAN_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Co * g->Ci * ntaps, st));
+  if (db) CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
+  dim3 grid(gx_, gy_, splits);
+  CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+    conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, pps, use_atomics);
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_pack_weights(const float *w, void *wp, int O, int I, int KH, int KW, int mode, int dtype, void *stream) {
+  CTAGAN_REQUIRE(w && wp && O > 0 && I > 0 && KH > 0 && KW > 0 && (mode == 0 || mode == 1), "pack_weights: bad arguments");
+  const long long total = (long long)O * I * KH * KW;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { pack_weights_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (T *)wp, O, I, KH, KW, mode); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}

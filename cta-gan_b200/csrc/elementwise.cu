@@ -1,0 +1,747 @@
+// Bandwidth-bound NHWC kernels around the convolutions: InstanceNorm statistics, fused normalise+activation+residual+
+// reflection-pad and its backward, pooling, bilinear 2x upsample + concat, plane means, casts.
+// All are coalesced along the channel (innermost) dimension with 16-byte vectors when C allows it.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// InstanceNorm statistics.  Shifted sums (shift = first pixel of the plane) in fp32 per thread, fp64 across threads.
+// grid (chunks, N); block 256 = PL pixel lanes x CV channel vectors.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) instnorm_partial_kernel(const T *__restrict__ x, double *__restrict__ acc, int HW, int C,
+                                                               int pix_per_block) {
+  const int CV = C / V;
+  const int n = blockIdx.y;
+  const int lanes = 256 / CV > 0 ? 256 / CV : 1;  // pixel lanes (CV <= 256 guaranteed by host)
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const T *base = x + (long long)n * HW * C;
+  float shift[V], s1[V], s2[V];
+  load_vec<T, V>(base + cv * V, shift);
+#pragma unroll
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  if (pl < lanes) {
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      float v[V];
+      load_vec<T, V>(base + (long long)p * C + cv * V, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float d = v[i] - shift[i];
+        s1[i] += d;
+        s2[i] = fmaf(d, d, s2[i]);
+      }
+    }
+  }
+  // combine pixel lanes through shared memory in fp64
+  __shared__ double sm[2][256];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    __syncthreads();
+    sm[0][threadIdx.x] = (pl < lanes) ? (double)s1[i] : 0.0;
+    sm[1][threadIdx.x] = (pl < lanes) ? (double)s2[i] : 0.0;
+    __syncthreads();
+    if (pl == 0) {
+      double a = 0.0, b = 0.0;
+      for (int l = 0; l < lanes; ++l) {
+        a += sm[0][l * CV + cv];
+        b += sm[1][l * CV + cv];
+      }
+      double *dst = acc + ((long long)n * C + cv * V + i) * 2;
+      atomicAdd(dst, a);
+      atomicAdd(dst + 1, b);
+    }
+  }
+}
+
+template <typename T>
+__global__ void instnorm_finalize_kernel(const T *__restrict__ x, const double *__restrict__ acc, float *__restrict__ stats, int N,
+                                         int HW, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const double shift = (double)to_f(x[(long long)n * HW * C + c]);
+  const double m1 = acc[2 * i] / HW, m2 = acc[2 * i + 1] / HW;
+  double var = m2 - m1 * m1;
+  if (var < 0) var = 0;
+  stats[2 * i] = (float)(shift + m1);
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// out[n,hp,wp,c] = act((x-mean)*rstd) + res ; gather form (one thread per output vector), reflect indices.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__ x, const float *__restrict__ stats,
+                                                           const T *__restrict__ res, int res_pad, T *__restrict__ out, int N, int H,
+                                                           int W, int C, int pad, int act) {
+  const int CV = C / V;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const long long total = (long long)N * Hp * Wp * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int wp = (int)(r % Wp);
+    r /= Wp;
+    const int hp = (int)(r % Hp);
+    const int n = (int)(r / Hp);
+    const int h = reflect_idx(hp - pad, H), w = reflect_idx(wp - pad, W);
+    float v[V];
+    load_vec<T, V>(x + (((long long)n * H + h) * W + w) * C + cv * V, v);
+    if (stats) {
+      const float *sp = stats + ((long long)n * C + cv * V) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = (v[i] - sp[2 * i]) * sp[2 * i + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = apply_act(v[i], act);
+    if (res) {
+      float rv[V];
+      const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
+      load_vec<T, V>(res + (((long long)n * Hr + h + res_pad) * Wr + w + res_pad) * C + cv * V, rv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] += rv[i];
+    }
+    store_vec<T, V>(out + idx * V, v);
+  }
+}
+
+// padded positions that reflect onto interior index h (<= 3 of them)
+__device__ __forceinline__ int fold_sources(int h, int H, int pad, int (&src)[3]) {
+  int cnt = 0;
+  src[cnt++] = h + pad;
+  if (pad > 0) {
+    if (h >= 1 && h <= pad) src[cnt++] = pad - h;
+    if (h <= H - 2 && h >= H - 1 - pad) src[cnt++] = 2 * (H - 1) + pad - h;
+  }
+  return cnt;
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void folded_grad(const T *__restrict__ gout, int n, int h, int w, int cv, int H, int W, int C, int pad,
+                                            float (&g)[V]) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  int hs[3], ws[3];
+  const int nh = fold_sources(h, H, pad, hs), nw = fold_sources(w, W, pad, ws);
+#pragma unroll
+  for (int i = 0; i < V; ++i) g[i] = 0.f;
+  for (int a = 0; a < nh; ++a)
+    for (int b = 0; b < nw; ++b) {
+      float t[V];
+      load_vec<T, V>(gout + (((long long)n * Hp + hs[a]) * Wp + ws[b]) * C + cv * V, t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[i] += t[i];
+    }
+}
+
+__device__ __forceinline__ float act_grad_from_sign(float pre, int act) {
+  if (act == CTAGAN_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+  if (act == CTAGAN_ACT_LRELU) return pre > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// pass 1: per-(n,c) sums of g and g*xhat.  grid (chunks, N)
+template <typename T, int V>
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restrict__ gout, const T *__restrict__ x,
+                                                              const float *__restrict__ stats, const T *__restrict__ addend,
+                                                              double *__restrict__ acc, int H, int W, int C, int pad, int act,
+                                                              int pix_per_block) {
+  const int CV = C / V;
+  const int n = blockIdx.y;
+  const int lanes = 256 / CV > 0 ? 256 / CV : 1;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int HW = H * W;
+  float mean[V], rstd[V], s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mean[i] = stats[((long long)n * C + cv * V + i) * 2];
+    rstd[i] = stats[((long long)n * C + cv * V + i) * 2 + 1];
+    s1[i] = s2[i] = 0.f;
+  }
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  if (pl < lanes) {
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const int h = p / W, w = p - h * W;
+      float g[V], xv[V];
+      folded_grad<T, V>(gout, n, h, w, cv, H, W, C, pad, g);
+      if (addend) {
+        float av[V];
+        load_vec<T, V>(addend + ((long long)n * HW + p) * C + cv * V, av);
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] += av[i];
+      }
+      load_vec<T, V>(x + ((long long)n * HW + p) * C + cv * V, xv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xh = (xv[i] - mean[i]) * rstd[i];
+        const float gg = g[i] * act_grad_from_sign(xh, act);
+        s1[i] += gg;
+        s2[i] = fmaf(gg, xh, s2[i]);
+      }
+    }
+  }
+  __shared__ double sm[2][256];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    __syncthreads();
+    sm[0][threadIdx.x] = (pl < lanes) ? (double)s1[i] : 0.0;
+    sm[1][threadIdx.x] = (pl < lanes) ? (double)s2[i] : 0.0;
+    __syncthreads();
+    if (pl == 0) {
+      double a = 0.0, b = 0.0;
+      for (int l = 0; l < lanes; ++l) {
+        a += sm[0][l * CV + cv];
+        b += sm[1][l * CV + cv];
+      }
+      double *dst = acc + ((long long)n * C + cv * V + i) * 2;
+      atomicAdd(dst, a);
+      atomicAdd(dst + 1, b);
+    }
+  }
+}
+
+// pass 2: g = fold(gout) + addend;  dx = rstd*(g*act' - mean - xhat*mean(. xhat))
+template <typename T, int V>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict__ gout, const T *__restrict__ x,
+                                                             const float *__restrict__ stats, const double *__restrict__ acc,
+                                                             const T *__restrict__ addend, T *__restrict__ dx,
+                                                             int N, int H, int W, int C, int pad, int act) {
+  const int CV = C / V;
+  const int HW = H * W;
+  const long long total = (long long)N * HW * CV;
+  const float inv_hw = 1.f / (float)HW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int p = (int)(r % HW);
+    const int n = (int)(r / HW);
+    const int h = p / W, w = p - h * W;
+    float g[V], o[V];
+    folded_grad<T, V>(gout, n, h, w, cv, H, W, C, pad, g);
+    if (addend) {
+      float av[V];
+      load_vec<T, V>(addend + idx * V, av);
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[i] += av[i];
+    }
+    if (stats) {
+      float xv[V];
+      load_vec<T, V>(x + idx * V, xv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const long long sc = (long long)n * C + cv * V + i;
+        const float mean = stats[2 * sc], rstd = stats[2 * sc + 1];
+        const float xh = (xv[i] - mean) * rstd;
+        const float gg = g[i] * act_grad_from_sign(xh, act);
+        const float m1 = (float)(acc[2 * sc] * (double)inv_hw), m2 = (float)(acc[2 * sc + 1] * (double)inv_hw);
+        o[i] = rstd * (gg - m1 - xh * m2);
+      }
+    } else if (act != CTAGAN_ACT_NONE) {
+      float xv[V];
+      load_vec<T, V>(x + idx * V, xv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = g[i] * act_grad_from_sign(xv[i], act);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = g[i];
+    }
+    store_vec<T, V>(dx + idx * V, o);
+  }
+}
+
+template <typename T, int V>
+__global__ void act_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ y, T *__restrict__ dx, long long nvec, int act) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
+    float g[V], yv[V], o[V];
+    load_vec<T, V>(gy + idx * V, g);
+    load_vec<T, V>(y + idx * V, yv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if (act == CTAGAN_ACT_TANH) o[i] = g[i] * (1.f - yv[i] * yv[i]);
+      else o[i] = g[i] * act_grad_from_sign(yv[i], act);
+    }
+    store_vec<T, V>(dx + idx * V, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MaxPool2d(2)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void maxpool2_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W, int C) {
+  const int CV = C / V, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int ow = (int)(r % Wo);
+    r /= Wo;
+    const int oh = (int)(r % Ho), n = (int)(r / Ho);
+    float m[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) m[i] = -INFINITY;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dxx = 0; dxx < 2; ++dxx) {
+        float v[V];
+        load_vec<T, V>(x + (((long long)n * H + 2 * oh + dy) * W + 2 * ow + dxx) * C + cv * V, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) m[i] = (v[i] > m[i] || v[i] != v[i]) ? v[i] : m[i];
+      }
+    store_vec<T, V>(y + idx * V, m);
+  }
+}
+
+template <typename T, int V>
+__global__ void maxpool2_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ x, const T *__restrict__ addend, T *__restrict__ gx, int N, int H,
+                                    int W, int C) {
+  const int CV = C / V, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int ow = (int)(r % Wo);
+    r /= Wo;
+    const int oh = (int)(r % Ho), n = (int)(r / Ho);
+    float v[4][V], g[V];
+    load_vec<T, V>(gy + idx * V, g);
+    for (int k = 0; k < 4; ++k)
+      load_vec<T, V>(x + (((long long)n * H + 2 * oh + (k >> 1)) * W + 2 * ow + (k & 1)) * C + cv * V, v[k]);
+    float o[4][V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      int arg = 0;
+      float m = v[0][i];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k][i] > m) { m = v[k][i]; arg = k; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][i] = (k == arg) ? g[i] : 0.f;
+    }
+    for (int k = 0; k < 4; ++k) {
+      const long long off = (((long long)n * H + 2 * oh + (k >> 1)) * W + 2 * ow + (k & 1)) * C + cv * V;
+      if (addend) {
+        float av[V];
+        load_vec<T, V>(addend + off, av);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[k][i] += av[i];
+      }
+      store_vec<T, V>(gx + off, o[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bilinear 2x upsample (align_corners=False) + concat.  For exact 2x: src = (o + 0.5)/2 - 0.5 clamped at 0,
+// i0 = floor(src), i1 = min(i0+1, H-1), lambda = src - i0   (ATen area_pixel_compute_source_index).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up2_coords(int o, int n_in, int &i0, int &i1, float &l1) {
+  float s = (o + 0.5f) * 0.5f - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+template <typename T, int V>
+__global__ void upsample2x_cat_fwd_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ out, int N, int H, int W,
+                                          int C1, int C2) {
+  const int C = C1 + C2, CV = C / V, CV1 = C1 / V;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV);
+    long long r = idx / CV;
+    const int ow = (int)(r % Wo);
+    r /= Wo;
+    const int oh = (int)(r % Ho), n = (int)(r / Ho);
+    float o[V];
+    if (cv < CV1) {
+      int h0, h1, w0, w1;
+      float lh, lw;
+      up2_coords(oh, H, h0, h1, lh);
+      up2_coords(ow, W, w0, w1, lw);
+      float a[V], b[V], c[V], d[V];
+      const T *base = x + (long long)n * H * W * C1 + cv * V;
+      load_vec<T, V>(base + ((long long)h0 * W + w0) * C1, a);
+      load_vec<T, V>(base + ((long long)h0 * W + w1) * C1, b);
+      load_vec<T, V>(base + ((long long)h1 * W + w0) * C1, c);
+      load_vec<T, V>(base + ((long long)h1 * W + w1) * C1, d);
+      const float hh0 = 1.f - lh, ww0 = 1.f - lw;
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = hh0 * (ww0 * a[i] + lw * b[i]) + lh * (ww0 * c[i] + lw * d[i]);
+    } else {
+      load_vec<T, V>(skip + (((long long)n * Ho + oh) * Wo + ow) * C2 + (cv - CV1) * V, o);
+    }
+    store_vec<T, V>(out + idx * V, o);
+  }
+}
+
+// gather form of the transposed bilinear operator: input pixel (h,w) collects from the <=3x3 output pixels that read it.
+template <typename T, int V>
+__global__ void upsample2x_cat_bwd_kernel(const T *__restrict__ gout, T *__restrict__ gx, T *__restrict__ gskip, int N, int H, int W,
+                                          int C1, int C2) {
+  const int C = C1 + C2, CV1 = C1 / V, CV2 = C2 / V;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total1 = (long long)N * H * W * CV1;
+  const long long total2 = gskip ? (long long)N * Ho * Wo * CV2 : 0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total1 + total2; idx += (long long)gridDim.x * blockDim.x) {
+    if (idx < total1) {
+      const int cv = (int)(idx % CV1);
+      long long r = idx / CV1;
+      const int w = (int)(r % W);
+      r /= W;
+      const int h = (int)(r % H), n = (int)(r / H);
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+      for (int oh = max(0, 2 * h - 2); oh <= min(Ho - 1, 2 * h + 2); ++oh) {
+        int h0, h1;
+        float lh;
+        up2_coords(oh, H, h0, h1, lh);
+        float wh = 0.f;
+        if (h0 == h) wh += 1.f - lh;
+        if (h1 == h) wh += lh;
+        if (wh == 0.f) continue;
+        for (int ow = max(0, 2 * w - 2); ow <= min(Wo - 1, 2 * w + 2); ++ow) {
+          int w0, w1;
+          float lw;
+          up2_coords(ow, W, w0, w1, lw);
+          float ww = 0.f;
+          if (w0 == w) ww += 1.f - lw;
+          if (w1 == w) ww += lw;
+          if (ww == 0.f) continue;
+          float g[V];
+          load_vec<T, V>(gout + (((long long)n * Ho + oh) * Wo + ow) * C + cv * V, g);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] = fmaf(wh * ww, g[i], acc[i]);
+        }
+      }
+      store_vec<T, V>(gx + idx * V, acc);
+    } else {
+      const long long j = idx - total1;
+      const int cv = (int)(j % CV2);
+      const long long pix = j / CV2;
+      float g[V];
+      load_vec<T, V>(gout + pix * C + C1 + cv * V, g);
+      store_vec<T, V>(gskip + j * V, g);
+    }
+  }
+}
+
+template <typename T>
+__global__ void copy_channels_kernel(const T *__restrict__ src, T *__restrict__ dst, long long pixels, int C, int ss, int so, int ds, int doff) {
+  const long long total = pixels * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long p = idx / C;
+    const int c = (int)(idx - p * C);
+    dst[p * ds + doff + c] = src[p * ss + so + c];
+  }
+}
+
+// plane mean: one warp per (n, c-group); small C (1) in practice.
+template <typename T>
+__global__ void plane_mean_fwd_kernel(const T *__restrict__ x, float *__restrict__ out, int HW, int C) {
+  const int n = blockIdx.x, c = blockIdx.y;
+  double s = 0.0;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) s += (double)to_f(x[((long long)n * HW + p) * C + c]);
+  __shared__ double sm[32];
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sm[i];
+    out[n * C + c] = (float)(t / HW);
+  }
+}
+
+template <typename T>
+__global__ void plane_mean_bwd_kernel(const float *__restrict__ gout, T *__restrict__ gx, int N, int HW, int C) {
+  const long long total = (long long)N * HW * C;
+  const float inv = 1.f / (float)HW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int n = (int)(idx / ((long long)HW * C));
+    gx[idx] = from_f<T>(gout[n * C + c] * inv);
+  }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S *__restrict__ s, D *__restrict__ d, long long n) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+    d[idx] = from_f<D>(to_f(s[idx]));
+}
+
+// fp32 NCHW (module boundary) <-> T NHWC (internal)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, T *__restrict__ dst, int N, int C, long long HW) {
+  const long long total = (long long)N * HW * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long long r = idx / C;
+    const long long p = r % HW;
+    const int n = (int)(r / HW);
+    dst[idx] = from_f<T>(src[((long long)n * C + c) * HW + p]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict__ dst, int N, int C, long long HW) {
+  const long long total = (long long)N * HW * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long p = idx % HW;
+    const long long r = idx / HW;
+    const int c = (int)(r % C);
+    const int n = (int)(r / C);
+    dst[idx] = to_f(src[((long long)n * HW + p) * C + c]);
+  }
+}
+
+// two 1-channel fp32 planes <-> one 2-channel NHWC tensor (torch.cat([a, b], 1) of trainer/reg.py:77 and its gradient split)
+template <typename T>
+__global__ void interleave2_kernel(const float *__restrict__ a, const float *__restrict__ b, T *__restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    dst[2 * i] = from_f<T>(a[i]);
+    dst[2 * i + 1] = from_f<T>(b[i]);
+  }
+}
+template <typename T>
+__global__ void deinterleave2_kernel(const T *__restrict__ src, float *__restrict__ a, float *__restrict__ b, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (a) a[i] = to_f(src[2 * i]);
+    if (b) b[i] = to_f(src[2 * i + 1]);
+  }
+}
+
+inline int ew_blocks(long long work) {
+  long long b = (work + 255) / 256;
+  const long long cap = (long long)ctagan_num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// choose the widest vector V in {max, 4, 2, 1} dividing all the given channel counts
+template <typename T>
+int pick_vec(int c1, int c2 = 0) {
+  for (int v = max_vec<T>(); v > 1; v >>= 1)
+    if (c1 % v == 0 && c2 % v == 0) return v;
+  return 1;
+}
+
+}  // namespace
+
+#define VEC_SWITCH(T, v, V, ...)                                   \
+  do {                                                             \
+    if (v == 8) { constexpr int V = sizeof(T) == 2 ? 8 : 4; __VA_ARGS__; }  \
+    else if (v == 4) { constexpr int V = 4; __VA_ARGS__; }         \
+    else if (v == 2) { constexpr int V = 2; __VA_ARGS__; }         \
+    else { constexpr int V = 1; __VA_ARGS__; }                     \
+  } while (0)
+
+static int reduce_chunks(int N, int HW, int C, int v, int &pix_per_block) {
+  const int CV = C / v;
+  const int lanes = 256 / CV > 0 ? 256 / CV : 1;
+  // aim for ~4 CTAs per SM overall, at least 8 pixels per lane
+  long long want = ((long long)ctagan_num_sms() * 4 + N - 1) / N;
+  long long maxc = (HW + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  pix_per_block = (int)((HW + want - 1) / want);
+  return (int)((HW + pix_per_block - 1) / pix_per_block);
+}
+
+extern "C" int ctagan_instnorm_stats(const void *x, float *stats, double *acc, int N, int HW, int C, int dtype, void *stream) {
+  CTAGAN_REQUIRE(x && stats && acc && N > 0 && HW > 0 && C > 0, "instnorm_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    int v = pick_vec<T>(C);
+    while (C / v > 256) { CTAGAN_REQUIRE(v < max_vec<T>(), "instnorm_stats: C=%d too large", C); v *= 2; }
+    int ppb;
+    const int chunks = reduce_chunks(N, HW, C, v, ppb);
+    dim3 grid(chunks, N);
+    VEC_SWITCH(T, v, V, instnorm_partial_kernel<T, V><<<grid, 256, 0, st>>>((const T *)x, acc, HW, C, ppb));
+    instnorm_finalize_kernel<T><<<cdiv((long long)N * C, 128), 128, 0, st>>>((const T *)x, acc, stats, N, HW, C);
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int res_pad, void *out, int N, int H, int W,
+                                   int C, int pad, int act, int dtype, void *stream) {
+  CTAGAN_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && pad < H && pad < W, "norm_act_pad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    const int v = pick_vec<T>(C);
+    const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / v);
+    VEC_SWITCH(T, v, V, norm_act_pad_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, stats, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act));
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
+                                       double *acc, int N, int H, int W, int C, int pad, int act, int dtype, void *stream) {
+  CTAGAN_REQUIRE(gout && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0, "norm_act_pad_bwd: bad arguments");
+  CTAGAN_REQUIRE(!(stats || act != CTAGAN_ACT_NONE) || x, "norm_act_pad_bwd: x required when stats/act given");
+  CTAGAN_REQUIRE(!stats || acc, "norm_act_pad_bwd: acc scratch required with stats");
+  CTAGAN_REQUIRE(act != CTAGAN_ACT_TANH, "norm_act_pad_bwd: tanh unsupported here (use act_bwd)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    int v = pick_vec<T>(C);
+    if (stats) {
+      while (C / v > 256) { CTAGAN_REQUIRE(v < max_vec<T>(), "norm_act_pad_bwd: C=%d too large", C); v *= 2; }
+      CTAGAN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
+      int ppb;
+      const int chunks = reduce_chunks(N, H * W, C, v, ppb);
+      dim3 grid(chunks, N);
+      VEC_SWITCH(T, v, V, norm_bwd_reduce_kernel<T, V><<<grid, 256, 0, st>>>((const T *)gout, (const T *)x, stats, (const T *)addend, acc, H, W, C, pad, act, ppb));
+    }
+    const long long total = (long long)N * H * W * (C / v);
+    VEC_SWITCH(T, v, V, norm_bwd_apply_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, N, H, W, C, pad, act));
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_act_bwd(const void *gy, const void *y, void *dx, int64_t n, int act, int dtype, void *stream) {
+  CTAGAN_REQUIRE(gy && y && dx && n > 0, "act_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    int v = max_vec<T>();
+    while (n % v) v >>= 1;
+    VEC_SWITCH(T, v, V, act_bwd_kernel<T, V><<<ew_blocks(n / v), 256, 0, st>>>((const T *)gy, (const T *)y, (T *)dx, n / v, act));
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_maxpool2_fwd(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream) {
+  CTAGAN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: bad arguments (even H, W required)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    const int v = pick_vec<T>(C);
+    const long long total = (long long)N * (H / 2) * (W / 2) * (C / v);
+    VEC_SWITCH(T, v, V, maxpool2_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, (T *)y, N, H, W, C));
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_maxpool2_bwd(const void *gy, const void *x, const void *addend, void *gx, int N, int H, int W, int C, int dtype, void *stream) {
+  CTAGAN_REQUIRE(gy && x && gx && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    const int v = pick_vec<T>(C);
+    const long long total = (long long)N * (H / 2) * (W / 2) * (C / v);
+    VEC_SWITCH(T, v, V, maxpool2_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gy, (const T *)x, (const T *)addend, (T *)gx, N, H, W, C));
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_upsample2x_cat_fwd(const void *x, const void *skip, void *out, int N, int H, int W, int C1, int C2, int dtype,
+                                         void *stream) {
+  CTAGAN_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0 && (C2 == 0 || skip), "upsample2x_cat_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    const int v = pick_vec<T>(C1, C2);
+    const long long total = (long long)N * 4 * H * W * ((C1 + C2) / v);
+    VEC_SWITCH(T, v, V, upsample2x_cat_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, (const T *)skip, (T *)out, N, H, W, C1, C2));
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_upsample2x_cat_bwd(const void *gout, void *gx, void *gskip, int N, int H, int W, int C1, int C2, int dtype,
+                                         void *stream) {
+  CTAGAN_REQUIRE(gout && gx && N > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0, "upsample2x_cat_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    const int v = pick_vec<T>(C1, C2);
+    const long long total = (long long)N * H * W * (C1 / v) + (gskip ? (long long)N * 4 * H * W * (C2 / v) : 0);
+    VEC_SWITCH(T, v, V, upsample2x_cat_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gout, (T *)gx, (T *)gskip, N, H, W, C1, C2));
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_copy_channels(const void *src, void *dst, int64_t pixels, int C, int src_stride, int src_off, int dst_stride,
+                                    int dst_off, int dtype, void *stream) {
+  CTAGAN_REQUIRE(src && dst && pixels > 0 && C > 0 && src_off + C <= src_stride && dst_off + C <= dst_stride, "copy_channels: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, {
+    copy_channels_kernel<T><<<ew_blocks(pixels * C), 256, 0, st>>>((const T *)src, (T *)dst, pixels, C, src_stride, src_off, dst_stride, dst_off);
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_plane_mean_fwd(const void *x, float *out, int N, int HW, int C, int dtype, void *stream) {
+  CTAGAN_REQUIRE(x && out && N > 0 && HW > 0 && C > 0 && C <= 65535, "plane_mean_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { plane_mean_fwd_kernel<T><<<dim3(N, C), 256, 0, st>>>((const T *)x, out, HW, C); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_plane_mean_bwd(const float *gout, void *gx, int N, int HW, int C, int dtype, void *stream) {
+  CTAGAN_REQUIRE(gout && gx && N > 0 && HW > 0 && C > 0, "plane_mean_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { plane_mean_bwd_kernel<T><<<ew_blocks((long long)N * HW * C), 256, 0, st>>>(gout, (T *)gx, N, HW, C); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_cast(const void *src, int sd, void *dst, int dd, int64_t n, void *stream) {
+  CTAGAN_REQUIRE(src && dst && n > 0, "cast: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ew_blocks(n);
+  if (sd == CTAGAN_F32 && dd == CTAGAN_BF16) cast_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float *)src, (bf16 *)dst, n);
+  else if (sd == CTAGAN_BF16 && dd == CTAGAN_F32) cast_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16 *)src, (float *)dst, n);
+  else if (sd == CTAGAN_F32 && dd == CTAGAN_F32) cast_kernel<float, float><<<blocks, 256, 0, st>>>((const float *)src, (float *)dst, n);
+  else if (sd == CTAGAN_BF16 && dd == CTAGAN_BF16) cast_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16 *)src, (bf16 *)dst, n);
+  else { ctagan_set_error("cast: bad dtypes"); return CTAGAN_ERR_ARG; }
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_nchw_to_nhwc(const float *src, void *dst, int N, int C, int64_t HW, int dtype, void *stream) {
+  CTAGAN_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { nchw_to_nhwc_kernel<T><<<ew_blocks((long long)N * C * HW), 256, 0, st>>>(src, (T *)dst, N, C, HW); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_nhwc_to_nchw(const void *src, float *dst, int N, int C, int64_t HW, int dtype, void *stream) {
+  CTAGAN_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { nhwc_to_nchw_kernel<T><<<ew_blocks((long long)N * C * HW), 256, 0, st>>>((const T *)src, dst, N, C, HW); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_interleave2(const float *a, const float *b, void *dst, int64_t n, int dtype, void *stream) {
+  CTAGAN_REQUIRE(a && b && dst && n > 0, "interleave2: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { interleave2_kernel<T><<<ew_blocks(n), 256, 0, st>>>(a, b, (T *)dst, n); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_deinterleave2(const void *src, float *a, float *b, int64_t n, int dtype, void *stream) {
+  CTAGAN_REQUIRE(src && (a || b) && n > 0, "deinterleave2: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { deinterleave2_kernel<T><<<ew_blocks(n), 256, 0, st>>>((const T *)src, a, b, n); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}

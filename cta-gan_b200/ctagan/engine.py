@@ -1,0 +1,445 @@
+"""Explicit forward/backward kernel schedules of the three networks on the hot path.
+
+Each network pass is ONE autograd node whose forward enqueues the fused kernel sequence and whose backward enqueues the
+hand-scheduled reverse sequence (dgrad / wgrad / InstanceNorm-backward with the reflection-pad fold), so no ATen kernel runs
+between the module boundaries.  Activations are NHWC in `precision` (bf16 fast mode, fp32 validation mode); raw conv
+outputs and (mean, rstd) are kept for backward, normalised activations are written once into the (reflection-)padded
+buffer the next convolution reads.
+
+Reference semantics followed (paths in the upstream tree): Model/CycleGan.py:6-103, Model/HdGan.py:148-256,
+trainer/reg.py:31-132, trainer/layers.py:71-104,156-183,216-300.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+from . import ops
+
+_PRECISION = {"value": torch.bfloat16}
+
+
+def set_precision(p):
+    """'bf16' (tensor-core fast mode) or 'fp32' (validation mode, <=1e-4 vs the fp32 reference)."""
+    _PRECISION["value"] = {"bf16": torch.bfloat16, "fp32": torch.float32, torch.bfloat16: torch.bfloat16,
+                           torch.float32: torch.float32}[p]
+
+
+def get_precision() -> torch.dtype:
+    return _PRECISION["value"]
+
+
+_ENGINE = {"value": L.ENGINE_AUTO}
+
+
+def set_conv_engine(e):
+    _ENGINE["value"] = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tc": L.ENGINE_TC}[e]
+
+
+class ConvPrim:
+    """A convolution weight W[O][I][K][K] with stride s and zero padding p, offering the three GEMMs that
+    Conv2d (fwd = fprop) and ConvTranspose2d (fwd = bprop) need.  Packed copies are cached per weight version."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, pad: int):
+        self.w, self.b = weight, bias
+        self.O, self.I, self.K, _ = weight.shape
+        self.s, self.p = stride, pad
+        self._cache: Dict[Tuple[int, torch.dtype], Tuple[int, int, torch.Tensor]] = {}
+
+    def packed(self, mode: int, dtype: torch.dtype) -> torch.Tensor:
+        key = (mode, dtype)
+        ver = (self.w._version, self.w.data_ptr())
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        wp = ops.pack_weights(self.w.detach(), mode, dtype)
+        self._cache[key] = (ver, wp)
+        return wp
+
+    # I-channel input -> O-channel output, strided  (Conv2d forward / ConvTranspose2d input-gradient)
+    def fprop(self, x, act=L.ACT_NONE, use_bias=True, pad=None):
+        N, Hi, Wi, Ci = x.shape
+        assert Ci == self.I, (Ci, self.I)
+        p = self.p if pad is None else pad
+        Ho = (Hi + 2 * p - self.K) // self.s + 1
+        Wo = (Wi + 2 * p - self.K) // self.s + 1
+        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, self.O, self.K, self.s, 1, p, act, ops.dt(x))
+        bias = self.b.detach() if (use_bias and self.b is not None) else None
+        return ops.conv_gather(x, self.packed(0, x.dtype), bias, g, _ENGINE["value"])
+
+    # O-channel input -> I-channel output of spatial size `out_hw`  (Conv2d input-gradient / ConvTranspose2d forward)
+    def bprop(self, dy, out_hw, act=L.ACT_NONE, bias=None, pad=None):
+        N, Ho, Wo, Co = dy.shape
+        assert Co == self.O, (Co, self.O)
+        p = self.p if pad is None else pad
+        g = ops.make_geom(N, Ho, Wo, Co, out_hw[0], out_hw[1], self.I, self.K, 1, self.s, self.K - 1 - p, act, ops.dt(dy))
+        return ops.conv_gather(dy, self.packed(1, dy.dtype), bias, g, _ENGINE["value"])
+
+    # dW[O][I][K][K] = sum gy(O-channel, strided side) x gx(I-channel, gathered side)
+    def wgrad(self, gy, gx, want_bias=False, pad=None):
+        N, Ho, Wo, Co = gy.shape
+        _, Hi, Wi, Ci = gx.shape
+        assert Co == self.O and Ci == self.I
+        p = self.p if pad is None else pad
+        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, self.K, self.s, 1, p, L.ACT_NONE, ops.dt(gy))
+        return ops.conv_wgrad(gy, gx, g, want_bias, _ENGINE["value"])
+
+
+def _zeros_like_param(p):
+    return torch.zeros_like(p)
+
+
+# ======================================================================================================================
+# ResNet-9 generator  (Model/CycleGan.py:23-71)
+# ======================================================================================================================
+
+
+class GeneratorPlan:
+    """Holds the ConvPrims of one Generator (parameters are the module's own nn.Parameters, fp32 OIHW)."""
+
+    def __init__(self, params: Sequence[torch.Tensor], n_blocks: int):
+        it = iter(params)
+        nxt = lambda: (next(it), next(it))
+        w, b = nxt(); self.head1 = ConvPrim(w, b, 1, 0)            # 7x7 on the reflect-padded image
+        w, b = nxt(); self.head4 = ConvPrim(w, b, 2, 1)
+        w, b = nxt(); self.head7 = ConvPrim(w, b, 2, 1)
+        self.blocks = []
+        for _ in range(n_blocks):
+            w1, b1 = nxt(); w2, b2 = nxt()
+            self.blocks.append((ConvPrim(w1, b1, 1, 0), ConvPrim(w2, b2, 1, 0)))
+        # ConvTranspose2d weight [Cin_T][Cout_T][3][3] == a stride-2 conv weight W[O=Cin_T][I=Cout_T]
+        w, b = nxt(); self.tail0 = ConvPrim(w, b, 2, 1)
+        w, b = nxt(); self.tail3 = ConvPrim(w, b, 2, 1)
+        w, b = nxt(); self.tail7 = ConvPrim(w, b, 1, 0)
+        self.n_blocks = n_blocks
+        self.params = list(params)
+
+
+def generator_forward(plan: GeneratorPlan, x_nchw: torch.Tensor, save: bool):
+    T = get_precision()
+    N, Cin, H, W = x_nchw.shape
+    x0 = ops.nchw_to_nhwc(x_nchw, T)
+    P0 = ops.norm_act_pad(x0, None, L.ACT_NONE, 3)
+    r1 = plan.head1.fprop(P0, use_bias=False); s1 = ops.instnorm_stats(r1)
+    A1 = ops.norm_act_pad(r1, s1, L.ACT_RELU, 0)
+    r2 = plan.head4.fprop(A1, use_bias=False); s2 = ops.instnorm_stats(r2)
+    A2 = ops.norm_act_pad(r2, s2, L.ACT_RELU, 0)
+    r3 = plan.head7.fprop(A2, use_bias=False); s3 = ops.instnorm_stats(r3)
+    nb = plan.n_blocks
+    X = ops.norm_act_pad(r3, s3, L.ACT_RELU, 1 if nb > 0 else 0)
+    blocks = []
+    for k, (c1, c2) in enumerate(plan.blocks):
+        ra = c1.fprop(X, use_bias=False); sa = ops.instnorm_stats(ra)
+        Tt = ops.norm_act_pad(ra, sa, L.ACT_RELU, 1)
+        rb = c2.fprop(Tt, use_bias=False); sb = ops.instnorm_stats(rb)
+        Xn = ops.norm_act_pad(rb, sb, L.ACT_NONE, 1 if k < nb - 1 else 0, res=X, res_pad=1)
+        if save:
+            blocks.append((X, ra, sa, Tt, rb, sb))
+        X = Xn
+    h4, w4 = X.shape[1], X.shape[2]
+    r4 = plan.tail0.bprop(X, (2 * h4, 2 * w4)); s4 = ops.instnorm_stats(r4)
+    A4 = ops.norm_act_pad(r4, s4, L.ACT_RELU, 0)
+    r5 = plan.tail3.bprop(A4, (4 * h4, 4 * w4)); s5 = ops.instnorm_stats(r5)
+    P5 = ops.norm_act_pad(r5, s5, L.ACT_RELU, 3)
+    y = plan.tail7.fprop(P5, act=L.ACT_TANH, use_bias=True)
+    out = ops.nhwc_to_nchw(y)
+    saved = (P0, r1, s1, A1, r2, s2, A2, r3, s3, blocks, X, r4, s4, A4, r5, s5, P5, y) if save else None
+    return out, saved
+
+
+def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: bool, need_dw: bool = True):
+    (P0, r1, s1, A1, r2, s2, A2, r3, s3, blocks, X9, r4, s4, A4, r5, s5, P5, y) = saved
+    T = y.dtype
+    grads: List[Optional[torch.Tensor]] = []
+
+    def wg(prim, gy, gx, bias=False):
+        if not need_dw:
+            return None, None
+        return prim.wgrad(gy, gx, want_bias=bias)
+
+    gy = ops.nchw_to_nhwc(dout, T)
+    dy7 = ops.act_bwd(gy, y, L.ACT_TANH)
+    dW7, db7 = wg(plan.tail7, dy7, P5, True)
+    dP5 = plan.tail7.bprop(dy7, (P5.shape[1], P5.shape[2]))
+    dr5 = ops.norm_act_pad_bwd(dP5, r5, s5, L.ACT_RELU, 3)
+    dA4 = plan.tail3.fprop(dr5, use_bias=False)
+    dWt3, _ = wg(plan.tail3, A4, dr5)
+    dr4 = ops.norm_act_pad_bwd(dA4, r4, s4, L.ACT_RELU, 0)
+    G = plan.tail0.fprop(dr4, use_bias=False)
+    dWt0, _ = wg(plan.tail0, X9, dr4)
+    block_grads = []
+    for (c1, c2), (Xk, ra, sa, Tt, rb, sb) in zip(reversed(plan.blocks), reversed(blocks)):
+        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0)
+        dW2, _ = wg(c2, drb, Tt)
+        dT = c2.bprop(drb, (Tt.shape[1], Tt.shape[2]))
+        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1)
+        dW1, _ = wg(c1, dra, Xk)
+        dXp = c1.bprop(dra, (Xk.shape[1], Xk.shape[2]))
+        G = ops.norm_act_pad_bwd(dXp, None, None, L.ACT_NONE, 1, addend=G)
+        block_grads.append((dW1, dW2))
+    block_grads.reverse()
+    dr3 = ops.norm_act_pad_bwd(G, r3, s3, L.ACT_RELU, 0)
+    dWh7, _ = wg(plan.head7, dr3, A2)
+    dA2 = plan.head7.bprop(dr3, (A2.shape[1], A2.shape[2]))
+    dr2 = ops.norm_act_pad_bwd(dA2, r2, s2, L.ACT_RELU, 0)
+    dWh4, _ = wg(plan.head4, dr2, A1)
+    dA1 = plan.head4.bprop(dr2, (A1.shape[1], A1.shape[2]))
+    dr1 = ops.norm_act_pad_bwd(dA1, r1, s1, L.ACT_RELU, 0)
+    dWh1, _ = wg(plan.head1, dr1, P0)
+    dx = None
+    if need_dx:
+        dP0 = plan.head1.bprop(dr1, (P0.shape[1], P0.shape[2]))
+        dx0 = ops.norm_act_pad_bwd(dP0, None, None, L.ACT_NONE, 3)
+        dx = ops.nhwc_to_nchw(dx0)
+    if need_dw:
+        # biases in front of a non-affine InstanceNorm are mathematically dead: zero gradient
+        z = lambda prim: torch.zeros_like(prim.b)
+        grads = [dWh1, z(plan.head1), dWh4, z(plan.head4), dWh7, z(plan.head7)]
+        for (c1, c2), (dW1, dW2) in zip(plan.blocks, block_grads):
+            grads += [dW1, z(c1), dW2, z(c2)]
+        grads += [dWt0, z(plan.tail0), dWt3, z(plan.tail3), dW7, db7]
+    else:
+        grads = [None] * len(plan.params)
+    return dx, grads
+
+
+# ======================================================================================================================
+# PatchGAN discriminator  (Model/CycleGan.py:73-103, Model/HdGan.py:148-256)
+# ======================================================================================================================
+
+
+class DiscriminatorPlan:
+    def __init__(self, params: Sequence[torch.Tensor]):
+        it = iter(params)
+        strides = [2, 2, 2, 1, 1]
+        self.convs = []
+        for s in strides:
+            w, b = next(it), next(it)
+            self.convs.append(ConvPrim(w, b, s, 1))
+        self.params = list(params)
+
+
+def discriminator_forward(plan: DiscriminatorPlan, x_nchw: torch.Tensor, save: bool):
+    """Returns the last feature map [N,1,h,w] fp32 and (optionally) the NHWC intermediates [a0..a3]."""
+    T = get_precision()
+    x0 = ops.nchw_to_nhwc(x_nchw, T)
+    c = plan.convs
+    a0 = c[0].fprop(x0, act=L.ACT_LRELU, use_bias=True)
+    acts, raws, stats = [a0], [], []
+    a = a0
+    for i in (1, 2, 3):
+        r = c[i].fprop(a, use_bias=False)
+        s = ops.instnorm_stats(r)
+        a = ops.norm_act_pad(r, s, L.ACT_LRELU, 0)
+        raws.append(r); stats.append(s); acts.append(a)
+    y4 = c[4].fprop(a, use_bias=True)
+    out = ops.nhwc_to_nchw(y4)
+    saved = (x0, acts, raws, stats, y4.shape, y4.dtype) if save else None
+    return out, acts, saved
+
+
+def discriminator_backward(plan: DiscriminatorPlan, saved, dout: torch.Tensor, need_dx: bool, need_dw: bool):
+    x0, acts, raws, stats, yshape, T = saved
+    c = plan.convs
+    dy = ops.nchw_to_nhwc(dout, T)
+    gw: List[Optional[torch.Tensor]] = [None] * 10
+    if need_dw:
+        gw[8], gw[9] = c[4].wgrad(dy, acts[3], want_bias=True)
+    da = c[4].bprop(dy, (acts[3].shape[1], acts[3].shape[2]))
+    for i in (3, 2, 1):
+        dr = ops.norm_act_pad_bwd(da, raws[i - 1], stats[i - 1], L.ACT_LRELU, 0)
+        if need_dw:
+            gw[2 * i], _ = c[i].wgrad(dr, acts[i - 1])
+            gw[2 * i + 1] = torch.zeros_like(c[i].b)
+        da = c[i].bprop(dr, (acts[i - 1].shape[1], acts[i - 1].shape[2]))
+    dy0 = ops.act_bwd(da, acts[0], L.ACT_LRELU)
+    if need_dw:
+        gw[0], gw[1] = c[0].wgrad(dy0, x0, want_bias=True)
+    dx = None
+    if need_dx:
+        dx0 = c[0].bprop(dy0, (x0.shape[1], x0.shape[2]))
+        dx = ops.nhwc_to_nchw(dx0)
+    return dx, gw
+
+
+# ======================================================================================================================
+# Registration U-Net  (trainer/reg.py:31-99, trainer/layers.py)
+# ======================================================================================================================
+
+REG_NDF = [32, 64, 64, 64, 64, 64, 64]
+REG_NUF = [64, 64, 64, 64, 64, 64, 32]
+
+
+class _ResBlock:
+    """x + IN(conv3(RP1(relu(IN(conv3(RP1(x)))))))   trainer/layers.py:257-300 (also Model/CycleGan.py:6-21)."""
+
+    def __init__(self, w1, b1, w2, b2):
+        self.c1, self.c2 = ConvPrim(w1, b1, 1, 0), ConvPrim(w2, b2, 1, 0)
+
+    def forward(self, a, save):
+        Pa = ops.norm_act_pad(a, None, L.ACT_NONE, 1)
+        ra = self.c1.fprop(Pa, use_bias=False); sa = ops.instnorm_stats(ra)
+        Tt = ops.norm_act_pad(ra, sa, L.ACT_RELU, 1)
+        rb = self.c2.fprop(Tt, use_bias=False); sb = ops.instnorm_stats(rb)
+        out = ops.norm_act_pad(rb, sb, L.ACT_NONE, 0, res=a, res_pad=0)
+        return out, ((Pa, ra, sa, Tt, rb, sb) if save else None)
+
+    def backward(self, saved, G, pre_act=None, pre_act_kind=L.ACT_NONE):
+        """G: grad w.r.t. the block output.  Returns (grad w.r.t. block input [through `pre_act_kind` of the producer when
+        pre_act is given], [dW1, db1, dW2, db2])."""
+        Pa, ra, sa, Tt, rb, sb = saved
+        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0)
+        dW2, _ = self.c2.wgrad(drb, Tt)
+        dT = self.c2.bprop(drb, (Tt.shape[1], Tt.shape[2]))
+        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1)
+        dW1, _ = self.c1.wgrad(dra, Pa)
+        dPa = self.c1.bprop(dra, (Pa.shape[1], Pa.shape[2]))
+        Ga = ops.norm_act_pad_bwd(dPa, pre_act, None, pre_act_kind, 1, addend=G)
+        return Ga, [dW1, torch.zeros_like(self.c1.b), dW2, torch.zeros_like(self.c2.b)]
+
+
+class RegPlan:
+    """Parameter order == state_dict order of Reg (80 tensors; oracle/restate.py:init_reg documents it)."""
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        it = iter(params)
+        nxt = lambda: (next(it), next(it))
+        self.down = []
+        for _ in REG_NDF:
+            w, b = nxt()
+            w1, b1 = nxt(); w2, b2 = nxt()
+            self.down.append((ConvPrim(w, b, 1, 1), _ResBlock(w1, b1, w2, b2)))
+        w, b = nxt(); self.c1 = ConvPrim(w, b, 1, 0)
+        self.t = []
+        for _ in range(3):
+            w1, b1 = nxt(); w2, b2 = nxt()
+            self.t.append(_ResBlock(w1, b1, w2, b2))
+        w, b = nxt(); self.c2 = ConvPrim(w, b, 1, 0)
+        self.up = []
+        for _ in REG_NUF:
+            w, b = nxt(); self.up.append(ConvPrim(w, b, 1, 1))
+        w1, b1 = nxt(); w2, b2 = nxt()
+        self.refine0 = _ResBlock(w1, b1, w2, b2)
+        w, b = nxt(); self.refine1 = ConvPrim(w, b, 1, 0)
+        w, b = nxt(); self.output = ConvPrim(w, b, 1, 1)
+        self.params = list(params)
+
+
+def reg_forward(plan: RegPlan, img_a: torch.Tensor, img_b: torch.Tensor, save: bool):
+    T = get_precision()
+    if img_a.shape[1] == 1 and img_b.shape[1] == 1:
+        x_in = ops.interleave2(img_a, img_b, T)
+    else:                                            # generic channel counts: boundary concat is plain plumbing
+        x_in = ops.nchw_to_nhwc(torch.cat([img_a, img_b], 1), T)
+    x = x_in
+    downs, skips = [], []
+    for conv, rb in plan.down:
+        a = conv.fprop(x, act=L.ACT_LRELU)
+        sk, rsaved = rb.forward(a, save)
+        pooled = ops.maxpool2_fwd(sk)
+        if save:
+            downs.append((x, a, rsaved, sk))
+        skips.append(sk)
+        x = pooled
+    m_in = x
+    m1 = plan.c1.fprop(m_in, act=L.ACT_LRELU)
+    tsaved, ts_in = [], []
+    t = m1
+    for rb in plan.t:
+        ts_in.append(t)
+        t, rs = rb.forward(t, save)
+        tsaved.append(rs)
+    m2 = plan.c2.fprop(t, act=L.ACT_LRELU)
+    x = m2
+    ups = []
+    for conv, sk in zip(plan.up, reversed(skips)):
+        u = ops.upsample2x_cat_fwd(x, sk)
+        xo = conv.fprop(u, act=L.ACT_LRELU)
+        if save:
+            ups.append((u, xo, x.shape[3]))
+        x = xo
+    rf, rfsaved = plan.refine0.forward(x, save)
+    r1 = plan.refine1.fprop(rf, act=L.ACT_LRELU)
+    fl = plan.output.fprop(r1, act=L.ACT_NONE)
+    out = ops.nhwc_to_nchw(fl)
+    saved = (downs, m_in, m1, ts_in, tsaved, t, m2, ups, x, rfsaved, rf, r1, fl.dtype) if save else None
+    return out, saved
+
+
+def reg_backward(plan: RegPlan, saved, dflow: torch.Tensor, need_da: bool, need_db: bool, in_channels=(1, 1)):
+    downs, m_in, m1, ts_in, tsaved, t_out, m2, ups, x_last, rfsaved, rf, r1, T = saved
+    dfl = ops.nchw_to_nhwc(dflow, T)
+    dWo, dbo = plan.output.wgrad(dfl, r1, want_bias=True)
+    dr1 = plan.output.bprop(dfl, (r1.shape[1], r1.shape[2]))
+    dy = ops.act_bwd(dr1, r1, L.ACT_LRELU)
+    dWr1, dbr1 = plan.refine1.wgrad(dy, rf, want_bias=True)
+    Grf = plan.refine1.bprop(dy, (rf.shape[1], rf.shape[2]))
+    # refine.0 res-block: its input is the LeakyReLU output of up_1 -> fold that activation's backward in
+    Gx, g_refine0 = plan.refine0.backward(rfsaved, Grf, pre_act=x_last, pre_act_kind=L.ACT_LRELU)
+    up_grads = []
+    skip_grads = []
+    dyo = Gx  # already multiplied by lrelu'(x_last)
+    for conv, (u, xo, C1) in zip(reversed(plan.up), reversed(ups)):
+        dW, db = conv.wgrad(dyo, u, want_bias=True)
+        du = conv.bprop(dyo, (u.shape[1], u.shape[2]))
+        gx, gskip = ops.upsample2x_cat_bwd(du, C1)
+        up_grads.append((dW, db))
+        skip_grads.append(gskip)
+        dyo = gx  # grad w.r.t. the previous up conv's post-activation output (or m2): activation backward applied below
+        # previous producer is a conv+lrelu: find its output tensor
+        prev_out = None
+        idx = len(up_grads)
+        if idx < len(ups):
+            prev_out = ups[len(ups) - 1 - idx][1]
+            dyo = ops.act_bwd(dyo, prev_out, L.ACT_LRELU)
+    up_grads.reverse()            # now in plan.up order
+    # dyo is grad w.r.t. m2 (post-lrelu)
+    dy = ops.act_bwd(dyo, m2, L.ACT_LRELU)
+    dWc2, dbc2 = plan.c2.wgrad(dy, t_out, want_bias=True)
+    Gt = plan.c2.bprop(dy, (t_out.shape[1], t_out.shape[2]))
+    t_grads = []
+    for i in (2, 1, 0):
+        if i == 0:
+            Gt, gr = plan.t[i].backward(tsaved[i], Gt, pre_act=m1, pre_act_kind=L.ACT_LRELU)
+        else:
+            Gt, gr = plan.t[i].backward(tsaved[i], Gt)
+        t_grads.append(gr)
+    t_grads.reverse()
+    dWc1, dbc1 = plan.c1.wgrad(Gt, m_in, want_bias=True)
+    Gp = plan.c1.bprop(Gt, (m_in.shape[1], m_in.shape[2]))      # grad w.r.t. pooled output of down_7
+    down_grads = []
+    # skip_grads was filled from up_1 (skip of down_1) to up_7 (skip of down_7): already in down-block order
+    for n in range(len(plan.down) - 1, -1, -1):
+        conv, rb = plan.down[n]
+        x_in, a, rsaved, sk = downs[n]
+        Gsk = ops.maxpool2_bwd(Gp, sk, addend=skip_grads[n])
+        Ga, gr = rb.backward(rsaved, Gsk, pre_act=a, pre_act_kind=L.ACT_LRELU)
+        dW, db = conv.wgrad(Ga, x_in, want_bias=True)
+        down_grads.append((dW, db, gr))
+        if n > 0:
+            Gp = conv.bprop(Ga, (x_in.shape[1], x_in.shape[2]))
+        elif need_da or need_db:
+            Gp = conv.bprop(Ga, (x_in.shape[1], x_in.shape[2]))
+    down_grads.reverse()
+    da = db_ = None
+    if need_da or need_db:
+        if tuple(in_channels) == (1, 1):
+            da, db_ = ops.deinterleave2(Gp, need_da, need_db)
+        else:
+            gin = ops.nhwc_to_nchw(Gp)
+            Ca = in_channels[0]
+            da = gin[:, :Ca].contiguous() if need_da else None
+            db_ = gin[:, Ca:].contiguous() if need_db else None
+    grads: List[torch.Tensor] = []
+    for dW, db, gr in down_grads:
+        grads += [dW, db] + gr
+    grads += [dWc1, dbc1]
+    for gr in t_grads:
+        grads += gr
+    grads += [dWc2, dbc2]
+    for dW, db in up_grads:
+        grads += [dW, db]
+    grads += g_refine0 + [dWr1, dbr1, dWo, dbo]
+    return da, db_, grads

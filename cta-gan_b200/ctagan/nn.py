@@ -1,0 +1,539 @@
+"""nn.Module surface of the hot path: same constructors, sub-module names, parameter creation order and state_dict layout
+as the reference (Model/CycleGan.py, Model/HdGan.py, trainer/reg.py, trainer/transformer.py, trainer/utils.py), with every
+forward/backward executed by the sm_100a kernels of libctagan.so through ctagan.engine."""
+from __future__ import annotations
+
+import functools
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+from . import lib as L
+from . import ops
+
+
+class _Slot(nn.Module):
+    """Parameter-free placeholder keeping nn.Sequential indices identical to the reference (pads, norms, activations:
+    their arithmetic is fused into the neighbouring kernels)."""
+
+    def __init__(self, what: str):
+        super().__init__()
+        self.what = what
+
+    def extra_repr(self):
+        return f"fused:{self.what}"
+
+    def forward(self, x):  # pragma: no cover - never called; the owning module runs the fused schedule
+        raise RuntimeError("fused placeholder: call the owning module")
+
+
+def _fresh_leaves(params, detach: bool):
+    return [p.detach() if detach else p for p in params]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Generator
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, *params):
+        need = any(ctx.needs_input_grad)      # all False under torch.no_grad()
+        out, saved = E.generator_forward(plan, x, save=need)
+        ctx.plan, ctx.saved = plan, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        need_dx = ctx.needs_input_grad[1]
+        need_dw = any(ctx.needs_input_grad[2:])
+        dx, grads = E.generator_backward(ctx.plan, ctx.saved, dout.contiguous(), need_dx, need_dw)
+        ctx.saved = None
+        return (None, dx, *grads)
+
+
+class ResidualBlock(nn.Module):
+    """Model/CycleGan.py:6-21.  conv_block indices: 0 pad, 1 conv, 2 IN, 3 ReLU, 4 pad, 5 conv, 6 IN."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self.conv_block = nn.Sequential(_Slot("reflect1"), nn.Conv2d(in_features, in_features, 3), _Slot("instnorm"),
+                                        _Slot("relu"), _Slot("reflect1"), nn.Conv2d(in_features, in_features, 3),
+                                        _Slot("instnorm"))
+
+    def forward(self, x):
+        raise RuntimeError("ResidualBlock is executed by its Generator's fused schedule")
+
+
+class Generator(nn.Module):
+    """ResNet generator, Model/CycleGan.py:23-71 (== Model/HdGan.py:65-113)."""
+
+    def __init__(self, input_nc, output_nc, n_residual_blocks=9):
+        super().__init__()
+        self.model_head = nn.Sequential(
+            _Slot("reflect3"), nn.Conv2d(input_nc, 64, 7), _Slot("instnorm"), _Slot("relu"),
+            nn.Conv2d(64, 128, 3, stride=2, padding=1), _Slot("instnorm"), _Slot("relu"),
+            nn.Conv2d(128, 256, 3, stride=2, padding=1), _Slot("instnorm"), _Slot("relu"))
+        self.model_body = nn.Sequential(*[ResidualBlock(256) for _ in range(n_residual_blocks)])
+        self.model_tail = nn.Sequential(
+            nn.ConvTranspose2d(256, 128, 3, stride=2, padding=1, output_padding=1), _Slot("instnorm"), _Slot("relu"),
+            nn.ConvTranspose2d(128, 64, 3, stride=2, padding=1, output_padding=1), _Slot("instnorm"), _Slot("relu"),
+            _Slot("reflect3"), nn.Conv2d(64, output_nc, 7), _Slot("tanh"))
+        self.n_residual_blocks = n_residual_blocks
+        self._plan = None
+
+    def _get_plan(self):
+        params = list(self.parameters())
+        if self._plan is None or any(a is not b for a, b in zip(self._plan.params, params)):
+            self._plan = E.GeneratorPlan(params, self.n_residual_blocks)
+        return self._plan
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, x):
+        if x.shape[2] % 4 or x.shape[3] % 4:
+            raise ValueError("Generator needs H and W to be multiples of 4")
+        plan = self._get_plan()
+        return _GeneratorFn.apply(plan, x, *plan.params)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Discriminators
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    """x -> last feature map [N,1,h,w]; intermediates are returned detached through `sink` (feature taps)."""
+
+    @staticmethod
+    def forward(ctx, plan, sink, x, *params):
+        need = any(ctx.needs_input_grad)
+        out, acts, saved = E.discriminator_forward(plan, x, save=need)
+        if sink is not None:
+            sink.extend(acts)
+        ctx.plan, ctx.saved = plan, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        need_dx = ctx.needs_input_grad[2]
+        need_dw = any(ctx.needs_input_grad[3:])
+        dx, gw = E.discriminator_backward(ctx.plan, ctx.saved, dout.contiguous(), need_dx, need_dw)
+        ctx.saved = None
+        return (None, None, dx, *gw)
+
+
+class _PlaneMeanFn(torch.autograd.Function):
+    """F.avg_pool2d(x, x.size()[2:]).view(N, -1) for a 1-channel map (Model/CycleGan.py:103)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, C, H, W = x.shape
+        ctx.shape = (N, H, W, C)
+        xx = x.contiguous()
+        if C != 1:
+            xx = ops.nchw_to_nhwc(xx, torch.float32)
+        return ops.plane_mean_fwd(xx.view(N, H, W, C))
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, C = ctx.shape
+        gx = ops.plane_mean_bwd(g.contiguous(), ctx.shape, torch.float32)
+        return gx.view(N, C, H, W) if C == 1 else ops.nhwc_to_nchw(gx)
+
+
+def plane_mean(x):
+    return _PlaneMeanFn.apply(x)
+
+
+class _DiscBase(nn.Module):
+    _plan = None
+
+    def _conv_params(self):
+        return list(self.parameters())
+
+    def _get_plan(self, detach=False):
+        params = self._conv_params()
+        if self._plan is None or any(a is not b for a, b in zip(self._plan.params, params)):
+            self._plan = E.DiscriminatorPlan(params)
+        return self._plan
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    def _run(self, x, sink=None, freeze=False):
+        plan = self._get_plan()
+        params = [p.detach() for p in plan.params] if freeze else plan.params
+        return _DiscriminatorFn.apply(plan, sink, x, *params)
+
+
+class Discriminator(_DiscBase):
+    """PatchGAN discriminator, Model/CycleGan.py:73-103 (== Model/HdGan.py:115-145).
+
+    `freeze=True` (extension) treats the weights as constants for this call: the generator phase of the trainers uses it,
+    because the reference computes and then discards these weight gradients."""
+
+    def __init__(self, input_nc):
+        super().__init__()
+        self.model = nn.Sequential(
+            nn.Conv2d(input_nc, 64, 4, stride=2, padding=1), _Slot("lrelu"),
+            nn.Conv2d(64, 128, 4, stride=2, padding=1), _Slot("instnorm"), _Slot("lrelu"),
+            nn.Conv2d(128, 256, 4, stride=2, padding=1), _Slot("instnorm"), _Slot("lrelu"),
+            nn.Conv2d(256, 512, 4, padding=1), _Slot("instnorm"), _Slot("lrelu"),
+            nn.Conv2d(512, 1, 4, padding=1))
+
+    def forward(self, x, freeze=False):
+        return plane_mean(self._run(x, freeze=freeze))
+
+
+class NLayerDiscriminator(_DiscBase):
+    """Model/HdGan.py:148-205 for the configuration the trainers use (ndf=64, n_layers=3, InstanceNorm, no sigmoid)."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_sigmoid=False, getIntermFeat=False):
+        super().__init__()
+        if ndf != 64 or n_layers != 3 or use_sigmoid:
+            raise NotImplementedError("only ndf=64, n_layers=3, use_sigmoid=False (the reference's live configuration)")
+        self.getIntermFeat, self.n_layers = getIntermFeat, n_layers
+        chans = [(input_nc, 64, 2), (64, 128, 2), (128, 256, 2), (256, 512, 1), (512, 1, 1)]
+        seqs = []
+        for j, (ci, co, s) in enumerate(chans):
+            mods = [nn.Conv2d(ci, co, 4, stride=s, padding=1)]
+            if 1 <= j <= 3:
+                mods.append(_Slot("instnorm"))
+            if j <= 3:
+                mods.append(_Slot("lrelu"))
+            seqs.append(mods)
+        if getIntermFeat:
+            for j, mods in enumerate(seqs):
+                setattr(self, "model" + str(j), nn.Sequential(*mods))
+        else:
+            self.model = nn.Sequential(*[m for mods in seqs for m in mods])
+
+    def forward(self, x):
+        sink: List[torch.Tensor] = []
+        last = self._run(x, sink=sink)
+        if self.getIntermFeat:
+            return [a.permute(0, 3, 1, 2).float() for a in sink] + [last]
+        return last
+
+
+class Discriminator_m(_DiscBase):
+    """Model/HdGan.py:207-256.  num_D=1 (the default every trainer uses) runs natively; the centre-crop multi-scale
+    branch (:251) is reproduced with one native discriminator pass per scale."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=None, use_sigmoid=False, num_D=1, getIntermFeat=True):
+        super().__init__()
+        self.num_D, self.n_layers, self.getIntermFeat = num_D, n_layers, getIntermFeat
+        self._scales = []
+        for i in range(num_D):
+            netD = NLayerDiscriminator(input_nc, ndf, n_layers, norm_layer, use_sigmoid, getIntermFeat)
+            if getIntermFeat:
+                for j in range(n_layers + 2):
+                    setattr(self, "scale" + str(i) + "_layer" + str(j), getattr(netD, "model" + str(j)))
+            else:
+                setattr(self, "layer" + str(i), netD.model)
+        self._plans = {}
+
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+    def _scale_params(self, i):
+        if self.getIntermFeat:
+            mods = [getattr(self, "scale" + str(i) + "_layer" + str(j)) for j in range(self.n_layers + 2)]
+        else:
+            mods = [getattr(self, "layer" + str(i))]
+        return [p for m in mods for p in m.parameters()]
+
+    def _scale_plan(self, i):
+        params = self._scale_params(i)
+        plan = self._plans.get(i)
+        if plan is None or any(a is not b for a, b in zip(plan.params, params)):
+            plan = E.DiscriminatorPlan(params)
+            self._plans[i] = plan
+        return plan
+
+    def forward(self, x, freeze=False):
+        result = []
+        cur = x
+        for i in range(self.num_D):
+            s = cur.size(2)
+            plan = self._scale_plan(self.num_D - 1 - i)
+            sink: List[torch.Tensor] = []
+            params = [p.detach() for p in plan.params] if freeze else plan.params
+            last = _DiscriminatorFn.apply(plan, sink, cur, *params)
+            if self.getIntermFeat:
+                result.append([a.permute(0, 3, 1, 2) for a in sink] + [last])
+            else:
+                result.append([last])
+            if i != self.num_D - 1:
+                c = int(s / 2)
+                o = (s - c) // 2
+                cur = cur[:, :, o:o + c, o:o + c].contiguous()
+        return result
+
+
+class GANLoss(nn.Module):
+    """Model/HdGan.py:258-293 (LSGAN): avg-pool the last map, MSE against a constant, scale weights [1.8, 0.2]."""
+
+    def __init__(self, use_lsgan=True, target_real_label=1.0, target_fake_label=0.0, tensor=None):
+        super().__init__()
+        if not use_lsgan:
+            raise NotImplementedError("only the LSGAN form is on the hot path")
+        self.real, self.fake = float(target_real_label), float(target_fake_label)
+
+    def __call__(self, input, target_is_real):
+        tgt = self.real if target_is_real else self.fake
+        if isinstance(input[0], list):
+            w = [1.8, 0.2]
+            loss = 0
+            for i, scale in enumerate(input):
+                loss = loss + mse_const(plane_mean(scale[-1]), tgt) * w[i]
+            return loss
+        return mse_const(plane_mean(input[-1]), tgt)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Registration network + warp
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+class _RegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, a, b, *params):
+        need = any(ctx.needs_input_grad)
+        out, saved = E.reg_forward(plan, a, b, save=need)
+        ctx.plan, ctx.saved = plan, saved
+        ctx.in_channels = (a.shape[1], b.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dflow):
+        da, db, grads = E.reg_backward(ctx.plan, ctx.saved, dflow.contiguous(), ctx.needs_input_grad[1], ctx.needs_input_grad[2],
+                                       ctx.in_channels)
+        ctx.saved = None
+        return (None, da, db, *grads)
+
+
+class _ParamConv(nn.Module):
+    """trainer/layers.py:71-104 `Conv`: holds `conv2d` (+ optional `resnet_block`); arithmetic runs in the fused schedule."""
+
+    def __init__(self, cin, cout, k, act, use_resnet=False):
+        super().__init__()
+        self.conv2d = nn.Conv2d(cin, cout, k, 1, (k - 1) // 2, bias=True)
+        self.resnet_block = _ResnetTransformer(cout, 1) if use_resnet else None
+        a = 0.2 if act == "leaky_relu" else 0.0
+        if act == "zeros":
+            nn.init.normal_(self.conv2d.weight, mean=0.0, std=1e-5)           # layers.py:44-45
+        else:
+            nn.init.kaiming_normal_(self.conv2d.weight, a=a, nonlinearity="relu" if act is None else act, mode="fan_in")
+        self.conv2d.bias.data.zero_()
+
+
+class _ResnetBlockParams(nn.Module):
+    """trainer/layers.py:243-300: conv_block indices 1 and 5 are the convolutions."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv_block = nn.Sequential(_Slot("reflect1"), nn.Conv2d(dim, dim, 3, bias=True), _Slot("instnorm"), _Slot("relu"),
+                                        _Slot("reflect1"), nn.Conv2d(dim, dim, 3, bias=True), _Slot("instnorm"))
+
+
+class _ResnetTransformer(nn.Module):
+    """trainer/layers.py:216-240 (all convs are created first, then re-drawn kaiming(relu) in traversal order)."""
+
+    def __init__(self, dim, n_blocks):
+        super().__init__()
+        self.model = nn.Sequential(*[_ResnetBlockParams(dim) for _ in range(n_blocks)])
+        for m in self.model.modules():
+            if type(m) == nn.Conv2d:
+                nn.init.kaiming_normal_(m.weight, a=0.0, nonlinearity="relu", mode="fan_in")
+                m.bias.data.zero_()
+
+
+class _DownBlockParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv_0 = _ParamConv(cin, cout, 3, "leaky_relu", use_resnet=True)
+
+
+class ResUnet(nn.Module):
+    """trainer/reg.py:31-75 for cfg 'A' (the only one defined)."""
+
+    def __init__(self, nc_a, nc_b, cfg="A", init_func="kaiming", init_to_identity=True):
+        super().__init__()
+        in_nf = nc_a + nc_b
+        skip = {}
+        for n, out_nf in enumerate(E.REG_NDF, start=1):
+            setattr(self, f"down_{n}", _DownBlockParams(in_nf, out_nf))
+            skip[n] = out_nf
+            in_nf = out_nf
+        self.c1 = _ParamConv(in_nf, 2 * in_nf, 1, "leaky_relu")
+        self.t = _ResnetTransformer(2 * in_nf, 3)
+        self.c2 = _ParamConv(2 * in_nf, in_nf, 1, "leaky_relu")
+        n = len(E.REG_NDF)
+        for out_nf in E.REG_NUF:
+            setattr(self, f"up_{n}", _ParamConv(in_nf + skip[n], out_nf, 3, "leaky_relu"))
+            in_nf = out_nf
+            n -= 1
+        self.refine = nn.Sequential(_ResnetTransformer(in_nf, 1), _ParamConv(in_nf, in_nf, 1, "leaky_relu"))
+        self.output = _ParamConv(in_nf, 2, 3, "zeros" if init_to_identity else None)
+
+
+class Reg(nn.Module):
+    """trainer/reg.py:101-132.  forward(img_a, img_b) -> (B, 2, H, W) flow in pixels (ch0 rows, ch1 cols)."""
+
+    def __init__(self, height, width, in_channels_a, in_channels_b):
+        super().__init__()
+        if height % 128 or width % 128 or height < 256 or width < 256:
+            raise ValueError("Reg needs H, W >= 256 and multiples of 128 (7 poolings; trainer/reg.py:15)")
+        self.oh, self.ow = height, width
+        self.in_channels_a, self.in_channels_b = in_channels_a, in_channels_b
+        self.offset_map = ResUnet(in_channels_a, in_channels_b)
+        self._plan = None
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, img_a, img_b, apply_on=None):
+        params = list(self.parameters())
+        if self._plan is None or any(a is not b for a, b in zip(self._plan.params, params)):
+            self._plan = E.RegPlan(params)
+        return _RegFn.apply(self._plan, img_a, img_b, *params)
+
+
+class _WarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, flow):
+        src, flow = src.contiguous().float(), flow.contiguous().float()
+        ctx.save_for_backward(src, flow)
+        return ops.warp_fwd(src, flow)
+
+    @staticmethod
+    def backward(ctx, g):
+        src, flow = ctx.saved_tensors
+        gs, gf = ops.warp_bwd(g.contiguous(), src, flow, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return gs, gf
+
+
+class Transformer_2D(nn.Module):
+    """trainer/transformer.py:7-31: one fused bilinear warp kernel (no materialised grid, no per-call H2D copy)."""
+
+    def forward(self, src, flow):
+        if src.shape[0] != flow.shape[0] or src.shape[2:] != flow.shape[2:] or flow.shape[1] != 2:
+            raise ValueError("Transformer_2D: src (B,C,H,W) and flow (B,2,H,W) must agree")
+        ops.ensure_device()
+        return _WarpFn.apply(src, flow)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Losses
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+class _L1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        ctx.save_for_backward(a, b)
+        return ops.l1_fwd(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = ops.l1_bwd(a, b, g.contiguous()) if ctx.needs_input_grad[0] else None
+        gb = ops.l1_bwd(b, a, g.contiguous()) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+class _MseConstFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, target):
+        p = p.contiguous().float()
+        ctx.save_for_backward(p)
+        ctx.target = target
+        return ops.mse_const_fwd(p, target)
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        return ops.mse_const_bwd(p, ctx.target, g.contiguous()), None
+
+
+class _SmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow):
+        flow = flow.contiguous().float()
+        ctx.save_for_backward(flow)
+        return ops.smooth_fwd(flow)
+
+    @staticmethod
+    def backward(ctx, g):
+        (flow,) = ctx.saved_tensors
+        return ops.smooth_bwd(flow, g.contiguous())
+
+
+class _MaskedL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, warped, b1, b2):
+        warped, b1, b2 = warped.contiguous().float(), b1.contiguous().float(), b2.contiguous().float()
+        ctx.save_for_backward(warped, b1, b2)
+        return ops.masked_l1_fwd(warped, b1, b2)
+
+    @staticmethod
+    def backward(ctx, g):
+        warped, b1, b2 = ctx.saved_tensors
+        return ops.masked_l1_bwd(warped, b1, b2, g.contiguous()), None, None
+
+
+def l1_loss(a, b):
+    ops.ensure_device()
+    return _L1Fn.apply(a, b)
+
+
+def mse_const(p, target: float):
+    ops.ensure_device()
+    return _MseConstFn.apply(p, float(target))
+
+
+def smooothing_loss(y_pred):
+    """trainer/utils.py:165-173 (the reference's spelling is kept: it is the public name)."""
+    ops.ensure_device()
+    return _SmoothFn.apply(y_pred)
+
+
+def masked_l1_loss(warped, real_b1, real_b2):
+    """The masked L1 of trainer/HdTrainer.py:726-735 as one fused pass (no in-place edits of the inputs)."""
+    ops.ensure_device()
+    return _MaskedL1Fn.apply(warped, real_b1, real_b2)
+
+
+class L1Loss(nn.Module):
+    def forward(self, a, b):
+        return l1_loss(a, b)
+
+
+class MSELoss(nn.Module):
+    """torch.nn.MSELoss for the only way the trainers use it: prediction vs a constant (1,1) target tensor."""
+
+    def forward(self, pred, target):
+        if torch.is_tensor(target):
+            if target.numel() != 1:
+                raise NotImplementedError("MSELoss here takes a broadcast constant target (CycTrainer.py:83-84)")
+            key = id(target)
+            tv = _TARGET_CACHE.get(key)
+            if tv is None:
+                tv = float(target.item())
+                _TARGET_CACHE[key] = tv
+            target = tv
+        return mse_const(pred, float(target))
+
+
+_TARGET_CACHE = {}

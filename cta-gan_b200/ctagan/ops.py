@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI.  torch is used only for device memory and streams: every function here
+enqueues hand-written sm_100a kernels from libctagan.so on torch's current stream."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ctagan ops need CUDA tensors (sm_100a); there is no CPU fallback")
+
+
+_checked_devices = set()
+
+
+def ensure_device():
+    dev = torch.cuda.current_device()
+    if dev not in _checked_devices:
+        L.check(L.load().ctagan_check_device(dev))
+        _checked_devices.add(dev)
+
+
+def dt(t: torch.Tensor) -> int:
+    return _DT[t.dtype]
+
+
+def make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, K, stride, dil, pad, act, dtype) -> L.ConvGeom:
+    return L.ConvGeom(N, Hi, Wi, Ci, Ho, Wo, Co, K, K, stride, dil, pad, pad, act, dtype)
+
+
+def conv_gather(x, wp, bias, g: L.ConvGeom, engine=L.ENGINE_AUTO):
+    """x[N,Hi,Wi,Ci] -> y[N,Ho,Wo,Co] (see ctagan_conv_gather)."""
+    _require_cuda(x, wp)
+    ensure_device()
+    y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
+    L.check(L.load().ctagan_conv_gather(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), engine, _stream()))
+    return y
+
+
+def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO):
+    _require_cuda(gy, gx)
+    dw = torch.empty((g.Co, g.Ci, g.KH, g.KW), dtype=torch.float32, device=gy.device)
+    db = torch.empty((g.Co,), dtype=torch.float32, device=gy.device) if want_bias else None
+    L.check(L.load().ctagan_conv_wgrad(ctypes.byref(g), _p(gy), _p(gx), _p(dw), _p(db), engine, _stream()))
+    return dw, db
+
+
+def pack_weights(w: torch.Tensor, mode: int, dtype: torch.dtype):
+    _require_cuda(w)
+    O, I, KH, KW = w.shape
+    shape = (O, KH, KW, I) if mode == 0 else (I, KH, KW, O)
+    wp = torch.empty(shape, dtype=dtype, device=w.device)
+    L.check(L.load().ctagan_pack_weights(_p(w), _p(wp), O, I, KH, KW, mode, _DT[dtype], _stream()))
+    return wp
+
+
+def instnorm_stats(x):
+    N, H, W, C = x.shape
+    stats = torch.empty((N, C, 2), dtype=torch.float32, device=x.device)
+    acc = torch.empty((N, C, 2), dtype=torch.float64, device=x.device)
+    L.check(L.load().ctagan_instnorm_stats(_p(x), _p(stats), _p(acc), N, H * W, C, dt(x), _stream()))
+    return stats
+
+
+def norm_act_pad(x, stats, act, pad, res=None, res_pad=0):
+    N, H, W, C = x.shape
+    out = torch.empty((N, H + 2 * pad, W + 2 * pad, C), dtype=x.dtype, device=x.device)
+    L.check(L.load().ctagan_norm_act_pad(_p(x), _p(stats), _p(res), res_pad, _p(out), N, H, W, C, pad, act, dt(x), _stream()))
+    return out
+
+
+def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None):
+    N, Hp, Wp, C = gout.shape
+    H, W = Hp - 2 * pad, Wp - 2 * pad
+    dx = torch.empty((N, H, W, C), dtype=gout.dtype, device=gout.device)
+    acc = torch.empty((N, C, 2), dtype=torch.float64, device=gout.device) if stats is not None else None
+    L.check(L.load().ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(acc), N, H, W, C, pad, act,
+                                             dt(gout), _stream()))
+    return dx
+
+
+def act_bwd(gy, y, act):
+    dx = torch.empty_like(gy)
+    L.check(L.load().ctagan_act_bwd(_p(gy), _p(y), _p(dx), gy.numel(), act, dt(gy), _stream()))
+    return dx
+
+
+def maxpool2_fwd(x):
+    N, H, W, C = x.shape
+    y = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    L.check(L.load().ctagan_maxpool2_fwd(_p(x), _p(y), N, H, W, C, dt(x), _stream()))
+    return y
+
+
+def maxpool2_bwd(gy, x, addend=None):
+    N, H, W, C = x.shape
+    gx = torch.empty_like(x)
+    L.check(L.load().ctagan_maxpool2_bwd(_p(gy), _p(x), _p(addend), _p(gx), N, H, W, C, dt(x), _stream()))
+    return gx
+
+
+def upsample2x_cat_fwd(x, skip):
+    N, H, W, C1 = x.shape
+    C2 = skip.shape[3]
+    out = torch.empty((N, 2 * H, 2 * W, C1 + C2), dtype=x.dtype, device=x.device)
+    L.check(L.load().ctagan_upsample2x_cat_fwd(_p(x), _p(skip), _p(out), N, H, W, C1, C2, dt(x), _stream()))
+    return out
+
+
+def upsample2x_cat_bwd(gout, C1):
+    N, Ho, Wo, C = gout.shape
+    H, W, C2 = Ho // 2, Wo // 2, C - C1
+    gx = torch.empty((N, H, W, C1), dtype=gout.dtype, device=gout.device)
+    gskip = torch.empty((N, Ho, Wo, C2), dtype=gout.dtype, device=gout.device)
+    L.check(L.load().ctagan_upsample2x_cat_bwd(_p(gout), _p(gx), _p(gskip), N, H, W, C1, C2, dt(gout), _stream()))
+    return gx, gskip
+
+
+def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype):
+    """fp32 NCHW (boundary) -> NHWC `dtype` (internal)."""
+    _require_cuda(x)
+    ensure_device()
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    N, C, H, W = x.shape
+    out = torch.empty((N, H, W, C), dtype=dtype, device=x.device)
+    L.check(L.load().ctagan_nchw_to_nhwc(_p(x), _p(out), N, C, H * W, _DT[dtype], _stream()))
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor):
+    N, H, W, C = x.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.load().ctagan_nhwc_to_nchw(_p(x), _p(out), N, C, H * W, dt(x), _stream()))
+    return out
+
+
+def plane_mean_fwd(x_nhwc):
+    N, H, W, C = x_nhwc.shape
+    out = torch.empty((N, C), dtype=torch.float32, device=x_nhwc.device)
+    L.check(L.load().ctagan_plane_mean_fwd(_p(x_nhwc), _p(out), N, H * W, C, dt(x_nhwc), _stream()))
+    return out
+
+
+def plane_mean_bwd(gout, shape, dtype):
+    N, H, W, C = shape
+    gx = torch.empty(shape, dtype=dtype, device=gout.device)
+    L.check(L.load().ctagan_plane_mean_bwd(_p(gout), _p(gx), N, H * W, C, _DT[dtype], _stream()))
+    return gx
+
+
+def warp_fwd(src, flow):
+    B, C, H, W = src.shape
+    out = torch.empty_like(src)
+    L.check(L.load().ctagan_warp_fwd(_p(src), _p(flow), _p(out), B, C, H, W, _stream()))
+    return out
+
+
+def warp_bwd(gout, src, flow, need_src=True, need_flow=True):
+    B, C, H, W = src.shape
+    gsrc = torch.empty_like(src) if need_src else None
+    gflow = torch.empty_like(flow) if need_flow else None
+    L.check(L.load().ctagan_warp_bwd(_p(gout), _p(src), _p(flow), _p(gsrc), _p(gflow), B, C, H, W, _stream()))
+    return gsrc, gflow
+
+
+def _scalar_out(ref):
+    return torch.empty((), dtype=torch.float32, device=ref.device), torch.empty((2,), dtype=torch.float64, device=ref.device)
+
+
+def l1_fwd(a, b):
+    loss, acc = _scalar_out(a)
+    L.check(L.load().ctagan_l1_fwd(_p(a), _p(b), _p(loss), _p(acc), a.numel(), _stream()))
+    return loss
+
+
+def l1_bwd(a, b, gloss):
+    ga = torch.empty_like(a)
+    L.check(L.load().ctagan_l1_bwd(_p(a), _p(b), _p(gloss), _p(ga), a.numel(), _stream()))
+    return ga
+
+
+def mse_const_fwd(p, target: float):
+    loss, acc = _scalar_out(p)
+    L.check(L.load().ctagan_mse_const_fwd(_p(p), float(target), _p(loss), _p(acc), p.numel(), _stream()))
+    return loss
+
+
+def mse_const_bwd(p, target: float, gloss):
+    gp = torch.empty_like(p)
+    L.check(L.load().ctagan_mse_const_bwd(_p(p), float(target), _p(gloss), _p(gp), p.numel(), _stream()))
+    return gp
+
+
+def smooth_fwd(flow):
+    B, C, H, W = flow.shape
+    loss, acc = _scalar_out(flow)
+    L.check(L.load().ctagan_smooth_fwd(_p(flow), _p(loss), _p(acc), B, C, H, W, _stream()))
+    return loss
+
+
+def smooth_bwd(flow, gloss):
+    B, C, H, W = flow.shape
+    g = torch.empty_like(flow)
+    L.check(L.load().ctagan_smooth_bwd(_p(flow), _p(gloss), _p(g), B, C, H, W, _stream()))
+    return g
+
+
+def masked_l1_fwd(warped, b1, b2):
+    loss, acc = _scalar_out(warped)
+    L.check(L.load().ctagan_masked_l1_fwd(_p(warped), _p(b1), _p(b2), _p(loss), _p(acc), warped.numel(), _stream()))
+    return loss
+
+
+def masked_l1_bwd(warped, b1, b2, gloss):
+    g = torch.empty_like(warped)
+    L.check(L.load().ctagan_masked_l1_bwd(_p(warped), _p(b1), _p(b2), _p(gloss), _p(g), warped.numel(), _stream()))
+    return g
+
+
+def interleave2(a, b, dtype):
+    """cat([a, b], 1) for 1-channel fp32 NCHW images -> NHWC [N,H,W,2] of `dtype`."""
+    _require_cuda(a, b)
+    ensure_device()
+    a = a.contiguous().float(); b = b.contiguous().float()
+    N, _, H, W = a.shape
+    out = torch.empty((N, H, W, 2), dtype=dtype, device=a.device)
+    L.check(L.load().ctagan_interleave2(_p(a), _p(b), _p(out), N * H * W, _DT[dtype], _stream()))
+    return out
+
+
+def deinterleave2(src, need_a=True, need_b=True):
+    N, H, W, _ = src.shape
+    a = torch.empty((N, 1, H, W), dtype=torch.float32, device=src.device) if need_a else None
+    b = torch.empty((N, 1, H, W), dtype=torch.float32, device=src.device) if need_b else None
+    L.check(L.load().ctagan_deinterleave2(_p(src), _p(a), _p(b), N * H * W, dt(src), _stream()))
+    return a, b

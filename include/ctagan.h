@@ -1,0 +1,155 @@
+/*
+ * ctagan.h -- C ABI of libctagan.so: the sm_100a kernels behind the CTA-GAN hot path.
+ *
+ * Plain pointers + sizes, no torch types.  Every function returns 0 on success or a non-zero code
+ * (ctagan_last_error() gives the message); nothing throws, nothing allocates device memory: the caller
+ * owns all buffers (activations, packed weights, workspaces) and passes the cudaStream_t to enqueue on
+ * (as void*).  All kernels are capturable in CUDA graphs.
+ *
+ * Layouts: activations are NHWC ("pixels x channels"), element type `dtype` (CTAGAN_F32 / CTAGAN_BF16);
+ * 1-channel images/flows at the module boundary are NCHW == NHWC.  Statistics, losses, weight gradients
+ * and master weights are fp32 (accumulators of reductions are fp64).
+ *
+ * The reference has no native FFI (it is pure PyTorch); each entry point below replaces the ATen/cuDNN
+ * call that the cited reference line dispatches (paths relative to the upstream tree).
+ */
+#ifndef CTAGAN_H_
+#define CTAGAN_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTAGAN_F32 0
+#define CTAGAN_BF16 1
+
+#define CTAGAN_ACT_NONE 0
+#define CTAGAN_ACT_RELU 1
+#define CTAGAN_ACT_LRELU 2 /* LeakyReLU(0.2) */
+#define CTAGAN_ACT_TANH 3
+
+#define CTAGAN_OK 0
+#define CTAGAN_ERR_ARG 1
+#define CTAGAN_ERR_CUDA 2
+#define CTAGAN_ERR_UNSUPPORTED 3
+
+int ctagan_version(void);
+const char *ctagan_last_error(void);
+/* 0 if device `dev` is compute capability 10.x, else CTAGAN_ERR_UNSUPPORTED (no other-arch fallback). */
+int ctagan_check_device(int dev);
+
+/*
+ * One "gather convolution" geometry covers Conv2d fwd/dgrad and ConvTranspose2d fwd/dgrad:
+ *   y[n,oh,ow,co] = act( bias[co] + sum_{kh,kw,ci} x[n,ih,iw,ci] * wp[co,kh,kw,ci] )
+ *   ih*dil = oh*stride + kh - pad_h   (tap skipped unless divisible and 0 <= ih < Hi), same for iw.
+ * Conv2d(s,p) fwd: stride=s, dil=1, pad=p.   Conv2d dgrad / ConvTranspose2d fwd: stride=1, dil=s, pad=K-1-p with
+ * flipped+transposed packed weights (ctagan_pack_weights mode 1).  Reflection padding is materialised by the
+ * producer (ctagan_norm_act_pad), so such convs run with pad=0 on the padded buffer.
+ */
+typedef struct {
+  int32_t N, Hi, Wi, Ci; /* input  NHWC */
+  int32_t Ho, Wo, Co;    /* output NHWC */
+  int32_t KH, KW;
+  int32_t stride, dil;
+  int32_t pad_h, pad_w;
+  int32_t act;   /* epilogue activation, CTAGAN_ACT_* */
+  int32_t dtype; /* element type of x, wp, y */
+} ctagan_conv_geom;
+
+/* Replaces nn.Conv2d / nn.ConvTranspose2d forward and the input-gradient half of their backward
+ * (Model/CycleGan.py:11,15,28,36,51,59,78-94; trainer/layers.py:83,280,293).  bias may be NULL (fp32[Co] otherwise).
+ * engine: 0 = auto, 1 = force CUDA-core (fp32-accumulate FFMA) kernel, 2 = force tcgen05 kernel (error if ineligible). */
+int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y,
+                       int engine, void *stream);
+
+/* Weight gradient (and optional bias gradient) of the same geometry:
+ *   dw[a,b,kh,kw] (+)= sum_{n,oh,ow} gy[n,oh,ow,a] * gx[n,ih,iw,b],  db[a] = sum gy[n,oh,ow,a]
+ * with (ih,iw) from (oh,ow,kh,kw) as above; g->Co == A (channels of gy), g->Ci == B (channels of gx); dw is fp32 in
+ * PyTorch's [A][B][KH][KW] order and is OVERWRITTEN (db too, may be NULL).  Conv2d: gy=dy, gx=x.  ConvTranspose2d: gy=x, gx=dy.
+ * Replaces the weight-gradient half of cudnn/ATen convolution_backward for the layers cited above. */
+int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db,
+                      int engine, void *stream);
+
+/* fp32 master weights W[O][I][KH][KW] -> packed `dtype` weights.
+ * mode 0: wp[O][kh][kw][I] = W[O][I][kh][kw];  mode 1: wp[I][kh][kw][O] = W[O][I][KH-1-kh][KW-1-kw]. */
+int ctagan_pack_weights(const float *w, void *wp, int O, int I, int KH, int KW, int mode, int dtype, void *stream);
+
+/* InstanceNorm2d statistics (affine=False, eps=1e-5, biased variance; Model/CycleGan.py:12,16,29,37,52,82,86,90,
+ * trainer/layers.py:14): x[N][HW][C] -> stats[N][C][2] = (mean, rstd) fp32.  acc: caller scratch, N*C*2 doubles. */
+int ctagan_instnorm_stats(const void *x, float *stats, double *acc, int N, int HW, int C, int dtype, void *stream);
+
+/* Fused InstanceNorm-apply + activation + residual add + reflection pad (one pass):
+ *   out[n,hp,wp,c] = act((x[n,h,w,c]-mean)*rstd) + res[n,h+res_pad,w+res_pad,c],  (h,w) = reflect(hp-pad, wp-pad)
+ * stats==NULL: no normalisation; res==NULL: no residual.  res has spatial size (H+2*res_pad, W+2*res_pad).
+ * Replaces InstanceNorm2d+ReLU/LeakyReLU+ReflectionPad2d+residual add (Model/CycleGan.py:10-21,27-30). */
+int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int res_pad, void *out,
+                        int N, int H, int W, int C, int pad, int act, int dtype, void *stream);
+
+/* Backward of the above.  gout is the gradient w.r.t. `out` (padded, size H+2*pad); x is the saved raw conv output
+ * (or, when stats==NULL, any tensor with the sign of the pre-activation, e.g. the post-activation output).
+ *   g  = (fold_reflect(gout) + addend) * act'(.)          (addend optional, unpadded; act' from x, stats)
+ *   dx = rstd*(g - mean(g) - xhat*mean(g*xhat))   (stats!=NULL)   or   g   (stats==NULL)
+ * The residual branch of the forward receives fold_reflect(gout) itself (call with stats=NULL, act=NONE).
+ * acc: N*C*2 doubles scratch (only with stats). */
+int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
+                            double *acc, int N, int H, int W, int C, int pad, int act, int dtype, void *stream);
+
+/* Pointwise activation backward for conv-epilogue activations: dx = gy * act'(y) computed from the OUTPUT y
+ * (relu/lrelu: sign(y); tanh: 1-y^2).  n elements. */
+int ctagan_act_bwd(const void *gy, const void *y, void *dx, int64_t n, int act, int dtype, void *stream);
+
+/* MaxPool2d(2) (trainer/layers.py:172) on NHWC; bwd routes to the first maximum in window scan order (ATen rule). */
+int ctagan_maxpool2_fwd(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream);
+/* gx = scatter(gy) + addend (addend optional: the skip-connection gradient of trainer/reg.py:94) */
+int ctagan_maxpool2_bwd(const void *gy, const void *x, const void *addend, void *gx, int N, int H, int W, int C, int dtype, void *stream);
+
+/* F.interpolate(x, 2x, mode='bilinear', align_corners=False) + torch.cat([up, skip], 1) (trainer/reg.py:93-94):
+ * x[N][H][W][C1], skip[N][2H][2W][C2] -> out[N][2H][2W][C1+C2].  bwd: gout -> gx (gskip is a strided read of gout). */
+int ctagan_upsample2x_cat_fwd(const void *x, const void *skip, void *out, int N, int H, int W, int C1, int C2, int dtype, void *stream);
+int ctagan_upsample2x_cat_bwd(const void *gout, void *gx, void *gskip, int N, int H, int W, int C1, int C2, int dtype, void *stream);
+
+/* Channel slice copy / concat helper: dst[n,p,dst_off:dst_off+C] = src[n,p,0:C]  (torch.cat, trainer/reg.py:77, p2pTrainer.py:131). */
+int ctagan_copy_channels(const void *src, void *dst, int64_t pixels, int C, int src_stride, int src_off, int dst_stride, int dst_off,
+                         int dtype, void *stream);
+
+/* Transformer_2D.forward (trainer/transformer.py:11-31): bilinear grid_sample(align_corners=True, padding_mode="border") of
+ * src[B][C][H][W] at (i + flow[b,0,i,j], j + flow[b,1,i,j]); fp32 in/out (module boundary).  bwd produces gsrc AND gflow. */
+int ctagan_warp_fwd(const float *src, const float *flow, float *out, int B, int C, int H, int W, void *stream);
+int ctagan_warp_bwd(const float *gout, const float *src, const float *flow, float *gsrc, float *gflow, int B, int C, int H, int W,
+                    void *stream);
+
+/* Fused single-pass losses; `loss` is one fp32 on the device, acc a 4-double scratch.  fp32 tensors.
+ * l1: torch.nn.L1Loss (CycTrainer.py:77);  mse_const: torch.nn.MSELoss vs a broadcast constant (CycTrainer.py:76,83-84);
+ * smooth: smooothing_loss (trainer/utils.py:165-173);  masked_l1: HdTrainer.py:726-735. */
+int ctagan_l1_fwd(const float *a, const float *b, float *loss, double *acc, int64_t n, void *stream);
+int ctagan_l1_bwd(const float *a, const float *b, const float *gloss, float *ga, int64_t n, void *stream);
+int ctagan_mse_const_fwd(const float *p, float target, float *loss, double *acc, int64_t n, void *stream);
+int ctagan_mse_const_bwd(const float *p, float target, const float *gloss, float *gp, int64_t n, void *stream);
+int ctagan_smooth_fwd(const float *flow, float *loss, double *acc, int B, int C, int H, int W, void *stream);
+int ctagan_smooth_bwd(const float *flow, const float *gloss, float *gflow, int B, int C, int H, int W, void *stream);
+int ctagan_masked_l1_fwd(const float *warped, const float *b1, const float *b2, float *loss, double *acc, int64_t n, void *stream);
+int ctagan_masked_l1_bwd(const float *warped, const float *b1, const float *b2, const float *gloss, float *gwarped, int64_t n, void *stream);
+
+/* Global average pool of a (N, HW, C) map -> (N, C) fp32 (Model/CycleGan.py:103; Model/HdGan.py:279,288) and its backward. */
+int ctagan_plane_mean_fwd(const void *x, float *out, int N, int HW, int C, int dtype, void *stream);
+int ctagan_plane_mean_bwd(const float *gout, void *gx, int N, int HW, int C, int dtype, void *stream);
+
+/* Module boundary: fp32 NCHW <-> internal NHWC of `dtype` (cast fused). */
+int ctagan_nchw_to_nhwc(const float *src, void *dst, int N, int C, int64_t HW, int dtype, void *stream);
+int ctagan_nhwc_to_nchw(const void *src, float *dst, int N, int C, int64_t HW, int dtype, void *stream);
+
+/* torch.cat([a, b], 1) of two 1-channel fp32 images into one 2-channel NHWC `dtype` tensor (trainer/reg.py:77) and the
+ * split of its gradient (a or b may be NULL).  n = pixels (N*H*W). */
+int ctagan_interleave2(const float *a, const float *b, void *dst, int64_t n, int dtype, void *stream);
+int ctagan_deinterleave2(const void *src, float *a, float *b, int64_t n, int dtype, void *stream);
+
+/* dtype conversion (fp32 <-> activation dtype), n elements. */
+int ctagan_cast(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTAGAN_H_ */
