@@ -32,6 +32,14 @@ def get_precision() -> torch.dtype:
 
 
 _ENGINE = {"value": L.ENGINE_AUTO}
+_CACHE_EPOCH = {"value": 0}
+
+
+def invalidate_weight_cache():
+    """Forget every packed (bf16 / re-laid-out) weight copy.  Needed (a) after out-of-band `.data` edits, which do not bump
+    the tensor version the cache is keyed on, and (b) right before CUDA-graph capture, so that the pack kernels are part of
+    the captured step and replays always see the current master weights."""
+    _CACHE_EPOCH["value"] += 1
 
 
 def set_conv_engine(e):
@@ -50,7 +58,7 @@ class ConvPrim:
 
     def packed(self, mode: int, dtype: torch.dtype) -> torch.Tensor:
         key = (mode, dtype)
-        ver = (self.w._version, self.w.data_ptr())
+        ver = (self.w._version, self.w.data_ptr(), _CACHE_EPOCH["value"])
         hit = self._cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]

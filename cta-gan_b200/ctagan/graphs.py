@@ -1,0 +1,104 @@
+"""CUDA-graph execution of the trainer iteration bodies.
+
+A Cyc step at batch 1 is ~1700 kernel launches for ~1.3 TFLOP: launch latency, not arithmetic, bounds an eager loop.  The
+iteration body is therefore captured once (torch.cuda.CUDAGraph: all libctagan kernels, the NCCL gradient all-reduce and the
+capturable Adam updates are stream-ordered and allocation-free on replay) and replayed per step.  Host-side logic that the
+reference keeps on the CPU (ReplayBuffer with Python `random`, trainer/utils.py:120-140) stays on the host BETWEEN graphs:
+the Cyc step is three graphs (generator phase, D_A phase, D_B phase) around the two buffer exchanges.
+
+Weight packing (fp32 master -> bf16 [O][kh][kw][I]) is part of the captured graphs: the packed-weight cache is invalidated
+right before capture, so every replay re-packs from the current master weights.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine as E
+from . import ops
+
+
+class GraphedTrainer:
+    def __init__(self, trainer, enabled: bool = True, warmup: int = 3):
+        self.t = trainer
+        self.enabled = enabled
+        self.warmup = warmup
+        self._graphs = None
+        self._launches = 0
+        self.is_cyc = hasattr(trainer, "phase_G")
+
+    # -- public ----------------------------------------------------------------------------------------------------------
+    def step_host(self, batch):
+        """One iteration from a host (pinned) batch: H2D copy into the static inputs, then the (graphed) step."""
+        tensors = self.t.load_batch(batch)
+        return self._run(tensors, copy_inputs=False)
+
+    def step_device(self, tensors):
+        """One iteration from device-resident tensors."""
+        return self._run(tensors, copy_inputs=True)
+
+    def launches_per_step(self) -> int:
+        return self._launches
+
+    # -- internals -------------------------------------------------------------------------------------------------------
+    def _run(self, tensors, copy_inputs):
+        t = self.t
+        if not self.enabled:
+            return t.step(tensors=list(tensors))
+        static = [t.inputs[k] for k in t.data_keys]
+        if copy_inputs:
+            for dst, src in zip(static, tensors):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        if self._graphs is None:
+            self._capture(static)
+        E.invalidate_weight_cache()          # eager users after us must not trust capture-time packed weights
+        if self.is_cyc:
+            gG, gDA, gDB = self._graphs
+            gG.replay()
+            fa = t.fake_A_buffer.push_and_pop(self._fake_A.clone())
+            fb = t.fake_B_buffer.push_and_pop(self._fake_B.clone())
+            self._sel_A.copy_(fa)
+            self._sel_B.copy_(fb)
+            gDA.replay()
+            gDB.replay()
+            t.last_losses = {"loss_G": self._loss_G, "loss_D_A": self._loss_DA, "loss_D_B": self._loss_DB}
+        else:
+            self._graphs[0].replay()
+            t.last_losses = self._losses
+        t.step_count += 1
+        return t.last_losses
+
+    def _capture(self, static):
+        t = self.t
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):                 # allocator / NCCL / optimizer-state warm-up, off the capture stream
+                t.step(tensors=static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        E.invalidate_weight_cache()
+        n0 = ops.launch_count()
+        if self.is_cyc:
+            real_A, real_B = static
+            gG = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gG):
+                self._fake_A, self._fake_B, self._loss_G = t.phase_G(real_A, real_B)
+            pool = gG.pool()
+            self._sel_A, self._sel_B = torch.empty_like(self._fake_A), torch.empty_like(self._fake_B)
+            self._sel_A.copy_(self._fake_A); self._sel_B.copy_(self._fake_B)
+            gDA = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gDA, pool=pool):
+                self._loss_DA = t.phase_D(t.netD_A, t.optimizer_D_A, t._sync_DA, real_A, self._sel_A)
+            gDB = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gDB, pool=pool):
+                self._loss_DB = t.phase_D(t.netD_B, t.optimizer_D_B, t._sync_DB, real_B, self._sel_B)
+            self._graphs = (gG, gDA, gDB)
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._losses = t.step(tensors=static)
+            t.step_count -= 1
+            self._graphs = (g,)
+        self._launches = ops.launch_count() - n0

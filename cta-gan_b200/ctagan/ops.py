@@ -27,6 +27,16 @@ def _require_cuda(*ts):
 
 
 _checked_devices = set()
+_LAUNCHES = {"n": 0}
+
+
+def launch_count() -> int:
+    """Number of libctagan kernels enqueued so far by this process (memsets are not counted)."""
+    return _LAUNCHES["n"]
+
+
+def _count(n=1):
+    _LAUNCHES["n"] += n
 
 
 def ensure_device():
@@ -49,6 +59,7 @@ def conv_gather(x, wp, bias, g: L.ConvGeom, engine=L.ENGINE_AUTO):
     _require_cuda(x, wp)
     ensure_device()
     y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
+    _count(1)
     L.check(L.load().ctagan_conv_gather(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), engine, _stream()))
     return y
 
@@ -57,6 +68,7 @@ def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO):
     _require_cuda(gy, gx)
     dw = torch.empty((g.Co, g.Ci, g.KH, g.KW), dtype=torch.float32, device=gy.device)
     db = torch.empty((g.Co,), dtype=torch.float32, device=gy.device) if want_bias else None
+    _count(1)
     L.check(L.load().ctagan_conv_wgrad(ctypes.byref(g), _p(gy), _p(gx), _p(dw), _p(db), engine, _stream()))
     return dw, db
 
@@ -66,6 +78,7 @@ def pack_weights(w: torch.Tensor, mode: int, dtype: torch.dtype):
     O, I, KH, KW = w.shape
     shape = (O, KH, KW, I) if mode == 0 else (I, KH, KW, O)
     wp = torch.empty(shape, dtype=dtype, device=w.device)
+    _count(1)
     L.check(L.load().ctagan_pack_weights(_p(w), _p(wp), O, I, KH, KW, mode, _DT[dtype], _stream()))
     return wp
 
@@ -74,6 +87,7 @@ def instnorm_stats(x):
     N, H, W, C = x.shape
     stats = torch.empty((N, C, 2), dtype=torch.float32, device=x.device)
     acc = torch.empty((N, C, 2), dtype=torch.float64, device=x.device)
+    _count(2)
     L.check(L.load().ctagan_instnorm_stats(_p(x), _p(stats), _p(acc), N, H * W, C, dt(x), _stream()))
     return stats
 
@@ -81,6 +95,7 @@ def instnorm_stats(x):
 def norm_act_pad(x, stats, act, pad, res=None, res_pad=0):
     N, H, W, C = x.shape
     out = torch.empty((N, H + 2 * pad, W + 2 * pad, C), dtype=x.dtype, device=x.device)
+    _count(1)
     L.check(L.load().ctagan_norm_act_pad(_p(x), _p(stats), _p(res), res_pad, _p(out), N, H, W, C, pad, act, dt(x), _stream()))
     return out
 
@@ -90,6 +105,7 @@ def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None):
     H, W = Hp - 2 * pad, Wp - 2 * pad
     dx = torch.empty((N, H, W, C), dtype=gout.dtype, device=gout.device)
     acc = torch.empty((N, C, 2), dtype=torch.float64, device=gout.device) if stats is not None else None
+    _count(2 if stats is not None else 1)
     L.check(L.load().ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(acc), N, H, W, C, pad, act,
                                              dt(gout), _stream()))
     return dx
@@ -97,6 +113,7 @@ def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None):
 
 def act_bwd(gy, y, act):
     dx = torch.empty_like(gy)
+    _count(1)
     L.check(L.load().ctagan_act_bwd(_p(gy), _p(y), _p(dx), gy.numel(), act, dt(gy), _stream()))
     return dx
 
@@ -104,6 +121,7 @@ def act_bwd(gy, y, act):
 def maxpool2_fwd(x):
     N, H, W, C = x.shape
     y = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    _count(1)
     L.check(L.load().ctagan_maxpool2_fwd(_p(x), _p(y), N, H, W, C, dt(x), _stream()))
     return y
 
@@ -111,6 +129,7 @@ def maxpool2_fwd(x):
 def maxpool2_bwd(gy, x, addend=None):
     N, H, W, C = x.shape
     gx = torch.empty_like(x)
+    _count(1)
     L.check(L.load().ctagan_maxpool2_bwd(_p(gy), _p(x), _p(addend), _p(gx), N, H, W, C, dt(x), _stream()))
     return gx
 
@@ -119,6 +138,7 @@ def upsample2x_cat_fwd(x, skip):
     N, H, W, C1 = x.shape
     C2 = skip.shape[3]
     out = torch.empty((N, 2 * H, 2 * W, C1 + C2), dtype=x.dtype, device=x.device)
+    _count(1)
     L.check(L.load().ctagan_upsample2x_cat_fwd(_p(x), _p(skip), _p(out), N, H, W, C1, C2, dt(x), _stream()))
     return out
 
@@ -128,6 +148,7 @@ def upsample2x_cat_bwd(gout, C1):
     H, W, C2 = Ho // 2, Wo // 2, C - C1
     gx = torch.empty((N, H, W, C1), dtype=gout.dtype, device=gout.device)
     gskip = torch.empty((N, Ho, Wo, C2), dtype=gout.dtype, device=gout.device)
+    _count(1)
     L.check(L.load().ctagan_upsample2x_cat_bwd(_p(gout), _p(gx), _p(gskip), N, H, W, C1, C2, dt(gout), _stream()))
     return gx, gskip
 
@@ -141,6 +162,7 @@ def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype):
         x = x.float()
     N, C, H, W = x.shape
     out = torch.empty((N, H, W, C), dtype=dtype, device=x.device)
+    _count(1)
     L.check(L.load().ctagan_nchw_to_nhwc(_p(x), _p(out), N, C, H * W, _DT[dtype], _stream()))
     return out
 
@@ -148,6 +170,7 @@ def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype):
 def nhwc_to_nchw(x: torch.Tensor):
     N, H, W, C = x.shape
     out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    _count(1)
     L.check(L.load().ctagan_nhwc_to_nchw(_p(x), _p(out), N, C, H * W, dt(x), _stream()))
     return out
 
@@ -155,6 +178,7 @@ def nhwc_to_nchw(x: torch.Tensor):
 def plane_mean_fwd(x_nhwc):
     N, H, W, C = x_nhwc.shape
     out = torch.empty((N, C), dtype=torch.float32, device=x_nhwc.device)
+    _count(1)
     L.check(L.load().ctagan_plane_mean_fwd(_p(x_nhwc), _p(out), N, H * W, C, dt(x_nhwc), _stream()))
     return out
 
@@ -162,6 +186,7 @@ def plane_mean_fwd(x_nhwc):
 def plane_mean_bwd(gout, shape, dtype):
     N, H, W, C = shape
     gx = torch.empty(shape, dtype=dtype, device=gout.device)
+    _count(1)
     L.check(L.load().ctagan_plane_mean_bwd(_p(gout), _p(gx), N, H * W, C, _DT[dtype], _stream()))
     return gx
 
@@ -169,6 +194,7 @@ def plane_mean_bwd(gout, shape, dtype):
 def warp_fwd(src, flow):
     B, C, H, W = src.shape
     out = torch.empty_like(src)
+    _count(1)
     L.check(L.load().ctagan_warp_fwd(_p(src), _p(flow), _p(out), B, C, H, W, _stream()))
     return out
 
@@ -177,6 +203,7 @@ def warp_bwd(gout, src, flow, need_src=True, need_flow=True):
     B, C, H, W = src.shape
     gsrc = torch.empty_like(src) if need_src else None
     gflow = torch.empty_like(flow) if need_flow else None
+    _count(1)
     L.check(L.load().ctagan_warp_bwd(_p(gout), _p(src), _p(flow), _p(gsrc), _p(gflow), B, C, H, W, _stream()))
     return gsrc, gflow
 
@@ -187,24 +214,28 @@ def _scalar_out(ref):
 
 def l1_fwd(a, b):
     loss, acc = _scalar_out(a)
+    _count(1)
     L.check(L.load().ctagan_l1_fwd(_p(a), _p(b), _p(loss), _p(acc), a.numel(), _stream()))
     return loss
 
 
 def l1_bwd(a, b, gloss):
     ga = torch.empty_like(a)
+    _count(1)
     L.check(L.load().ctagan_l1_bwd(_p(a), _p(b), _p(gloss), _p(ga), a.numel(), _stream()))
     return ga
 
 
 def mse_const_fwd(p, target: float):
     loss, acc = _scalar_out(p)
+    _count(1)
     L.check(L.load().ctagan_mse_const_fwd(_p(p), float(target), _p(loss), _p(acc), p.numel(), _stream()))
     return loss
 
 
 def mse_const_bwd(p, target: float, gloss):
     gp = torch.empty_like(p)
+    _count(1)
     L.check(L.load().ctagan_mse_const_bwd(_p(p), float(target), _p(gloss), _p(gp), p.numel(), _stream()))
     return gp
 
@@ -212,6 +243,7 @@ def mse_const_bwd(p, target: float, gloss):
 def smooth_fwd(flow):
     B, C, H, W = flow.shape
     loss, acc = _scalar_out(flow)
+    _count(1)
     L.check(L.load().ctagan_smooth_fwd(_p(flow), _p(loss), _p(acc), B, C, H, W, _stream()))
     return loss
 
@@ -219,18 +251,21 @@ def smooth_fwd(flow):
 def smooth_bwd(flow, gloss):
     B, C, H, W = flow.shape
     g = torch.empty_like(flow)
+    _count(1)
     L.check(L.load().ctagan_smooth_bwd(_p(flow), _p(gloss), _p(g), B, C, H, W, _stream()))
     return g
 
 
 def masked_l1_fwd(warped, b1, b2):
     loss, acc = _scalar_out(warped)
+    _count(1)
     L.check(L.load().ctagan_masked_l1_fwd(_p(warped), _p(b1), _p(b2), _p(loss), _p(acc), warped.numel(), _stream()))
     return loss
 
 
 def masked_l1_bwd(warped, b1, b2, gloss):
     g = torch.empty_like(warped)
+    _count(1)
     L.check(L.load().ctagan_masked_l1_bwd(_p(warped), _p(b1), _p(b2), _p(gloss), _p(g), warped.numel(), _stream()))
     return g
 
@@ -242,6 +277,7 @@ def interleave2(a, b, dtype):
     a = a.contiguous().float(); b = b.contiguous().float()
     N, _, H, W = a.shape
     out = torch.empty((N, H, W, 2), dtype=dtype, device=a.device)
+    _count(1)
     L.check(L.load().ctagan_interleave2(_p(a), _p(b), _p(out), N * H * W, _DT[dtype], _stream()))
     return out
 
@@ -250,5 +286,6 @@ def deinterleave2(src, need_a=True, need_b=True):
     N, H, W, _ = src.shape
     a = torch.empty((N, 1, H, W), dtype=torch.float32, device=src.device) if need_a else None
     b = torch.empty((N, 1, H, W), dtype=torch.float32, device=src.device) if need_b else None
+    _count(1)
     L.check(L.load().ctagan_deinterleave2(_p(src), _p(a), _p(b), N * H * W, dt(src), _stream()))
     return a, b

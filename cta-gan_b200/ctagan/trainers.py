@@ -1,0 +1,446 @@
+"""Trainer entry points of the reference (trainer/{Cyc,Reg,Hd,p2p}Trainer.py) re-hosted on the sm_100a kernels.
+
+Kept from the reference: class names, `__init__(config)` with the Yaml keys, `train()`, `test()`, `update_learning_rate()`
+(bugs included: CycTrainer.py:117-126 forgets optimizer_D_A; HdTrainer.py:163-164 never decays D), Adam(betas=(0.5, 0.999)),
+the exact order of forward/backward/step calls of every iteration body, checkpoint file names.
+Replaced: DICOM datasets / Visdom (not in scope) by a synthetic CT-like slice stream and an
+every-N-steps stdout logger without per-iteration host syncs; `.cuda()` hard-coding by LOCAL_RANK-aware devices; and a
+data-parallel gradient all-reduce (NCCL) when launched under torchrun.
+
+Each trainer exposes `step(batch)` = one iteration body, which is what bench.py times and tests/ compare with the oracle.
+"""
+from __future__ import annotations
+
+import itertools
+import os
+import random
+import time
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import engine as E
+from . import nn as N
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class SyntheticSlices:
+    """CT-like slices in [-1, 1] (air = -1), as trainer/datasets.py:74-82 produces; pinned host tensors, per-rank seed."""
+
+    def __init__(self, batch: int, size: int, n_batches: int, seed: int, keys=("A", "B"), pool: int = 4):
+        g = torch.Generator().manual_seed(seed)
+        yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
+        disc = ((yy - size / 2) ** 2 + (xx - size / 2) ** 2) <= (0.4 * size) ** 2
+        self.batches = []
+        for _ in range(pool):
+            a = torch.where(disc, torch.rand(batch, 1, size, size, generator=g) * 0.6 - 0.3, torch.full((batch, 1, size, size), -1.0))
+            b = (torch.roll(a, shifts=(2, -3), dims=(2, 3)) + 0.02 * torch.randn(batch, 1, size, size, generator=g)).clamp_(-1, 1)
+            d = {}
+            for k in keys:
+                src = a if k.startswith("A") else b
+                if k == "B1":     # windowed copy of B2 (centre 50 / width 400 HU window, trainer/datasets.py:45-56)
+                    hu = (b * 0.5 + 0.5) * 4095 - 1024
+                    src = (((hu - (50 - 200)) / 400).clamp(0, 1) - 0.5) / 0.5
+                d[k] = src.clone().pin_memory() if torch.cuda.is_available() else src.clone()
+            self.batches.append(d)
+        self.n_batches = n_batches
+
+    def __len__(self):
+        return self.n_batches
+
+    def __iter__(self):
+        for i in range(self.n_batches):
+            yield self.batches[i % len(self.batches)]
+
+
+class GradSync:
+    """Data-parallel gradient averaging: one flat NCCL all-reduce per optimiser group (weak scaling over slices; every op
+    on the path is per-sample, so N ranks x b slices == 1 rank x N*b slices up to reduction order)."""
+
+    def __init__(self, params: Iterable[torch.Tensor]):
+        self.params = [p for p in params]
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def __call__(self):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in self.params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(self.world)
+        torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+
+class _TrainerBase:
+    name = "base"
+    data_keys = ("A", "B")
+
+    def __init__(self, config: dict):
+        if not torch.cuda.is_available():
+            raise RuntimeError("the CTA-GAN B200 trainers need a CUDA device (sm_100a); there is no CPU fallback")
+        self.config = dict(config)
+        c = self.config
+        c.setdefault("precision", "bf16")
+        c.setdefault("log_every", 50)
+        c.setdefault("synthetic_batches", 100)
+        c.setdefault("save_checkpoints", True)
+        self.rank, self.world, self.local_rank = _dist_env()
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.device)
+        E.set_precision(c["precision"])
+        self.step_count = 0
+        self.last_losses: Dict[str, torch.Tensor] = {}
+
+    # -- helpers -------------------------------------------------------------------------------------------------------
+    def _adam(self, params, lr):
+        return torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), fused=True, capturable=True)
+
+    def _alloc_inputs(self):
+        c = self.config
+        shape = (c["batchSize"], c["input_nc"], c["size"], c["size"])
+        return {k: torch.empty(shape, dtype=torch.float32, device=self.device) for k in self.data_keys}
+
+    def _loader(self, list_key="train_list", seed_offset=0):
+        c = self.config
+        path = c.get(list_key)
+        if c.get("synthetic", True) or not (path and os.path.exists(path)):
+            return SyntheticSlices(c["batchSize"], c["size"], c["synthetic_batches"], 42 + self.rank + seed_offset, self.data_keys)
+        raise NotImplementedError("DICOM list datasets (trainer/datasets.py) are outside the hot path; set synthetic: true")
+
+    def load_batch(self, batch):
+        """H2D copy of one batch into the preallocated device inputs (CycTrainer.py:80-82,140-141)."""
+        for k in self.data_keys:
+            self.inputs[k].copy_(batch[k], non_blocking=True)
+        return [self.inputs[k] for k in self.data_keys]
+
+    def _log(self, epoch, i, n):
+        if self.rank == 0 and self.step_count % self.config["log_every"] == 0:
+            msg = " | ".join(f"{k}: {float(v):.4f}" for k, v in self.last_losses.items())
+            print(f"[{self.name}] epoch {epoch} batch {i + 1}/{n} -- {msg}", flush=True)
+
+    def _save(self, epoch, nets: Dict[str, torch.nn.Module]):
+        c = self.config
+        if self.rank != 0 or not c.get("save_checkpoints") or not c.get("save_root"):
+            return
+        os.makedirs(c["save_root"], exist_ok=True)
+        for fname, net in nets.items():
+            torch.save(net.state_dict(), os.path.join(c["save_root"], fname.format(st=str(epoch))))
+
+    def train(self):
+        c = self.config
+        for epoch in range(c["epoch"] + 1, c["n_epochs"] + 1 + c["decay_epoch"]):
+            if epoch > c["n_epochs"]:
+                self.update_learning_rate()
+            loader = self._loader()
+            for i, batch in enumerate(loader):
+                self.step(batch)
+                self._log(epoch, i, len(loader))
+            self._save(epoch, self.checkpoint_nets())
+
+    @torch.no_grad()
+    def test(self, loader=None):
+        """Generator-only inference loop (CycTrainer.py:238-360 hot part: `fake_B = netG_A2B(real_A)`), batch-split across
+        ranks without any collective; returns mean MAE / PSNR of the synthetic pairs."""
+        loader = loader or self._loader("test_list", seed_offset=1000)
+        mae = psnr = 0.0
+        n = 0
+        ka, kb = self.data_keys[0], self.data_keys[-1]
+        for batch in loader:
+            a = batch[ka].to(self.device, non_blocking=True)
+            b = batch[kb].to(self.device, non_blocking=True)
+            fake = self.netG_A2B(a)
+            mae += float((fake - b).abs().mean())
+            mse = float(((fake - b) ** 2).mean())
+            psnr += 10.0 * torch.log10(torch.tensor(4.0 / max(mse, 1e-12))).item()
+            n += 1
+        out = {"MAE": mae / max(n, 1), "PSNR": psnr / max(n, 1), "slices": n * self.config["batchSize"]}
+        if self.rank == 0:
+            print(f"[{self.name}] test: {out}", flush=True)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CycleGAN  (trainer/CycTrainer.py)
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+class Cyc_Trainer(_TrainerBase):
+    name = "CycleGan"
+
+    def __init__(self, config):
+        super().__init__(config)
+        c = self.config
+        dev = self.device
+        self.netG_A2B = N.Generator(c["input_nc"], c["output_nc"]).to(dev)            # CycTrainer.py:64-71 creation order
+        self.netD_B = N.Discriminator(c["input_nc"]).to(dev)
+        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c["lr"])
+        self.netG_B2A = N.Generator(c["input_nc"], c["output_nc"]).to(dev)
+        self.netD_A = N.Discriminator(c["input_nc"]).to(dev)
+        self.optimizer_G = self._adam(itertools.chain(self.netG_A2B.parameters(), self.netG_B2A.parameters()), c["lr"])
+        self.optimizer_D_A = self._adam(self.netD_A.parameters(), c["lr"])
+        self.MSE_loss, self.L1_loss = N.MSELoss(), N.L1Loss()
+        self.inputs = self._alloc_inputs()
+        self.target_real, self.target_fake = 1.0, 0.0
+        from .replay import ReplayBuffer
+        self.fake_A_buffer, self.fake_B_buffer = ReplayBuffer(), ReplayBuffer()
+        self._sync_G = GradSync(itertools.chain(self.netG_A2B.parameters(), self.netG_B2A.parameters()))
+        self._sync_DA, self._sync_DB = GradSync(self.netD_A.parameters()), GradSync(self.netD_B.parameters())
+
+    def update_learning_rate(self):
+        c = self.config
+        lr = c["lr"] - c["lr"] / c["decay_epoch"]
+        for opt in (self.optimizer_D_B, self.optimizer_G):          # optimizer_D_A is skipped, as in CycTrainer.py:117-126
+            for g in opt.param_groups:
+                g["lr"] = lr
+        c["lr"] = lr
+
+    def checkpoint_nets(self):
+        return {"{st}.pth": self.netG_A2B, "netD_B_{st}.pth": self.netD_B, "netG_B2A_{st}.pth": self.netG_B2A,
+                "netD_A_{st}.pth": self.netD_A}
+
+    # the three phases are separate methods so that they can be captured as CUDA graphs around the host-side ReplayBuffer
+    def phase_G(self, real_A, real_B):
+        c = self.config
+        self.optimizer_G.zero_grad(set_to_none=True)
+        fake_B = self.netG_A2B(real_A)                                                     # CycTrainer.py:144-146
+        loss_GAN_A2B = c["Adv_lamda"] * self.MSE_loss(self.netD_B(fake_B, freeze=True), self.target_real)
+        fake_A = self.netG_B2A(real_B)                                                     # :148-150
+        loss_GAN_B2A = c["Adv_lamda"] * self.MSE_loss(self.netD_A(fake_A, freeze=True), self.target_real)
+        recovered_A = self.netG_B2A(fake_B)                                                # :153-157
+        loss_cycle_ABA = c["Cyc_lamda"] * self.L1_loss(recovered_A, real_A)
+        recovered_B = self.netG_A2B(fake_A)
+        loss_cycle_BAB = c["Cyc_lamda"] * self.L1_loss(recovered_B, real_B)
+        loss_Total = loss_GAN_A2B + loss_GAN_B2A + loss_cycle_ABA + loss_cycle_BAB         # :160-162
+        loss_Total.backward()
+        self._sync_G()
+        self.optimizer_G.step()
+        return fake_A.detach(), fake_B.detach(), loss_Total.detach()
+
+    def phase_D(self, netD, opt, sync, real, fake):
+        c = self.config
+        opt.zero_grad(set_to_none=True)                                                    # :165-178 / :182-197
+        loss_real = c["Adv_lamda"] * self.MSE_loss(netD(real), self.target_real)
+        loss_fake = c["Adv_lamda"] * self.MSE_loss(netD(fake), self.target_fake)
+        loss_D = loss_real + loss_fake
+        loss_D.backward()
+        sync()
+        opt.step()
+        return loss_D.detach()
+
+    def step(self, batch=None, tensors=None):
+        real_A, real_B = tensors if tensors is not None else self.load_batch(batch)
+        fake_A, fake_B, loss_G = self.phase_G(real_A, real_B)
+        fake_A = self.fake_A_buffer.push_and_pop(fake_A)                                   # :170
+        loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, fake_A)
+        fake_B = self.fake_B_buffer.push_and_pop(fake_B)                                   # :189
+        loss_D_B = self.phase_D(self.netD_B, self.optimizer_D_B, self._sync_DB, real_B, fake_B)
+        self.step_count += 1
+        self.last_losses = {"loss_G": loss_G, "loss_D_A": loss_D_A, "loss_D_B": loss_D_B}
+        return self.last_losses
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Reg-GAN  (trainer/RegTrainer.py) and the two Hd stages (trainer/HdTrainer.py)
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+class Reg_Trainer(_TrainerBase):
+    name = "RegGan"
+    lam_corr, lam_adv, lr_d = "Corr_lamda", "Adv_lamda", "lr"
+
+    def _make_D(self):
+        return N.Discriminator(self.config["input_nc"])
+
+    def __init__(self, config):
+        super().__init__(config)
+        c = self.config
+        dev = self.device
+        self.netG_A2B = N.Generator(c["input_nc"], c["output_nc"]).to(dev)              # RegTrainer.py:94-101
+        self.netD_B = self._make_D().to(dev)
+        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c[self.lr_d])
+        self.R_A = N.Reg(c["size"], c["size"], c["input_nc"], c["input_nc"]).to(dev)
+        self.spatial_transform = N.Transformer_2D().to(dev)
+        self.optimizer_R_A = self._adam(self.R_A.parameters(), c["lr"])
+        self.optimizer_G = self._adam(self.netG_A2B.parameters(), c["lr"])
+        self.MSE_loss, self.L1_loss = N.MSELoss(), N.L1Loss()
+        self.criterionGAN = N.GANLoss()
+        self.inputs = self._alloc_inputs()
+        self.target_real, self.target_fake = 1.0, 0.0
+        self._sync_GR = GradSync(itertools.chain(self.R_A.parameters(), self.netG_A2B.parameters()))
+        self._sync_D = GradSync(self.netD_B.parameters())
+
+    def update_learning_rate(self):
+        c = self.config
+        lr = c["lr"] - c["lr"] / c["decay_epoch"]
+        for opt in (self.optimizer_D_B, self.optimizer_R_A, self.optimizer_G):           # RegTrainer.py:150-161
+            for g in opt.param_groups:
+                g["lr"] = lr
+        c["lr"] = lr
+
+    def checkpoint_nets(self):
+        return {"netG_A2B_{st}.pth": self.netG_A2B, "R_A_{st}.pth": self.R_A, "netD_B_{st}.pth": self.netD_B}
+
+    def _adv_G(self, fake_B):
+        return self.MSE_loss(self.netD_B(fake_B, freeze=True), self.target_real)
+
+    def _loss_D(self, fake_B, real_B):
+        c = self.config
+        return c[self.lam_adv] * self.MSE_loss(self.netD_B(fake_B), self.target_fake) + \
+            c[self.lam_adv] * self.MSE_loss(self.netD_B(real_B), self.target_real)
+
+    def _extra_G_losses(self, SysRegist_A2B, tensors):
+        return None
+
+    def step(self, batch=None, tensors=None):
+        c = self.config
+        tensors = tensors if tensors is not None else self.load_batch(batch)
+        real_A, real_B = tensors[0], tensors[-1]
+        self.optimizer_R_A.zero_grad(set_to_none=True)                                     # RegTrainer.py:173-187
+        self.optimizer_G.zero_grad(set_to_none=True)
+        fake_B = self.netG_A2B(real_A)
+        Trans = self.R_A(fake_B, real_B)
+        SysRegist_A2B = self.spatial_transform(fake_B, Trans)
+        SR_loss = c[self.lam_corr] * self.L1_loss(SysRegist_A2B, real_B)
+        adv_loss = c[self.lam_adv] * self._adv_G(fake_B)
+        SM_loss = c["Smooth_lamda"] * N.smooothing_loss(Trans)
+        toal_loss = SM_loss + adv_loss + SR_loss
+        extra = self._extra_G_losses(SysRegist_A2B, tensors)
+        if extra is not None:
+            toal_loss = toal_loss + extra
+        toal_loss.backward()
+        self._sync_GR()
+        self.optimizer_R_A.step()
+        self.optimizer_G.step()
+
+        self.optimizer_D_B.zero_grad(set_to_none=True)                                     # :189-198
+        with torch.no_grad():
+            fake_B = self.netG_A2B(real_A)
+        loss_D_B = self._loss_D(fake_B, real_B)
+        loss_D_B.backward()
+        self._sync_D()
+        self.optimizer_D_B.step()
+        self.step_count += 1
+        self.last_losses = {"SR_loss": SR_loss.detach(), "adv_loss": adv_loss.detach(), "SM_loss": SM_loss.detach(),
+                            "toal_loss": toal_loss.detach(), "loss_D_B": loss_D_B.detach()}
+        return self.last_losses
+
+
+class Hd_Trainer_x1(Reg_Trainer):
+    """Stage 1 of CTA-GAN (trainer/HdTrainer.py:94-280): the Reg-GAN body on the A2/B2 inputs with the Hd loss weights."""
+    name = "HdGan_x1"
+    data_keys = ("A2", "B1", "B2")
+    lam_corr, lam_adv, lr_d = "Corr_lamda1", "Adv_lamda1", "lrd"
+
+    def update_learning_rate(self):
+        c = self.config
+        lr = c["lr"] - c["lr"] / c["decay_epoch"]
+        for opt in (self.optimizer_R_A, self.optimizer_G):
+            for g in opt.param_groups:
+                g["lr"] = lr
+        for g in self.optimizer_D_B.param_groups:      # HdTrainer.py:163-164 writes a no-op key: D never decays
+            g["lrd"] = c["lrd"] - c["lrd"] / c["decay_epoch"]
+        c["lr"] = lr
+
+
+class Hd_Trainer_x2(Hd_Trainer_x1):
+    """Stage 2 (trainer/HdTrainer.py:605-803): Discriminator_m + GANLoss and the additional masked L1 (:726-735)."""
+    name = "HdGan_x2"
+
+    def _make_D(self):
+        return N.Discriminator_m(self.config["input_nc"])
+
+    def _adv_G(self, fake_B):
+        return self.criterionGAN(self.netD_B(fake_B, freeze=True), True)
+
+    def _loss_D(self, fake_B, real_B):
+        c = self.config
+        return c[self.lam_adv] * (self.criterionGAN(self.netD_B(fake_B), False) + self.criterionGAN(self.netD_B(real_B), True)) / 2
+
+    def _extra_G_losses(self, SysRegist_A2B, tensors):
+        real_B1, real_B2 = tensors[1], tensors[2]
+        return self.config["Corr_lamda2"] * N.masked_l1_loss(SysRegist_A2B, real_B1, real_B2)
+
+    def train(self):
+        c = self.config
+        for fname, net in (("netG_A2B_x_45.pth", self.netG_A2B), ("R_A_x_45.pth", self.R_A)):    # HdTrainer.py:697-699
+            path = os.path.join(c.get("save_root") or "", fname)
+            if os.path.exists(path):
+                net.load_state_dict(torch.load(path, map_location=self.device))
+        super().train()
+
+
+Hd_Trainer_x = Hd_Trainer_x1          # train.py:42: "change the name Hd_Trainer_x1/Hd_Trainer_x2 to Hd_Trainer_x"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# pix2pix  (trainer/p2pTrainer.py)
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+class P2p_Trainer(_TrainerBase):
+    name = "P2p"
+
+    def __init__(self, config):
+        super().__init__(config)
+        c = self.config
+        dev = self.device
+        self.netG_A2B = N.Generator(c["input_nc"], c["output_nc"]).to(dev)               # p2pTrainer.py:60-63
+        self.netD_B = N.Discriminator(c["input_nc"] * 2).to(dev)
+        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c["lr"])
+        self.optimizer_G = self._adam(self.netG_A2B.parameters(), c["lr"])
+        self.MSE_loss, self.L1_loss = N.MSELoss(), N.L1Loss()
+        self.inputs = self._alloc_inputs()
+        self.target_real, self.target_fake = 1.0, 0.0
+        self._sync_G, self._sync_D = GradSync(self.netG_A2B.parameters()), GradSync(self.netD_B.parameters())
+
+    def update_learning_rate(self):
+        c = self.config
+        lr = c["lr"] - c["lr"] / c["decay_epoch"]
+        for opt in (self.optimizer_D_B, self.optimizer_G):
+            for g in opt.param_groups:
+                g["lr"] = lr
+        c["lr"] = lr
+
+    def checkpoint_nets(self):
+        return {"netG_A2B_{st}.pth": self.netG_A2B, "netD_B_{st}.pth": self.netD_B}
+
+    def step(self, batch=None, tensors=None):
+        c = self.config
+        real_A, real_B = tensors if tensors is not None else self.load_batch(batch)
+        self.optimizer_G.zero_grad(set_to_none=True)                                       # p2pTrainer.py:127-137
+        fake_B = self.netG_A2B(real_A)
+        loss_L1 = self.L1_loss(fake_B, real_B) * c["P2P_lamda"]
+        pred_fake = self.netD_B(torch.cat((real_A, fake_B), 1), freeze=True)
+        loss_GAN_A2B = self.MSE_loss(pred_fake, self.target_real) * c["Adv_lamda"]
+        toal_loss = loss_L1 + loss_GAN_A2B
+        toal_loss.backward()
+        self._sync_G()
+        self.optimizer_G.step()
+
+        self.optimizer_D_B.zero_grad(set_to_none=True)                                     # :139-148 (prediction is scaled)
+        with torch.no_grad():
+            fake_B = self.netG_A2B(real_A)
+        pred_fake0 = self.netD_B(torch.cat((real_A, fake_B), 1)) * c["Adv_lamda"]
+        pred_real = self.netD_B(torch.cat((real_A, real_B), 1)) * c["Adv_lamda"]
+        loss_D_B = self.MSE_loss(pred_fake0, self.target_fake) + self.MSE_loss(pred_real, self.target_real)
+        loss_D_B.backward()
+        self._sync_D()
+        self.optimizer_D_B.step()
+        self.step_count += 1
+        self.last_losses = {"loss_L1": loss_L1.detach(), "loss_GAN_A2B": loss_GAN_A2B.detach(), "toal_loss": toal_loss.detach(),
+                            "loss_D_B": loss_D_B.detach()}
+        return self.last_losses

@@ -141,7 +141,8 @@ def test_reg_fp32(fp32_mode, golden):
     assert fl.shape == (1, 2, 256, 256)
     assert maxrel(fl, golden["reg.flow_256"]) <= 1e-4, maxrel(fl, golden["reg.flow_256"])
     _seed(1); wbig = torch.randn_like(sd["offset_map.output.conv2d.weight"]) * 0.05
-    net.offset_map.output.conv2d.weight.data.copy_(wbig.cuda())
+    with torch.no_grad():                                   # in-place update that bumps the version counter, as load_state_dict / Adam do
+        net.offset_map.output.conv2d.weight.copy_(wbig.cuda())
     xa = ra.cuda().requires_grad_(True)
     fl = net(xa, rb.cuda())
     assert maxrel(fl, golden["reg.flow_256_bigw"]) <= 1e-4
