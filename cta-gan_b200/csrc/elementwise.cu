@@ -208,23 +208,34 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
   }
 }
 
-// pass 2: g = fold(gout) + addend;  dx = rstd*(g*act' - mean - xhat*mean(. xhat))
+// pass 2: g = fold(gout) + addend;  dx = rstd*(g*act' - mean - xhat*mean(. xhat)), written with a zero margin of `out_pad`
+// pixels on every side (the layout the stride-1 input-gradient convolution consumes as a plain VALID convolution).
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict__ gout, const T *__restrict__ x,
                                                              const float *__restrict__ stats, const double *__restrict__ acc,
                                                              const T *__restrict__ addend, T *__restrict__ dx,
-                                                             int N, int H, int W, int C, int pad, int act) {
+                                                             int N, int H, int W, int C, int pad, int act, int out_pad) {
   const int CV = C / V;
   const int HW = H * W;
-  const long long total = (long long)N * HW * CV;
+  const int Ho = H + 2 * out_pad, Wo = W + 2 * out_pad;
+  const long long total = (long long)N * Ho * Wo * CV;
   const float inv_hw = 1.f / (float)HW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % CV);
-    long long r = idx / CV;
-    const int p = (int)(r % HW);
-    const int n = (int)(r / HW);
-    const int h = p / W, w = p - h * W;
+  for (long long oidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; oidx < total; oidx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(oidx % CV);
+    long long r = oidx / CV;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const int h = ho - out_pad, w = wo - out_pad;
     float g[V], o[V];
+    if (h < 0 || h >= H || w < 0 || w >= W) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.f;
+      store_vec<T, V>(dx + oidx * V, o);
+      continue;
+    }
+    const long long idx = (((long long)n * H + h) * W + w) * CV + cv;
     folded_grad<T, V>(gout, n, h, w, cv, H, W, C, pad, g);
     if (addend) {
       float av[V];
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = g[i];
     }
-    store_vec<T, V>(dx + idx * V, o);
+    store_vec<T, V>(dx + oidx * V, o);
   }
 }
 
@@ -589,8 +600,9 @@ extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const void
 }
 
 extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
-                                       double *acc, int N, int H, int W, int C, int pad, int act, int dtype, void *stream) {
-  CTAGAN_REQUIRE(gout && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0, "norm_act_pad_bwd: bad arguments");
+                                       double *acc, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype,
+                                       void *stream) {
+  CTAGAN_REQUIRE(gout && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && out_pad >= 0, "norm_act_pad_bwd: bad arguments");
   CTAGAN_REQUIRE(!(stats || act != CTAGAN_ACT_NONE) || x, "norm_act_pad_bwd: x required when stats/act given");
   CTAGAN_REQUIRE(!stats || acc, "norm_act_pad_bwd: acc scratch required with stats");
   CTAGAN_REQUIRE(act != CTAGAN_ACT_TANH, "norm_act_pad_bwd: tanh unsupported here (use act_bwd)");
@@ -605,8 +617,8 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
       dim3 grid(chunks, N);
       VEC_SWITCH(T, v, V, norm_bwd_reduce_kernel<T, V><<<grid, 256, 0, st>>>((const T *)gout, (const T *)x, stats, (const T *)addend, acc, H, W, C, pad, act, ppb));
     }
-    const long long total = (long long)N * H * W * (C / v);
-    VEC_SWITCH(T, v, V, norm_bwd_apply_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, N, H, W, C, pad, act));
+    const long long total = (long long)N * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / v);
+    VEC_SWITCH(T, v, V, norm_bwd_apply_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, N, H, W, C, pad, act, out_pad));
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;

@@ -100,14 +100,14 @@ def norm_act_pad(x, stats, act, pad, res=None, res_pad=0):
     return out
 
 
-def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None):
+def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None, out_pad=0):
     N, Hp, Wp, C = gout.shape
     H, W = Hp - 2 * pad, Wp - 2 * pad
-    dx = torch.empty((N, H, W, C), dtype=gout.dtype, device=gout.device)
+    dx = torch.empty((N, H + 2 * out_pad, W + 2 * out_pad, C), dtype=gout.dtype, device=gout.device)
     acc = torch.empty((N, C, 2), dtype=torch.float64, device=gout.device) if stats is not None else None
     _count(2 if stats is not None else 1)
     L.check(L.load().ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(acc), N, H, W, C, pad, act,
-                                             dt(gout), _stream()))
+                                             out_pad, dt(gout), _stream()))
     return dx
 
 

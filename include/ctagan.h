@@ -93,9 +93,11 @@ int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int 
  *   g  = (fold_reflect(gout) + addend) * act'(.)          (addend optional, unpadded; act' from x, stats)
  *   dx = rstd*(g - mean(g) - xhat*mean(g*xhat))   (stats!=NULL)   or   g   (stats==NULL)
  * The residual branch of the forward receives fold_reflect(gout) itself (call with stats=NULL, act=NONE).
+ * dx is written as [N][H+2*out_pad][W+2*out_pad][C] with a zero margin of out_pad pixels: with out_pad = K-1-p the stride-1
+ * input-gradient convolution that consumes it becomes a plain VALID convolution (the tcgen05 engine's native form).
  * acc: N*C*2 doubles scratch (only with stats). */
 int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
-                            double *acc, int N, int H, int W, int C, int pad, int act, int dtype, void *stream);
+                            double *acc, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype, void *stream);
 
 /* Pointwise activation backward for conv-epilogue activations: dx = gy * act'(y) computed from the OUTPUT y
  * (relu/lrelu: sign(y); tanh: 1-y^2).  n elements. */
