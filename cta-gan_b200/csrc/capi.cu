@@ -6,7 +6,9 @@ int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void
 int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
 // tcgen05 engine (conv_tc.cu): return CTAGAN_ERR_UNSUPPORTED when the geometry does not tile
 int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
-int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
+int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                         size_t workspace_bytes, cudaStream_t st);
+size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g);
 
@@ -49,6 +51,7 @@ static int check_geom(const ctagan_conv_geom *g, const char *who) {
   CTAGAN_REQUIRE(g->KH > 0 && g->KW > 0 && g->stride > 0 && g->dil > 0, "%s: bad kernel/stride/dilation", who);
   CTAGAN_REQUIRE(g->dtype == CTAGAN_F32 || g->dtype == CTAGAN_BF16, "%s: bad dtype", who);
   CTAGAN_REQUIRE(g->act >= 0 && g->act <= 3, "%s: bad activation", who);
+  CTAGAN_REQUIRE(g->gy_margin >= 0, "%s: bad gy_margin", who);
   return CTAGAN_OK;
 }
 
@@ -63,13 +66,18 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
   return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
 }
 
-extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, int engine,
-                                 void *stream) {
+extern "C" size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine) {
+  if (!g || engine == 1) return 0;
+  return ctagan_conv_wgrad_tc_workspace(g);
+}
+
+extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                                 size_t workspace_bytes, int engine, void *stream) {
   int rc = check_geom(g, "conv_wgrad");
   if (rc) return rc;
   CTAGAN_REQUIRE(gy && gx && dw, "conv_wgrad: null pointer");
   CTAGAN_REQUIRE(engine >= 0 && engine <= 2, "conv_wgrad: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == 2 || (engine == 0 && ctagan_conv_wgrad_tc_eligible(g))) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, st);
+  if (engine == 2 || (engine == 0 && ctagan_conv_wgrad_tc_eligible(g))) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
   return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, st);
 }

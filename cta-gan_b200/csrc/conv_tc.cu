@@ -143,6 +143,199 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *smem_dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// MN-major operand (the contiguous dimension is M or N, K runs across 128-byte rows), SWIZZLE_128B:
+// canonical layout ((64 elems, m slabs),(8 rows, k groups)) : ((1, LBO),(128 B, SBO)); LBO = byte distance between 64-element slabs,
+// SBO = 1024 B between 8-row groups.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
+
+struct WgParams {
+  int ntaps, KW;
+  int Co, Ci;
+  int stride, pad;
+  int margin;                 // gy zero border that is skipped
+  int rb, cb;                 // chunk grid per image (row blocks x col blocks)
+  int bkh, bkw;               // chunk = bkh x bkw output pixels (= 64)
+  int total_chunks, chunks_per_split;
+  int ci_tiles;
+  float *ws;                  // [splits][Co][ntaps][Ci] fp32 partials
+};
+
+constexpr int WG_M = 128;       // Co tile
+constexpr int WG_KPIX = 64;     // pixels per K chunk
+constexpr int WG_SLAB = WG_KPIX * 128;   // bytes of one [64 px][64 ch] slab
+
+template <int BNW>
+struct WgConfig {
+  static constexpr int A_BYTES = (WG_M / 64) * WG_SLAB;      // 16 KB
+  static constexpr int B_BYTES = (BNW / 64) * WG_SLAB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BNW >= 256 ? 4 : 5;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = BNW < 32 ? 32 : BNW;
+};
+
+// dW[co][tap][ci] partial over one K split:  D[co][ci] = sum_pix gy[pix][co] * gx[pix + tap][ci]   (both operands MN-major)
+template <int BNW>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_gx, const WgParams p) {
+  using Cfg = WgConfig<BNW>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + Cfg::STAGES;
+  uint64_t *tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int ci_t = t % p.ci_tiles; t /= p.ci_tiles;
+  const int co_t = t % (p.Co / WG_M); t /= (p.Co / WG_M);
+  const int tap = t;
+  const int kh = tap / p.KW, kw = tap - kh * p.KW;
+  const int split = blockIdx.y;
+  const int chunk0 = split * p.chunks_per_split;
+  const int chunk1 = min(p.total_chunks, chunk0 + p.chunks_per_split);
+  const int n_iters = chunk1 - chunk0;
+  const int co0 = co_t * WG_M, ci0 = ci_t * BNW;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_gy);
+    tma_prefetch_desc(&map_gx);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        int ch = chunk0 + it;
+        const int cbi = ch % p.cb; ch /= p.cb;
+        const int rbi = ch % p.rb;
+        const int n = ch / p.rb;
+        const int oh0 = p.margin + rbi * p.bkh, ow0 = p.margin + cbi * p.bkw;     // gy coordinates of the chunk origin
+        uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
+        uint8_t *b_dst = a_dst + Cfg::A_BYTES;
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < WG_M / 64; ++sl) tma_load_4d(&map_gy, &full_bar[s], a_dst + sl * WG_SLAB, co0 + sl * 64, ow0, oh0, n);
+        const int iw0 = ow0 * p.stride + kw - p.pad, ih0 = oh0 * p.stride + kh - p.pad;
+#pragma unroll
+        for (int sl = 0; sl < BNW / 64; ++sl) tma_load_4d(&map_gx, &full_bar[s], b_dst + sl * WG_SLAB, ci0 + sl * 64, iw0, ih0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(WG_M, BNW);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_KPIX / UMMA_K; ++k) {
+          // 16 pixels (K) = 16 rows of 128 B = 2048 B further into every slab
+          const uint64_t adesc = make_mnmajor_sw128_desc(a_addr + k * 2048, WG_SLAB);
+          const uint64_t bdesc = make_mnmajor_sw128_desc(b_addr + k * 2048, WG_SLAB);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;          // co within the tile
+    float *dst = p.ws + (((long long)split * p.Co + co0 + row) * p.ntaps + tap) * p.Ci + ci0;
+    if (n_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BNW; c += 32) {
+      uint32_t r[32];
+      if (n_iters > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = 0u;
+      }
+      uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) d4[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// dw[co][ci][tap] = sum_s ws[s][co][tap][ci]     (also the [co][tap][ci] -> PyTorch OIHW transpose)
+__global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci) {
+  const long long total = (long long)Co * ntaps * Ci;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Ci);
+    long long r = idx / Ci;
+    const int tap = (int)(r % ntaps);
+    const int co = (int)(r / ntaps);
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[(long long)k * total + idx];
+    dw[((long long)co * Ci + ci) * ntaps + tap] = s;
+  }
+}
+
+// db[c] = sum over pixels of gy[p][c]   (bias gradient, only when requested)
+__global__ void colsum_kernel(const bf16 *__restrict__ gy, float *__restrict__ db, long long pixels, int C) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lanes = blockDim.x >> 5, pl = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C)
+    for (long long p = pl; p < pixels; p += lanes) s += __bfloat162float(gy[p * C + c]);
+  __shared__ float sm[32][33];
+  sm[pl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += sm[l][threadIdx.x & 31];
+    db[c] = t;
+  }
+}
+
 template <int BN>
 struct TcConfig {
   static constexpr int A_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB
@@ -392,9 +585,117 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   return CTAGAN_ERR_UNSUPPORTED;
 }
 
-int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g) { (void)g; return 0; }
-int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st) {
-  (void)g; (void)gy; (void)gx; (void)dw; (void)db; (void)st;
-  ctagan_set_error("conv_wgrad: geometry not supported by the tcgen05 engine");
-  return CTAGAN_ERR_UNSUPPORTED;
+namespace {
+
+// 4-D bf16 NHWC tensor [N][H][W][C]; box {64 ch, bw, bh, 1}; traversal stride `estr` along W and H (strided convolutions)
+int make_map_4d(CUtensorMap *map, const void *base, int N, int H, int W, int C, int bw, int bh, int estr_hw) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    ctagan_set_error("cuTensorMapEncodeTiled unavailable from the driver");
+    return CTAGAN_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estr_hw, (cuuint32_t)estr_hw, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctagan_set_error("cuTensorMapEncodeTiled(4d) failed (%d): N=%d H=%d W=%d C=%d box=%dx%d estr=%d", (int)r, N, H, W, C, bh, bw, estr_hw);
+    return CTAGAN_ERR_CUDA;
+  }
+  return CTAGAN_OK;
+}
+
+struct WgPlan {
+  int bnw, bkw, bkh, rb, cb, total_chunks, splits, cps, tiles;
+};
+
+bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
+  if (g->dtype != CTAGAN_BF16 || g->dil != 1) return false;
+  if (g->stride != 1) return false;                       // strided form: phase split (later)
+  if (g->Co % WG_M || g->Ci % 64) return false;
+  if (g->KH * g->KW > MAX_TAPS) return false;
+  const int m = g->gy_margin;
+  const int Hvld = g->Ho - 2 * m, Wvld = g->Wo - 2 * m;
+  if (Hvld <= 0 || Wvld <= 0) return false;
+  if ((long long)g->N * Hvld * Wvld < 2048) return false;  // tiny maps stay on the CUDA-core kernel
+  pl.bnw = (g->Ci % 256 == 0) ? 256 : (g->Ci % 128 == 0 ? 128 : 64);
+  pl.bkw = Wvld >= 64 ? 64 : (Wvld > 16 ? 32 : 16);
+  pl.bkh = 64 / pl.bkw;
+  pl.rb = (Hvld + pl.bkh - 1) / pl.bkh;
+  pl.cb = (Wvld + pl.bkw - 1) / pl.bkw;
+  pl.total_chunks = g->N * pl.rb * pl.cb;
+  pl.tiles = g->KH * g->KW * (g->Co / WG_M) * (g->Ci / pl.bnw);
+  int splits = (ctagan_num_sms() + pl.tiles - 1) / pl.tiles;
+  const int max_splits = (pl.total_chunks + 3) / 4;         // at least 4 chunks (256 pixels) per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  pl.cps = (pl.total_chunks + splits - 1) / splits;
+  pl.splits = (pl.total_chunks + pl.cps - 1) / pl.cps;
+  return true;
+}
+
+template <int BNW>
+int launch_wg(const CUtensorMap &my, const CUtensorMap &mx, const WgParams &p, dim3 grid, cudaStream_t st) {
+  using Cfg = WgConfig<BNW>;
+  static bool configured = false;
+  if (!configured) {
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  conv_wgrad_tc_kernel<BNW><<<grid, 192, Cfg::SMEM_BYTES, st>>>(my, mx, p);
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+}  // namespace
+
+int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g) {
+  WgPlan pl;
+  return plan_wgrad(g, pl) ? 1 : 0;
+}
+
+size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g) {
+  WgPlan pl;
+  if (!plan_wgrad(g, pl)) return 0;
+  return (size_t)pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+}
+
+int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                         size_t workspace_bytes, cudaStream_t st) {
+  WgPlan pl;
+  if (!plan_wgrad(g, pl)) {
+    ctagan_set_error("conv_wgrad: geometry not supported by the tcgen05 engine");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  const size_t need = (size_t)pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+  CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_wgrad(tc): workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+  CUtensorMap my, mx;
+  int rc = make_map_4d(&my, gy, g->N, g->Ho, g->Wo, g->Co, pl.bkw, pl.bkh, 1);
+  if (rc) return rc;
+  rc = make_map_4d(&mx, gx, g->N, g->Hi, g->Wi, g->Ci, pl.bkw, pl.bkh, g->stride);
+  if (rc) return rc;
+  WgParams p;
+  p.ntaps = g->KH * g->KW; p.KW = g->KW; p.Co = g->Co; p.Ci = g->Ci; p.stride = g->stride; p.pad = g->pad_h;
+  p.margin = g->gy_margin; p.rb = pl.rb; p.cb = pl.cb; p.bkh = pl.bkh; p.bkw = pl.bkw;
+  p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.ci_tiles = g->Ci / pl.bnw; p.ws = (float *)workspace;
+  dim3 grid((unsigned)pl.tiles, (unsigned)pl.splits);
+  switch (pl.bnw) {
+    case 256: rc = launch_wg<256>(my, mx, p, grid, st); break;
+    case 128: rc = launch_wg<128>(my, mx, p, grid, st); break;
+    default: rc = launch_wg<64>(my, mx, p, grid, st); break;
+  }
+  if (rc) return rc;
+  const long long total = (long long)g->Co * p.ntaps * g->Ci;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ctagan_num_sms() * 8) blocks = ctagan_num_sms() * 8;
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>((const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci);
+  CTAGAN_LAUNCH_OK();
+  if (db) {
+    colsum_kernel<<<(g->Co + 31) / 32, 1024, 0, st>>>((const bf16 *)gy, db, (long long)g->N * g->Ho * g->Wo, g->Co);
+    CTAGAN_LAUNCH_OK();
+  }
+  return CTAGAN_OK;
 }

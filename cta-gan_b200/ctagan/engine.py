@@ -86,12 +86,12 @@ class ConvPrim:
         return ops.conv_gather(dy, self.packed(1, dy.dtype), bias, g, _ENGINE["value"])
 
     # dW[O][I][K][K] = sum gy(O-channel, strided side) x gx(I-channel, gathered side)
-    def wgrad(self, gy, gx, want_bias=False, pad=None):
+    def wgrad(self, gy, gx, want_bias=False, pad=None, gy_margin=0):
         N, Ho, Wo, Co = gy.shape
         _, Hi, Wi, Ci = gx.shape
         assert Co == self.O and Ci == self.I
         p = self.p if pad is None else pad
-        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, self.K, self.s, 1, p, L.ACT_NONE, ops.dt(gy))
+        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, self.K, self.s, 1, p, L.ACT_NONE, ops.dt(gy), gy_margin)
         return ops.conv_wgrad(gy, gx, g, want_bias, _ENGINE["value"])
 
 
@@ -162,10 +162,10 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
     T = y.dtype
     grads: List[Optional[torch.Tensor]] = []
 
-    def wg(prim, gy, gx, bias=False):
+    def wg(prim, gy, gx, bias=False, margin=0):
         if not need_dw:
             return None, None
-        return prim.wgrad(gy, gx, want_bias=bias)
+        return prim.wgrad(gy, gx, want_bias=bias, pad=(margin if margin else None), gy_margin=margin)
 
     gy = ops.nchw_to_nhwc(dout, T)
     dy7 = ops.act_bwd(gy, y, L.ACT_TANH)
@@ -179,12 +179,13 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
     dWt0, _ = wg(plan.tail0, X9, dr4)
     block_grads = []
     for (c1, c2), (Xk, ra, sa, Tt, rb, sb) in zip(reversed(plan.blocks), reversed(blocks)):
-        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0)
-        dW2, _ = wg(c2, drb, Tt)
-        dT = c2.bprop(drb, (Tt.shape[1], Tt.shape[2]))
-        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1)
-        dW1, _ = wg(c1, dra, Xk)
-        dXp = c1.bprop(dra, (Xk.shape[1], Xk.shape[2]))
+        m = c2.K - 1                                                      # zero margin: dgrad becomes a VALID conv
+        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0, out_pad=m)
+        dW2, _ = wg(c2, drb, Tt, margin=m)
+        dT = c2.bprop(drb, (Tt.shape[1], Tt.shape[2]), pad=m)
+        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1, out_pad=m)
+        dW1, _ = wg(c1, dra, Xk, margin=m)
+        dXp = c1.bprop(dra, (Xk.shape[1], Xk.shape[2]), pad=m)
         G = ops.norm_act_pad_bwd(dXp, None, None, L.ACT_NONE, 1, addend=G)
         block_grads.append((dW1, dW2))
     block_grads.reverse()

@@ -21,7 +21,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 
 class ConvGeom(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("N", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "KH", "KW", "stride", "dil", "pad_h", "pad_w", "act", "dtype")]
+                ("N", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "KH", "KW", "stride", "dil", "pad_h", "pad_w", "act", "dtype", "gy_margin")]
 
 
 def _ctype_of(decl: str):
@@ -40,9 +40,9 @@ def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[object, List[object
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int)\s+(ctagan_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(const\s+char\s*\*|int|size_t)\s+(ctagan_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3)
-        restype = ctypes.c_char_p if "char" in ret else ctypes.c_int
+        restype = ctypes.c_char_p if "char" in ret else (ctypes.c_size_t if ret == "size_t" else ctypes.c_int)
         args = args.strip()
         argtypes = [] if args in ("", "void") else [_ctype_of(a) for a in args.split(",")]
         protos[name] = (restype, argtypes)

@@ -50,8 +50,8 @@ def dt(t: torch.Tensor) -> int:
     return _DT[t.dtype]
 
 
-def make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, K, stride, dil, pad, act, dtype) -> L.ConvGeom:
-    return L.ConvGeom(N, Hi, Wi, Ci, Ho, Wo, Co, K, K, stride, dil, pad, pad, act, dtype)
+def make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, K, stride, dil, pad, act, dtype, gy_margin=0) -> L.ConvGeom:
+    return L.ConvGeom(N, Hi, Wi, Ci, Ho, Wo, Co, K, K, stride, dil, pad, pad, act, dtype, gy_margin)
 
 
 def conv_gather(x, wp, bias, g: L.ConvGeom, engine=L.ENGINE_AUTO):
@@ -68,8 +68,10 @@ def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO):
     _require_cuda(gy, gx)
     dw = torch.empty((g.Co, g.Ci, g.KH, g.KW), dtype=torch.float32, device=gy.device)
     db = torch.empty((g.Co,), dtype=torch.float32, device=gy.device) if want_bias else None
-    _count(1)
-    L.check(L.load().ctagan_conv_wgrad(ctypes.byref(g), _p(gy), _p(gx), _p(dw), _p(db), engine, _stream()))
+    ws_bytes = L.load().ctagan_conv_wgrad_workspace_bytes(ctypes.byref(g), engine)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device) if ws_bytes else None
+    _count(2 if ws_bytes else 1)
+    L.check(L.load().ctagan_conv_wgrad(ctypes.byref(g), _p(gy), _p(gx), _p(dw), _p(db), _p(ws), ws_bytes, engine, _stream()))
     return dw, db
 
 

@@ -57,6 +57,7 @@ typedef struct {
   int32_t pad_h, pad_w;
   int32_t act;   /* epilogue activation, CTAGAN_ACT_* */
   int32_t dtype; /* element type of x, wp, y */
+  int32_t gy_margin; /* wgrad only: gy carries an all-zero border of this many pixels (a hint: it is skipped) */
 } ctagan_conv_geom;
 
 /* Replaces nn.Conv2d / nn.ConvTranspose2d forward and the input-gradient half of their backward
@@ -71,7 +72,9 @@ int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp,
  * PyTorch's [A][B][KH][KW] order and is OVERWRITTEN (db too, may be NULL).  Conv2d: gy=dy, gx=x.  ConvTranspose2d: gy=x, gx=dy.
  * Replaces the weight-gradient half of cudnn/ATen convolution_backward for the layers cited above. */
 int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db,
-                      int engine, void *stream);
+                      void *workspace, size_t workspace_bytes, int engine, void *stream);
+/* Scratch bytes ctagan_conv_wgrad needs for this geometry/engine (split-K partial sums of the tcgen05 engine; 0 for CUDA-core). */
+size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine);
 
 /* fp32 master weights W[O][I][KH][KW] -> packed `dtype` weights.
  * mode 0: wp[O][kh][kw][I] = W[O][I][kh][kw];  mode 1: wp[I][kh][kw][O] = W[O][I][KH-1-kh][KW-1-kw]. */
