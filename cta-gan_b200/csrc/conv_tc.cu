@@ -26,14 +26,20 @@ constexpr int UMMA_K = 16;
 constexpr int MAX_TAPS = 49;
 
 struct TcParams {
+  int mode;                    // 0: pitch trick (2-D map, stride-1 VALID conv on a padded input); 1: 4-D boxes (any stride / zero pad)
   int n_taps;
-  int tap_pix_off[MAX_TAPS];   // row offset of the tap in the flattened input
-  int tap_w_col[MAX_TAPS];     // column (element) offset of the tap in the packed weight row: tap * Ci
+  short tap_dh[MAX_TAPS];      // input offset of the tap relative to (i*stride, j*stride)
+  short tap_dw[MAX_TAPS];
+  int tap_w_col[MAX_TAPS];     // column (element) offset of the tap in the packed weight row
   int Ci, Co;
-  int Hv, Wv;                  // virtual (input) grid per image
-  int Hov, Wov;                // valid output extent in that grid
+  int stride;                  // input step per output position (mode 1)
+  int Hv, Wv;                  // mode 0: virtual (input) grid per image
+  int bw_log2;                 // mode 1: tile = (128 >> bw_log2) rows x (1 << bw_log2) cols of output positions
+  int tiles_w;                 // mode 1: tiles along the width
+  int Hov, Wov;                // valid extent of the output-position grid (i, j)
   int tiles_per_img;
-  int out_H, out_W;            // output tensor spatial dims
+  int out_H, out_W;            // output tensor spatial dims; position (i,j) is stored at (i*sy+ay, j*sx+ax)
+  int sy, sx, ay, ax;
   int act;
   const float *bias;
   bf16 *out;
@@ -360,8 +366,11 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.x / p.tiles_per_img;
   const int tile = blockIdx.x - img * p.tiles_per_img;
-  const int q_local0 = tile * TILE_M;                         // first virtual position of this tile inside the image
+  const int q_local0 = tile * TILE_M;                         // mode 0: first virtual position of this tile inside the image
   const long long q0 = (long long)img * p.Hv * p.Wv + q_local0;
+  const int BW = 1 << p.bw_log2;
+  const int tile_i0 = (tile / p.tiles_w) * (TILE_M >> p.bw_log2);   // mode 1: tile origin in output positions
+  const int tile_j0 = (tile % p.tiles_w) * BW;
   const int co0 = blockIdx.y * BN;
   const int k_chunks = p.Ci / CHUNK_K;
   const int n_iters = p.n_taps * k_chunks;
@@ -392,7 +401,11 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
         uint8_t *b_dst = a_dst + Cfg::A_BYTES;
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        tma_load_2d(&map_x, &full_bar[s], a_dst, kc * CHUNK_K, (int)(q0 + p.tap_pix_off[tap]));
+        if (p.mode == 0)
+          tma_load_2d(&map_x, &full_bar[s], a_dst, kc * CHUNK_K, (int)(q0 + p.tap_dh[tap] * p.Wv + p.tap_dw[tap]));
+        else
+          tma_load_4d(&map_x, &full_bar[s], a_dst, kc * CHUNK_K, tile_j0 * p.stride + p.tap_dw[tap],
+                      tile_i0 * p.stride + p.tap_dh[tap], img);
         tma_load_2d(&map_w, &full_bar[s], b_dst, p.tap_w_col[tap] + kc * CHUNK_K, co0);
       }
     }
@@ -421,10 +434,16 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     // ===== epilogue: warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31 =====
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int ql = q_local0 + row;
-    const int i = ql / p.Wv, j = ql - i * p.Wv;
-    const bool valid = (i < p.Hov) && (j < p.Wov);
-    bf16 *out_row = p.out + (((long long)img * p.out_H + i) * p.out_W + j) * p.Co + co0;
+    int i, j;
+    if (p.mode == 0) {
+      const int ql = q_local0 + row;
+      i = ql / p.Wv; j = ql - i * p.Wv;
+    } else {
+      i = tile_i0 + (row >> p.bw_log2); j = tile_j0 + (row & (BW - 1));
+    }
+    const int oi = i * p.sy + p.ay, oj = j * p.sx + p.ax;
+    const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W;
+    bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -524,58 +543,33 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
   return CTAGAN_OK;
 }
 
-int pick_bn(const ctagan_conv_geom *g) {
-  const long long m_tiles = (long long)g->N * (((long long)g->Ho * g->Wi + TILE_M - 1) / TILE_M);
+int pick_bn(long long m_tiles, int Co) {
   const int sms = ctagan_num_sms();
-  // largest N tile that still gives every SM a CTA; N=64 tiles are shared-memory-bandwidth bound (A re-read per 32 cycles)
+  // largest N tile that still gives every SM a CTA (operand traffic from L2 per FLOP falls with the tile size)
   for (int bn : {256, 128, 64}) {
-    if (g->Co % bn) continue;
-    if (m_tiles * (g->Co / bn) >= sms || bn == 64) return bn;
+    if (Co % bn) continue;
+    if (m_tiles * (Co / bn) >= sms || bn == 64) return bn;
   }
   return 0;
 }
 
-}  // namespace
+int make_map_4d(CUtensorMap *map, const void *base, int N, int H, int W, int C, int bw, int bh, int estr_hw);
 
-int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g) {
-  if (g->dtype != CTAGAN_BF16) return 0;
-  if (g->stride != 1 || g->dil != 1 || g->pad_h != 0 || g->pad_w != 0) return 0;
-  if (g->Ci % CHUNK_K) return 0;
-  if (g->Co % 64) return 0;
-  if (g->KH * g->KW > MAX_TAPS) return 0;
-  if (g->Ho != g->Hi - g->KH + 1 || g->Wo != g->Wi - g->KW + 1) return 0;
-  if ((long long)g->N * g->Ho * g->Wo < 1024) return 0;   // tiny maps: launch-latency bound either way, CUDA-core kernel
-  return 1;
-}
-
-int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st) {
-  if (!ctagan_conv_gather_tc_eligible(g)) {
-    ctagan_set_error("conv_gather: geometry not supported by the tcgen05 engine (needs bf16, stride 1, pad 0 on a padded input, Ci%%64==0, Co%%64==0)");
-    return CTAGAN_ERR_UNSUPPORTED;
-  }
-  CTAGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(y) & 15) == 0,
-                 "conv_gather(tc): pointers must be 16-byte aligned");
-  TcParams p;
-  memset(&p, 0, sizeof(p));
-  p.n_taps = g->KH * g->KW;
-  for (int kh = 0; kh < g->KH; ++kh)
-    for (int kw = 0; kw < g->KW; ++kw) {
-      p.tap_pix_off[kh * g->KW + kw] = kh * g->Wi + kw;
-      p.tap_w_col[kh * g->KW + kw] = (kh * g->KW + kw) * g->Ci;
-    }
-  p.Ci = g->Ci; p.Co = g->Co;
-  p.Hv = g->Hi; p.Wv = g->Wi; p.Hov = g->Ho; p.Wov = g->Wo;
-  p.tiles_per_img = (int)(((long long)g->Ho * g->Wi + TILE_M - 1) / TILE_M);
-  p.out_H = g->Ho; p.out_W = g->Wo;
-  p.act = g->act; p.bias = bias; p.out = (bf16 *)y;
+// launch one tcgen05 conv with the tap table already in p; x described by (mode 0) [rows][Ci] or (mode 1) [N][Hi][Wi][Ci]
+int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, int w_cols, cudaStream_t st) {
   CUtensorMap mx, mw;
-  int rc = make_map_2d(&mx, x, (uint64_t)g->N * g->Hi * g->Wi, (uint64_t)g->Ci, TILE_M);
+  int rc;
+  if (p.mode == 0) {
+    rc = make_map_2d(&mx, x, (uint64_t)N * Hi * Wi, (uint64_t)p.Ci, TILE_M);
+  } else {
+    const int BW = 1 << p.bw_log2, BH = TILE_M >> p.bw_log2;
+    rc = make_map_4d(&mx, x, N, Hi, Wi, p.Ci, BW * p.stride, BH * p.stride, p.stride);
+  }
   if (rc) return rc;
-  const int bn = pick_bn(g);
-  rc = make_map_2d(&mw, wp, (uint64_t)g->Co, (uint64_t)p.n_taps * g->Ci, (uint32_t)bn);
+  const int bn = pick_bn((long long)N * p.tiles_per_img, p.Co);
+  rc = make_map_2d(&mw, wp, (uint64_t)p.Co, (uint64_t)w_cols, (uint32_t)bn);
   if (rc) return rc;
-  dim3 grid((unsigned)(g->N * p.tiles_per_img), (unsigned)(g->Co / bn));
+  dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)(p.Co / bn));
   switch (bn) {
     case 256: return launch_tc<256>(mx, mw, p, grid, st);
     case 128: return launch_tc<128>(mx, mw, p, grid, st);
@@ -583,6 +577,100 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   }
   ctagan_set_error("conv_gather(tc): no tile configuration");
   return CTAGAN_ERR_UNSUPPORTED;
+}
+
+int ceil_log2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+}  // namespace
+
+// Which tcgen05 formulation serves this geometry: 0 none, 1 pitch trick, 2 strided 4-D boxes, 3 output-phase decomposition
+static int tc_gather_kind(const ctagan_conv_geom *g) {
+  if (g->dtype != CTAGAN_BF16) return 0;
+  if (g->Ci % CHUNK_K || g->Co % 64) return 0;
+  if (g->KH * g->KW > MAX_TAPS) return 0;
+  if ((long long)g->N * g->Ho * g->Wo < 1024) return 0;   // tiny maps: launch-latency bound either way -> CUDA-core kernel
+  if (g->dil == 1) {
+    if (g->stride == 1 && g->pad_h == 0 && g->pad_w == 0 && g->Ho == g->Hi - g->KH + 1 && g->Wo == g->Wi - g->KW + 1) return 1;
+    if (g->stride <= 2 && g->Wo >= 16) return 2;
+    return 0;
+  }
+  if (g->dil == 2 && g->stride == 1 && g->Wo >= 32 && (g->Ho % 2 == 0) && (g->Wo % 2 == 0)) return 3;
+  return 0;
+}
+
+int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g) { return tc_gather_kind(g) != 0; }
+
+int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st) {
+  const int kind = tc_gather_kind(g);
+  if (!kind) {
+    ctagan_set_error("conv_gather: geometry not supported by the tcgen05 engine (bf16, Ci%%64==0, Co%%64==0, stride<=2 / dil<=2)");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  CTAGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                 "conv_gather(tc): pointers must be 16-byte aligned");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.Ci = g->Ci; p.Co = g->Co; p.stride = g->stride;
+  p.out_H = g->Ho; p.out_W = g->Wo; p.sy = p.sx = 1; p.ay = p.ax = 0;
+  p.act = g->act; p.bias = bias; p.out = (bf16 *)y;
+  const int ntaps = g->KH * g->KW;
+  const int w_cols = ntaps * g->Ci;
+  if (kind == 1 || kind == 2) {
+    p.n_taps = ntaps;
+    for (int kh = 0; kh < g->KH; ++kh)
+      for (int kw = 0; kw < g->KW; ++kw) {
+        const int t = kh * g->KW + kw;
+        p.tap_dh[t] = (short)(kh - g->pad_h);
+        p.tap_dw[t] = (short)(kw - g->pad_w);
+        p.tap_w_col[t] = t * g->Ci;
+      }
+    p.Hov = g->Ho; p.Wov = g->Wo;
+    if (kind == 1) {
+      p.mode = 0; p.Hv = g->Hi; p.Wv = g->Wi;
+      p.tiles_per_img = (int)(((long long)g->Ho * g->Wi + TILE_M - 1) / TILE_M);
+    } else {
+      p.mode = 1;
+      p.bw_log2 = ceil_log2(g->Wo < 128 ? g->Wo : 128);
+      const int BW = 1 << p.bw_log2, BH = TILE_M >> p.bw_log2;
+      p.tiles_w = (g->Wo + BW - 1) / BW;
+      p.tiles_per_img = p.tiles_w * ((g->Ho + BH - 1) / BH);
+    }
+    return run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_cols, st);
+  }
+  // kind 3: input dilation 2 (input gradient of a stride-2 conv == ConvTranspose2d forward).  Output pixel h = 2i + r reads
+  // x[i + e - u] with weight tap kh' = 2u + a (a = (r + pad) & 1, e = (r + pad - a) / 2): one stride-1 launch per output parity.
+  for (int rh = 0; rh < 2; ++rh)
+    for (int rw = 0; rw < 2; ++rw) {
+      const int ah = (rh + g->pad_h) & 1, eh = (rh + g->pad_h - ah) / 2;
+      const int aw = (rw + g->pad_w) & 1, ew = (rw + g->pad_w - aw) / 2;
+      int t = 0;
+      for (int kh = ah; kh < g->KH; kh += 2)
+        for (int kw = aw; kw < g->KW; kw += 2) {
+          // gather form: y[h] += x[(h + kh - pad)/2] * wp[kh]  ->  with h = 2i + rh:  x[i + (rh + kh - pad)/2]
+          p.tap_dh[t] = (short)((rh + kh - g->pad_h) / 2);
+          p.tap_dw[t] = (short)((rw + kw - g->pad_w) / 2);
+          p.tap_w_col[t] = (kh * g->KW + kw) * g->Ci;
+          ++t;
+        }
+      (void)eh; (void)ew;
+      if (t == 0) continue;
+      p.n_taps = t;
+      p.mode = 1; p.stride = 1;
+      p.Hov = g->Ho / 2; p.Wov = g->Wo / 2;
+      p.sy = p.sx = 2; p.ay = rh; p.ax = rw;
+      p.bw_log2 = ceil_log2(p.Wov < 128 ? p.Wov : 128);
+      const int BW = 1 << p.bw_log2, BH = TILE_M >> p.bw_log2;
+      p.tiles_w = (p.Wov + BW - 1) / BW;
+      p.tiles_per_img = p.tiles_w * ((p.Hov + BH - 1) / BH);
+      int rc = run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_cols, st);
+      if (rc) return rc;
+    }
+  return CTAGAN_OK;
 }
 
 namespace {
@@ -614,7 +702,7 @@ struct WgPlan {
 
 bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
   if (g->dtype != CTAGAN_BF16 || g->dil != 1) return false;
-  if (g->stride != 1) return false;                       // strided form: phase split (later)
+  if (g->stride > 2) return false;
   if (g->Co % WG_M || g->Ci % 64) return false;
   if (g->KH * g->KW > MAX_TAPS) return false;
   const int m = g->gy_margin;
@@ -675,7 +763,7 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   CUtensorMap my, mx;
   int rc = make_map_4d(&my, gy, g->N, g->Ho, g->Wo, g->Co, pl.bkw, pl.bkh, 1);
   if (rc) return rc;
-  rc = make_map_4d(&mx, gx, g->N, g->Hi, g->Wi, g->Ci, pl.bkw, pl.bkh, g->stride);
+  rc = make_map_4d(&mx, gx, g->N, g->Hi, g->Wi, g->Ci, pl.bkw * g->stride, pl.bkh * g->stride, g->stride);
   if (rc) return rc;
   WgParams p;
   p.ntaps = g->KH * g->KW; p.KW = g->KW; p.Co = g->Co; p.Ci = g->Ci; p.stride = g->stride; p.pad = g->pad_h;

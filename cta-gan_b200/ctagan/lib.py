@@ -40,7 +40,7 @@ def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[object, List[object
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int|size_t)\s+(ctagan_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(const\s+char\s*\*|int|size_t)\s*(ctagan_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         restype = ctypes.c_char_p if "char" in ret else (ctypes.c_size_t if ret == "size_t" else ctypes.c_int)
         args = args.strip()

@@ -1,0 +1,80 @@
+"""GPU parity of the tcgen05/TMEM/TMA convolution engine (forced: engine='tc') against PyTorch fp32 convolutions on the same
+bf16-rounded operands, at the tensor-core-sized shapes of the hot path.  bf16 mode tolerance (north_star): <= 2e-2 outputs,
+<= 5e-2 gradients; measured ~3e-3 (one bf16 ulp of the stored output) / ~1e-6 for the fp32 weight gradients."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import maxrel, nchw, nhwc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, N, Ci, Co, H, W, K, stride, pad  (H, W = unpadded input)
+    ("res3x3_valid_b1", 1, 256, 256, 66, 66, 3, 1, 0),
+    ("res3x3_valid_b3", 3, 256, 256, 66, 66, 3, 1, 0),
+    ("down1_s2", 1, 64, 128, 256, 256, 3, 2, 1),
+    ("down2_s2", 2, 128, 256, 128, 128, 3, 2, 1),
+    ("disc1_k4s2", 2, 64, 128, 128, 128, 4, 2, 1),
+    ("disc3_k4s1_odd", 2, 256, 512, 32, 32, 4, 1, 1),
+    ("reg_3x3_same", 1, 64, 64, 64, 64, 3, 1, 1),
+    ("wide_512", 1, 64, 64, 40, 512, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tc_conv_engine(case):
+    from ctagan import engine as E, lib as L
+    name, N, Ci, Co, H, W, K, s, p = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Ci, H, W, generator=g).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Co, Ci, K, K, generator=g) / (Ci * K * K) ** 0.5).bfloat16().float().requires_grad_(True)
+    b = torch.randn(Co, generator=g)
+    y = F.conv2d(x, w, b, stride=s, padding=p)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    Ho, Wo = y.shape[2], y.shape[3]
+    prim = E.ConvPrim(w.detach().cuda(), b.cuda(), s, p)
+    xd, dyd = nhwc(x.detach()).cuda().bfloat16(), nhwc(dy).cuda().bfloat16()
+    E.set_conv_engine("tc")
+    try:
+        yd = prim.fprop(xd, use_bias=True)
+        assert maxrel(nchw(yd.float()), y) <= 2e-2, ("fprop", maxrel(nchw(yd.float()), y))
+        if s == 1 and p == 0:
+            m = K - 1                      # the engine's native dgrad form: zero-margined dy, VALID conv
+            dyz = torch.zeros(N, Ho + 2 * m, Wo + 2 * m, Co, device="cuda", dtype=torch.bfloat16)
+            dyz[:, m:m + Ho, m:m + Wo] = dyd
+            dxd = prim.bprop(dyz, (H, W), pad=m)
+            dw, db = prim.wgrad(dyz, xd, want_bias=True, pad=m, gy_margin=m)
+        else:
+            dxd = prim.bprop(dyd, (H, W))
+            dw, db = prim.wgrad(dyd, xd, want_bias=True)
+        assert maxrel(nchw(dxd.float()), x.grad) <= 2e-2, ("dgrad", maxrel(nchw(dxd.float()), x.grad))
+        assert maxrel(dw, w.grad) <= 1e-3, ("wgrad", maxrel(dw, w.grad))
+        assert maxrel(db, dy.sum((0, 2, 3))) <= 1e-3
+    finally:
+        E.set_conv_engine("auto")
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 128, 64, 64), (2, 128, 64, 128, 128)])
+def test_tc_conv_transpose(shape):
+    from ctagan import engine as E
+    N, Ci, Co, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, Ci, H, W, generator=g).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn(Ci, Co, 3, 3, generator=g) / (Ci * 9) ** 0.5).bfloat16().float().requires_grad_(True)
+    y = F.conv_transpose2d(x, wt, None, stride=2, padding=1, output_padding=1)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    prim = E.ConvPrim(wt.detach().cuda(), None, 2, 1)
+    xd, dyd = nhwc(x.detach()).cuda().bfloat16(), nhwc(dy).cuda().bfloat16()
+    E.set_conv_engine("tc")
+    try:
+        yd = prim.bprop(xd, (2 * H, 2 * W))
+        assert maxrel(nchw(yd.float()), y) <= 2e-2
+        dxd = prim.fprop(dyd, use_bias=False)
+        assert maxrel(nchw(dxd.float()), x.grad) <= 2e-2
+        dw, _ = prim.wgrad(xd, dyd)
+        assert maxrel(dw, wt.grad) <= 1e-3
+    finally:
+        E.set_conv_engine("auto")
