@@ -708,7 +708,7 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
   const int m = g->gy_margin;
   const int Hvld = g->Ho - 2 * m, Wvld = g->Wo - 2 * m;
   if (Hvld <= 0 || Wvld <= 0) return false;
-  if ((long long)g->N * Hvld * Wvld < 2048) return false;  // tiny maps stay on the CUDA-core kernel
+  if ((long long)g->N * Hvld * Wvld < 1024) return false;  // tiny maps stay on the CUDA-core kernel
   pl.bnw = (g->Ci % 256 == 0) ? 256 : (g->Ci % 128 == 0 ? 128 : 64);
   pl.bkw = Wvld >= 64 ? 64 : (Wvld > 16 ? 32 : 16);
   pl.bkh = 64 / pl.bkw;

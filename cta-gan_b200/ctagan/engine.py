@@ -42,6 +42,18 @@ def invalidate_weight_cache():
     _CACHE_EPOCH["value"] += 1
 
 
+def _after_optimizer_step(optimizer, args, kwargs):
+    # torch's fused Adam updates parameters without bumping their version counters: any optimizer step invalidates
+    invalidate_weight_cache()
+
+
+try:    # global hook: every torch.optim step (also user-written loops around the drop-in modules) refreshes the packed weights
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(_after_optimizer_step)
+except ImportError:     # pragma: no cover
+    pass
+
+
 def set_conv_engine(e):
     _ENGINE["value"] = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tc": L.ENGINE_TC}[e]
 
