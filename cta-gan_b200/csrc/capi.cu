@@ -10,6 +10,11 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
                          size_t workspace_bytes, cudaStream_t st);
 size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g);
+// degenerate (1-2 channel) convolutions (conv_small.cu)
+int ctagan_conv_small_kind(const ctagan_conv_geom *g);
+int ctagan_conv_gather_small(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
+int ctagan_conv_wgrad_thin_eligible(const ctagan_conv_geom *g);
+int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
 int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g);
 
 static thread_local char g_err[512] = "";
@@ -60,14 +65,17 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
   int rc = check_geom(g, "conv_gather");
   if (rc) return rc;
   CTAGAN_REQUIRE(x && wp && y, "conv_gather: null pointer");
-  CTAGAN_REQUIRE(engine >= 0 && engine <= 2, "conv_gather: bad engine");
+  CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_gather: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == 2 || (engine == 0 && ctagan_conv_gather_tc_eligible(g))) return ctagan_conv_gather_tc(g, x, wp, bias, y, st);
+  if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, st);
+  if (engine != 3 && ctagan_conv_small_kind(g)) return ctagan_conv_gather_small(g, x, wp, bias, y, st);
+  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, st);
   return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
 }
 
 extern "C" size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine) {
-  if (!g || engine == 1) return 0;
+  if (!g || engine == 1 || engine == 3) return 0;
+  if (engine == 0 && ctagan_conv_wgrad_thin_eligible(g)) return 0;
   return ctagan_conv_wgrad_tc_workspace(g);
 }
 
@@ -76,8 +84,10 @@ extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, cons
   int rc = check_geom(g, "conv_wgrad");
   if (rc) return rc;
   CTAGAN_REQUIRE(gy && gx && dw, "conv_wgrad: null pointer");
-  CTAGAN_REQUIRE(engine >= 0 && engine <= 2, "conv_wgrad: bad engine");
+  CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_wgrad: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == 2 || (engine == 0 && ctagan_conv_wgrad_tc_eligible(g))) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
+  if (engine == 2) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
+  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, st);
+  if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
   return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, st);
 }

@@ -1,0 +1,262 @@
+// CUDA-core kernels for the degenerate convolutions of the path: one or two channels on one side of the GEMM
+// (generator 7x7 head Cin=1 and tail Cout=1, discriminator first layer Cin=1|2 and last layer Cout=1).  They are <1% of the FLOPs
+// but touch the largest activations (64 x 256^2); on tensor-core tiles 63/64 of the work would be padding, so they are written
+// as bandwidth-style kernels: weights in shared memory, activations streamed once with 16-byte accesses.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool tap_in(const ctagan_conv_geom &g, int o, int k, int pad, int in_extent, int &i_out) {
+  int num = o * g.stride + k - pad;
+  if (num < 0) return false;
+  if (g.dil > 1) {
+    if (num % g.dil) return false;
+    num /= g.dil;
+  }
+  i_out = num;
+  return num < in_extent;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// few -> many:  Ci <= 2, Co % 8 == 0.   thread = (pixel, 8 output channels); block = 32 pixels x 64 output channels.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_fewin_kernel(ctagan_conv_geom g, const T *__restrict__ x, const T *__restrict__ wp,
+                                                         const float *__restrict__ bias, T *__restrict__ y) {
+  extern __shared__ float ws[];   // [ntaps*Ci][64]
+  const int ntaps = g.KH * g.KW, KC = ntaps * g.Ci;
+  const int co_blk = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < KC * 64; i += 256) {
+    const int k = i / 64, c = i - k * 64;
+    ws[i] = (co_blk + c < g.Co) ? to_f(wp[(long long)(co_blk + c) * KC + k]) : 0.f;
+  }
+  __syncthreads();
+  const long long M = (long long)g.N * g.Ho * g.Wo;
+  const int cg = threadIdx.x & 7;
+  const long long m = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (m >= M || co_blk + cg * 8 >= g.Co) return;
+  const int ow = (int)(m % g.Wo);
+  const long long q = m / g.Wo;
+  const int oh = (int)(q % g.Ho), n = (int)(q / g.Ho);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[co_blk + cg * 8 + j] : 0.f;
+  for (int kh = 0; kh < g.KH; ++kh) {
+    int ih;
+    if (!tap_in(g, oh, kh, g.pad_h, g.Hi, ih)) continue;
+    for (int kw = 0; kw < g.KW; ++kw) {
+      int iw;
+      if (!tap_in(g, ow, kw, g.pad_w, g.Wi, iw)) continue;
+      const T *xp = x + (((long long)n * g.Hi + ih) * g.Wi + iw) * g.Ci;
+      const float *wrow = ws + (kh * g.KW + kw) * g.Ci * 64 + cg * 8;
+      for (int ci = 0; ci < g.Ci; ++ci) {
+        const float xv = to_f(xp[ci]);
+        const float4 w0 = *reinterpret_cast<const float4 *>(wrow + ci * 64);
+        const float4 w1 = *reinterpret_cast<const float4 *>(wrow + ci * 64 + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], g.act);
+  store_vec<T, 8>(y + m * g.Co + co_blk + cg * 8, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// many -> few:  Co <= 2, Ci % 64 == 0.   8 threads per pixel, each owning 8 of every 64 input channels (one 16-byte load
+// per tap per 64-channel group), shuffle-reduced at the end.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_fewout_kernel(ctagan_conv_geom g, const T *__restrict__ x, const T *__restrict__ wp,
+                                                          const float *__restrict__ bias, T *__restrict__ y) {
+  extern __shared__ float ws[];   // [Co][ntaps][Ci]
+  const int ntaps = g.KH * g.KW, KC = ntaps * g.Ci;
+  for (int i = threadIdx.x; i < g.Co * KC; i += 256) ws[i] = to_f(wp[i]);
+  __syncthreads();
+  const long long M = (long long)g.N * g.Ho * g.Wo;
+  const int cs = threadIdx.x & 7;
+  long long m = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool live = m < M;
+  if (!live) m = M - 1;
+  const int ow = (int)(m % g.Wo);
+  const long long q = m / g.Wo;
+  const int oh = (int)(q % g.Ho), n = (int)(q / g.Ho);
+  float acc[2] = {0.f, 0.f};
+  for (int kh = 0; kh < g.KH; ++kh) {
+    int ih;
+    if (!tap_in(g, oh, kh, g.pad_h, g.Hi, ih)) continue;
+    for (int kw = 0; kw < g.KW; ++kw) {
+      int iw;
+      if (!tap_in(g, ow, kw, g.pad_w, g.Wi, iw)) continue;
+      const T *xp = x + (((long long)n * g.Hi + ih) * g.Wi + iw) * g.Ci + cs * 8;
+      const float *wrow = ws + (kh * g.KW + kw) * g.Ci + cs * 8;
+      for (int c0 = 0; c0 < g.Ci; c0 += 64) {
+        float xv[8];
+        load_vec<T, 8>(xp + c0, xv);
+        for (int co = 0; co < g.Co; ++co) {
+          const float4 w0 = *reinterpret_cast<const float4 *>(wrow + co * KC + c0);
+          const float4 w1 = *reinterpret_cast<const float4 *>(wrow + co * KC + c0 + 4);
+          float s = acc[co];
+          s = fmaf(xv[0], w0.x, s); s = fmaf(xv[1], w0.y, s); s = fmaf(xv[2], w0.z, s); s = fmaf(xv[3], w0.w, s);
+          s = fmaf(xv[4], w1.x, s); s = fmaf(xv[5], w1.y, s); s = fmaf(xv[6], w1.z, s); s = fmaf(xv[7], w1.w, s);
+          acc[co] = s;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 2; ++co) {
+    acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
+    acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
+    acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 4);
+  }
+  if (live && cs == 0) {
+    for (int co = 0; co < g.Co; ++co) y[m * g.Co + co] = from_f<T>(apply_act(acc[co] + (bias ? bias[co] : 0.f), g.act));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// thin weight gradients.  V = the wide tensor (C channels), S = the thin one (SC <= 2 channels).
+//   gy_thin == 0 :  gy is wide (V at output positions), gx is thin   -> dw[c][sc][tap]   (head 7x7 Cin=1, discriminator layer 0)
+//   gy_thin == 1 :  gx is wide (V at input positions),  gy is thin   -> dw[sc][c][tap]   (tail 7x7 Cout=1, discriminator last layer)
+// thread = (channel c of a 64-channel block, kernel row kh); it walks along image rows keeping KW accumulators.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int THIN_MAXKW = 7;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(ctagan_conv_geom g, const T *__restrict__ gy, const T *__restrict__ gx,
+                                                              float *__restrict__ dw, float *__restrict__ db, int gy_thin,
+                                                              int rows_per_block) {
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int kh = blockIdx.z * 4 + (threadIdx.x >> 6);
+  const int C = gy_thin ? g.Ci : g.Co;            // wide channel count
+  const int SC = gy_thin ? g.Co : g.Ci;           // thin channel count (1 or 2)
+  const int ntaps = g.KH * g.KW;
+  // rows of the wide tensor handled by this block
+  const int VH = gy_thin ? g.Hi : g.Ho, VW = gy_thin ? g.Wi : g.Wo;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  const long long row1 = min((long long)g.N * VH, row0 + rows_per_block);
+  const bool active = (c < C) && (kh < g.KH);
+  float acc[2][THIN_MAXKW];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int k = 0; k < THIN_MAXKW; ++k) acc[s][k] = 0.f;
+  float bsum = 0.f;
+  if (active) {
+    for (long long r = row0; r < row1; ++r) {
+      const int n = (int)(r / VH), vh = (int)(r - (long long)n * VH);
+      // matching row of the thin tensor for this kernel row
+      int sh;
+      bool row_ok;
+      if (!gy_thin) {                               // V = gy[oh], S = gx[oh*s + kh - pad]
+        sh = vh * g.stride + kh - g.pad_h;
+        row_ok = sh >= 0 && sh < g.Hi;
+      } else {                                      // V = gx[ih], S = gy[oh], oh*s + kh - pad = ih  (stride 1 only)
+        sh = vh + g.pad_h - kh;
+        row_ok = sh >= 0 && sh < g.Ho;
+      }
+      const T *vrow = (gy_thin ? gx : gy) + ((long long)n * VH + vh) * VW * C + c;
+      const int SW = gy_thin ? g.Wo : g.Wi, SH = gy_thin ? g.Ho : g.Hi;
+      const T *srow = (gy_thin ? gy : gx) + ((long long)n * SH + (row_ok ? sh : 0)) * SW * SC;
+      for (int vw = 0; vw < VW; ++vw) {
+        const float v = to_f(vrow[(long long)vw * C]);
+        if (!gy_thin && kh == 0 && blockIdx.z == 0) bsum += v;
+        if (!row_ok) continue;
+#pragma unroll
+        for (int kw = 0; kw < THIN_MAXKW; ++kw) {
+          if (kw >= g.KW) break;
+          const int sw = gy_thin ? (vw + g.pad_w - kw) : (vw * g.stride + kw - g.pad_w);
+          if (sw < 0 || sw >= SW) continue;
+          for (int s = 0; s < SC; ++s) acc[s][kw] = fmaf(v, to_f(srow[(long long)sw * SC + s]), acc[s][kw]);
+        }
+      }
+    }
+    for (int s = 0; s < SC; ++s)
+      for (int kw = 0; kw < g.KW; ++kw) {
+        // dw is [A][B][KH][KW] with A = gy channels, B = gx channels
+        const long long idx = gy_thin ? (((long long)s * C + c) * ntaps + kh * g.KW + kw) : (((long long)c * SC + s) * ntaps + kh * g.KW + kw);
+        atomicAdd(dw + idx, acc[s][kw]);
+      }
+    if (db && !gy_thin && kh == 0 && blockIdx.z == 0) atomicAdd(db + c, bsum);
+  }
+  // bias gradient of the thin-gy case: db[sc] = sum of gy (done by the first channel block / kernel-row group)
+  if (db && gy_thin && blockIdx.y == 0 && blockIdx.z == 0) {
+    // rows of gy matching this block's share: split gy rows evenly over gridDim.x
+    const long long total = (long long)g.N * g.Ho * g.Wo;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * per, p1 = min(total, p0 + per);
+    for (int s = 0; s < SC; ++s) {
+      float t = 0.f;
+      for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) t += to_f(gy[p * SC + s]);
+      t = warp_sum(t);
+      if ((threadIdx.x & 31) == 0) atomicAdd(db + s, t);
+    }
+  }
+}
+
+}  // namespace
+
+int ctagan_conv_small_kind(const ctagan_conv_geom *g) {
+  if (g->Ci <= 2 && g->Co % 8 == 0 && g->KH * g->KW * g->Ci * 64 * 4 <= 48 * 1024) return 1;
+  if (g->Co <= 2 && g->Ci % 64 == 0 && (long long)g->Co * g->KH * g->KW * g->Ci * 4 <= 96 * 1024) return 2;
+  return 0;
+}
+
+int ctagan_conv_gather_small(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st) {
+  const int kind = ctagan_conv_small_kind(g);
+  const long long M = (long long)g->N * g->Ho * g->Wo;
+  if (kind == 1) {
+    dim3 grid(cdiv(M, 32), cdiv(g->Co, 64));
+    const size_t smem = (size_t)g->KH * g->KW * g->Ci * 64 * sizeof(float);
+    CTAGAN_DISPATCH_DTYPE(g->dtype, T, { conv_fewin_kernel<T><<<grid, 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y); });
+  } else if (kind == 2) {
+    const size_t smem = (size_t)g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+    CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+      static bool configured = false;
+      if (!configured) {
+        CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_fewout_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+      }
+      conv_fewout_kernel<T><<<cdiv(M, 32), 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+    });
+  } else {
+    ctagan_set_error("conv_gather_small: geometry is not degenerate");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+int ctagan_conv_wgrad_thin_eligible(const ctagan_conv_geom *g) {
+  if (g->dil != 1 || g->KW > THIN_MAXKW || g->KH > 8) return 0;
+  if (g->Ci <= 2 && g->Co >= 8) return 1;                       // gx thin
+  if (g->Co <= 2 && g->Ci >= 8 && g->stride == 1) return 2;     // gy thin
+  return 0;
+}
+
+int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st) {
+  const int kind = ctagan_conv_wgrad_thin_eligible(g);
+  if (!kind) {
+    ctagan_set_error("conv_wgrad_thin: geometry is not degenerate");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  const int gy_thin = kind == 2;
+  const int C = gy_thin ? g->Ci : g->Co;
+  const int VH = gy_thin ? g->Hi : g->Ho;
+  const long long rows = (long long)g->N * VH;
+  CTAGAN_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Co * g->Ci * g->KH * g->KW, st));
+  if (db) CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
+  const int ch_blocks = cdiv(C, 64), kh_blocks = cdiv(g->KH, 4);
+  long long want = (4LL * ctagan_num_sms()) / ((long long)ch_blocks * kh_blocks);
+  if (want < 1) want = 1;
+  if (want > rows) want = rows;
+  const int rpb = (int)((rows + want - 1) / want);
+  dim3 grid(cdiv(rows, rpb), ch_blocks, kh_blocks);
+  CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+    conv_wgrad_thin_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, gy_thin, rpb);
+  });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}

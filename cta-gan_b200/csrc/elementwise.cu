@@ -562,7 +562,7 @@ static int reduce_chunks(int N, int HW, int C, int v, int &pix_per_block) {
   const int lanes = 256 / CV > 0 ? 256 / CV : 1;
   // aim for ~4 CTAs per SM overall, at least 8 pixels per lane
   long long want = ((long long)ctagan_num_sms() * 4 + N - 1) / N;
-  long long maxc = (HW + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+  long long maxc = (HW + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   pix_per_block = (int)((HW + want - 1) / want);

@@ -55,7 +55,7 @@ except ImportError:     # pragma: no cover
 
 
 def set_conv_engine(e):
-    _ENGINE["value"] = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tc": L.ENGINE_TC}[e]
+    _ENGINE["value"] = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tc": L.ENGINE_TC, "generic": L.ENGINE_GENERIC}[e]
 
 
 class ConvPrim:
@@ -216,7 +216,7 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
         dx = ops.nhwc_to_nchw(dx0)
     if need_dw:
         # biases in front of a non-affine InstanceNorm are mathematically dead: zero gradient
-        z = lambda prim: torch.zeros_like(prim.b)
+        z = lambda prim: None          # (None == no gradient: Adam leaves the dead parameter untouched)
         grads = [dWh1, z(plan.head1), dWh4, z(plan.head4), dWh7, z(plan.head7)]
         for (c1, c2), (dW1, dW2) in zip(plan.blocks, block_grads):
             grads += [dW1, z(c1), dW2, z(c2)]
@@ -273,7 +273,7 @@ def discriminator_backward(plan: DiscriminatorPlan, saved, dout: torch.Tensor, n
         dr = ops.norm_act_pad_bwd(da, raws[i - 1], stats[i - 1], L.ACT_LRELU, 0)
         if need_dw:
             gw[2 * i], _ = c[i].wgrad(dr, acts[i - 1])
-            gw[2 * i + 1] = torch.zeros_like(c[i].b)
+            gw[2 * i + 1] = None            # bias in front of InstanceNorm: mathematically dead
         da = c[i].bprop(dr, (acts[i - 1].shape[1], acts[i - 1].shape[2]))
     dy0 = ops.act_bwd(da, acts[0], L.ACT_LRELU)
     if need_dw:
@@ -318,7 +318,7 @@ class _ResBlock:
         dW1, _ = self.c1.wgrad(dra, Pa)
         dPa = self.c1.bprop(dra, (Pa.shape[1], Pa.shape[2]))
         Ga = ops.norm_act_pad_bwd(dPa, pre_act, None, pre_act_kind, 1, addend=G)
-        return Ga, [dW1, torch.zeros_like(self.c1.b), dW2, torch.zeros_like(self.c2.b)]
+        return Ga, [dW1, None, dW2, None]      # biases in front of InstanceNorm are dead
 
 
 class RegPlan:

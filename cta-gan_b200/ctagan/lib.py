@@ -16,7 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC, ENGINE_GENERIC = 0, 1, 2, 3
 
 
 class ConvGeom(ctypes.Structure):

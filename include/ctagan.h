@@ -62,7 +62,8 @@ typedef struct {
 
 /* Replaces nn.Conv2d / nn.ConvTranspose2d forward and the input-gradient half of their backward
  * (Model/CycleGan.py:11,15,28,36,51,59,78-94; trainer/layers.py:83,280,293).  bias may be NULL (fp32[Co] otherwise).
- * engine: 0 = auto, 1 = force CUDA-core (fp32-accumulate FFMA) kernel, 2 = force tcgen05 kernel (error if ineligible). */
+ * engine: 0 = auto, 1 = CUDA-core kernels (fp32-accumulate FFMA; specialised ones for 1-2 channel layers), 2 = force the
+ * tcgen05 kernel (error if ineligible), 3 = generic CUDA-core implicit-GEMM kernel only (cross-check). */
 int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y,
                        int engine, void *stream);
 

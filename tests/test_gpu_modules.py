@@ -35,9 +35,10 @@ def _check_grads(module, leaf, skip_dead=True, tol=2e-3):
     ref_max = max(float(p.grad.abs().max()) for p in leaf.values())
     for k, p in module.named_parameters():
         ref = leaf[k].grad
-        if float(ref.abs().max()) <= 1e-6 * ref_max:      # dead pre-InstanceNorm biases: exact zero on our side
-            assert float(p.grad.abs().max()) <= 1e-5 * ref_max, k
+        if float(ref.abs().max()) <= 1e-6 * ref_max:      # dead pre-InstanceNorm biases: no gradient at all on our side
+            assert p.grad is None or float(p.grad.abs().max()) <= 1e-5 * ref_max, k
             continue
+        assert p.grad is not None, k
         e = l2rel(p.grad, ref)
         if e > worst[1]:
             worst = (k, e)
