@@ -124,66 +124,76 @@ __global__ void __launch_bounds__(256) conv_fewout_kernel(ctagan_conv_geom g, co
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int THIN_MAXKW = 7;
 
-template <typename T>
+// Register-window version: thread = (channel c, kernel row kh).  For U consecutive positions of the wide tensor it loads U wide
+// values and the (U-1)*STRIDE+KW thin values they touch once, then issues U*KW FMAs (>= 60% of the instruction stream).
+template <typename T, int KW, int STRIDE>
 __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(ctagan_conv_geom g, const T *__restrict__ gy, const T *__restrict__ gx,
                                                               float *__restrict__ dw, float *__restrict__ db, int gy_thin,
                                                               int rows_per_block) {
+  constexpr int U = 8;
+  constexpr int WIN = (U - 1) * STRIDE + KW;
   const int c = blockIdx.y * 64 + (threadIdx.x & 63);
   const int kh = blockIdx.z * 4 + (threadIdx.x >> 6);
   const int C = gy_thin ? g.Ci : g.Co;            // wide channel count
   const int SC = gy_thin ? g.Co : g.Ci;           // thin channel count (1 or 2)
-  const int ntaps = g.KH * g.KW;
-  // rows of the wide tensor handled by this block
+  const int ntaps = g.KH * KW;
   const int VH = gy_thin ? g.Hi : g.Ho, VW = gy_thin ? g.Wi : g.Wo;
+  const int SW = gy_thin ? g.Wo : g.Wi, SH = gy_thin ? g.Ho : g.Hi;
   const long long row0 = (long long)blockIdx.x * rows_per_block;
   const long long row1 = min((long long)g.N * VH, row0 + rows_per_block);
   const bool active = (c < C) && (kh < g.KH);
-  float acc[2][THIN_MAXKW];
-#pragma unroll
-  for (int s = 0; s < 2; ++s)
-#pragma unroll
-    for (int k = 0; k < THIN_MAXKW; ++k) acc[s][k] = 0.f;
   float bsum = 0.f;
   if (active) {
-    for (long long r = row0; r < row1; ++r) {
-      const int n = (int)(r / VH), vh = (int)(r - (long long)n * VH);
-      // matching row of the thin tensor for this kernel row
-      int sh;
-      bool row_ok;
-      if (!gy_thin) {                               // V = gy[oh], S = gx[oh*s + kh - pad]
-        sh = vh * g.stride + kh - g.pad_h;
-        row_ok = sh >= 0 && sh < g.Hi;
-      } else {                                      // V = gx[ih], S = gy[oh], oh*s + kh - pad = ih  (stride 1 only)
-        sh = vh + g.pad_h - kh;
-        row_ok = sh >= 0 && sh < g.Ho;
-      }
-      const T *vrow = (gy_thin ? gx : gy) + ((long long)n * VH + vh) * VW * C + c;
-      const int SW = gy_thin ? g.Wo : g.Wi, SH = gy_thin ? g.Ho : g.Hi;
-      const T *srow = (gy_thin ? gy : gx) + ((long long)n * SH + (row_ok ? sh : 0)) * SW * SC;
-      for (int vw = 0; vw < VW; ++vw) {
-        const float v = to_f(vrow[(long long)vw * C]);
-        if (!gy_thin && kh == 0 && blockIdx.z == 0) bsum += v;
-        if (!row_ok) continue;
+    for (int s = 0; s < SC; ++s) {
+      float acc[KW];
 #pragma unroll
-        for (int kw = 0; kw < THIN_MAXKW; ++kw) {
-          if (kw >= g.KW) break;
-          const int sw = gy_thin ? (vw + g.pad_w - kw) : (vw * g.stride + kw - g.pad_w);
-          if (sw < 0 || sw >= SW) continue;
-          for (int s = 0; s < SC; ++s) acc[s][kw] = fmaf(v, to_f(srow[(long long)sw * SC + s]), acc[s][kw]);
+      for (int k = 0; k < KW; ++k) acc[k] = 0.f;
+      for (long long r = row0; r < row1; ++r) {
+        const int n = (int)(r / VH), vh = (int)(r - (long long)n * VH);
+        const int sh = gy_thin ? (vh + g.pad_h - kh) : (vh * STRIDE + kh - g.pad_h);
+        const bool row_ok = sh >= 0 && sh < SH;
+        const T *vrow = (gy_thin ? gx : gy) + ((long long)n * VH + vh) * VW * C + c;
+        if (!row_ok) {
+          if (!gy_thin && s == 0 && kh == 0 && blockIdx.z == 0 && db)
+            for (int vw = 0; vw < VW; ++vw) bsum += to_f(vrow[(long long)vw * C]);
+          continue;
+        }
+        const T *srow = (gy_thin ? gy : gx) + ((long long)n * SH + sh) * SW * SC + s;
+        for (int vw0 = 0; vw0 < VW; vw0 += U) {
+          float v[U], win[WIN];
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = (vw0 + u < VW) ? to_f(vrow[(long long)(vw0 + u) * C]) : 0.f;
+          // window start in the thin row: gy wide: sw = vw*STRIDE + kw - pad ; gy thin (stride 1): sw = vw + pad - kw
+          const int wbase = gy_thin ? (vw0 + g.pad_w - (KW - 1)) : (vw0 * STRIDE - g.pad_w);
+#pragma unroll
+          for (int j = 0; j < WIN; ++j) {
+            const int sw = wbase + j;
+            win[j] = (sw >= 0 && sw < SW) ? to_f(srow[(long long)sw * SC]) : 0.f;
+          }
+          if (!gy_thin && s == 0 && kh == 0 && blockIdx.z == 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) bsum += v[u];
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int kw = 0; kw < KW; ++kw) {
+              const int j = gy_thin ? (u - kw + KW - 1) : (u * STRIDE + kw);
+              acc[kw] = fmaf(v[u], win[j], acc[kw]);
+            }
         }
       }
-    }
-    for (int s = 0; s < SC; ++s)
-      for (int kw = 0; kw < g.KW; ++kw) {
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
         // dw is [A][B][KH][KW] with A = gy channels, B = gx channels
-        const long long idx = gy_thin ? (((long long)s * C + c) * ntaps + kh * g.KW + kw) : (((long long)c * SC + s) * ntaps + kh * g.KW + kw);
-        atomicAdd(dw + idx, acc[s][kw]);
+        const long long idx = gy_thin ? (((long long)s * C + c) * ntaps + kh * KW + kw) : (((long long)c * SC + s) * ntaps + kh * KW + kw);
+        atomicAdd(dw + idx, acc[kw]);
       }
+    }
     if (db && !gy_thin && kh == 0 && blockIdx.z == 0) atomicAdd(db + c, bsum);
   }
-  // bias gradient of the thin-gy case: db[sc] = sum of gy (done by the first channel block / kernel-row group)
+  // bias gradient of the thin-gy case: db[sc] = sum of gy (first channel block / kernel-row group only)
   if (db && gy_thin && blockIdx.y == 0 && blockIdx.z == 0) {
-    // rows of gy matching this block's share: split gy rows evenly over gridDim.x
     const long long total = (long long)g.N * g.Ho * g.Wo;
     const long long per = (total + gridDim.x - 1) / gridDim.x;
     const long long p0 = blockIdx.x * per, p1 = min(total, p0 + per);
@@ -230,7 +240,10 @@ int ctagan_conv_gather_small(const ctagan_conv_geom *g, const void *x, const voi
 }
 
 int ctagan_conv_wgrad_thin_eligible(const ctagan_conv_geom *g) {
-  if (g->dil != 1 || g->KW > THIN_MAXKW || g->KH > 8) return 0;
+  if (g->dil != 1 || g->KH > 8) return 0;
+  const bool shape_ok = (g->KW == 7 && g->stride == 1) || (g->KW == 4 && g->stride <= 2) || (g->KW == 3 && g->stride == 1) ||
+                        (g->KW == 1 && g->stride == 1);
+  if (!shape_ok) return 0;
   if (g->Ci <= 2 && g->Co >= 8) return 1;                       // gx thin
   if (g->Co <= 2 && g->Ci >= 8 && g->stride == 1) return 2;     // gy thin
   return 0;
@@ -249,14 +262,20 @@ int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void
   CTAGAN_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Co * g->Ci * g->KH * g->KW, st));
   if (db) CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
   const int ch_blocks = cdiv(C, 64), kh_blocks = cdiv(g->KH, 4);
-  long long want = (4LL * ctagan_num_sms()) / ((long long)ch_blocks * kh_blocks);
+  long long want = (2LL * ctagan_num_sms()) / ((long long)ch_blocks * kh_blocks);
   if (want < 1) want = 1;
   if (want > rows) want = rows;
   const int rpb = (int)((rows + want - 1) / want);
   dim3 grid(cdiv(rows, rpb), ch_blocks, kh_blocks);
+#define THIN_LAUNCH(KW_, S_) conv_wgrad_thin_kernel<T, KW_, S_><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, gy_thin, rpb)
   CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
-    conv_wgrad_thin_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, gy_thin, rpb);
+    if (g->KW == 7) THIN_LAUNCH(7, 1);
+    else if (g->KW == 4 && g->stride == 1) THIN_LAUNCH(4, 1);
+    else if (g->KW == 4) THIN_LAUNCH(4, 2);
+    else if (g->KW == 3) THIN_LAUNCH(3, 1);
+    else THIN_LAUNCH(1, 1);
   });
+#undef THIN_LAUNCH
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }

@@ -592,7 +592,7 @@ static int tc_gather_kind(const ctagan_conv_geom *g) {
   if (g->dtype != CTAGAN_BF16) return 0;
   if (g->Ci % CHUNK_K || g->Co % 64) return 0;
   if (g->KH * g->KW > MAX_TAPS) return 0;
-  if ((long long)g->N * g->Ho * g->Wo < 1024) return 0;   // tiny maps: launch-latency bound either way -> CUDA-core kernel
+  if ((long long)g->N * g->Ho * g->Wo < 512) return 0;    // tiny maps: launch-latency bound either way -> CUDA-core kernel
   if (g->dil == 1) {
     if (g->stride == 1 && g->pad_h == 0 && g->pad_w == 0 && g->Ho == g->Hi - g->KH + 1 && g->Wo == g->Wi - g->KW + 1) return 1;
     if (g->stride <= 2 && g->Wo >= 16) return 2;
@@ -708,7 +708,7 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
   const int m = g->gy_margin;
   const int Hvld = g->Ho - 2 * m, Wvld = g->Wo - 2 * m;
   if (Hvld <= 0 || Wvld <= 0) return false;
-  if ((long long)g->N * Hvld * Wvld < 1024) return false;  // tiny maps stay on the CUDA-core kernel
+  if ((long long)g->N * Hvld * Wvld < 512) return false;   // tiny maps stay on the CUDA-core kernel
   pl.bnw = (g->Ci % 256 == 0) ? 256 : (g->Ci % 128 == 0 ? 128 : 64);
   pl.bkw = Wvld >= 64 ? 64 : (Wvld > 16 ? 32 : 16);
   pl.bkh = 64 / pl.bkw;

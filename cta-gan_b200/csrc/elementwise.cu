@@ -128,6 +128,10 @@ __device__ __forceinline__ int fold_sources(int h, int H, int pad, int (&src)[3]
 template <typename T, int V>
 __device__ __forceinline__ void folded_grad(const T *__restrict__ gout, int n, int h, int w, int cv, int H, int W, int C, int pad,
                                             float (&g)[V]) {
+  if (pad == 0) {
+    load_vec<T, V>(gout + (((long long)n * H + h) * W + w) * C + cv * V, g);
+    return;
+  }
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   int hs[3], ws[3];
   const int nh = fold_sources(h, H, pad, hs), nw = fold_sources(w, W, pad, ws);
@@ -562,7 +566,7 @@ static int reduce_chunks(int N, int HW, int C, int v, int &pix_per_block) {
   const int lanes = 256 / CV > 0 ? 256 / CV : 1;
   // aim for ~4 CTAs per SM overall, at least 8 pixels per lane
   long long want = ((long long)ctagan_num_sms() * 4 + N - 1) / N;
-  long long maxc = (HW + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
+  long long maxc = (HW + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   pix_per_block = (int)((HW + want - 1) / want);
