@@ -78,6 +78,11 @@ class ConvPrim:
         self._cache[key] = (ver, wp)
         return wp
 
+    def prepack(self, dtype: torch.dtype, modes=(0, 1)):
+        """Materialise the packed copies on the CURRENT stream (call before forking work onto side streams)."""
+        for m in modes:
+            self.packed(m, dtype)
+
     # I-channel input -> O-channel output, strided  (Conv2d forward / ConvTranspose2d input-gradient)
     def fprop(self, x, act=L.ACT_NONE, use_bias=True, pad=None):
         N, Hi, Wi, Ci = x.shape
@@ -135,6 +140,12 @@ class GeneratorPlan:
         w, b = nxt(); self.tail7 = ConvPrim(w, b, 1, 0)
         self.n_blocks = n_blocks
         self.params = list(params)
+
+    def prims(self):
+        out = [self.head1, self.head4, self.head7]
+        for c1, c2 in self.blocks:
+            out += [c1, c2]
+        return out + [self.tail0, self.tail3, self.tail7]
 
 
 def generator_forward(plan: GeneratorPlan, x_nchw: torch.Tensor, save: bool):
@@ -240,6 +251,9 @@ class DiscriminatorPlan:
             w, b = next(it), next(it)
             self.convs.append(ConvPrim(w, b, s, 1))
         self.params = list(params)
+
+    def prims(self):
+        return list(self.convs)
 
 
 def discriminator_forward(plan: DiscriminatorPlan, x_nchw: torch.Tensor, save: bool):

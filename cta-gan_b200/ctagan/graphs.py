@@ -4,7 +4,8 @@ A Cyc step at batch 1 is ~1700 kernel launches for ~1.3 TFLOP: launch latency, n
 iteration body is therefore captured once (torch.cuda.CUDAGraph: all libctagan kernels, the NCCL gradient all-reduce and the
 capturable Adam updates are stream-ordered and allocation-free on replay) and replayed per step.  Host-side logic that the
 reference keeps on the CPU (ReplayBuffer with Python `random`, trainer/utils.py:120-140) stays on the host BETWEEN graphs:
-the Cyc step is three graphs (generator phase, D_A phase, D_B phase) around the two buffer exchanges.
+the Cyc step is two graphs (generator phase; both discriminator phases) around the buffer exchanges.  Inside each graph the two
+independent chains of the phase are forked onto two streams (see Cyc_Trainer.phase_G), i.e. parallel branches of the CUDA graph.
 
 Weight packing (fp32 master -> bf16 [O][kh][kw][I]) is part of the captured graphs: the packed-weight cache is invalidated
 right before capture, so every replay re-packs from the current master weights.
@@ -53,14 +54,13 @@ class GraphedTrainer:
             self._capture(static)
         E.invalidate_weight_cache()          # eager users after us must not trust capture-time packed weights
         if self.is_cyc:
-            gG, gDA, gDB = self._graphs
+            gG, gD = self._graphs
             gG.replay()
             fa = t.fake_A_buffer.push_and_pop(self._fake_A.clone())
             fb = t.fake_B_buffer.push_and_pop(self._fake_B.clone())
             self._sel_A.copy_(fa)
             self._sel_B.copy_(fb)
-            gDA.replay()
-            gDB.replay()
+            gD.replay()
             t.last_losses = {"loss_G": self._loss_G, "loss_D_A": self._loss_DA, "loss_D_B": self._loss_DB}
         else:
             self._graphs[0].replay()
@@ -88,13 +88,10 @@ class GraphedTrainer:
             pool = gG.pool()
             self._sel_A, self._sel_B = torch.empty_like(self._fake_A), torch.empty_like(self._fake_B)
             self._sel_A.copy_(self._fake_A); self._sel_B.copy_(self._fake_B)
-            gDA = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gDA, pool=pool):
-                self._loss_DA = t.phase_D(t.netD_A, t.optimizer_D_A, t._sync_DA, real_A, self._sel_A)
-            gDB = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gDB, pool=pool):
-                self._loss_DB = t.phase_D(t.netD_B, t.optimizer_D_B, t._sync_DB, real_B, self._sel_B)
-            self._graphs = (gG, gDA, gDB)
+            gD = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gD, pool=pool):
+                self._loss_DA, self._loss_DB = t.phase_DD(real_A, self._sel_A, real_B, self._sel_B)
+            self._graphs = (gG, gD)
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

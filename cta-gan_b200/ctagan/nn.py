@@ -95,6 +95,12 @@ class Generator(nn.Module):
         self._plan = None
         return super()._apply(fn, *a, **k)
 
+    def prepack(self):
+        """Pack the current weights (bf16 / re-laid-out copies) on the current stream; lets several passes of this network run
+        concurrently on side streams afterwards."""
+        for prim in self._get_plan().prims():
+            prim.prepack(E.get_precision())
+
     def forward(self, x):
         if x.shape[2] % 4 or x.shape[3] % 4:
             raise ValueError("Generator needs H and W to be multiples of 4")
@@ -166,6 +172,10 @@ class _DiscBase(nn.Module):
     def _apply(self, fn, *a, **k):
         self._plan = None
         return super()._apply(fn, *a, **k)
+
+    def prepack(self):
+        for prim in self._get_plan().prims():
+            prim.prepack(E.get_precision())
 
     def _run(self, x, sink=None, freeze=False):
         plan = self._get_plan()

@@ -212,42 +212,79 @@ class Cyc_Trainer(_TrainerBase):
         return {"{st}.pth": self.netG_A2B, "netD_B_{st}.pth": self.netD_B, "netG_B2A_{st}.pth": self.netG_B2A,
                 "netD_A_{st}.pth": self.netD_A}
 
-    # the three phases are separate methods so that they can be captured as CUDA graphs around the host-side ReplayBuffer
+    # The phases are separate methods so that they can be captured as CUDA graphs around the host-side ReplayBuffer.
+    # At batch 1 every kernel is latency-bound (132 CTAs for a few microseconds), so the two independent chains of the generator
+    # phase (A: G_A2B(real_A) -> D_B -> G_B2A(fake_B);  B: G_B2A(real_B) -> D_A -> G_A2B(fake_A)) run on two streams; autograd
+    # replays each backward node on its forward stream, so the backward chains overlap the same way.  Same for the two D phases.
+    def _side_streams(self):
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        return self._streams
+
     def phase_G(self, real_A, real_B):
         c = self.config
+        cur = torch.cuda.current_stream()
         self.optimizer_G.zero_grad(set_to_none=True)
-        fake_B = self.netG_A2B(real_A)                                                     # CycTrainer.py:144-146
-        loss_GAN_A2B = c["Adv_lamda"] * self.MSE_loss(self.netD_B(fake_B, freeze=True), self.target_real)
-        fake_A = self.netG_B2A(real_B)                                                     # :148-150
-        loss_GAN_B2A = c["Adv_lamda"] * self.MSE_loss(self.netD_A(fake_A, freeze=True), self.target_real)
-        recovered_A = self.netG_B2A(fake_B)                                                # :153-157
-        loss_cycle_ABA = c["Cyc_lamda"] * self.L1_loss(recovered_A, real_A)
-        recovered_B = self.netG_A2B(fake_A)
-        loss_cycle_BAB = c["Cyc_lamda"] * self.L1_loss(recovered_B, real_B)
-        loss_Total = loss_GAN_A2B + loss_GAN_B2A + loss_cycle_ABA + loss_cycle_BAB         # :160-162
+        for net in (self.netG_A2B, self.netG_B2A, self.netD_A, self.netD_B):
+            net.prepack()
+        sA, sB = self._side_streams()
+        sA.wait_stream(cur); sB.wait_stream(cur)
+        with torch.cuda.stream(sA):
+            fake_B = self.netG_A2B(real_A)                                                 # CycTrainer.py:144-146
+            loss_GAN_A2B = c["Adv_lamda"] * self.MSE_loss(self.netD_B(fake_B, freeze=True), self.target_real)
+            recovered_A = self.netG_B2A(fake_B)                                            # :153-154
+            loss_cycle_ABA = c["Cyc_lamda"] * self.L1_loss(recovered_A, real_A)
+            loss_A = loss_GAN_A2B + loss_cycle_ABA
+        with torch.cuda.stream(sB):
+            fake_A = self.netG_B2A(real_B)                                                 # :148-150
+            loss_GAN_B2A = c["Adv_lamda"] * self.MSE_loss(self.netD_A(fake_A, freeze=True), self.target_real)
+            recovered_B = self.netG_A2B(fake_A)                                            # :156-157
+            loss_cycle_BAB = c["Cyc_lamda"] * self.L1_loss(recovered_B, real_B)
+            loss_B = loss_GAN_B2A + loss_cycle_BAB
+        cur.wait_stream(sA); cur.wait_stream(sB)
+        for t in (loss_A, loss_B, fake_A, fake_B):
+            t.record_stream(cur)
+        loss_Total = loss_A + loss_B                                                       # :160-162
         loss_Total.backward()
         self._sync_G()
         self.optimizer_G.step()
         return fake_A.detach(), fake_B.detach(), loss_Total.detach()
 
     def phase_D(self, netD, opt, sync, real, fake):
+        """One discriminator update (:165-178 / :182-197).  real and fake go through the network as ONE batch: InstanceNorm is
+        per sample, so this is the same arithmetic as the reference's two passes with half the kernel launches."""
         c = self.config
-        opt.zero_grad(set_to_none=True)                                                    # :165-178 / :182-197
-        loss_real = c["Adv_lamda"] * self.MSE_loss(netD(real), self.target_real)
-        loss_fake = c["Adv_lamda"] * self.MSE_loss(netD(fake), self.target_fake)
+        opt.zero_grad(set_to_none=True)
+        B = real.shape[0]
+        pred = netD(torch.cat([real, fake], 0))
+        loss_real = c["Adv_lamda"] * self.MSE_loss(pred[:B], self.target_real)
+        loss_fake = c["Adv_lamda"] * self.MSE_loss(pred[B:], self.target_fake)
         loss_D = loss_real + loss_fake
         loss_D.backward()
         sync()
         opt.step()
         return loss_D.detach()
 
+    def phase_DD(self, real_A, fake_A, real_B, fake_B):
+        """Both discriminator updates; they touch disjoint networks, so they run concurrently on the two side streams."""
+        cur = torch.cuda.current_stream()
+        self.netD_A.prepack(); self.netD_B.prepack()
+        sA, sB = self._side_streams()
+        sA.wait_stream(cur); sB.wait_stream(cur)
+        with torch.cuda.stream(sA):
+            loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, fake_A)
+        with torch.cuda.stream(sB):
+            loss_D_B = self.phase_D(self.netD_B, self.optimizer_D_B, self._sync_DB, real_B, fake_B)
+        cur.wait_stream(sA); cur.wait_stream(sB)
+        loss_D_A.record_stream(cur); loss_D_B.record_stream(cur)
+        return loss_D_A, loss_D_B
+
     def step(self, batch=None, tensors=None):
         real_A, real_B = tensors if tensors is not None else self.load_batch(batch)
         fake_A, fake_B, loss_G = self.phase_G(real_A, real_B)
         fake_A = self.fake_A_buffer.push_and_pop(fake_A)                                   # :170
-        loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, fake_A)
         fake_B = self.fake_B_buffer.push_and_pop(fake_B)                                   # :189
-        loss_D_B = self.phase_D(self.netD_B, self.optimizer_D_B, self._sync_DB, real_B, fake_B)
+        loss_D_A, loss_D_B = self.phase_DD(real_A, fake_A, real_B, fake_B)
         self.step_count += 1
         self.last_losses = {"loss_G": loss_G, "loss_D_A": loss_D_A, "loss_D_B": loss_D_B}
         return self.last_losses
