@@ -13,6 +13,7 @@
 // warps 2..5 = epilogue (tcgen05.ld -> bias/activation -> bf16 -> global).  STAGES-deep mbarrier ring between producer
 // and MMA; tcgen05.commit releases stages and signals the epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -41,6 +42,9 @@ struct TcParams {
   int out_H, out_W;            // output tensor spatial dims; position (i,j) is stored at (i*sy+ay, j*sx+ax)
   int sy, sx, ay, ax;
   int act;
+  int n_stages;                // pipeline depth actually used (<= TcConfig::STAGES)
+  int dbg;                     // tuning/debug knobs (0 in production)
+  long long *prof;             // optional per-phase clock64 stamps of CTA 0 (developer probe)
   const float *bias;
   bf16 *out;
 };
@@ -342,20 +346,23 @@ __global__ void colsum_kernel(const bf16 *__restrict__ gy, float *__restrict__ d
   }
 }
 
-template <int BN>
+// One pipeline stage carries KCH consecutive 64-channel chunks of one filter tap (KCH x {A 128x64, B BNx64}).  Measured on B200:
+// a producer iteration (mbarrier try_wait + expect_tx + TMA issue) costs ~300 + 100 cycles per TMA op and an MMA-issuer iteration
+// (try_wait + commit) ~500 cycles, so a 64-channel stage (128..512 tensor cycles) is issue-bound; KCH=2 halves that overhead.
+template <int BN, int KCH>
 struct TcConfig {
-  static constexpr int A_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB
+  static constexpr int A_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB per chunk
   static constexpr int B_BYTES = BN * CHUNK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int STAGE_BYTES = KCH * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-template <int BN>
+template <int BN, int KCH>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
-  using Cfg = TcConfig<BN>;
+  using Cfg = TcConfig<BN, KCH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -372,8 +379,8 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const int tile_i0 = (tile / p.tiles_w) * (TILE_M >> p.bw_log2);   // mode 1: tile origin in output positions
   const int tile_j0 = (tile % p.tiles_w) * BW;
   const int co0 = blockIdx.y * BN;
-  const int k_chunks = p.Ci / CHUNK_K;
-  const int n_iters = p.n_taps * k_chunks;
+  const int groups = p.Ci / (CHUNK_K * KCH);                  // stages per tap
+  const int NS = p.n_stages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -393,40 +400,51 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap = it / k_chunks, kc = it - tap * k_chunks;
-        uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
-        uint8_t *b_dst = a_dst + Cfg::A_BYTES;
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        if (p.mode == 0)
-          tma_load_2d(&map_x, &full_bar[s], a_dst, kc * CHUNK_K, (int)(q0 + p.tap_dh[tap] * p.Wv + p.tap_dw[tap]));
-        else
-          tma_load_4d(&map_x, &full_bar[s], a_dst, kc * CHUNK_K, tile_j0 * p.stride + p.tap_dw[tap],
-                      tile_i0 * p.stride + p.tap_dh[tap], img);
-        tma_load_2d(&map_w, &full_bar[s], b_dst, p.tap_w_col[tap] + kc * CHUNK_K, co0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tap = 0; tap < p.n_taps; ++tap) {
+        const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], wcol = p.tap_w_col[tap];
+        const int row2d = (int)(q0 + dh * p.Wv + dw);
+        const int c1 = tile_j0 * p.stride + dw, c2 = tile_i0 * p.stride + dh;
+        for (int gk = 0; gk < groups; ++gk) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
+          uint8_t *b_dst = a_dst + KCH * Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KCH; ++k) {
+            const int ch = (gk * KCH + k) * CHUNK_K;
+            if (p.mode == 0) tma_load_2d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, row2d);
+            else tma_load_4d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
+            tma_load_2d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, wcol + ch, co0);
+          }
+          if (++s == NS) { s = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+      const int n_iters = p.n_taps * groups;
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr);
+        const uint32_t b_addr = a_addr + KCH * Cfg::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < CHUNK_K / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < KCH; ++k) {
+          const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k * Cfg::A_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * Cfg::B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < CHUNK_K / UMMA_K; ++kk) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (it > 0 || k > 0 || kk > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs retire (implies fence::before_thread_sync)
+        if (++s == NS) { s = 0; ph ^= 1u; }
       }
       umma_commit(tmem_full_bar);     // accumulator complete
     }
@@ -530,26 +548,38 @@ int make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols
   return CTAGAN_OK;
 }
 
-template <int BN>
+template <int BN, int KCH>
 int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, dim3 grid, cudaStream_t st) {
-  using Cfg = TcConfig<BN>;
+  using Cfg = TcConfig<BN, KCH>;
   static bool configured = false;
   if (!configured) {
-    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_valid_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_valid_kernel<BN, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  conv_tc_valid_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(mx, mw, p);
+  TcParams q = p;
+  q.n_stages = Cfg::STAGES;
+  if (const char *env = getenv("CTAGAN_TC_STAGES")) {
+    const int ns = atoi(env);
+    if (ns >= 1 && ns <= Cfg::STAGES) q.n_stages = ns;
+  }
+  conv_tc_valid_kernel<BN, KCH><<<grid, 192, Cfg::SMEM_BYTES, st>>>(mx, mw, q);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
 
 int pick_bn(long long m_tiles, int Co) {
   const int sms = ctagan_num_sms();
-  // largest N tile that still gives every SM a CTA (operand traffic from L2 per FLOP falls with the tile size)
-  for (int bn : {256, 128, 64}) {
-    if (Co % bn) continue;
-    if (m_tiles * (Co / bn) >= sms || bn == 64) return bn;
+  if (const char *env = getenv("CTAGAN_TC_BN")) {          // tuning override
+    const int bn = atoi(env);
+    if ((bn == 64 || bn == 128 || bn == 256) && Co % bn == 0) return bn;
   }
+  // Operand traffic from L2 per FLOP falls with the tile size (each SM sustains ~60 B/clk of TMA traffic: a 128x64 tile is
+  // bandwidth-bound at ~32% of the tensor peak, 128x128 at ~48%, 128x256 at ~64%), while small grids leave SMs idle.  Measured on B200
+  // (3x3 256->256, 64x64 maps): N=256 wins once it fills the chip; N=128 is best from ~1/3 of the SMs up (and lets two independent
+  // generator chains of a batch-1 step share the chip); N=64 only for the smallest grids.
+  if (Co % 256 == 0 && m_tiles * (Co / 256) >= sms) return 256;
+  if (Co % 128 == 0 && m_tiles * (Co / 128) >= sms / 3) return 128;
+  if (Co % 64 == 0) return 64;
   return 0;
 }
 
@@ -570,10 +600,19 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
   rc = make_map_2d(&mw, wp, (uint64_t)p.Co, (uint64_t)w_cols, (uint32_t)bn);
   if (rc) return rc;
   dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)(p.Co / bn));
-  switch (bn) {
-    case 256: return launch_tc<256>(mx, mw, p, grid, st);
-    case 128: return launch_tc<128>(mx, mw, p, grid, st);
-    case 64: return launch_tc<64>(mx, mw, p, grid, st);
+  int kch = (p.Ci % 128 == 0 && bn < 256) ? 2 : 1;      // BN=256 keeps 64-channel stages (4 of them fit; 2-chunk stages would leave 2)
+  if (kch == 2) {
+    switch (bn) {
+      case 256: return launch_tc<256, 2>(mx, mw, p, grid, st);
+      case 128: return launch_tc<128, 2>(mx, mw, p, grid, st);
+      case 64: return launch_tc<64, 2>(mx, mw, p, grid, st);
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_tc<256, 1>(mx, mw, p, grid, st);
+      case 128: return launch_tc<128, 1>(mx, mw, p, grid, st);
+      case 64: return launch_tc<64, 1>(mx, mw, p, grid, st);
+    }
   }
   ctagan_set_error("conv_gather(tc): no tile configuration");
   return CTAGAN_ERR_UNSUPPORTED;
