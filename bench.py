@@ -244,8 +244,7 @@ def run_ours(args):
     e2e_ms_total = float(ms2)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     b, s = cfg["batchSize"], cfg["size"]
     slices = args.steps * b * world
@@ -281,8 +280,14 @@ def run_ours(args):
     elif world > 1:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank runs end with os._exit: tearing down a NCCL communicator that captured CUDA graphs still reference can block."""
+    sys.stdout.flush(); sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
