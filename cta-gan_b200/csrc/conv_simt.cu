@@ -262,6 +262,46 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, T *__restrict__
   }
 }
 
+constexpr int PACK_MAX_ITEMS = 48;
+struct PackTable {
+  int n;
+  long long start[PACK_MAX_ITEMS + 1];      // prefix sums of element counts
+  const float *w[PACK_MAX_ITEMS];
+  void *wp[PACK_MAX_ITEMS];
+  int O[PACK_MAX_ITEMS], I[PACK_MAX_ITEMS], KH[PACK_MAX_ITEMS], KW[PACK_MAX_ITEMS], mode[PACK_MAX_ITEMS];
+};
+
+// one launch re-packs every weight of a network (all layers x both layouts): the table rides in the kernel parameters
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_constant__ PackTable t) {
+  const long long total = t.start[t.n];
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < total; gidx += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = t.n - 1;                  // binary search for the item holding gidx
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (t.start[mid] <= gidx) lo = mid; else hi = mid - 1;
+    }
+    const int it = lo;
+    long long r = gidx - t.start[it];
+    const int O = t.O[it], I = t.I[it], KH = t.KH[it], KW = t.KW[it];
+    T *dst = reinterpret_cast<T *>(t.wp[it]);
+    const long long idx = r;
+    if (t.mode[it] == 0) {
+      const int i = (int)(r % I); r /= I;
+      const int kw = (int)(r % KW); r /= KW;
+      const int kh = (int)(r % KH); r /= KH;
+      const int o = (int)r;
+      dst[idx] = from_f<T>(t.w[it][(((long long)o * I + i) * KH + kh) * KW + kw]);
+    } else {
+      const int o = (int)(r % O); r /= O;
+      const int kw = (int)(r % KW); r /= KW;
+      const int kh = (int)(r % KH); r /= KH;
+      const int i = (int)r;
+      dst[idx] = from_f<T>(t.w[it][(((long long)o * I + i) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)]);
+    }
+  }
+}
+
 }  // namespace
 
 int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st) {
@@ -306,5 +346,29 @@ extern "C" int ctagan_pack_weights(const float *w, void *wp, int O, int I, int K
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   CTAGAN_DISPATCH_DTYPE(dtype, T, { pack_weights_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (T *)wp, O, I, KH, KW, mode); });
   CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_pack_weights_multi(const ctagan_pack_item *items, int n_items, int dtype, void *stream) {
+  CTAGAN_REQUIRE(items && n_items > 0, "pack_weights_multi: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < n_items; base += PACK_MAX_ITEMS) {
+    PackTable t;
+    t.n = n_items - base < PACK_MAX_ITEMS ? n_items - base : PACK_MAX_ITEMS;
+    t.start[0] = 0;
+    for (int k = 0; k < t.n; ++k) {
+      const ctagan_pack_item &it = items[base + k];
+      CTAGAN_REQUIRE(it.w && it.wp && it.O > 0 && it.I > 0 && it.KH > 0 && it.KW > 0 && (it.mode == 0 || it.mode == 1),
+                     "pack_weights_multi: bad item %d", base + k);
+      t.w[k] = it.w; t.wp[k] = it.wp; t.O[k] = it.O; t.I[k] = it.I; t.KH[k] = it.KH; t.KW[k] = it.KW; t.mode[k] = it.mode;
+      t.start[k + 1] = t.start[k] + (long long)it.O * it.I * it.KH * it.KW;
+    }
+    const long long total = t.start[t.n];
+    long long blocks = (total + 1023) / 1024;
+    const long long cap = (long long)ctagan_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    CTAGAN_DISPATCH_DTYPE(dtype, T, { pack_weights_multi_kernel<T><<<(int)blocks, 256, 0, st>>>(t); });
+    CTAGAN_LAUNCH_OK();
+  }
   return CTAGAN_OK;
 }

@@ -3,6 +3,11 @@
 // All are coalesced along the channel (innermost) dimension with 16-byte vectors when C allows it.
 #include "common.cuh"
 
+// All index arithmetic in this file is 32-bit (64-bit integer division costs ~100 instructions on the SM and dominated these
+// latency-bound kernels); the host wrappers reject tensors with >= 2^31 elements.
+typedef int idx_t;
+#define CTAGAN_FITS32(expr) CTAGAN_REQUIRE((int64_t)(expr) < (int64_t)0x7fffffff, "tensor too large for 32-bit indexing")
+
 namespace {
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -22,7 +27,7 @@ __global__ void __launch_bounds__(256) instnorm_partial_kernel(const T *__restri
   const int n = blockIdx.y;
   const int lanes = 256 / CV > 0 ? 256 / CV : 1;  // pixel lanes (CV <= 256 guaranteed by host)
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  const T *base = x + (long long)n * HW * C;
+  const T *base = x + (idx_t)n * HW * C;
   float shift[V], s1[V], s2[V];
   load_vec<T, V>(base + cv * V, shift);
 #pragma unroll
@@ -30,15 +35,26 @@ __global__ void __launch_bounds__(256) instnorm_partial_kernel(const T *__restri
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   if (pl < lanes) {
-    for (int p = p0 + pl; p < p1; p += lanes) {
-      float v[V];
-      load_vec<T, V>(base + (long long)p * C + cv * V, v);
+    constexpr int U = 4;                       // independent loads in flight per thread
+    for (int p = p0 + pl; p < p1; p += lanes * U) {
+      float v[U][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float d = v[i] - shift[i];
-        s1[i] += d;
-        s2[i] = fmaf(d, d, s2[i]);
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + u * lanes;
+        if (pp < p1) load_vec<T, V>(base + (idx_t)pp * C + cv * V, v[u]);
+        else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[u][i] = shift[i];
+        }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float d = v[u][i] - shift[i];
+          s1[i] += d;
+          s2[i] = fmaf(d, d, s2[i]);
+        }
     }
   }
   // combine pixel lanes through shared memory in fp64
@@ -55,7 +71,7 @@ __global__ void __launch_bounds__(256) instnorm_partial_kernel(const T *__restri
         a += sm[0][l * CV + cv];
         b += sm[1][l * CV + cv];
       }
-      double *dst = acc + ((long long)n * C + cv * V + i) * 2;
+      double *dst = acc + ((idx_t)n * C + cv * V + i) * 2;
       atomicAdd(dst, a);
       atomicAdd(dst + 1, b);
     }
@@ -68,7 +84,7 @@ __global__ void instnorm_finalize_kernel(const T *__restrict__ x, const double *
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i - n * C;
-  const double shift = (double)to_f(x[(long long)n * HW * C + c]);
+  const double shift = (double)to_f(x[(idx_t)n * HW * C + c]);
   const double m1 = acc[2 * i] / HW, m2 = acc[2 * i + 1] / HW;
   double var = m2 - m1 * m1;
   if (var < 0) var = 0;
@@ -85,19 +101,19 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__
                                                            int W, int C, int pad, int act) {
   const int CV = C / V;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-  const long long total = (long long)N * Hp * Wp * CV;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const idx_t total = (idx_t)N * Hp * Wp * CV;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    idx_t r = idx / CV;
     const int wp = (int)(r % Wp);
     r /= Wp;
     const int hp = (int)(r % Hp);
     const int n = (int)(r / Hp);
     const int h = reflect_idx(hp - pad, H), w = reflect_idx(wp - pad, W);
     float v[V];
-    load_vec<T, V>(x + (((long long)n * H + h) * W + w) * C + cv * V, v);
+    load_vec<T, V>(x + (((idx_t)n * H + h) * W + w) * C + cv * V, v);
     if (stats) {
-      const float *sp = stats + ((long long)n * C + cv * V) * 2;
+      const float *sp = stats + ((idx_t)n * C + cv * V) * 2;
 #pragma unroll
       for (int i = 0; i < V; ++i) v[i] = (v[i] - sp[2 * i]) * sp[2 * i + 1];
     }
@@ -106,7 +122,7 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__
     if (res) {
       float rv[V];
       const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
-      load_vec<T, V>(res + (((long long)n * Hr + h + res_pad) * Wr + w + res_pad) * C + cv * V, rv);
+      load_vec<T, V>(res + (((idx_t)n * Hr + h + res_pad) * Wr + w + res_pad) * C + cv * V, rv);
 #pragma unroll
       for (int i = 0; i < V; ++i) v[i] += rv[i];
     }
@@ -125,25 +141,33 @@ __device__ __forceinline__ int fold_sources(int h, int H, int pad, int (&src)[3]
   return cnt;
 }
 
+__device__ __forceinline__ bool fold_is_border(int h, int w, int H, int W, int pad) {
+  return pad > 0 && ((h >= 1 && h <= pad) || (h <= H - 2 && h >= H - 1 - pad) || (w >= 1 && w <= pad) || (w <= W - 2 && w >= W - 1 - pad));
+}
+
+// adds the mirrored (reflection) sources of a border pixel; the main source (h+pad, w+pad) is loaded by the caller
 template <typename T, int V>
-__device__ __forceinline__ void folded_grad(const T *__restrict__ gout, int n, int h, int w, int cv, int H, int W, int C, int pad,
-                                            float (&g)[V]) {
-  if (pad == 0) {
-    load_vec<T, V>(gout + (((long long)n * H + h) * W + w) * C + cv * V, g);
-    return;
-  }
+__device__ __noinline__ void fold_extras(const T *__restrict__ gout, int n, int h, int w, int cv, int H, int W, int C, int pad,
+                                         float (&g)[V]) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   int hs[3], ws[3];
   const int nh = fold_sources(h, H, pad, hs), nw = fold_sources(w, W, pad, ws);
-#pragma unroll
-  for (int i = 0; i < V; ++i) g[i] = 0.f;
   for (int a = 0; a < nh; ++a)
     for (int b = 0; b < nw; ++b) {
+      if (a == 0 && b == 0) continue;
       float t[V];
-      load_vec<T, V>(gout + (((long long)n * Hp + hs[a]) * Wp + ws[b]) * C + cv * V, t);
+      load_vec<T, V>(gout + (((idx_t)n * Hp + hs[a]) * Wp + ws[b]) * C + cv * V, t);
 #pragma unroll
       for (int i = 0; i < V; ++i) g[i] += t[i];
     }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void folded_grad(const T *__restrict__ gout, int n, int h, int w, int cv, int H, int W, int C, int pad,
+                                            float (&g)[V]) {
+  const int Wp = W + 2 * pad;
+  load_vec<T, V>(gout + (((idx_t)n * (H + 2 * pad) + h + pad) * Wp + w + pad) * C + cv * V, g);
+  if (fold_is_border(h, w, H, W, pad)) fold_extras<T, V>(gout, n, h, w, cv, H, W, C, pad, g);
 }
 
 __device__ __forceinline__ float act_grad_from_sign(float pre, int act) {
@@ -166,30 +190,49 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
   float mean[V], rstd[V], s1[V], s2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    mean[i] = stats[((long long)n * C + cv * V + i) * 2];
-    rstd[i] = stats[((long long)n * C + cv * V + i) * 2 + 1];
+    mean[i] = stats[((idx_t)n * C + cv * V + i) * 2];
+    rstd[i] = stats[((idx_t)n * C + cv * V + i) * 2 + 1];
     s1[i] = s2[i] = 0.f;
   }
   const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   if (pl < lanes) {
-    for (int p = p0 + pl; p < p1; p += lanes) {
-      const int h = p / W, w = p - h * W;
-      float g[V], xv[V];
-      folded_grad<T, V>(gout, n, h, w, cv, H, W, C, pad, g);
-      if (addend) {
-        float av[V];
-        load_vec<T, V>(addend + ((long long)n * HW + p) * C + cv * V, av);
+    constexpr int U = 4;                       // independent loads in flight per thread
+    const int Wp = W + 2 * pad;
+    for (int p = p0 + pl; p < p1; p += lanes * U) {
+      float g[U][V], xv[U][V];
+      int hh[U], ww[U];
 #pragma unroll
-        for (int i = 0; i < V; ++i) g[i] += av[i];
-      }
-      load_vec<T, V>(x + ((long long)n * HW + p) * C + cv * V, xv);
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + u * lanes;
+        const bool ok = pp < p1;
+        const int pc = ok ? pp : p;
+        hh[u] = pc / W; ww[u] = pc - hh[u] * W;
+        load_vec<T, V>(gout + (((idx_t)n * (H + 2 * pad) + hh[u] + pad) * Wp + ww[u] + pad) * C + cv * V, g[u]);
+        load_vec<T, V>(x + ((idx_t)n * HW + pc) * C + cv * V, xv[u]);
+        if (addend) {
+          float av[V];
+          load_vec<T, V>(addend + ((idx_t)n * HW + pc) * C + cv * V, av);
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (xv[i] - mean[i]) * rstd[i];
-        const float gg = g[i] * act_grad_from_sign(xh, act);
-        s1[i] += gg;
-        s2[i] = fmaf(gg, xh, s2[i]);
+          for (int i = 0; i < V; ++i) g[u][i] += av[i];
+        }
+        if (!ok) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) g[u][i] = 0.f;
+          hh[u] = -1;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (hh[u] >= 0 && fold_is_border(hh[u], ww[u], H, W, pad)) fold_extras<T, V>(gout, n, hh[u], ww[u], cv, H, W, C, pad, g[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float xh = (xv[u][i] - mean[i]) * rstd[i];
+          const float gg = g[u][i] * act_grad_from_sign(xh, act);
+          s1[i] += gg;
+          s2[i] = fmaf(gg, xh, s2[i]);
+        }
     }
   }
   __shared__ double sm[2][256];
@@ -205,7 +248,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
         a += sm[0][l * CV + cv];
         b += sm[1][l * CV + cv];
       }
-      double *dst = acc + ((long long)n * C + cv * V + i) * 2;
+      double *dst = acc + ((idx_t)n * C + cv * V + i) * 2;
       atomicAdd(dst, a);
       atomicAdd(dst + 1, b);
     }
@@ -222,11 +265,11 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
   const int CV = C / V;
   const int HW = H * W;
   const int Ho = H + 2 * out_pad, Wo = W + 2 * out_pad;
-  const long long total = (long long)N * Ho * Wo * CV;
+  const idx_t total = (idx_t)N * Ho * Wo * CV;
   const float inv_hw = 1.f / (float)HW;
-  for (long long oidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; oidx < total; oidx += (long long)gridDim.x * blockDim.x) {
+  for (idx_t oidx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; oidx < total; oidx += (idx_t)gridDim.x * blockDim.x) {
     const int cv = (int)(oidx % CV);
-    long long r = oidx / CV;
+    idx_t r = oidx / CV;
     const int wo = (int)(r % Wo);
     r /= Wo;
     const int ho = (int)(r % Ho);
@@ -239,7 +282,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
       store_vec<T, V>(dx + oidx * V, o);
       continue;
     }
-    const long long idx = (((long long)n * H + h) * W + w) * CV + cv;
+    const idx_t idx = (((idx_t)n * H + h) * W + w) * CV + cv;
     folded_grad<T, V>(gout, n, h, w, cv, H, W, C, pad, g);
     if (addend) {
       float av[V];
@@ -252,7 +295,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
       load_vec<T, V>(x + idx * V, xv);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const long long sc = (long long)n * C + cv * V + i;
+        const idx_t sc = (idx_t)n * C + cv * V + i;
         const float mean = stats[2 * sc], rstd = stats[2 * sc + 1];
         const float xh = (xv[i] - mean) * rstd;
         const float gg = g[i] * act_grad_from_sign(xh, act);
@@ -273,8 +316,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
 }
 
 template <typename T, int V>
-__global__ void act_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ y, T *__restrict__ dx, long long nvec, int act) {
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (long long)gridDim.x * blockDim.x) {
+__global__ void act_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ y, T *__restrict__ dx, idx_t nvec, int act) {
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (idx_t)gridDim.x * blockDim.x) {
     float g[V], yv[V], o[V];
     load_vec<T, V>(gy + idx * V, g);
     load_vec<T, V>(y + idx * V, yv);
@@ -293,10 +336,10 @@ __global__ void act_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ y
 template <typename T, int V>
 __global__ void maxpool2_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W, int C) {
   const int CV = C / V, Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)N * Ho * Wo * CV;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const idx_t total = (idx_t)N * Ho * Wo * CV;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    idx_t r = idx / CV;
     const int ow = (int)(r % Wo);
     r /= Wo;
     const int oh = (int)(r % Ho), n = (int)(r / Ho);
@@ -306,7 +349,7 @@ __global__ void maxpool2_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, 
     for (int dy = 0; dy < 2; ++dy)
       for (int dxx = 0; dxx < 2; ++dxx) {
         float v[V];
-        load_vec<T, V>(x + (((long long)n * H + 2 * oh + dy) * W + 2 * ow + dxx) * C + cv * V, v);
+        load_vec<T, V>(x + (((idx_t)n * H + 2 * oh + dy) * W + 2 * ow + dxx) * C + cv * V, v);
 #pragma unroll
         for (int i = 0; i < V; ++i) m[i] = (v[i] > m[i] || v[i] != v[i]) ? v[i] : m[i];
       }
@@ -318,17 +361,17 @@ template <typename T, int V>
 __global__ void maxpool2_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ x, const T *__restrict__ addend, T *__restrict__ gx, int N, int H,
                                     int W, int C) {
   const int CV = C / V, Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)N * Ho * Wo * CV;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const idx_t total = (idx_t)N * Ho * Wo * CV;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    idx_t r = idx / CV;
     const int ow = (int)(r % Wo);
     r /= Wo;
     const int oh = (int)(r % Ho), n = (int)(r / Ho);
     float v[4][V], g[V];
     load_vec<T, V>(gy + idx * V, g);
     for (int k = 0; k < 4; ++k)
-      load_vec<T, V>(x + (((long long)n * H + 2 * oh + (k >> 1)) * W + 2 * ow + (k & 1)) * C + cv * V, v[k]);
+      load_vec<T, V>(x + (((idx_t)n * H + 2 * oh + (k >> 1)) * W + 2 * ow + (k & 1)) * C + cv * V, v[k]);
     float o[4][V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -341,7 +384,7 @@ __global__ void maxpool2_bwd_kernel(const T *__restrict__ gy, const T *__restric
       for (int k = 0; k < 4; ++k) o[k][i] = (k == arg) ? g[i] : 0.f;
     }
     for (int k = 0; k < 4; ++k) {
-      const long long off = (((long long)n * H + 2 * oh + (k >> 1)) * W + 2 * ow + (k & 1)) * C + cv * V;
+      const idx_t off = (((idx_t)n * H + 2 * oh + (k >> 1)) * W + 2 * ow + (k & 1)) * C + cv * V;
       if (addend) {
         float av[V];
         load_vec<T, V>(addend + off, av);
@@ -370,10 +413,10 @@ __global__ void upsample2x_cat_fwd_kernel(const T *__restrict__ x, const T *__re
                                           int C1, int C2) {
   const int C = C1 + C2, CV = C / V, CV1 = C1 / V;
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long total = (long long)N * Ho * Wo * CV;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const idx_t total = (idx_t)N * Ho * Wo * CV;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % CV);
-    long long r = idx / CV;
+    idx_t r = idx / CV;
     const int ow = (int)(r % Wo);
     r /= Wo;
     const int oh = (int)(r % Ho), n = (int)(r / Ho);
@@ -384,16 +427,16 @@ __global__ void upsample2x_cat_fwd_kernel(const T *__restrict__ x, const T *__re
       up2_coords(oh, H, h0, h1, lh);
       up2_coords(ow, W, w0, w1, lw);
       float a[V], b[V], c[V], d[V];
-      const T *base = x + (long long)n * H * W * C1 + cv * V;
-      load_vec<T, V>(base + ((long long)h0 * W + w0) * C1, a);
-      load_vec<T, V>(base + ((long long)h0 * W + w1) * C1, b);
-      load_vec<T, V>(base + ((long long)h1 * W + w0) * C1, c);
-      load_vec<T, V>(base + ((long long)h1 * W + w1) * C1, d);
+      const T *base = x + (idx_t)n * H * W * C1 + cv * V;
+      load_vec<T, V>(base + ((idx_t)h0 * W + w0) * C1, a);
+      load_vec<T, V>(base + ((idx_t)h0 * W + w1) * C1, b);
+      load_vec<T, V>(base + ((idx_t)h1 * W + w0) * C1, c);
+      load_vec<T, V>(base + ((idx_t)h1 * W + w1) * C1, d);
       const float hh0 = 1.f - lh, ww0 = 1.f - lw;
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = hh0 * (ww0 * a[i] + lw * b[i]) + lh * (ww0 * c[i] + lw * d[i]);
     } else {
-      load_vec<T, V>(skip + (((long long)n * Ho + oh) * Wo + ow) * C2 + (cv - CV1) * V, o);
+      load_vec<T, V>(skip + (((idx_t)n * Ho + oh) * Wo + ow) * C2 + (cv - CV1) * V, o);
     }
     store_vec<T, V>(out + idx * V, o);
   }
@@ -405,12 +448,12 @@ __global__ void upsample2x_cat_bwd_kernel(const T *__restrict__ gout, T *__restr
                                           int C1, int C2) {
   const int C = C1 + C2, CV1 = C1 / V, CV2 = C2 / V;
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long total1 = (long long)N * H * W * CV1;
-  const long long total2 = gskip ? (long long)N * Ho * Wo * CV2 : 0;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total1 + total2; idx += (long long)gridDim.x * blockDim.x) {
+  const idx_t total1 = (idx_t)N * H * W * CV1;
+  const idx_t total2 = gskip ? (idx_t)N * Ho * Wo * CV2 : 0;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total1 + total2; idx += (idx_t)gridDim.x * blockDim.x) {
     if (idx < total1) {
       const int cv = (int)(idx % CV1);
-      long long r = idx / CV1;
+      idx_t r = idx / CV1;
       const int w = (int)(r % W);
       r /= W;
       const int h = (int)(r % H), n = (int)(r / H);
@@ -434,16 +477,16 @@ __global__ void upsample2x_cat_bwd_kernel(const T *__restrict__ gout, T *__restr
           if (w1 == w) ww += lw;
           if (ww == 0.f) continue;
           float g[V];
-          load_vec<T, V>(gout + (((long long)n * Ho + oh) * Wo + ow) * C + cv * V, g);
+          load_vec<T, V>(gout + (((idx_t)n * Ho + oh) * Wo + ow) * C + cv * V, g);
 #pragma unroll
           for (int i = 0; i < V; ++i) acc[i] = fmaf(wh * ww, g[i], acc[i]);
         }
       }
       store_vec<T, V>(gx + idx * V, acc);
     } else {
-      const long long j = idx - total1;
+      const idx_t j = idx - total1;
       const int cv = (int)(j % CV2);
-      const long long pix = j / CV2;
+      const idx_t pix = j / CV2;
       float g[V];
       load_vec<T, V>(gout + pix * C + C1 + cv * V, g);
       store_vec<T, V>(gskip + j * V, g);
@@ -452,10 +495,10 @@ __global__ void upsample2x_cat_bwd_kernel(const T *__restrict__ gout, T *__restr
 }
 
 template <typename T>
-__global__ void copy_channels_kernel(const T *__restrict__ src, T *__restrict__ dst, long long pixels, int C, int ss, int so, int ds, int doff) {
-  const long long total = pixels * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long p = idx / C;
+__global__ void copy_channels_kernel(const T *__restrict__ src, T *__restrict__ dst, idx_t pixels, int C, int ss, int so, int ds, int doff) {
+  const idx_t total = pixels * C;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
+    const idx_t p = idx / C;
     const int c = (int)(idx - p * C);
     dst[p * ds + doff + c] = src[p * ss + so + c];
   }
@@ -466,7 +509,7 @@ template <typename T>
 __global__ void plane_mean_fwd_kernel(const T *__restrict__ x, float *__restrict__ out, int HW, int C) {
   const int n = blockIdx.x, c = blockIdx.y;
   double s = 0.0;
-  for (int p = threadIdx.x; p < HW; p += blockDim.x) s += (double)to_f(x[((long long)n * HW + p) * C + c]);
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) s += (double)to_f(x[((idx_t)n * HW + p) * C + c]);
   __shared__ double sm[32];
   s = warp_sum_d(s);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -480,64 +523,64 @@ __global__ void plane_mean_fwd_kernel(const T *__restrict__ x, float *__restrict
 
 template <typename T>
 __global__ void plane_mean_bwd_kernel(const float *__restrict__ gout, T *__restrict__ gx, int N, int HW, int C) {
-  const long long total = (long long)N * HW * C;
+  const idx_t total = (idx_t)N * HW * C;
   const float inv = 1.f / (float)HW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C);
-    const int n = (int)(idx / ((long long)HW * C));
+    const int n = (int)(idx / ((idx_t)HW * C));
     gx[idx] = from_f<T>(gout[n * C + c] * inv);
   }
 }
 
 template <typename S, typename D>
-__global__ void cast_kernel(const S *__restrict__ s, D *__restrict__ d, long long n) {
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+__global__ void cast_kernel(const S *__restrict__ s, D *__restrict__ d, idx_t n) {
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (idx_t)gridDim.x * blockDim.x)
     d[idx] = from_f<D>(to_f(s[idx]));
 }
 
 // fp32 NCHW (module boundary) <-> T NHWC (internal)
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, T *__restrict__ dst, int N, int C, long long HW) {
-  const long long total = (long long)N * HW * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, T *__restrict__ dst, int N, int C, idx_t HW) {
+  const idx_t total = (idx_t)N * HW * C;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C);
-    const long long r = idx / C;
-    const long long p = r % HW;
+    const idx_t r = idx / C;
+    const idx_t p = r % HW;
     const int n = (int)(r / HW);
-    dst[idx] = from_f<T>(src[((long long)n * C + c) * HW + p]);
+    dst[idx] = from_f<T>(src[((idx_t)n * C + c) * HW + p]);
   }
 }
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict__ dst, int N, int C, long long HW) {
-  const long long total = (long long)N * HW * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long p = idx % HW;
-    const long long r = idx / HW;
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict__ dst, int N, int C, idx_t HW) {
+  const idx_t total = (idx_t)N * HW * C;
+  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
+    const idx_t p = idx % HW;
+    const idx_t r = idx / HW;
     const int c = (int)(r % C);
     const int n = (int)(r / C);
-    dst[idx] = to_f(src[((long long)n * HW + p) * C + c]);
+    dst[idx] = to_f(src[((idx_t)n * HW + p) * C + c]);
   }
 }
 
 // two 1-channel fp32 planes <-> one 2-channel NHWC tensor (torch.cat([a, b], 1) of trainer/reg.py:77 and its gradient split)
 template <typename T>
-__global__ void interleave2_kernel(const float *__restrict__ a, const float *__restrict__ b, T *__restrict__ dst, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+__global__ void interleave2_kernel(const float *__restrict__ a, const float *__restrict__ b, T *__restrict__ dst, idx_t n) {
+  for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (idx_t)gridDim.x * blockDim.x) {
     dst[2 * i] = from_f<T>(a[i]);
     dst[2 * i + 1] = from_f<T>(b[i]);
   }
 }
 template <typename T>
-__global__ void deinterleave2_kernel(const T *__restrict__ src, float *__restrict__ a, float *__restrict__ b, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+__global__ void deinterleave2_kernel(const T *__restrict__ src, float *__restrict__ a, float *__restrict__ b, idx_t n) {
+  for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (idx_t)gridDim.x * blockDim.x) {
     if (a) a[i] = to_f(src[2 * i]);
     if (b) b[i] = to_f(src[2 * i + 1]);
   }
 }
 
-inline int ew_blocks(long long work) {
-  long long b = (work + 255) / 256;
-  const long long cap = (long long)ctagan_num_sms() * 16;
+inline int ew_blocks(idx_t work) {
+  idx_t b = (work + 255) / 256;
+  const idx_t cap = (idx_t)ctagan_num_sms() * 16;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -565,8 +608,8 @@ static int reduce_chunks(int N, int HW, int C, int v, int &pix_per_block) {
   const int CV = C / v;
   const int lanes = 256 / CV > 0 ? 256 / CV : 1;
   // aim for ~4 CTAs per SM overall, at least 8 pixels per lane
-  long long want = ((long long)ctagan_num_sms() * 4 + N - 1) / N;
-  long long maxc = (HW + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+  idx_t want = ((idx_t)ctagan_num_sms() * 4 + N - 1) / N;
+  idx_t maxc = (HW + (idx_t)lanes * 16 - 1) / ((idx_t)lanes * 16);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   pix_per_block = (int)((HW + want - 1) / want);
@@ -575,6 +618,7 @@ static int reduce_chunks(int N, int HW, int C, int v, int &pix_per_block) {
 
 extern "C" int ctagan_instnorm_stats(const void *x, float *stats, double *acc, int N, int HW, int C, int dtype, void *stream) {
   CTAGAN_REQUIRE(x && stats && acc && N > 0 && HW > 0 && C > 0, "instnorm_stats: bad arguments");
+  CTAGAN_FITS32((int64_t)N * HW * C);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
@@ -584,7 +628,7 @@ extern "C" int ctagan_instnorm_stats(const void *x, float *stats, double *acc, i
     const int chunks = reduce_chunks(N, HW, C, v, ppb);
     dim3 grid(chunks, N);
     VEC_SWITCH(T, v, V, instnorm_partial_kernel<T, V><<<grid, 256, 0, st>>>((const T *)x, acc, HW, C, ppb));
-    instnorm_finalize_kernel<T><<<cdiv((long long)N * C, 128), 128, 0, st>>>((const T *)x, acc, stats, N, HW, C);
+    instnorm_finalize_kernel<T><<<cdiv((idx_t)N * C, 128), 128, 0, st>>>((const T *)x, acc, stats, N, HW, C);
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
@@ -593,10 +637,11 @@ extern "C" int ctagan_instnorm_stats(const void *x, float *stats, double *acc, i
 extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int res_pad, void *out, int N, int H, int W,
                                    int C, int pad, int act, int dtype, void *stream) {
   CTAGAN_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && pad < H && pad < W, "norm_act_pad: bad arguments");
+  CTAGAN_FITS32((int64_t)N * (H + 2 * pad) * (W + 2 * pad) * C);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C);
-    const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad) * (C / v);
+    const idx_t total = (idx_t)N * (H + 2 * pad) * (W + 2 * pad) * (C / v);
     VEC_SWITCH(T, v, V, norm_act_pad_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, stats, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act));
   });
   CTAGAN_LAUNCH_OK();
@@ -607,6 +652,7 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
                                        double *acc, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype,
                                        void *stream) {
   CTAGAN_REQUIRE(gout && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && out_pad >= 0, "norm_act_pad_bwd: bad arguments");
+  CTAGAN_FITS32((int64_t)N * (H + 2 * pad + 2 * out_pad) * (W + 2 * pad + 2 * out_pad) * C);
   CTAGAN_REQUIRE(!(stats || act != CTAGAN_ACT_NONE) || x, "norm_act_pad_bwd: x required when stats/act given");
   CTAGAN_REQUIRE(!stats || acc, "norm_act_pad_bwd: acc scratch required with stats");
   CTAGAN_REQUIRE(act != CTAGAN_ACT_TANH, "norm_act_pad_bwd: tanh unsupported here (use act_bwd)");
@@ -621,7 +667,7 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
       dim3 grid(chunks, N);
       VEC_SWITCH(T, v, V, norm_bwd_reduce_kernel<T, V><<<grid, 256, 0, st>>>((const T *)gout, (const T *)x, stats, (const T *)addend, acc, H, W, C, pad, act, ppb));
     }
-    const long long total = (long long)N * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / v);
+    const idx_t total = (idx_t)N * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / v);
     VEC_SWITCH(T, v, V, norm_bwd_apply_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, N, H, W, C, pad, act, out_pad));
   });
   CTAGAN_LAUNCH_OK();
@@ -630,6 +676,7 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
 
 extern "C" int ctagan_act_bwd(const void *gy, const void *y, void *dx, int64_t n, int act, int dtype, void *stream) {
   CTAGAN_REQUIRE(gy && y && dx && n > 0, "act_bwd: bad arguments");
+  CTAGAN_FITS32(n);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     int v = max_vec<T>();
@@ -642,10 +689,11 @@ extern "C" int ctagan_act_bwd(const void *gy, const void *y, void *dx, int64_t n
 
 extern "C" int ctagan_maxpool2_fwd(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream) {
   CTAGAN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: bad arguments (even H, W required)");
+  CTAGAN_FITS32((int64_t)N * H * W * C);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C);
-    const long long total = (long long)N * (H / 2) * (W / 2) * (C / v);
+    const idx_t total = (idx_t)N * (H / 2) * (W / 2) * (C / v);
     VEC_SWITCH(T, v, V, maxpool2_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, (T *)y, N, H, W, C));
   });
   CTAGAN_LAUNCH_OK();
@@ -654,10 +702,11 @@ extern "C" int ctagan_maxpool2_fwd(const void *x, void *y, int N, int H, int W, 
 
 extern "C" int ctagan_maxpool2_bwd(const void *gy, const void *x, const void *addend, void *gx, int N, int H, int W, int C, int dtype, void *stream) {
   CTAGAN_REQUIRE(gy && x && gx && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad arguments");
+  CTAGAN_FITS32((int64_t)N * H * W * C);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C);
-    const long long total = (long long)N * (H / 2) * (W / 2) * (C / v);
+    const idx_t total = (idx_t)N * (H / 2) * (W / 2) * (C / v);
     VEC_SWITCH(T, v, V, maxpool2_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gy, (const T *)x, (const T *)addend, (T *)gx, N, H, W, C));
   });
   CTAGAN_LAUNCH_OK();
@@ -667,10 +716,11 @@ extern "C" int ctagan_maxpool2_bwd(const void *gy, const void *x, const void *ad
 extern "C" int ctagan_upsample2x_cat_fwd(const void *x, const void *skip, void *out, int N, int H, int W, int C1, int C2, int dtype,
                                          void *stream) {
   CTAGAN_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0 && (C2 == 0 || skip), "upsample2x_cat_fwd: bad arguments");
+  CTAGAN_FITS32((int64_t)N * 4 * H * W * (C1 + C2));
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C1, C2);
-    const long long total = (long long)N * 4 * H * W * ((C1 + C2) / v);
+    const idx_t total = (idx_t)N * 4 * H * W * ((C1 + C2) / v);
     VEC_SWITCH(T, v, V, upsample2x_cat_fwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, (const T *)skip, (T *)out, N, H, W, C1, C2));
   });
   CTAGAN_LAUNCH_OK();
@@ -680,10 +730,11 @@ extern "C" int ctagan_upsample2x_cat_fwd(const void *x, const void *skip, void *
 extern "C" int ctagan_upsample2x_cat_bwd(const void *gout, void *gx, void *gskip, int N, int H, int W, int C1, int C2, int dtype,
                                          void *stream) {
   CTAGAN_REQUIRE(gout && gx && N > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0, "upsample2x_cat_bwd: bad arguments");
+  CTAGAN_FITS32((int64_t)N * 4 * H * W * (C1 + C2));
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C1, C2);
-    const long long total = (long long)N * H * W * (C1 / v) + (gskip ? (long long)N * 4 * H * W * (C2 / v) : 0);
+    const idx_t total = (idx_t)N * H * W * (C1 / v) + (gskip ? (idx_t)N * 4 * H * W * (C2 / v) : 0);
     VEC_SWITCH(T, v, V, upsample2x_cat_bwd_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gout, (T *)gx, (T *)gskip, N, H, W, C1, C2));
   });
   CTAGAN_LAUNCH_OK();
@@ -693,6 +744,7 @@ extern "C" int ctagan_upsample2x_cat_bwd(const void *gout, void *gx, void *gskip
 extern "C" int ctagan_copy_channels(const void *src, void *dst, int64_t pixels, int C, int src_stride, int src_off, int dst_stride,
                                     int dst_off, int dtype, void *stream) {
   CTAGAN_REQUIRE(src && dst && pixels > 0 && C > 0 && src_off + C <= src_stride && dst_off + C <= dst_stride, "copy_channels: bad arguments");
+  CTAGAN_FITS32((int64_t)pixels * (src_stride > dst_stride ? src_stride : dst_stride));
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     copy_channels_kernel<T><<<ew_blocks(pixels * C), 256, 0, st>>>((const T *)src, (T *)dst, pixels, C, src_stride, src_off, dst_stride, dst_off);
@@ -703,6 +755,7 @@ extern "C" int ctagan_copy_channels(const void *src, void *dst, int64_t pixels, 
 
 extern "C" int ctagan_plane_mean_fwd(const void *x, float *out, int N, int HW, int C, int dtype, void *stream) {
   CTAGAN_REQUIRE(x && out && N > 0 && HW > 0 && C > 0 && C <= 65535, "plane_mean_fwd: bad arguments");
+  CTAGAN_FITS32((int64_t)N * HW * C);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, { plane_mean_fwd_kernel<T><<<dim3(N, C), 256, 0, st>>>((const T *)x, out, HW, C); });
   CTAGAN_LAUNCH_OK();
@@ -711,14 +764,16 @@ extern "C" int ctagan_plane_mean_fwd(const void *x, float *out, int N, int HW, i
 
 extern "C" int ctagan_plane_mean_bwd(const float *gout, void *gx, int N, int HW, int C, int dtype, void *stream) {
   CTAGAN_REQUIRE(gout && gx && N > 0 && HW > 0 && C > 0, "plane_mean_bwd: bad arguments");
+  CTAGAN_FITS32((int64_t)N * HW * C);
   cudaStream_t st = (cudaStream_t)stream;
-  CTAGAN_DISPATCH_DTYPE(dtype, T, { plane_mean_bwd_kernel<T><<<ew_blocks((long long)N * HW * C), 256, 0, st>>>(gout, (T *)gx, N, HW, C); });
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { plane_mean_bwd_kernel<T><<<ew_blocks((idx_t)N * HW * C), 256, 0, st>>>(gout, (T *)gx, N, HW, C); });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
 
 extern "C" int ctagan_cast(const void *src, int sd, void *dst, int dd, int64_t n, void *stream) {
   CTAGAN_REQUIRE(src && dst && n > 0, "cast: bad arguments");
+  CTAGAN_FITS32(n);
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = ew_blocks(n);
   if (sd == CTAGAN_F32 && dd == CTAGAN_BF16) cast_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float *)src, (bf16 *)dst, n);
@@ -732,22 +787,25 @@ extern "C" int ctagan_cast(const void *src, int sd, void *dst, int dd, int64_t n
 
 extern "C" int ctagan_nchw_to_nhwc(const float *src, void *dst, int N, int C, int64_t HW, int dtype, void *stream) {
   CTAGAN_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
+  CTAGAN_FITS32((int64_t)N * C * HW);
   cudaStream_t st = (cudaStream_t)stream;
-  CTAGAN_DISPATCH_DTYPE(dtype, T, { nchw_to_nhwc_kernel<T><<<ew_blocks((long long)N * C * HW), 256, 0, st>>>(src, (T *)dst, N, C, HW); });
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { nchw_to_nhwc_kernel<T><<<ew_blocks((idx_t)N * C * HW), 256, 0, st>>>(src, (T *)dst, N, C, HW); });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
 
 extern "C" int ctagan_nhwc_to_nchw(const void *src, float *dst, int N, int C, int64_t HW, int dtype, void *stream) {
   CTAGAN_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad arguments");
+  CTAGAN_FITS32((int64_t)N * C * HW);
   cudaStream_t st = (cudaStream_t)stream;
-  CTAGAN_DISPATCH_DTYPE(dtype, T, { nhwc_to_nchw_kernel<T><<<ew_blocks((long long)N * C * HW), 256, 0, st>>>((const T *)src, dst, N, C, HW); });
+  CTAGAN_DISPATCH_DTYPE(dtype, T, { nhwc_to_nchw_kernel<T><<<ew_blocks((idx_t)N * C * HW), 256, 0, st>>>((const T *)src, dst, N, C, HW); });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
 
 extern "C" int ctagan_interleave2(const float *a, const float *b, void *dst, int64_t n, int dtype, void *stream) {
   CTAGAN_REQUIRE(a && b && dst && n > 0, "interleave2: bad arguments");
+  CTAGAN_FITS32(2 * n);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, { interleave2_kernel<T><<<ew_blocks(n), 256, 0, st>>>(a, b, (T *)dst, n); });
   CTAGAN_LAUNCH_OK();
@@ -756,6 +814,7 @@ extern "C" int ctagan_interleave2(const float *a, const float *b, void *dst, int
 
 extern "C" int ctagan_deinterleave2(const void *src, float *a, float *b, int64_t n, int dtype, void *stream) {
   CTAGAN_REQUIRE(src && (a || b) && n > 0, "deinterleave2: bad arguments");
+  CTAGAN_FITS32(2 * n);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, { deinterleave2_kernel<T><<<ew_blocks(n), 256, 0, st>>>((const T *)src, a, b, n); });
   CTAGAN_LAUNCH_OK();

@@ -83,6 +83,28 @@ class ConvPrim:
         for m in modes:
             self.packed(m, dtype)
 
+    def _version_key(self):
+        return (self.w._version, self.w.data_ptr(), _CACHE_EPOCH["value"])
+
+    def stale_entries(self, dtype: torch.dtype, modes=(0, 1)):
+        """(w, destination buffer, mode) for every packed copy that is out of date; marks them fresh (the caller packs them all
+        with ONE ctagan_pack_weights_multi launch).  Destination buffers persist, so CUDA graphs see stable pointers."""
+        out = []
+        ver = self._version_key()
+        for m in modes:
+            key = (m, dtype)
+            hit = self._cache.get(key)
+            if hit is not None and hit[0] == ver:
+                continue
+            if hit is not None and hit[1].dtype == dtype:
+                buf = hit[1]
+            else:
+                shape = (self.O, self.K, self.K, self.I) if m == 0 else (self.I, self.K, self.K, self.O)
+                buf = torch.empty(shape, dtype=dtype, device=self.w.device)
+            self._cache[key] = (ver, buf)
+            out.append((self.w.detach(), buf, m))
+        return out
+
     # I-channel input -> O-channel output, strided  (Conv2d forward / ConvTranspose2d input-gradient)
     def fprop(self, x, act=L.ACT_NONE, use_bias=True, pad=None):
         N, Hi, Wi, Ci = x.shape
@@ -112,8 +134,13 @@ class ConvPrim:
         return ops.conv_wgrad(gy, gx, g, want_bias, _ENGINE["value"])
 
 
-def _zeros_like_param(p):
-    return torch.zeros_like(p)
+def prepack_prims(prims, dtype):
+    """Re-pack every stale weight copy of a network with one kernel launch."""
+    entries = []
+    for prim in prims:
+        entries += prim.stale_entries(dtype)
+    if entries:
+        ops.pack_weights_multi(entries, dtype)
 
 
 # ======================================================================================================================

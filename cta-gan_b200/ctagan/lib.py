@@ -24,11 +24,18 @@ class ConvGeom(ctypes.Structure):
                 ("N", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "KH", "KW", "stride", "dil", "pad_h", "pad_w", "act", "dtype", "gy_margin")]
 
 
+class PackItem(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p), ("wp", ctypes.c_void_p), ("O", ctypes.c_int32), ("I", ctypes.c_int32), ("KH", ctypes.c_int32),
+                ("KW", ctypes.c_int32), ("mode", ctypes.c_int32)]
+
+
 def _ctype_of(decl: str):
     d = decl.strip()
     if "*" in d:
         if "ctagan_conv_geom" in d:
             return ctypes.POINTER(ConvGeom)
+        if "ctagan_pack_item" in d:
+            return ctypes.POINTER(PackItem)
         return ctypes.c_void_p
     base = d.split()[0] if d.split()[0] != "const" else d.split()[1]
     return {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
@@ -39,6 +46,7 @@ def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[object, List[object
     """{symbol: (restype, [argtypes])} for every prototype in include/ctagan.h."""
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
     protos = {}
     for m in re.finditer(r"(const\s+char\s*\*|int|size_t)\s*(ctagan_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3)

@@ -98,8 +98,7 @@ class Generator(nn.Module):
     def prepack(self):
         """Pack the current weights (bf16 / re-laid-out copies) on the current stream; lets several passes of this network run
         concurrently on side streams afterwards."""
-        for prim in self._get_plan().prims():
-            prim.prepack(E.get_precision())
+        E.prepack_prims(self._get_plan().prims(), E.get_precision())
 
     def forward(self, x):
         if x.shape[2] % 4 or x.shape[3] % 4:
@@ -174,8 +173,7 @@ class _DiscBase(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def prepack(self):
-        for prim in self._get_plan().prims():
-            prim.prepack(E.get_precision())
+        E.prepack_prims(self._get_plan().prims(), E.get_precision())
 
     def _run(self, x, sink=None, freeze=False):
         plan = self._get_plan()

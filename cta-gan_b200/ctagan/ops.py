@@ -291,3 +291,15 @@ def deinterleave2(src, need_a=True, need_b=True):
     _count(1)
     L.check(L.load().ctagan_deinterleave2(_p(src), _p(a), _p(b), N * H * W, dt(src), _stream()))
     return a, b
+
+
+def pack_weights_multi(entries, dtype):
+    """entries: list of (w fp32 OIHW, wp packed buffer, mode).  One kernel launch for all of them."""
+    n = len(entries)
+    arr = (L.PackItem * n)()
+    for k, (w, wp, mode) in enumerate(entries):
+        O, I, KH, KW = w.shape
+        arr[k] = L.PackItem(w.data_ptr(), wp.data_ptr(), O, I, KH, KW, mode)
+    ensure_device()
+    _count((n + 47) // 48)
+    L.check(L.load().ctagan_pack_weights_multi(arr, n, _DT[dtype], _stream()))

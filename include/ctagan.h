@@ -81,6 +81,15 @@ size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine);
  * mode 0: wp[O][kh][kw][I] = W[O][I][kh][kw];  mode 1: wp[I][kh][kw][O] = W[O][I][KH-1-kh][KW-1-kw]. */
 int ctagan_pack_weights(const float *w, void *wp, int O, int I, int KH, int KW, int mode, int dtype, void *stream);
 
+/* The same for many weights in ONE launch (all layers of a network x both layouts, after every optimiser step).
+ * `items` is a host array; it is copied into the kernel parameters. */
+typedef struct {
+  const float *w;
+  void *wp;
+  int32_t O, I, KH, KW, mode;
+} ctagan_pack_item;
+int ctagan_pack_weights_multi(const ctagan_pack_item *items, int n_items, int dtype, void *stream);
+
 /* InstanceNorm2d statistics (affine=False, eps=1e-5, biased variance; Model/CycleGan.py:12,16,29,37,52,82,86,90,
  * trainer/layers.py:14): x[N][HW][C] -> stats[N][C][2] = (mean, rstd) fp32.  acc: caller scratch, N*C*2 doubles. */
 int ctagan_instnorm_stats(const void *x, float *stats, double *acc, int N, int HW, int C, int dtype, void *stream);
