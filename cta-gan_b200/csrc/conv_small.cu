@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) conv_fewout_kernel(ctagan_conv_geom g, co
       const T *xp = x + (((long long)n * g.Hi + ih) * g.Wi + iw) * g.Ci + cs * 8;
       const float *wrow = ws + (kh * g.KW + kw) * g.Ci + cs * 8;
       for (int c0 = 0; c0 < g.Ci; c0 += 64) {
+        if (c0 + cs * 8 >= g.Ci) break;
         float xv[8];
         load_vec<T, 8>(xp + c0, xv);
         for (int co = 0; co < g.Co; ++co) {
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(ctagan_conv_geom g
 
 int ctagan_conv_small_kind(const ctagan_conv_geom *g) {
   if (g->Ci <= 2 && g->Co % 8 == 0 && g->KH * g->KW * g->Ci * 64 * 4 <= 48 * 1024) return 1;
-  if (g->Co <= 2 && g->Ci % 64 == 0 && (long long)g->Co * g->KH * g->KW * g->Ci * 4 <= 96 * 1024) return 2;
+  if (g->Co <= 2 && g->Ci % 8 == 0 && (long long)g->Co * g->KH * g->KW * g->Ci * 4 <= 96 * 1024) return 2;
   return 0;
 }
 

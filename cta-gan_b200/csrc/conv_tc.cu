@@ -31,7 +31,7 @@ struct TcParams {
   int n_taps;
   short tap_dh[MAX_TAPS];      // input offset of the tap relative to (i*stride, j*stride)
   short tap_dw[MAX_TAPS];
-  int tap_w_col[MAX_TAPS];     // column (element) offset of the tap in the packed weight row
+  int tap_w_col[MAX_TAPS];     // tap index in the packed weight [O][tap][Ci] (3-D map: channels past Ci are zero-filled)
   int Ci, Co;
   int stride;                  // input step per output position (mode 1)
   int Hv, Wv;                  // mode 0: virtual (input) grid per image
@@ -153,6 +153,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *smem_dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *smem_dst, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
@@ -217,7 +224,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int t = blockIdx.x;
   const int ci_t = t % p.ci_tiles; t /= p.ci_tiles;
-  const int co_t = t % (p.Co / WG_M); t /= (p.Co / WG_M);
+  const int co_tiles = (p.Co + WG_M - 1) / WG_M;
+  const int co_t = t % co_tiles; t /= co_tiles;
   const int tap = t;
   const int kh = tap / p.KW, kw = tap - kh * p.KW;
   const int split = blockIdx.y;
@@ -288,6 +296,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;          // co within the tile
     float *dst = p.ws + (((long long)split * p.Co + co0 + row) * p.ntaps + tap) * p.Ci + ci0;
+    const bool row_ok = co0 + row < p.Co;
     if (n_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -302,9 +311,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
 #pragma unroll
         for (int e = 0; e < 32; ++e) r[e] = 0u;
       }
-      uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
+      if (row_ok && ci0 + c < p.Ci) {           // Ci is a multiple of 32 here
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) d4[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+        for (int g = 0; g < 8; ++g) d4[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+      }
     }
   }
   tc_fence_before();
@@ -379,7 +390,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const int tile_i0 = (tile / p.tiles_w) * (TILE_M >> p.bw_log2);   // mode 1: tile origin in output positions
   const int tile_j0 = (tile % p.tiles_w) * BW;
   const int co0 = blockIdx.y * BN;
-  const int groups = p.Ci / (CHUNK_K * KCH);                  // stages per tap
+  const int groups = (p.Ci + CHUNK_K * KCH - 1) / (CHUNK_K * KCH);   // stages per tap (channel tail = TMA zero fill)
   const int NS = p.n_stages;
 
   if (warp == 0 && lane == 0) {
@@ -416,7 +427,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const int ch = (gk * KCH + k) * CHUNK_K;
             if (p.mode == 0) tma_load_2d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, row2d);
             else tma_load_4d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
-            tma_load_2d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, wcol + ch, co0);
+            tma_load_3d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, ch, wcol, co0);
           }
           if (++s == NS) { s = 0; ph ^= 1u; }
         }
@@ -469,7 +480,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
       tmem_ld_wait();
-      if (valid) {
+      if (valid && co0 + c < p.Co) {            // Co is a multiple of 32 here; tiles may overhang it
         float v[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
@@ -548,6 +559,27 @@ int make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols
   return CTAGAN_OK;
 }
 
+// packed weights [O][taps][Ci] as a 3-D map, box {64 ch, 1 tap, box_rows}: channel / row overhang is zero-filled by TMA
+int make_map_w3d(CUtensorMap *map, const void *base, int O, int taps, int Ci, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    ctagan_set_error("cuTensorMapEncodeTiled unavailable from the driver");
+    return CTAGAN_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)Ci, (cuuint64_t)taps, (cuuint64_t)O};
+  cuuint64_t strides[2] = {(cuuint64_t)Ci * 2, (cuuint64_t)taps * Ci * 2};
+  cuuint32_t box[3] = {CHUNK_K, 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctagan_set_error("cuTensorMapEncodeTiled(w3d) failed (%d): O=%d taps=%d Ci=%d box_rows=%u", (int)r, O, taps, Ci, box_rows);
+    return CTAGAN_ERR_CUDA;
+  }
+  return CTAGAN_OK;
+}
+
 template <int BN, int KCH>
 int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, dim3 grid, cudaStream_t st) {
   using Cfg = TcConfig<BN, KCH>;
@@ -579,14 +611,14 @@ int pick_bn(long long m_tiles, int Co) {
   // generator chains of a batch-1 step share the chip); N=64 only for the smallest grids.
   if (Co % 256 == 0 && m_tiles * (Co / 256) >= sms) return 256;
   if (Co % 128 == 0 && m_tiles * (Co / 128) >= sms / 3) return 128;
-  if (Co % 64 == 0) return 64;
+  return 64;                                 // also Co = 32 / 96 ...: the tile overhang is zero-filled and masked
   return 0;
 }
 
 int make_map_4d(CUtensorMap *map, const void *base, int N, int H, int W, int C, int bw, int bh, int estr_hw);
 
 // launch one tcgen05 conv with the tap table already in p; x described by (mode 0) [rows][Ci] or (mode 1) [N][Hi][Wi][Ci]
-int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, int w_cols, cudaStream_t st) {
+int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, int w_taps, cudaStream_t st) {
   CUtensorMap mx, mw;
   int rc;
   if (p.mode == 0) {
@@ -597,9 +629,9 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
   }
   if (rc) return rc;
   const int bn = pick_bn((long long)N * p.tiles_per_img, p.Co);
-  rc = make_map_2d(&mw, wp, (uint64_t)p.Co, (uint64_t)w_cols, (uint32_t)bn);
+  rc = make_map_w3d(&mw, wp, p.Co, w_taps, p.Ci, (uint32_t)bn);
   if (rc) return rc;
-  dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)(p.Co / bn));
+  dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
   int kch = (p.Ci % 128 == 0 && bn < 256) ? 2 : 1;      // BN=256 keeps 64-channel stages (4 of them fit; 2-chunk stages would leave 2)
   if (kch == 2) {
     switch (bn) {
@@ -629,7 +661,7 @@ int ceil_log2(int v) {
 // Which tcgen05 formulation serves this geometry: 0 none, 1 pitch trick, 2 strided 4-D boxes, 3 output-phase decomposition
 static int tc_gather_kind(const ctagan_conv_geom *g) {
   if (g->dtype != CTAGAN_BF16) return 0;
-  if (g->Ci % CHUNK_K || g->Co % 64) return 0;
+  if (g->Ci % 8 || g->Ci < 32 || g->Co % 32) return 0;       // 16-byte pixel rows; channel tails are TMA zero fill + masked stores
   if (g->KH * g->KW > MAX_TAPS) return 0;
   if ((long long)g->N * g->Ho * g->Wo < 512) return 0;    // tiny maps: launch-latency bound either way -> CUDA-core kernel
   if (g->dil == 1) {
@@ -658,7 +690,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   p.out_H = g->Ho; p.out_W = g->Wo; p.sy = p.sx = 1; p.ay = p.ax = 0;
   p.act = g->act; p.bias = bias; p.out = (bf16 *)y;
   const int ntaps = g->KH * g->KW;
-  const int w_cols = ntaps * g->Ci;
+  const int w_taps = ntaps;
   if (kind == 1 || kind == 2) {
     p.n_taps = ntaps;
     for (int kh = 0; kh < g->KH; ++kh)
@@ -666,7 +698,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
         const int t = kh * g->KW + kw;
         p.tap_dh[t] = (short)(kh - g->pad_h);
         p.tap_dw[t] = (short)(kw - g->pad_w);
-        p.tap_w_col[t] = t * g->Ci;
+        p.tap_w_col[t] = t;
       }
     p.Hov = g->Ho; p.Wov = g->Wo;
     if (kind == 1) {
@@ -679,7 +711,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
       p.tiles_w = (g->Wo + BW - 1) / BW;
       p.tiles_per_img = p.tiles_w * ((g->Ho + BH - 1) / BH);
     }
-    return run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_cols, st);
+    return run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_taps, st);
   }
   // kind 3: input dilation 2 (input gradient of a stride-2 conv == ConvTranspose2d forward).  Output pixel h = 2i + r reads
   // x[i + e - u] with weight tap kh' = 2u + a (a = (r + pad) & 1, e = (r + pad - a) / 2): one stride-1 launch per output parity.
@@ -693,7 +725,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
           // gather form: y[h] += x[(h + kh - pad)/2] * wp[kh]  ->  with h = 2i + rh:  x[i + (rh + kh - pad)/2]
           p.tap_dh[t] = (short)((rh + kh - g->pad_h) / 2);
           p.tap_dw[t] = (short)((rw + kw - g->pad_w) / 2);
-          p.tap_w_col[t] = (kh * g->KW + kw) * g->Ci;
+          p.tap_w_col[t] = kh * g->KW + kw;
           ++t;
         }
       (void)eh; (void)ew;
@@ -706,7 +738,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
       const int BW = 1 << p.bw_log2, BH = TILE_M >> p.bw_log2;
       p.tiles_w = (p.Wov + BW - 1) / BW;
       p.tiles_per_img = p.tiles_w * ((p.Hov + BH - 1) / BH);
-      int rc = run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_cols, st);
+      int rc = run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_taps, st);
       if (rc) return rc;
     }
   return CTAGAN_OK;
@@ -742,19 +774,19 @@ struct WgPlan {
 bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
   if (g->dtype != CTAGAN_BF16 || g->dil != 1) return false;
   if (g->stride > 2) return false;
-  if (g->Co % WG_M || g->Ci % 64) return false;
+  if (g->Co % 32 || g->Ci % 32) return false;              // tiles overhang with TMA zero fill, stores are masked
   if (g->KH * g->KW > MAX_TAPS) return false;
   const int m = g->gy_margin;
   const int Hvld = g->Ho - 2 * m, Wvld = g->Wo - 2 * m;
   if (Hvld <= 0 || Wvld <= 0) return false;
   if ((long long)g->N * Hvld * Wvld < 512) return false;   // tiny maps stay on the CUDA-core kernel
-  pl.bnw = (g->Ci % 256 == 0) ? 256 : (g->Ci % 128 == 0 ? 128 : 64);
+  pl.bnw = g->Ci > 128 ? 256 : (g->Ci > 64 ? 128 : 64);
   pl.bkw = Wvld >= 64 ? 64 : (Wvld > 16 ? 32 : 16);
   pl.bkh = 64 / pl.bkw;
   pl.rb = (Hvld + pl.bkh - 1) / pl.bkh;
   pl.cb = (Wvld + pl.bkw - 1) / pl.bkw;
   pl.total_chunks = g->N * pl.rb * pl.cb;
-  pl.tiles = g->KH * g->KW * (g->Co / WG_M) * (g->Ci / pl.bnw);
+  pl.tiles = g->KH * g->KW * ((g->Co + WG_M - 1) / WG_M) * ((g->Ci + pl.bnw - 1) / pl.bnw);
   int splits = (ctagan_num_sms() + pl.tiles - 1) / pl.tiles;
   const int max_splits = (pl.total_chunks + 3) / 4;         // at least 4 chunks (256 pixels) per CTA
   if (splits > max_splits) splits = max_splits;
@@ -807,7 +839,7 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   WgParams p;
   p.ntaps = g->KH * g->KW; p.KW = g->KW; p.Co = g->Co; p.Ci = g->Ci; p.stride = g->stride; p.pad = g->pad_h;
   p.margin = g->gy_margin; p.rb = pl.rb; p.cb = pl.cb; p.bkh = pl.bkh; p.bkw = pl.bkw;
-  p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.ci_tiles = g->Ci / pl.bnw; p.ws = (float *)workspace;
+  p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.ci_tiles = (g->Ci + pl.bnw - 1) / pl.bnw; p.ws = (float *)workspace;
   dim3 grid((unsigned)pl.tiles, (unsigned)pl.splits);
   switch (pl.bnw) {
     case 256: rc = launch_wg<256>(my, mx, p, grid, st); break;

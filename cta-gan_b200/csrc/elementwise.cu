@@ -1,6 +1,7 @@
 // Bandwidth-bound NHWC kernels around the convolutions: InstanceNorm statistics, fused normalise+activation+residual+
 // reflection-pad and its backward, pooling, bilinear 2x upsample + concat, plane means, casts.
 // All are coalesced along the channel (innermost) dimension with 16-byte vectors when C allows it.
+#include <stdlib.h>
 #include "common.cuh"
 
 // All index arithmetic in this file is 32-bit (64-bit integer division costs ~100 instructions on the SM and dominated these
@@ -609,7 +610,9 @@ static int reduce_chunks(int N, int HW, int C, int v, int &pix_per_block) {
   const int lanes = 256 / CV > 0 ? 256 / CV : 1;
   // aim for ~4 CTAs per SM overall, at least 8 pixels per lane
   idx_t want = ((idx_t)ctagan_num_sms() * 4 + N - 1) / N;
-  idx_t maxc = (HW + (idx_t)lanes * 16 - 1) / ((idx_t)lanes * 16);
+  static int ppl = 0;
+  if (!ppl) { const char *e = getenv("CTAGAN_RED_PPL"); ppl = e ? atoi(e) : 16; if (ppl < 1) ppl = 16; }
+  idx_t maxc = (HW + (idx_t)lanes * ppl - 1) / ((idx_t)lanes * ppl);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   pix_per_block = (int)((HW + want - 1) / want);

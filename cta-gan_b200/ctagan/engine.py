@@ -136,6 +136,11 @@ class ConvPrim:
 
 def prepack_prims(prims, dtype):
     """Re-pack every stale weight copy of a network with one kernel launch."""
+    import os
+    if os.environ.get("CTAGAN_PACK_MULTI", "1") == "0":
+        for prim in prims:
+            prim.prepack(dtype)
+        return
     entries = []
     for prim in prims:
         entries += prim.stale_entries(dtype)
