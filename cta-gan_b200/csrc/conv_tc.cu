@@ -340,26 +340,36 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restr
   }
 }
 
-// db[c] = sum over pixels of gy[p][c]   (bias gradient, only when requested)
-__global__ void colsum_kernel(const bf16 *__restrict__ gy, float *__restrict__ db, long long pixels, int C) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lanes = blockDim.x >> 5, pl = threadIdx.x >> 5;
-  float s = 0.f;
-  if (c < C)
-    for (long long p = pl; p < pixels; p += lanes) s += __bfloat162float(gy[p * C + c]);
-  __shared__ float sm[32][33];
-  sm[pl][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (pl == 0 && c < C) {
-    float t = 0.f;
-    for (int l = 0; l < lanes; ++l) t += sm[l][threadIdx.x & 31];
-    db[c] = t;
+// db[c] = sum over pixels of gy[p][c]   (bias gradient, only when requested).  grid.x = pixel chunks; block = 8 pixel lanes x 32
+// channel pairs (C <= 64 per pass); partial sums go to db by fp32 atomics (db is zeroed by the caller).
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16 *__restrict__ gy, float *__restrict__ db, long long pixels, int C,
+                                                     long long pix_per_block) {
+  const int cp = threadIdx.x & 31, pl = threadIdx.x >> 5;      // channel pair, pixel lane
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(pixels, p0 + pix_per_block);
+  __shared__ float sm[8][64];
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + cp * 2;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < C)
+      for (long long p = p0 + pl; p < p1; p += 8) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(gy + p * C + c);
+        s0 += __bfloat162float(v.x);
+        s1 += __bfloat162float(v.y);
+      }
+    __syncthreads();
+    sm[pl][cp * 2] = s0;
+    sm[pl][cp * 2 + 1] = s1;
+    __syncthreads();
+    if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) t += sm[l][threadIdx.x];
+      atomicAdd(db + c0 + threadIdx.x, t);
+    }
   }
 }
 
-// One pipeline stage carries KCH consecutive 64-channel chunks of one filter tap (KCH x {A 128x64, B BNx64}).  Measured on B200:
-// a producer iteration (mbarrier try_wait + expect_tx + TMA issue) costs ~300 + 100 cycles per TMA op and an MMA-issuer iteration
-// (try_wait + commit) ~500 cycles, so a 64-channel stage (128..512 tensor cycles) is issue-bound; KCH=2 halves that overhead.
 template <int BN, int KCH>
 struct TcConfig {
   static constexpr int A_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB per chunk
@@ -853,7 +863,12 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>((const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci);
   CTAGAN_LAUNCH_OK();
   if (db) {
-    colsum_kernel<<<(g->Co + 31) / 32, 1024, 0, st>>>((const bf16 *)gy, db, (long long)g->N * g->Ho * g->Wo, g->Co);
+    const long long pixels = (long long)g->N * g->Ho * g->Wo;
+    long long blocks = (pixels + 511) / 512;
+    if (blocks > 2LL * ctagan_num_sms()) blocks = 2LL * ctagan_num_sms();
+    const long long ppb = (pixels + blocks - 1) / blocks;
+    CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
+    colsum_kernel<<<(int)((pixels + ppb - 1) / ppb), 256, 0, st>>>((const bf16 *)gy, db, pixels, g->Co, ppb);
     CTAGAN_LAUNCH_OK();
   }
   return CTAGAN_OK;

@@ -11,6 +11,32 @@ typedef int idx_t;
 
 namespace {
 
+// (mean, rstd) of V consecutive channels = 2V consecutive floats of stats[N][C][2]: fetched with 16-byte loads
+template <int V>
+__device__ __forceinline__ void load_stats(const float *__restrict__ sp, float (&mean)[V], float (&rstd)[V]) {
+  if constexpr (V >= 2) {
+#pragma unroll
+    for (int i = 0; i < V; i += 2) {
+      const float4 t = *reinterpret_cast<const float4 *>(sp + 2 * i);
+      mean[i] = t.x; rstd[i] = t.y; mean[i + 1] = t.z; rstd[i + 1] = t.w;
+    }
+  } else {
+    mean[0] = sp[0]; rstd[0] = sp[1];
+  }
+}
+template <int V>
+__device__ __forceinline__ void load_acc_means(const double *__restrict__ ap, float inv_hw, float (&m1)[V], float (&m2)[V]) {
+  if constexpr (V >= 2) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const double2 t = *reinterpret_cast<const double2 *>(ap + 2 * i);
+      m1[i] = (float)(t.x * (double)inv_hw); m2[i] = (float)(t.y * (double)inv_hw);
+    }
+  } else {
+    m1[0] = (float)(ap[0] * (double)inv_hw); m2[0] = (float)(ap[1] * (double)inv_hw);
+  }
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
@@ -114,9 +140,10 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__
     float v[V];
     load_vec<T, V>(x + (((idx_t)n * H + h) * W + w) * C + cv * V, v);
     if (stats) {
-      const float *sp = stats + ((idx_t)n * C + cv * V) * 2;
+      float mean[V], rstd[V];
+      load_stats<V>(stats + ((idx_t)n * C + cv * V) * 2, mean, rstd);
 #pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = (v[i] - sp[2 * i]) * sp[2 * i + 1];
+      for (int i = 0; i < V; ++i) v[i] = (v[i] - mean[i]) * rstd[i];
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = apply_act(v[i], act);
@@ -189,12 +216,9 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
   const int HW = H * W;
   float mean[V], rstd[V], s1[V], s2[V];
+  load_stats<V>(stats + ((idx_t)n * C + cv * V) * 2, mean, rstd);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    mean[i] = stats[((idx_t)n * C + cv * V + i) * 2];
-    rstd[i] = stats[((idx_t)n * C + cv * V + i) * 2 + 1];
-    s1[i] = s2[i] = 0.f;
-  }
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   if (pl < lanes) {
     constexpr int U = 4;                       // independent loads in flight per thread
@@ -292,16 +316,16 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
       for (int i = 0; i < V; ++i) g[i] += av[i];
     }
     if (stats) {
-      float xv[V];
+      float xv[V], mean[V], rstd[V], m1[V], m2[V];
       load_vec<T, V>(x + idx * V, xv);
+      const idx_t sc0 = (idx_t)n * C + cv * V;
+      load_stats<V>(stats + 2 * sc0, mean, rstd);
+      load_acc_means<V>(acc + 2 * sc0, inv_hw, m1, m2);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const idx_t sc = (idx_t)n * C + cv * V + i;
-        const float mean = stats[2 * sc], rstd = stats[2 * sc + 1];
-        const float xh = (xv[i] - mean) * rstd;
+        const float xh = (xv[i] - mean[i]) * rstd[i];
         const float gg = g[i] * act_grad_from_sign(xh, act);
-        const float m1 = (float)(acc[2 * sc] * (double)inv_hw), m2 = (float)(acc[2 * sc + 1] * (double)inv_hw);
-        o[i] = rstd * (gg - m1 - xh * m2);
+        o[i] = rstd[i] * (gg - m1[i] - xh * m2[i]);
       }
     } else if (act != CTAGAN_ACT_NONE) {
       float xv[V];

@@ -267,6 +267,10 @@ class Discriminator_m(_DiscBase):
             self._plans[i] = plan
         return plan
 
+    def prepack(self):
+        for i in range(self.num_D):
+            E.prepack_prims(self._scale_plan(i).prims(), E.get_precision())
+
     def forward(self, x, freeze=False):
         result = []
         cur = x
@@ -410,11 +414,18 @@ class Reg(nn.Module):
         self._plan = None
         return super()._apply(fn, *a, **k)
 
-    def forward(self, img_a, img_b, apply_on=None):
+    def _get_plan(self):
         params = list(self.parameters())
         if self._plan is None or any(a is not b for a, b in zip(self._plan.params, params)):
             self._plan = E.RegPlan(params)
-        return _RegFn.apply(self._plan, img_a, img_b, *params)
+        return self._plan
+
+    def prepack(self):
+        E.prepack_prims(self._get_plan().prims(), E.get_precision())
+
+    def forward(self, img_a, img_b, apply_on=None):
+        plan = self._get_plan()
+        return _RegFn.apply(plan, img_a, img_b, *plan.params)
 
 
 class _WarpFn(torch.autograd.Function):

@@ -348,6 +348,8 @@ class Reg_Trainer(_TrainerBase):
         real_A, real_B = tensors[0], tensors[-1]
         self.optimizer_R_A.zero_grad(set_to_none=True)                                     # RegTrainer.py:173-187
         self.optimizer_G.zero_grad(set_to_none=True)
+        for net in (self.netG_A2B, self.R_A, self.netD_B):      # one re-pack launch per network (weights changed last step)
+            net.prepack()
         fake_B = self.netG_A2B(real_A)
         Trans = self.R_A(fake_B, real_B)
         SysRegist_A2B = self.spatial_transform(fake_B, Trans)
@@ -364,6 +366,7 @@ class Reg_Trainer(_TrainerBase):
         self.optimizer_G.step()
 
         self.optimizer_D_B.zero_grad(set_to_none=True)                                     # :189-198
+        self.netG_A2B.prepack()                                  # the generator was just updated
         with torch.no_grad():
             fake_B = self.netG_A2B(real_A)
         loss_D_B = self._loss_D(fake_B, real_B)
