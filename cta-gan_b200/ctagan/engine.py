@@ -393,6 +393,17 @@ class RegPlan:
         w, b = nxt(); self.output = ConvPrim(w, b, 1, 1)
         self.params = list(params)
 
+    def prims(self):
+        out = []
+        for conv, rb in self.down:
+            out += [conv, rb.c1, rb.c2]
+        out.append(self.c1)
+        for rb in self.t:
+            out += [rb.c1, rb.c2]
+        out.append(self.c2)
+        out += list(self.up) + [self.refine0.c1, self.refine0.c2, self.refine1, self.output]
+        return out
+
 
 def reg_forward(plan: RegPlan, img_a: torch.Tensor, img_b: torch.Tensor, save: bool):
     T = get_precision()
