@@ -118,6 +118,148 @@ __global__ void __launch_bounds__(256) conv_fewout_kernel(ctagan_conv_geom g, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Register-tiled versions for stride 1, dilation 1 (the 7x7 generator head/tail at full resolution, where these layers cost most).
+// Each thread produces PX = 4 consecutive output pixels of one row, so that every weight fetched from shared memory feeds 4x the
+// FMAs and the input row segment (PX + KW - 1 positions) is loaded once per kernel row and reused across the KW taps.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PX = 4;
+
+// many -> few (Co <= 2): 8 threads per pixel group, each owning 8 of every 64 input channels.
+template <typename T, int KW>
+__global__ void __launch_bounds__(256) conv_fewout_tiled_kernel(ctagan_conv_geom g, const T *__restrict__ x, const T *__restrict__ wp,
+                                                                const float *__restrict__ bias, T *__restrict__ y) {
+  extern __shared__ float ws[];   // [Co][ntaps][Ci]
+  const int ntaps = g.KH * KW, KC = ntaps * g.Ci;
+  for (int i = threadIdx.x; i < g.Co * KC; i += 256) ws[i] = to_f(wp[i]);
+  __syncthreads();
+  const int groups_w = (g.Wo + PX - 1) / PX;
+  const long long G = (long long)g.N * g.Ho * groups_w;
+  const int cs = threadIdx.x & 7;
+  long long gi = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool live = gi < G;
+  if (!live) gi = G - 1;
+  const int gw = (int)(gi % groups_w);
+  const long long q = gi / groups_w;
+  const int oh = (int)(q % g.Ho), n = (int)(q / g.Ho);
+  const int ow0 = gw * PX;
+  float acc[2][PX];
+#pragma unroll
+  for (int co = 0; co < 2; ++co)
+#pragma unroll
+    for (int p = 0; p < PX; ++p) acc[co][p] = 0.f;
+  for (int c0 = 0; c0 < g.Ci; c0 += 64) {
+    if (c0 + cs * 8 >= g.Ci) break;
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int ih = oh + kh - g.pad_h;
+      if (ih < 0 || ih >= g.Hi) continue;
+      float xw[PX + KW - 1][8];
+      const T *xrow = x + ((long long)n * g.Hi + ih) * g.Wi * g.Ci + c0 + cs * 8;
+#pragma unroll
+      for (int j = 0; j < PX + KW - 1; ++j) {
+        const int iw = ow0 + j - g.pad_w;
+        if (iw >= 0 && iw < g.Wi) load_vec<T, 8>(xrow + (long long)iw * g.Ci, xw[j]);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xw[j][e] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const float *wrow = ws + (kh * KW + kw) * g.Ci + c0 + cs * 8;
+        for (int co = 0; co < g.Co; ++co) {
+          const float4 w0 = *reinterpret_cast<const float4 *>(wrow + co * KC);
+          const float4 w1 = *reinterpret_cast<const float4 *>(wrow + co * KC + 4);
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            float s = acc[co][p];
+            s = fmaf(xw[p + kw][0], w0.x, s); s = fmaf(xw[p + kw][1], w0.y, s); s = fmaf(xw[p + kw][2], w0.z, s); s = fmaf(xw[p + kw][3], w0.w, s);
+            s = fmaf(xw[p + kw][4], w1.x, s); s = fmaf(xw[p + kw][5], w1.y, s); s = fmaf(xw[p + kw][6], w1.z, s); s = fmaf(xw[p + kw][7], w1.w, s);
+            acc[co][p] = s;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 2; ++co)
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      float v = acc[co][p];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      acc[co][p] = v;
+    }
+  if (live && cs == 0) {
+    const long long base = ((long long)n * g.Ho + oh) * g.Wo + ow0;
+    for (int p = 0; p < PX && ow0 + p < g.Wo; ++p)
+      for (int co = 0; co < g.Co; ++co)
+        y[(base + p) * g.Co + co] = from_f<T>(apply_act(acc[co][p] + (bias ? bias[co] : 0.f), g.act));
+  }
+}
+
+// few -> many (Ci <= 2): thread = (pixel group of 4, 8 output channels)
+template <typename T, int KW>
+__global__ void __launch_bounds__(256) conv_fewin_tiled_kernel(ctagan_conv_geom g, const T *__restrict__ x, const T *__restrict__ wp,
+                                                               const float *__restrict__ bias, T *__restrict__ y) {
+  extern __shared__ float ws[];   // [ntaps*Ci][64]
+  const int ntaps = g.KH * KW, KC = ntaps * g.Ci;
+  const int co_blk = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < KC * 64; i += 256) {
+    const int k = i / 64, c = i - k * 64;
+    ws[i] = (co_blk + c < g.Co) ? to_f(wp[(long long)(co_blk + c) * KC + k]) : 0.f;
+  }
+  __syncthreads();
+  const int groups_w = (g.Wo + PX - 1) / PX;
+  const long long G = (long long)g.N * g.Ho * groups_w;
+  const int cg = threadIdx.x & 7;
+  const long long gi = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (gi >= G || co_blk + cg * 8 >= g.Co) return;
+  const int gw = (int)(gi % groups_w);
+  const long long q = gi / groups_w;
+  const int oh = (int)(q % g.Ho), n = (int)(q / g.Ho);
+  const int ow0 = gw * PX;
+  float acc[PX][8];
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = bias ? bias[co_blk + cg * 8 + j] : 0.f;
+  for (int ci = 0; ci < g.Ci; ++ci)
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int ih = oh + kh - g.pad_h;
+      if (ih < 0 || ih >= g.Hi) continue;
+      float xw[PX + KW - 1];
+      const T *xrow = x + ((long long)n * g.Hi + ih) * g.Wi * g.Ci + ci;
+#pragma unroll
+      for (int j = 0; j < PX + KW - 1; ++j) {
+        const int iw = ow0 + j - g.pad_w;
+        xw[j] = (iw >= 0 && iw < g.Wi) ? to_f(xrow[(long long)iw * g.Ci]) : 0.f;
+      }
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const float *wrow = ws + ((kh * KW + kw) * g.Ci + ci) * 64 + cg * 8;
+        const float4 w0 = *reinterpret_cast<const float4 *>(wrow);
+        const float4 w1 = *reinterpret_cast<const float4 *>(wrow + 4);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const float xv = xw[p + kw];
+          acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]); acc[p][2] = fmaf(xv, w0.z, acc[p][2]);
+          acc[p][3] = fmaf(xv, w0.w, acc[p][3]); acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
+          acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
+        }
+      }
+    }
+  const long long base = ((long long)n * g.Ho + oh) * g.Wo + ow0;
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    if (ow0 + p >= g.Wo) break;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = apply_act(acc[p][j], g.act);
+    store_vec<T, 8>(y + (base + p) * g.Co + co_blk + cg * 8, acc[p]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // thin weight gradients.  V = the wide tensor (C channels), S = the thin one (SC <= 2 channels).
 //   gy_thin == 0 :  gy is wide (V at output positions), gx is thin   -> dw[c][sc][tap]   (head 7x7 Cin=1, discriminator layer 0)
 //   gy_thin == 1 :  gx is wide (V at input positions),  gy is thin   -> dw[sc][c][tap]   (tail 7x7 Cout=1, discriminator last layer)
@@ -207,6 +349,104 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(ctagan_conv_geom g
   }
 }
 
+// Vectorised thin weight gradient for stride 1: thread = (8-channel slice, kernel row); one 16-byte load of the wide tensor and
+// KW (warp-broadcast) scalars of the thin one feed 8*KW FMAs.  block = 4 streams x (8 slices x 8 kernel rows); each stream walks a
+// contiguous range of wide-tensor pixels; streams are combined in shared memory, blocks by fp32 atomics.
+template <typename T, int KW>
+__global__ void __launch_bounds__(256) conv_wgrad_thin_vec_kernel(ctagan_conv_geom g, const T *__restrict__ gy, const T *__restrict__ gx,
+                                                                  float *__restrict__ dw, float *__restrict__ db, int gy_thin,
+                                                                  long long pix_per_stream) {
+  __shared__ float red[64 * KW * 8];
+  const int t = threadIdx.x;
+  const int stream = t >> 6, cs = t & 7, kh = (t >> 3) & 7;
+  const int C = gy_thin ? g.Ci : g.Co;            // wide channel count
+  const int SC = gy_thin ? g.Co : g.Ci;           // thin channel count (1 or 2)
+  const int c = blockIdx.y * 64 + cs * 8;
+  const int ntaps = g.KH * KW;
+  const int VH = gy_thin ? g.Hi : g.Ho, VW = gy_thin ? g.Wi : g.Wo;
+  const int SW = gy_thin ? g.Wo : g.Wi, SH = gy_thin ? g.Ho : g.Hi;
+  const long long total = (long long)g.N * VH * VW;
+  const long long p0 = ((long long)blockIdx.x * 4 + stream) * pix_per_stream;
+  const long long p1 = min(total, p0 + pix_per_stream);
+  const bool active = (c < C) && (kh < g.KH);
+  const T *V = gy_thin ? gx : gy;
+  const T *S = gy_thin ? gy : gx;
+  for (int s = 0; s < SC; ++s) {
+    float acc[KW][8];
+#pragma unroll
+    for (int k = 0; k < KW; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active && p0 < p1) {
+      int vw = (int)(p0 % VW);
+      long long r = p0 / VW;                      // n*VH + vh
+      int vh = (int)(r % VH);
+      int n = (int)(r / VH);
+      for (long long p = p0; p < p1; ++p) {
+        const int sh = gy_thin ? (vh + g.pad_h - kh) : (vh + kh - g.pad_h);
+        float v[8];
+        load_vec<T, 8>(V + p * C + c, v);
+        if (!gy_thin && s == 0 && kh == 0 && db) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bsum[e] += v[e];
+        }
+        if (sh >= 0 && sh < SH) {
+          const T *srow = S + ((long long)n * SH + sh) * SW * SC + s;
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw) {
+            const int sw = gy_thin ? (vw + g.pad_w - kw) : (vw + kw - g.pad_w);
+            const float sv = (sw >= 0 && sw < SW) ? to_f(srow[(long long)sw * SC]) : 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[kw][e] = fmaf(v[e], sv, acc[kw][e]);
+          }
+        }
+        if (++vw == VW) { vw = 0; if (++vh == VH) { vh = 0; ++n; } }
+      }
+    }
+    // combine the 4 streams of the block, then one atomic per output per block
+    for (int i = t; i < 64 * KW * 8; i += 256) red[i] = 0.f;
+    __syncthreads();
+    if (active) {
+      float *mine = red + (t & 63) * (KW * 8);
+#pragma unroll
+      for (int k = 0; k < KW; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(mine + k * 8 + e, acc[k][e]);
+    }
+    __syncthreads();
+    if (stream == 0 && active) {
+      const float *mine = red + (t & 63) * (KW * 8);
+#pragma unroll
+      for (int k = 0; k < KW; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int cc = c + e;
+          // dw is [A][B][KH][KW] with A = gy channels, B = gx channels
+          const long long idx = gy_thin ? (((long long)s * C + cc) * ntaps + kh * KW + k) : (((long long)cc * SC + s) * ntaps + kh * KW + k);
+          atomicAdd(dw + idx, mine[k * 8 + e]);
+        }
+    }
+    if (db && !gy_thin && s == 0 && kh == 0 && c < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(db + c + e, bsum[e]);
+    }
+    __syncthreads();
+  }
+  // bias gradient of the thin-gy case: db[sc] = sum of gy (first channel block only)
+  if (db && gy_thin && blockIdx.y == 0) {
+    const long long tot = (long long)g.N * g.Ho * g.Wo;
+    const long long per = (tot + gridDim.x - 1) / gridDim.x;
+    const long long q0 = blockIdx.x * per, q1 = min(tot, q0 + per);
+    for (int s = 0; s < SC; ++s) {
+      float tsum = 0.f;
+      for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) tsum += to_f(gy[q * SC + s]);
+      tsum = warp_sum(tsum);
+      if ((threadIdx.x & 31) == 0) atomicAdd(db + s, tsum);
+    }
+  }
+}
+
 }  // namespace
 
 int ctagan_conv_small_kind(const ctagan_conv_geom *g) {
@@ -218,7 +458,31 @@ int ctagan_conv_small_kind(const ctagan_conv_geom *g) {
 int ctagan_conv_gather_small(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st) {
   const int kind = ctagan_conv_small_kind(g);
   const long long M = (long long)g->N * g->Ho * g->Wo;
-  if (kind == 1) {
+  const bool tiled = g->stride == 1 && g->dil == 1 && (g->KW == 7 || g->KW == 4 || g->KW == 3);
+  const long long Gr = (long long)g->N * g->Ho * ((g->Wo + PX - 1) / PX);
+  if (kind == 1 && tiled) {
+    dim3 grid(cdiv(Gr, 32), cdiv(g->Co, 64));
+    const size_t smem = (size_t)g->KH * g->KW * g->Ci * 64 * sizeof(float);
+    CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+      if (g->KW == 7) conv_fewin_tiled_kernel<T, 7><<<grid, 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+      else if (g->KW == 4) conv_fewin_tiled_kernel<T, 4><<<grid, 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+      else conv_fewin_tiled_kernel<T, 3><<<grid, 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+    });
+  } else if (kind == 2 && tiled) {
+    const size_t smem = (size_t)g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+    CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+      static bool configured = false;
+      if (!configured) {
+        CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_fewout_tiled_kernel<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_fewout_tiled_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_fewout_tiled_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+      }
+      if (g->KW == 7) conv_fewout_tiled_kernel<T, 7><<<cdiv(Gr, 32), 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+      else if (g->KW == 4) conv_fewout_tiled_kernel<T, 4><<<cdiv(Gr, 32), 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+      else conv_fewout_tiled_kernel<T, 3><<<cdiv(Gr, 32), 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y);
+    });
+  } else if (kind == 1) {
     dim3 grid(cdiv(M, 32), cdiv(g->Co, 64));
     const size_t smem = (size_t)g->KH * g->KW * g->Ci * 64 * sizeof(float);
     CTAGAN_DISPATCH_DTYPE(g->dtype, T, { conv_fewin_kernel<T><<<grid, 256, smem, st>>>(*g, (const T *)x, (const T *)wp, bias, (T *)y); });
@@ -262,6 +526,26 @@ int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void
   const long long rows = (long long)g->N * VH;
   CTAGAN_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Co * g->Ci * g->KH * g->KW, st));
   if (db) CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
+  if (g->stride == 1 && C % 8 == 0 && g->KH <= 8 && (g->KW == 7 || g->KW == 4 || g->KW == 3 || g->KW == 1)) {
+    const int VW = gy_thin ? g->Wi : g->Wo;
+    const long long total = rows * VW;
+    const int chb = cdiv(C, 64);
+    long long blocks = (2LL * ctagan_num_sms() + chb - 1) / chb;
+    if (blocks * 4 * 32 > total) blocks = (total + 127) / 128;       // at least 32 pixels per stream
+    if (blocks < 1) blocks = 1;
+    const long long pps = (total + blocks * 4 - 1) / (blocks * 4);
+    dim3 grid((unsigned)((total + pps * 4 - 1) / (pps * 4)), chb);
+#define THINV_LAUNCH(KW_) conv_wgrad_thin_vec_kernel<T, KW_><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, gy_thin, pps)
+    CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+      if (g->KW == 7) THINV_LAUNCH(7);
+      else if (g->KW == 4) THINV_LAUNCH(4);
+      else if (g->KW == 3) THINV_LAUNCH(3);
+      else THINV_LAUNCH(1);
+    });
+#undef THINV_LAUNCH
+    CTAGAN_LAUNCH_OK();
+    return CTAGAN_OK;
+  }
   const int ch_blocks = cdiv(C, 64), kh_blocks = cdiv(g->KH, 4);
   long long want = (2LL * ctagan_num_sms()) / ((long long)ch_blocks * kh_blocks);
   if (want < 1) want = 1;
