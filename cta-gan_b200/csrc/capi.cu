@@ -5,7 +5,8 @@
 int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
 int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
 // tcgen05 engine (conv_tc.cu): return CTAGAN_ERR_UNSUPPORTED when the geometry does not tile
-int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
+int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
+                          cudaStream_t st);
 int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
                          size_t workspace_bytes, cudaStream_t st);
 size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g);
@@ -67,9 +68,9 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
   CTAGAN_REQUIRE(x && wp && y, "conv_gather: null pointer");
   CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_gather: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, st);
+  if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, st);
   if (engine != 3 && ctagan_conv_small_kind(g)) return ctagan_conv_gather_small(g, x, wp, bias, y, st);
-  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, st);
+  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, st);
   return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
 }
 
@@ -90,4 +91,25 @@ extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, cons
   if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, st);
   if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
   return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, st);
+}
+
+// Which engine ctagan_conv_gather would run for this geometry: 1 CUDA-core generic, 2 tcgen05, 4 CUDA-core specialised (1-2 channels)
+extern "C" int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine) {
+  if (!g) return 0;
+  if (engine == 2) return 2;
+  if (engine != 3 && ctagan_conv_small_kind(g)) return 4;
+  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return 2;
+  return 1;
+}
+
+extern "C" int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
+                                        int engine, void *stream) {
+  int rc = check_geom(g, "conv_gather_stats");
+  if (rc) return rc;
+  CTAGAN_REQUIRE(x && wp && y && stat_acc, "conv_gather_stats: null pointer");
+  if (ctagan_conv_gather_engine(g, engine) != 2) {
+    ctagan_set_error("conv_gather_stats: fused statistics need the tcgen05 engine (use ctagan_conv_gather + ctagan_instnorm_stats)");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_acc, (cudaStream_t)stream);
 }

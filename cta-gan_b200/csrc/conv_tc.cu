@@ -47,6 +47,7 @@ struct TcParams {
   long long *prof;             // optional per-phase clock64 stamps of CTA 0 (developer probe)
   const float *bias;
   bf16 *out;
+  double *stat_acc;            // optional [N][Co][2]: per-(n,co) sum and sum of squares of the fp32 conv output (pre-zeroed by the caller)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -485,11 +486,46 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    __shared__ float stat_red[2][4][2][32];       // [chunk parity][epilogue warp][sum | sumsq][column]
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
       tmem_ld_wait();
+      if (p.stat_acc != nullptr) {
+        // InstanceNorm statistics fused into the epilogue: column sums over the warp's 32 rows by a butterfly that halves the data per
+        // step (31 shuffles per quantity), the 4 epilogue warps are combined in shared memory, one fp64 atomic pair per column and CTA.
+        float s1[32], s2[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float t = valid ? __uint_as_float(r[e]) : 0.f;
+          s1[e] = t;
+          s2[e] = t * t;
+        }
+#pragma unroll
+        for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
+          const bool upper = (lane & step) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float keep1 = upper ? s1[i + n / 2] : s1[i], send1 = upper ? s1[i] : s1[i + n / 2];
+            const float keep2 = upper ? s2[i + n / 2] : s2[i], send2 = upper ? s2[i] : s2[i + n / 2];
+            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
+            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+          }
+        }
+        // lane l now holds the sums of column l
+        const int par = (c >> 5) & 1;
+        stat_red[par][quarter][0][lane] = s1[0];
+        stat_red[par][quarter][1][lane] = s2[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && co0 + c + lane < p.Co) {
+          const float a = stat_red[par][0][0][lane] + stat_red[par][1][0][lane] + stat_red[par][2][0][lane] + stat_red[par][3][0][lane];
+          const float b = stat_red[par][0][1][lane] + stat_red[par][1][1][lane] + stat_red[par][2][1][lane] + stat_red[par][3][1][lane];
+          double *dst = p.stat_acc + ((long long)img * p.Co + co0 + c + lane) * 2;
+          atomicAdd(dst, (double)a);
+          atomicAdd(dst + 1, (double)b);
+        }
+      }
       if (valid && co0 + c < p.Co) {            // Co is a multiple of 32 here; tiles may overhang it
         float v[32];
 #pragma unroll
@@ -685,7 +721,8 @@ static int tc_gather_kind(const ctagan_conv_geom *g) {
 
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g) { return tc_gather_kind(g) != 0; }
 
-int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st) {
+int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
+                          cudaStream_t st) {
   const int kind = tc_gather_kind(g);
   if (!kind) {
     ctagan_set_error("conv_gather: geometry not supported by the tcgen05 engine (bf16, Ci%%64==0, Co%%64==0, stride<=2 / dil<=2)");
@@ -698,7 +735,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   memset(&p, 0, sizeof(p));
   p.Ci = g->Ci; p.Co = g->Co; p.stride = g->stride;
   p.out_H = g->Ho; p.out_W = g->Wo; p.sy = p.sx = 1; p.ay = p.ax = 0;
-  p.act = g->act; p.bias = bias; p.out = (bf16 *)y;
+  p.act = g->act; p.bias = bias; p.out = (bf16 *)y; p.stat_acc = stat_acc;
   const int ntaps = g->KH * g->KW;
   const int w_taps = ntaps;
   if (kind == 1 || kind == 2) {

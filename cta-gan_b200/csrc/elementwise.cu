@@ -119,6 +119,17 @@ __global__ void instnorm_finalize_kernel(const T *__restrict__ x, const double *
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
 }
 
+// (sum, sum of squares) accumulated by the convolution epilogue -> (mean, rstd)
+__global__ void instnorm_finalize_sums_kernel(const double *__restrict__ acc, float *__restrict__ stats, int NC, int HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const double2 t = *reinterpret_cast<const double2 *>(acc + 2 * i);
+  const double m = t.x / HW;
+  double var = t.y / HW - m * m;
+  if (var < 0) var = 0;
+  *reinterpret_cast<float2 *>(stats + 2 * i) = make_float2((float)m, (float)(1.0 / sqrt(var + 1e-5)));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // out[n,hp,wp,c] = act((x-mean)*rstd) + res ; gather form (one thread per output vector), reflect indices.
 // ---------------------------------------------------------------------------------------------------------------
@@ -844,6 +855,13 @@ extern "C" int ctagan_deinterleave2(const void *src, float *a, float *b, int64_t
   CTAGAN_FITS32(2 * n);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, { deinterleave2_kernel<T><<<ew_blocks(n), 256, 0, st>>>((const T *)src, a, b, n); });
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_instnorm_finalize_sums(const double *acc, float *stats, int N, int HW, int C, void *stream) {
+  CTAGAN_REQUIRE(acc && stats && N > 0 && HW > 0 && C > 0, "instnorm_finalize_sums: bad arguments");
+  instnorm_finalize_sums_kernel<<<cdiv((long long)N * C, 128), 128, 0, (cudaStream_t)stream>>>(acc, stats, N * C, HW);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }

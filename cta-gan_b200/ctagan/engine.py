@@ -116,6 +116,14 @@ class ConvPrim:
         bias = self.b.detach() if (use_bias and self.b is not None) else None
         return ops.conv_gather(x, self.packed(0, x.dtype), bias, g, _ENGINE["value"])
 
+    def fprop_stats(self, x, pool):
+        """fprop of a layer followed by InstanceNorm (bias dead): raw output + (mean, rstd), statistics fused when possible."""
+        N, Hi, Wi, Ci = x.shape
+        Ho = (Hi + 2 * self.p - self.K) // self.s + 1
+        Wo = (Wi + 2 * self.p - self.K) // self.s + 1
+        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, self.O, self.K, self.s, 1, self.p, L.ACT_NONE, ops.dt(x))
+        return ops.conv_gather_stats(x, self.packed(0, x.dtype), None, g, pool, _ENGINE["value"])
+
     # O-channel input -> I-channel output of spatial size `out_hw`  (Conv2d input-gradient / ConvTranspose2d forward)
     def bprop(self, dy, out_hw, act=L.ACT_NONE, bias=None, pad=None):
         N, Ho, Wo, Co = dy.shape
@@ -123,6 +131,12 @@ class ConvPrim:
         p = self.p if pad is None else pad
         g = ops.make_geom(N, Ho, Wo, Co, out_hw[0], out_hw[1], self.I, self.K, 1, self.s, self.K - 1 - p, act, ops.dt(dy))
         return ops.conv_gather(dy, self.packed(1, dy.dtype), bias, g, _ENGINE["value"])
+
+    def bprop_stats(self, dy, out_hw, pool):
+        """ConvTranspose2d forward followed by InstanceNorm."""
+        N, Ho, Wo, Co = dy.shape
+        g = ops.make_geom(N, Ho, Wo, Co, out_hw[0], out_hw[1], self.I, self.K, 1, self.s, self.K - 1 - self.p, L.ACT_NONE, ops.dt(dy))
+        return ops.conv_gather_stats(dy, self.packed(1, dy.dtype), None, g, pool, _ENGINE["value"])
 
     # dW[O][I][K][K] = sum gy(O-channel, strided side) x gx(I-channel, gathered side)
     def wgrad(self, gy, gx, want_bias=False, pad=None, gy_margin=0):
@@ -184,27 +198,28 @@ def generator_forward(plan: GeneratorPlan, x_nchw: torch.Tensor, save: bool):
     T = get_precision()
     N, Cin, H, W = x_nchw.shape
     x0 = ops.nchw_to_nhwc(x_nchw, T)
+    pool = ops.ZeroPool(2 * N * (64 + 128 + 256 + 512 * plan.n_blocks + 128 + 64), x0.device) if T == torch.bfloat16 else None
     P0 = ops.norm_act_pad(x0, None, L.ACT_NONE, 3)
-    r1 = plan.head1.fprop(P0, use_bias=False); s1 = ops.instnorm_stats(r1)
+    r1, s1 = plan.head1.fprop_stats(P0, pool)
     A1 = ops.norm_act_pad(r1, s1, L.ACT_RELU, 0)
-    r2 = plan.head4.fprop(A1, use_bias=False); s2 = ops.instnorm_stats(r2)
+    r2, s2 = plan.head4.fprop_stats(A1, pool)
     A2 = ops.norm_act_pad(r2, s2, L.ACT_RELU, 0)
-    r3 = plan.head7.fprop(A2, use_bias=False); s3 = ops.instnorm_stats(r3)
+    r3, s3 = plan.head7.fprop_stats(A2, pool)
     nb = plan.n_blocks
     X = ops.norm_act_pad(r3, s3, L.ACT_RELU, 1 if nb > 0 else 0)
     blocks = []
     for k, (c1, c2) in enumerate(plan.blocks):
-        ra = c1.fprop(X, use_bias=False); sa = ops.instnorm_stats(ra)
+        ra, sa = c1.fprop_stats(X, pool)
         Tt = ops.norm_act_pad(ra, sa, L.ACT_RELU, 1)
-        rb = c2.fprop(Tt, use_bias=False); sb = ops.instnorm_stats(rb)
+        rb, sb = c2.fprop_stats(Tt, pool)
         Xn = ops.norm_act_pad(rb, sb, L.ACT_NONE, 1 if k < nb - 1 else 0, res=X, res_pad=1)
         if save:
             blocks.append((X, ra, sa, Tt, rb, sb))
         X = Xn
     h4, w4 = X.shape[1], X.shape[2]
-    r4 = plan.tail0.bprop(X, (2 * h4, 2 * w4)); s4 = ops.instnorm_stats(r4)
+    r4, s4 = plan.tail0.bprop_stats(X, (2 * h4, 2 * w4), pool)
     A4 = ops.norm_act_pad(r4, s4, L.ACT_RELU, 0)
-    r5 = plan.tail3.bprop(A4, (4 * h4, 4 * w4)); s5 = ops.instnorm_stats(r5)
+    r5, s5 = plan.tail3.bprop_stats(A4, (4 * h4, 4 * w4), pool)
     P5 = ops.norm_act_pad(r5, s5, L.ACT_RELU, 3)
     y = plan.tail7.fprop(P5, act=L.ACT_TANH, use_bias=True)
     out = ops.nhwc_to_nchw(y)
@@ -296,9 +311,9 @@ def discriminator_forward(plan: DiscriminatorPlan, x_nchw: torch.Tensor, save: b
     a0 = c[0].fprop(x0, act=L.ACT_LRELU, use_bias=True)
     acts, raws, stats = [a0], [], []
     a = a0
+    pool = ops.ZeroPool(2 * x0.shape[0] * (128 + 256 + 512), x0.device) if T == torch.bfloat16 else None
     for i in (1, 2, 3):
-        r = c[i].fprop(a, use_bias=False)
-        s = ops.instnorm_stats(r)
+        r, s = c[i].fprop_stats(a, pool)
         a = ops.norm_act_pad(r, s, L.ACT_LRELU, 0)
         raws.append(r); stats.append(s); acts.append(a)
     y4 = c[4].fprop(a, use_bias=True)
@@ -347,9 +362,10 @@ class _ResBlock:
 
     def forward(self, a, save):
         Pa = ops.norm_act_pad(a, None, L.ACT_NONE, 1)
-        ra = self.c1.fprop(Pa, use_bias=False); sa = ops.instnorm_stats(ra)
+        pool = ops.ZeroPool(4 * a.shape[0] * self.c1.O, a.device) if a.dtype == torch.bfloat16 else None
+        ra, sa = self.c1.fprop_stats(Pa, pool)
         Tt = ops.norm_act_pad(ra, sa, L.ACT_RELU, 1)
-        rb = self.c2.fprop(Tt, use_bias=False); sb = ops.instnorm_stats(rb)
+        rb, sb = self.c2.fprop_stats(Tt, pool)
         out = ops.norm_act_pad(rb, sb, L.ACT_NONE, 0, res=a, res_pad=0)
         return out, ((Pa, ra, sa, Tt, rb, sb) if save else None)
 

@@ -64,6 +64,39 @@ def conv_gather(x, wp, bias, g: L.ConvGeom, engine=L.ENGINE_AUTO):
     return y
 
 
+class ZeroPool:
+    """One zero-filled fp64 buffer per network pass, handed out in slices: the accumulators of all fused-statistics convolutions of
+    the pass are cleared by a single memset instead of one per layer."""
+
+    def __init__(self, n_doubles: int, device):
+        self.buf = torch.zeros((max(n_doubles, 2),), dtype=torch.float64, device=device)
+        self.off = 0
+
+    def take(self, n: int):
+        if self.off + n > self.buf.numel():
+            return torch.zeros((n,), dtype=torch.float64, device=self.buf.device)
+        out = self.buf[self.off:self.off + n]
+        self.off += n
+        return out
+
+
+def conv_gather_stats(x, wp, bias, g: L.ConvGeom, pool: "ZeroPool", engine=L.ENGINE_AUTO):
+    """Convolution + InstanceNorm statistics.  Returns (y, stats[N][Co][2] = (mean, rstd)).  On the tcgen05 engine the sums come out
+    of the conv epilogue (no extra pass over y); otherwise conv followed by the shifted-sum statistics kernels."""
+    lib = L.load()
+    if pool is not None and lib.ctagan_conv_gather_engine(ctypes.byref(g), engine) == 2:
+        ensure_device()
+        y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
+        acc = pool.take(g.N * g.Co * 2)
+        stats = torch.empty((g.N, g.Co, 2), dtype=torch.float32, device=x.device)
+        _count(2)
+        L.check(lib.ctagan_conv_gather_stats(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(acc), engine, _stream()))
+        L.check(lib.ctagan_instnorm_finalize_sums(_p(acc), _p(stats), g.N, g.Ho * g.Wo, g.Co, _stream()))
+        return y, stats
+    y = conv_gather(x, wp, bias, g, engine)
+    return y, instnorm_stats(y)
+
+
 def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO):
     _require_cuda(gy, gx)
     dw = torch.empty((g.Co, g.Ci, g.KH, g.KW), dtype=torch.float32, device=gy.device)

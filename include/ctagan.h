@@ -67,6 +67,15 @@ typedef struct {
 int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y,
                        int engine, void *stream);
 
+/* ctagan_conv_gather with the InstanceNorm statistics fused into the epilogue (tcgen05 engine only; CTAGAN_ERR_UNSUPPORTED
+ * otherwise -- query with ctagan_conv_gather_engine): stat_acc[N][Co][2] (fp64, PRE-ZEROED by the caller) receives the per-(n,co)
+ * sum and sum of squares of the fp32 convolution output; ctagan_instnorm_finalize_sums turns them into (mean, rstd). */
+int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
+                             int engine, void *stream);
+/* engine ctagan_conv_gather would use: 1 CUDA-core generic, 2 tcgen05, 4 CUDA-core specialised (1-2 channel layers) */
+int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine);
+int ctagan_instnorm_finalize_sums(const double *acc, float *stats, int N, int HW, int C, void *stream);
+
 /* Weight gradient (and optional bias gradient) of the same geometry:
  *   dw[a,b,kh,kw] (+)= sum_{n,oh,ow} gy[n,oh,ow,a] * gx[n,ih,iw,b],  db[a] = sum gy[n,oh,ow,a]
  * with (ih,iw) from (oh,ow,kh,kw) as above; g->Co == A (channels of gy), g->Ci == B (channels of gx); dw is fp32 in

@@ -82,3 +82,31 @@ def test_tc_conv_transpose(shape):
         assert maxrel(dw, wt.grad) <= 1e-3
     finally:
         E.set_conv_engine("auto")
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 256, 66, 66, 3, 1, 0), (3, 64, 128, 64, 64, 3, 2, 1), (2, 256, 512, 32, 32, 4, 1, 1)])
+def test_tc_fused_instancenorm_statistics(shape):
+    """The (mean, rstd) that come out of the conv epilogue equal the statistics of the stored output."""
+    from ctagan import engine as E, ops
+    N, Ci, Co, H, W, K, s, p = shape
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(N, H, W, Ci, generator=g) * 1.5 + 0.3).cuda().bfloat16()
+    w = (torch.randn(Co, Ci, K, K, generator=g) / (Ci * K * K) ** 0.5).cuda()
+    prim = E.ConvPrim(w, None, s, p)
+    Ho, Wo = (H + 2 * p - K) // s + 1, (W + 2 * p - K) // s + 1
+    pool = ops.ZeroPool(2 * N * Co, x.device)
+    y, stats = prim.fprop_stats(x, pool)
+    assert y.shape == (N, Ho, Wo, Co) and pool.off == 2 * N * Co          # the fused (tcgen05) path was taken
+    yf = y.float()
+    mean = yf.mean((1, 2)); var = yf.var((1, 2), unbiased=False)
+    assert float((stats[..., 0] - mean).abs().max()) <= 2e-3 * float(var.sqrt().max())
+    assert maxrel(stats[..., 1], (var + 1e-5).rsqrt()) <= 2e-3
+    # transposed convolution (4 output-phase launches accumulate into the same sums)
+    if s == 2:
+        wt = (torch.randn(Co, Ci, 3, 3, generator=g) / (Co * 9) ** 0.5).cuda()
+        primT = E.ConvPrim(wt, None, 2, 1)
+        xt = torch.randn(N, 32, 32, Co, generator=g).cuda().bfloat16()
+        pool = ops.ZeroPool(2 * N * Ci, x.device)
+        yt, st = primT.bprop_stats(xt, (64, 64), pool)
+        ytf = yt.float()
+        assert maxrel(st[..., 1], (ytf.var((1, 2), unbiased=False) + 1e-5).rsqrt()) <= 2e-3
