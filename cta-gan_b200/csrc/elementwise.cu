@@ -133,8 +133,22 @@ __global__ void instnorm_finalize_sums_kernel(const double *__restrict__ acc, fl
 // ---------------------------------------------------------------------------------------------------------------
 // out[n,hp,wp,c] = act((x-mean)*rstd) + res ; gather form (one thread per output vector), reflect indices.
 // ---------------------------------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void stats_from_sums(const double *__restrict__ ap, float inv_hw, float (&mean)[V], float (&rstd)[V]) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const double2 t = *reinterpret_cast<const double2 *>(ap + 2 * i);
+    const double m = t.x * (double)inv_hw;
+    double var = t.y * (double)inv_hw - m * m;
+    if (var < 0) var = 0;
+    mean[i] = (float)m;
+    rstd[i] = rsqrtf((float)var + 1e-5f);
+  }
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__ x, const float *__restrict__ stats,
+                                                           const double *__restrict__ sums, float *__restrict__ stats_out,
                                                            const T *__restrict__ res, int res_pad, T *__restrict__ out, int N, int H,
                                                            int W, int C, int pad, int act) {
   const int CV = C / V;
@@ -153,6 +167,18 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__
     if (stats) {
       float mean[V], rstd[V];
       load_stats<V>(stats + ((idx_t)n * C + cv * V) * 2, mean, rstd);
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = (v[i] - mean[i]) * rstd[i];
+    } else if (sums) {
+      float mean[V], rstd[V];
+      stats_from_sums<V>(sums + ((idx_t)n * C + cv * V) * 2, 1.f / (float)(H * W), mean, rstd);
+      if (stats_out && hp == 0 && wp == 0) {     // one thread per (n, channel vector) publishes (mean, rstd) for the backward pass
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          stats_out[((idx_t)n * C + cv * V + i) * 2] = mean[i];
+          stats_out[((idx_t)n * C + cv * V + i) * 2 + 1] = rstd[i];
+        }
+      }
 #pragma unroll
       for (int i = 0; i < V; ++i) v[i] = (v[i] - mean[i]) * rstd[i];
     }
@@ -672,23 +698,24 @@ extern "C" int ctagan_instnorm_stats(const void *x, float *stats, double *acc, i
   return CTAGAN_OK;
 }
 
-extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int res_pad, void *out, int N, int H, int W,
-                                   int C, int pad, int act, int dtype, void *stream) {
+extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const double *sums, float *stats_out, const void *res, int res_pad,
+                                   void *out, int N, int H, int W, int C, int pad, int act, int dtype, void *stream) {
+  CTAGAN_REQUIRE(!(stats && sums), "norm_act_pad: give either stats or sums");
   CTAGAN_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && pad < H && pad < W, "norm_act_pad: bad arguments");
   CTAGAN_FITS32((int64_t)N * (H + 2 * pad) * (W + 2 * pad) * C);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C);
     const idx_t total = (idx_t)N * (H + 2 * pad) * (W + 2 * pad) * (C / v);
-    VEC_SWITCH(T, v, V, norm_act_pad_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, stats, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act));
+    VEC_SWITCH(T, v, V, norm_act_pad_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, stats, sums, stats_out, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act));
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
 
 extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
-                                       double *acc, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype,
-                                       void *stream) {
+                                       double *acc, int acc_is_zero, int N, int H, int W, int C, int pad, int act, int out_pad,
+                                       int dtype, void *stream) {
   CTAGAN_REQUIRE(gout && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && out_pad >= 0, "norm_act_pad_bwd: bad arguments");
   CTAGAN_FITS32((int64_t)N * (H + 2 * pad + 2 * out_pad) * (W + 2 * pad + 2 * out_pad) * C);
   CTAGAN_REQUIRE(!(stats || act != CTAGAN_ACT_NONE) || x, "norm_act_pad_bwd: x required when stats/act given");
@@ -699,7 +726,7 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
     int v = pick_vec<T>(C);
     if (stats) {
       while (C / v > 256) { CTAGAN_REQUIRE(v < max_vec<T>(), "norm_act_pad_bwd: C=%d too large", C); v *= 2; }
-      CTAGAN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
+      if (!acc_is_zero) CTAGAN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
       int ppb;
       const int chunks = reduce_chunks(N, H * W, C, v, ppb);
       dim3 grid(chunks, N);

@@ -237,35 +237,36 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
             return None, None
         return prim.wgrad(gy, gx, want_bias=bias, pad=(margin if margin else None), gy_margin=margin)
 
+    bpool = ops.ZeroPool(2 * y.shape[0] * (64 + 128 + 256 + 512 * plan.n_blocks + 128 + 64), y.device)
     gy = ops.nchw_to_nhwc(dout, T)
     dy7 = ops.act_bwd(gy, y, L.ACT_TANH)
     dW7, db7 = wg(plan.tail7, dy7, P5, True)
     dP5 = plan.tail7.bprop(dy7, (P5.shape[1], P5.shape[2]))
-    dr5 = ops.norm_act_pad_bwd(dP5, r5, s5, L.ACT_RELU, 3)
+    dr5 = ops.norm_act_pad_bwd(dP5, r5, s5, L.ACT_RELU, 3, pool=bpool)
     dA4 = plan.tail3.fprop(dr5, use_bias=False)
     dWt3, _ = wg(plan.tail3, A4, dr5)
-    dr4 = ops.norm_act_pad_bwd(dA4, r4, s4, L.ACT_RELU, 0)
+    dr4 = ops.norm_act_pad_bwd(dA4, r4, s4, L.ACT_RELU, 0, pool=bpool)
     G = plan.tail0.fprop(dr4, use_bias=False)
     dWt0, _ = wg(plan.tail0, X9, dr4)
     block_grads = []
     for (c1, c2), (Xk, ra, sa, Tt, rb, sb) in zip(reversed(plan.blocks), reversed(blocks)):
         m = c2.K - 1                                                      # zero margin: dgrad becomes a VALID conv
-        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0, out_pad=m)
+        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0, out_pad=m, pool=bpool)
         dW2, _ = wg(c2, drb, Tt, margin=m)
         dT = c2.bprop(drb, (Tt.shape[1], Tt.shape[2]), pad=m)
-        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1, out_pad=m)
+        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1, out_pad=m, pool=bpool)
         dW1, _ = wg(c1, dra, Xk, margin=m)
         dXp = c1.bprop(dra, (Xk.shape[1], Xk.shape[2]), pad=m)
         G = ops.norm_act_pad_bwd(dXp, None, None, L.ACT_NONE, 1, addend=G)
         block_grads.append((dW1, dW2))
     block_grads.reverse()
-    dr3 = ops.norm_act_pad_bwd(G, r3, s3, L.ACT_RELU, 0)
+    dr3 = ops.norm_act_pad_bwd(G, r3, s3, L.ACT_RELU, 0, pool=bpool)
     dWh7, _ = wg(plan.head7, dr3, A2)
     dA2 = plan.head7.bprop(dr3, (A2.shape[1], A2.shape[2]))
-    dr2 = ops.norm_act_pad_bwd(dA2, r2, s2, L.ACT_RELU, 0)
+    dr2 = ops.norm_act_pad_bwd(dA2, r2, s2, L.ACT_RELU, 0, pool=bpool)
     dWh4, _ = wg(plan.head4, dr2, A1)
     dA1 = plan.head4.bprop(dr2, (A1.shape[1], A1.shape[2]))
-    dr1 = ops.norm_act_pad_bwd(dA1, r1, s1, L.ACT_RELU, 0)
+    dr1 = ops.norm_act_pad_bwd(dA1, r1, s1, L.ACT_RELU, 0, pool=bpool)
     dWh1, _ = wg(plan.head1, dr1, P0)
     dx = None
     if need_dx:

@@ -88,11 +88,9 @@ def conv_gather_stats(x, wp, bias, g: L.ConvGeom, pool: "ZeroPool", engine=L.ENG
         ensure_device()
         y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
         acc = pool.take(g.N * g.Co * 2)
-        stats = torch.empty((g.N, g.Co, 2), dtype=torch.float32, device=x.device)
-        _count(2)
+        _count(1)
         L.check(lib.ctagan_conv_gather_stats(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(acc), engine, _stream()))
-        L.check(lib.ctagan_instnorm_finalize_sums(_p(acc), _p(stats), g.N, g.Ho * g.Wo, g.Co, _stream()))
-        return y, stats
+        return y, LazyStats(acc, g.N, g.Co)
     y = conv_gather(x, wp, bias, g, engine)
     return y, instnorm_stats(y)
 
@@ -127,21 +125,41 @@ def instnorm_stats(x):
     return stats
 
 
+class LazyStats:
+    """(sum, sum of squares) accumulated by a conv epilogue; the first norm_act_pad that consumes it publishes fp32 (mean, rstd)."""
+
+    def __init__(self, sums, N, C):
+        self.sums = sums
+        self.stats = torch.empty((N, C, 2), dtype=torch.float32, device=sums.device)
+
+
 def norm_act_pad(x, stats, act, pad, res=None, res_pad=0):
     N, H, W, C = x.shape
     out = torch.empty((N, H + 2 * pad, W + 2 * pad, C), dtype=x.dtype, device=x.device)
     _count(1)
-    L.check(L.load().ctagan_norm_act_pad(_p(x), _p(stats), _p(res), res_pad, _p(out), N, H, W, C, pad, act, dt(x), _stream()))
+    if isinstance(stats, LazyStats):
+        L.check(L.load().ctagan_norm_act_pad(_p(x), None, _p(stats.sums), _p(stats.stats), _p(res), res_pad, _p(out), N, H, W, C, pad, act,
+                                             dt(x), _stream()))
+    else:
+        L.check(L.load().ctagan_norm_act_pad(_p(x), _p(stats), None, None, _p(res), res_pad, _p(out), N, H, W, C, pad, act, dt(x),
+                                             _stream()))
     return out
 
 
-def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None, out_pad=0):
+def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None, out_pad=0, pool=None):
     N, Hp, Wp, C = gout.shape
     H, W = Hp - 2 * pad, Wp - 2 * pad
+    if isinstance(stats, LazyStats):
+        stats = stats.stats
     dx = torch.empty((N, H + 2 * out_pad, W + 2 * out_pad, C), dtype=gout.dtype, device=gout.device)
-    acc = torch.empty((N, C, 2), dtype=torch.float64, device=gout.device) if stats is not None else None
+    acc, zeroed = None, 0
+    if stats is not None:
+        if pool is not None:
+            acc, zeroed = pool.take(N * C * 2), 1
+        else:
+            acc = torch.empty((N, C, 2), dtype=torch.float64, device=gout.device)
     _count(2 if stats is not None else 1)
-    L.check(L.load().ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(acc), N, H, W, C, pad, act,
+    L.check(L.load().ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(acc), zeroed, N, H, W, C, pad, act,
                                              out_pad, dt(gout), _stream()))
     return dx
 

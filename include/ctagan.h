@@ -106,9 +106,11 @@ int ctagan_instnorm_stats(const void *x, float *stats, double *acc, int N, int H
 /* Fused InstanceNorm-apply + activation + residual add + reflection pad (one pass):
  *   out[n,hp,wp,c] = act((x[n,h,w,c]-mean)*rstd) + res[n,h+res_pad,w+res_pad,c],  (h,w) = reflect(hp-pad, wp-pad)
  * stats==NULL: no normalisation; res==NULL: no residual.  res has spatial size (H+2*res_pad, W+2*res_pad).
+ * Instead of `stats` the fp64 (sum, sum of squares) accumulator of ctagan_conv_gather_stats may be passed as `sums`: mean/rstd are then
+ * derived on the fly (no finalize launch) and, if stats_out != NULL, published there as fp32 (mean, rstd) for the backward pass.
  * Replaces InstanceNorm2d+ReLU/LeakyReLU+ReflectionPad2d+residual add (Model/CycleGan.py:10-21,27-30). */
-int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int res_pad, void *out,
-                        int N, int H, int W, int C, int pad, int act, int dtype, void *stream);
+int ctagan_norm_act_pad(const void *x, const float *stats, const double *sums, float *stats_out, const void *res, int res_pad,
+                        void *out, int N, int H, int W, int C, int pad, int act, int dtype, void *stream);
 
 /* Backward of the above.  gout is the gradient w.r.t. `out` (padded, size H+2*pad); x is the saved raw conv output
  * (or, when stats==NULL, any tensor with the sign of the pre-activation, e.g. the post-activation output).
@@ -117,9 +119,10 @@ int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int 
  * The residual branch of the forward receives fold_reflect(gout) itself (call with stats=NULL, act=NONE).
  * dx is written as [N][H+2*out_pad][W+2*out_pad][C] with a zero margin of out_pad pixels: with out_pad = K-1-p the stride-1
  * input-gradient convolution that consumes it becomes a plain VALID convolution (the tcgen05 engine's native form).
- * acc: N*C*2 doubles scratch (only with stats). */
+ * acc: N*C*2 doubles scratch (only with stats); acc_is_zero != 0 promises it is already cleared (one memset per pass). */
 int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
-                            double *acc, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype, void *stream);
+                            double *acc, int acc_is_zero, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype,
+                            void *stream);
 
 /* Pointwise activation backward for conv-epilogue activations: dx = gy * act'(y) computed from the OUTPUT y
  * (relu/lrelu: sign(y); tanh: 1-y^2).  n elements. */
