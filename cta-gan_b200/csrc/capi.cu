@@ -6,7 +6,7 @@ int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void
 int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
 // tcgen05 engine (conv_tc.cu): return CTAGAN_ERR_UNSUPPORTED when the geometry does not tile
 int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                          cudaStream_t st);
+                          float *stat_out, cudaStream_t st);
 int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
                          size_t workspace_bytes, cudaStream_t st);
 size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g);
@@ -68,9 +68,9 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
   CTAGAN_REQUIRE(x && wp && y, "conv_gather: null pointer");
   CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_gather: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, st);
+  if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, st);
   if (engine != 3 && ctagan_conv_small_kind(g)) return ctagan_conv_gather_small(g, x, wp, bias, y, st);
-  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, st);
+  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, st);
   return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
 }
 
@@ -103,7 +103,7 @@ extern "C" int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine) 
 }
 
 extern "C" int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                                        int engine, void *stream) {
+                                        float *stats_out, int engine, void *stream) {
   int rc = check_geom(g, "conv_gather_stats");
   if (rc) return rc;
   CTAGAN_REQUIRE(x && wp && y && stat_acc, "conv_gather_stats: null pointer");
@@ -111,5 +111,5 @@ extern "C" int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x
     ctagan_set_error("conv_gather_stats: fused statistics need the tcgen05 engine (use ctagan_conv_gather + ctagan_instnorm_stats)");
     return CTAGAN_ERR_UNSUPPORTED;
   }
-  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_acc, (cudaStream_t)stream);
+  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_acc, stats_out, (cudaStream_t)stream);
 }

@@ -48,6 +48,9 @@ struct TcParams {
   const float *bias;
   bf16 *out;
   double *stat_acc;            // optional [N][Co][2]: per-(n,co) sum and sum of squares of the fp32 conv output (pre-zeroed by the caller)
+  float *stat_out;             // optional [N][Co][2] (mean, rstd), written by the last CTA to finish (ticket right after stat_acc)
+  int stat_n, stat_hw;         // images and pixels per (n,co) plane
+  unsigned int stat_total_ctas;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -555,6 +558,29 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       }
     }
   }
+  // "last CTA finalises": once every CTA of the layer has added its partial sums, the last one turns them into (mean, rstd)
+  if (p.stat_out != nullptr && warp >= 2) {
+    __shared__ unsigned int ticket_s;
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      unsigned int *ticket = reinterpret_cast<unsigned int *>(p.stat_acc + (long long)p.stat_n * p.Co * 2);
+      ticket_s = atomicAdd(ticket, 1u);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (ticket_s == p.stat_total_ctas - 1) {
+      __threadfence();
+      const double inv = 1.0 / (double)p.stat_hw;
+      for (int i = threadIdx.x - 64; i < p.stat_n * p.Co; i += 128) {
+        const double s1 = __ldcg(p.stat_acc + 2 * i), s2 = __ldcg(p.stat_acc + 2 * i + 1);
+        const double m = s1 * inv;
+        double var = s2 * inv - m * m;
+        if (var < 0) var = 0;
+        p.stat_out[2 * i] = (float)m;
+        p.stat_out[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -678,6 +704,7 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
   rc = make_map_w3d(&mw, wp, p.Co, w_taps, p.Ci, (uint32_t)bn);
   if (rc) return rc;
   dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
+  if (p.stat_total_ctas == 0) p.stat_total_ctas = grid.x * grid.y;       // (phase-decomposed launches preset the sum over phases)
   int kch = (p.Ci % 128 == 0 && bn < 256) ? 2 : 1;      // BN=256 keeps 64-channel stages (4 of them fit; 2-chunk stages would leave 2)
   if (kch == 2) {
     switch (bn) {
@@ -722,7 +749,7 @@ static int tc_gather_kind(const ctagan_conv_geom *g) {
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g) { return tc_gather_kind(g) != 0; }
 
 int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                          cudaStream_t st) {
+                          float *stat_out, cudaStream_t st) {
   const int kind = tc_gather_kind(g);
   if (!kind) {
     ctagan_set_error("conv_gather: geometry not supported by the tcgen05 engine (bf16, Ci%%64==0, Co%%64==0, stride<=2 / dil<=2)");
@@ -735,7 +762,8 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   memset(&p, 0, sizeof(p));
   p.Ci = g->Ci; p.Co = g->Co; p.stride = g->stride;
   p.out_H = g->Ho; p.out_W = g->Wo; p.sy = p.sx = 1; p.ay = p.ax = 0;
-  p.act = g->act; p.bias = bias; p.out = (bf16 *)y; p.stat_acc = stat_acc;
+  p.act = g->act; p.bias = bias; p.out = (bf16 *)y; p.stat_acc = stat_acc; p.stat_out = stat_acc ? stat_out : nullptr;
+  p.stat_n = g->N; p.stat_hw = g->Ho * g->Wo;
   const int ntaps = g->KH * g->KW;
   const int w_taps = ntaps;
   if (kind == 1 || kind == 2) {
@@ -762,6 +790,23 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   }
   // kind 3: input dilation 2 (input gradient of a stride-2 conv == ConvTranspose2d forward).  Output pixel h = 2i + r reads
   // x[i + e - u] with weight tap kh' = 2u + a (a = (r + pad) & 1, e = (r + pad - a) / 2): one stride-1 launch per output parity.
+  if (p.stat_out) {
+    // all four output-parity launches add into the same sums: the ticket counts the CTAs of all of them
+    const int Hq = g->Ho / 2, Wq = g->Wo / 2;
+    const int bwl = ceil_log2(Wq < 128 ? Wq : 128);
+    const int BWq = 1 << bwl, BHq = TILE_M >> bwl;
+    const int tiles = ((Wq + BWq - 1) / BWq) * ((Hq + BHq - 1) / BHq);
+    const int bn = pick_bn((long long)g->N * tiles, g->Co);
+    int launches = 0;
+    for (int rh = 0; rh < 2; ++rh)
+      for (int rw = 0; rw < 2; ++rw) {
+        int t = 0;
+        for (int kh = (rh + g->pad_h) & 1; kh < g->KH; kh += 2)
+          for (int kw = (rw + g->pad_w) & 1; kw < g->KW; kw += 2) ++t;
+        if (t) ++launches;
+      }
+    p.stat_total_ctas = (unsigned)(launches * g->N * tiles * ((g->Co + bn - 1) / bn));
+  }
   for (int rh = 0; rh < 2; ++rh)
     for (int rw = 0; rw < 2; ++rw) {
       const int ah = (rh + g->pad_h) & 1, eh = (rh + g->pad_h - ah) / 2;

@@ -198,7 +198,7 @@ def generator_forward(plan: GeneratorPlan, x_nchw: torch.Tensor, save: bool):
     T = get_precision()
     N, Cin, H, W = x_nchw.shape
     x0 = ops.nchw_to_nhwc(x_nchw, T)
-    pool = ops.ZeroPool(2 * N * (64 + 128 + 256 + 512 * plan.n_blocks + 128 + 64), x0.device) if T == torch.bfloat16 else None
+    pool = ops.ZeroPool(2 * N * (64 + 128 + 256 + 512 * plan.n_blocks + 128 + 64) + 64, x0.device) if T == torch.bfloat16 else None
     P0 = ops.norm_act_pad(x0, None, L.ACT_NONE, 3)
     r1, s1 = plan.head1.fprop_stats(P0, pool)
     A1 = ops.norm_act_pad(r1, s1, L.ACT_RELU, 0)
@@ -312,7 +312,7 @@ def discriminator_forward(plan: DiscriminatorPlan, x_nchw: torch.Tensor, save: b
     a0 = c[0].fprop(x0, act=L.ACT_LRELU, use_bias=True)
     acts, raws, stats = [a0], [], []
     a = a0
-    pool = ops.ZeroPool(2 * x0.shape[0] * (128 + 256 + 512), x0.device) if T == torch.bfloat16 else None
+    pool = ops.ZeroPool(2 * x0.shape[0] * (128 + 256 + 512) + 8, x0.device) if T == torch.bfloat16 else None
     for i in (1, 2, 3):
         r, s = c[i].fprop_stats(a, pool)
         a = ops.norm_act_pad(r, s, L.ACT_LRELU, 0)
@@ -363,7 +363,7 @@ class _ResBlock:
 
     def forward(self, a, save):
         Pa = ops.norm_act_pad(a, None, L.ACT_NONE, 1)
-        pool = ops.ZeroPool(4 * a.shape[0] * self.c1.O, a.device) if a.dtype == torch.bfloat16 else None
+        pool = ops.ZeroPool(4 * a.shape[0] * self.c1.O + 4, a.device) if a.dtype == torch.bfloat16 else None
         ra, sa = self.c1.fprop_stats(Pa, pool)
         Tt = ops.norm_act_pad(ra, sa, L.ACT_RELU, 1)
         rb, sb = self.c2.fprop_stats(Tt, pool)

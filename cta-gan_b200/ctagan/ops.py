@@ -87,10 +87,11 @@ def conv_gather_stats(x, wp, bias, g: L.ConvGeom, pool: "ZeroPool", engine=L.ENG
     if pool is not None and lib.ctagan_conv_gather_engine(ctypes.byref(g), engine) == 2:
         ensure_device()
         y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
-        acc = pool.take(g.N * g.Co * 2)
+        acc = pool.take(g.N * g.Co * 2 + 1)            # + the ticket of the in-kernel finalize
+        stats = torch.empty((g.N, g.Co, 2), dtype=torch.float32, device=x.device)
         _count(1)
-        L.check(lib.ctagan_conv_gather_stats(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(acc), engine, _stream()))
-        return y, LazyStats(acc, g.N, g.Co)
+        L.check(lib.ctagan_conv_gather_stats(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(acc), _p(stats), engine, _stream()))
+        return y, stats
     y = conv_gather(x, wp, bias, g, engine)
     return y, instnorm_stats(y)
 

@@ -69,9 +69,11 @@ int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp,
 
 /* ctagan_conv_gather with the InstanceNorm statistics fused into the epilogue (tcgen05 engine only; CTAGAN_ERR_UNSUPPORTED
  * otherwise -- query with ctagan_conv_gather_engine): stat_acc[N][Co][2] (fp64, PRE-ZEROED by the caller) receives the per-(n,co)
- * sum and sum of squares of the fp32 convolution output; ctagan_instnorm_finalize_sums turns them into (mean, rstd). */
+ * sum and sum of squares of the fp32 convolution output.  stat_acc must hold N*Co*2 + 1 doubles, all zero: the extra one is the
+ * ticket of the "last CTA finalises" step that writes stats_out[N][Co][2] = (mean, rstd) (optional; without it use
+ * ctagan_instnorm_finalize_sums or pass the sums to ctagan_norm_act_pad). */
 int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                             int engine, void *stream);
+                             float *stats_out, int engine, void *stream);
 /* engine ctagan_conv_gather would use: 1 CUDA-core generic, 2 tcgen05, 4 CUDA-core specialised (1-2 channel layers) */
 int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine);
 int ctagan_instnorm_finalize_sums(const double *acc, float *stats, int N, int HW, int C, void *stream);
