@@ -590,6 +590,247 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Resident-A variant of the pitch-trick kernel.  The nine taps of a 3x3 filter read almost the same input rows: tap (kh,kw) is
+// the run [q0 + kh*Wv + kw, +128) of the flattened input.  So the CTA loads the union of those runs ONCE per 64-channel chunk
+// (R = 128 + (KH-1)*Wv + KW-1 rows, e.g. 262 instead of 9 x 128) and every tap's A operand is the same shared-memory block with
+// the descriptor start address shifted by (kh*Wv + kw) rows of 128 bytes.  Only the weights stream through the mbarrier ring.
+// L2->SM operand traffic per CTA drops from taps*(A+B) to A_union + taps*B  (3x3, 256 ch, BN=64: 864 KB -> 429 KB).
+// ---------------------------------------------------------------------------------------------------------------------
+struct ResAParams {
+  int rows_box;        // rows per TMA box of the resident block (multiple of 8, <= 256)
+  int n_box;           // boxes per chunk
+  int chunks;          // 64-channel chunks (<= 8)
+  int b_stages;
+  int base_offset_mode;  // 0: none, 1: descriptor base_offset = (row shift & 7)
+};
+
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr, uint32_t base_off) {
+  return make_kmajor_sw128_desc(smem_addr) | ((uint64_t)(base_off & 7u) << 49);
+}
+
+template <int BN>
+struct ResACfg {
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int B_BYTES = BN * CHUNK_K * 2;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_resA_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p,
+                    const ResAParams rp) {
+  using Cfg = ResACfg<BN>;
+  constexpr int CPS = 256 / BN;             // chunks per weight stage
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_chunk_bytes = rp.rows_box * rp.n_box * 128;
+  uint8_t *b_ring = smem + rp.chunks * a_chunk_bytes;
+  uint64_t *a_full = reinterpret_cast<uint64_t *>(b_ring + rp.b_stages * (256 / BN) * Cfg::B_BYTES);
+  uint64_t *full_bar = a_full + 8;
+  uint64_t *empty_bar = full_bar + 8;
+  uint64_t *tmem_full_bar = empty_bar + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x / p.tiles_per_img;
+  const int tile = blockIdx.x - img * p.tiles_per_img;
+  const int q_local0 = tile * TILE_M;
+  const long long q0 = (long long)img * p.Hv * p.Wv + q_local0;
+  const int BW = 1 << p.bw_log2;          // (mode 0 only: the 4-D addressing fields below are never used)
+  const int tile_i0 = 0, tile_j0 = 0;
+  const int co0 = blockIdx.y * BN;
+  const int NSB = rp.b_stages;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident input block: one barrier per channel chunk so that the MMAs start as soon as chunk 0 has landed
+      for (int kc = 0; kc < rp.chunks; ++kc) {
+        mbar_expect_tx(&a_full[kc], (uint32_t)a_chunk_bytes);
+        for (int b = 0; b < rp.n_box; ++b)
+          tma_load_2d(&map_x, &a_full[kc], smem + kc * a_chunk_bytes + b * rp.rows_box * 128, kc * CHUNK_K, (int)(q0 + b * rp.rows_box));
+      }
+      // weight ring: one stage = CPS consecutive 64-channel chunks of one tap (always 32 KB = 512 tensor cycles of MMAs, which
+      // covers the ~500-700 cycles a single lane needs per stage for try_wait / expect_tx / TMA issue / commit)
+      int s = 0;
+      uint32_t ph = 0;
+      const int groups = (rp.chunks + CPS - 1) / CPS;
+      for (int tap = 0; tap < p.n_taps; ++tap)
+        for (int gk = 0; gk < groups; ++gk) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], CPS * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < CPS; ++k)
+            tma_load_3d(&map_w, &full_bar[s], b_ring + (s * CPS + k) * Cfg::B_BYTES, (gk * CPS + k) * CHUNK_K, p.tap_w_col[tap], co0);
+          if (++s == NSB) { s = 0; ph ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      bool first = true;
+      const int groups = (rp.chunks + CPS - 1) / CPS;
+      for (int tap = 0; tap < p.n_taps; ++tap) {
+        const uint32_t shift = (uint32_t)(p.tap_dh[tap] * p.Wv + p.tap_dw[tap]);        // rows of 128 bytes
+        for (int gk = 0; gk < groups; ++gk) {
+          if (tap == 0)
+            for (int k = 0; k < CPS; ++k)
+              if (gk * CPS + k < rp.chunks) mbar_wait(&a_full[gk * CPS + k], 0);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < CPS; ++k) {
+            // the tap's A operand = the resident block shifted by `shift` rows: the 128B swizzle is a function of the absolute
+            // shared-memory address bits, so a start address that is not 1024-byte aligned needs no descriptor base offset (measured)
+            const uint32_t a_addr = smem_u32(smem + (gk * CPS + k) * a_chunk_bytes) + shift * 128u;
+            const uint64_t adesc = make_kmajor_sw128_desc_off(a_addr, rp.base_offset_mode ? shift : 0u);
+            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + (s * CPS + k) * Cfg::B_BYTES));
+#pragma unroll
+            for (int kk = 0; kk < CHUNK_K / UMMA_K; ++kk) {
+              umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (first && kk == 0) ? 0u : 1u);
+            }
+            first = false;
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == NSB) { s = 0; ph ^= 1u; }
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31 =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int i, j;
+    if (p.mode == 0) {
+      const int ql = q_local0 + row;
+      i = ql / p.Wv; j = ql - i * p.Wv;
+    } else {
+      i = tile_i0 + (row >> p.bw_log2); j = tile_j0 + (row & (BW - 1));
+    }
+    const int oi = i * p.sy + p.ay, oj = j * p.sx + p.ax;
+    const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W;
+    bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    __shared__ float stat_red[2][4][2][32];       // [chunk parity][epilogue warp][sum | sumsq][column]
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      if (p.stat_acc != nullptr) {
+        // InstanceNorm statistics fused into the epilogue: column sums over the warp's 32 rows by a butterfly that halves the data per
+        // step (31 shuffles per quantity), the 4 epilogue warps are combined in shared memory, one fp64 atomic pair per column and CTA.
+        float s1[32], s2[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float t = valid ? __uint_as_float(r[e]) : 0.f;
+          s1[e] = t;
+          s2[e] = t * t;
+        }
+#pragma unroll
+        for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
+          const bool upper = (lane & step) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float keep1 = upper ? s1[i + n / 2] : s1[i], send1 = upper ? s1[i] : s1[i + n / 2];
+            const float keep2 = upper ? s2[i + n / 2] : s2[i], send2 = upper ? s2[i] : s2[i + n / 2];
+            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
+            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+          }
+        }
+        // lane l now holds the sums of column l
+        const int par = (c >> 5) & 1;
+        stat_red[par][quarter][0][lane] = s1[0];
+        stat_red[par][quarter][1][lane] = s2[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && co0 + c + lane < p.Co) {
+          const float a = stat_red[par][0][0][lane] + stat_red[par][1][0][lane] + stat_red[par][2][0][lane] + stat_red[par][3][0][lane];
+          const float b = stat_red[par][0][1][lane] + stat_red[par][1][1][lane] + stat_red[par][2][1][lane] + stat_red[par][3][1][lane];
+          double *dst = p.stat_acc + ((long long)img * p.Co + co0 + c + lane) * 2;
+          atomicAdd(dst, (double)a);
+          atomicAdd(dst + 1, (double)b);
+        }
+      }
+      if (valid && co0 + c < p.Co) {            // Co is a multiple of 32 here; tiles may overhang it
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+        if (p.bias) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] += __ldg(p.bias + co0 + c + e);
+        }
+        if (p.act != CTAGAN_ACT_NONE) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], p.act);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(out_row + c);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * g + 0], v[8 * g + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * g + 2], v[8 * g + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * g + 4], v[8 * g + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * g + 6], v[8 * g + 7]);
+          pk.x = *reinterpret_cast<uint32_t *>(&h0);
+          pk.y = *reinterpret_cast<uint32_t *>(&h1);
+          pk.z = *reinterpret_cast<uint32_t *>(&h2);
+          pk.w = *reinterpret_cast<uint32_t *>(&h3);
+          dst[g] = pk;
+        }
+      }
+    }
+  }
+  // "last CTA finalises": once every CTA of the layer has added its partial sums, the last one turns them into (mean, rstd)
+  if (p.stat_out != nullptr && warp >= 2) {
+    __shared__ unsigned int ticket_s;
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      unsigned int *ticket = reinterpret_cast<unsigned int *>(p.stat_acc + (long long)p.stat_n * p.Co * 2);
+      ticket_s = atomicAdd(ticket, 1u);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (ticket_s == p.stat_total_ctas - 1) {
+      __threadfence();
+      const double inv = 1.0 / (double)p.stat_hw;
+      for (int i = threadIdx.x - 64; i < p.stat_n * p.Co; i += 128) {
+        const double s1 = __ldcg(p.stat_acc + 2 * i), s2 = __ldcg(p.stat_acc + 2 * i + 1);
+        const double m = s1 * inv;
+        double var = s2 * inv - m * m;
+        if (var < 0) var = 0;
+        p.stat_out[2 * i] = (float)m;
+        p.stat_out[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -671,6 +912,18 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
   return CTAGAN_OK;
 }
 
+template <int BN>
+int launch_resA(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const ResAParams &rp, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_resA_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    configured = true;
+  }
+  conv_tc_resA_kernel<BN><<<grid, 192, smem, st>>>(mx, mw, p, rp);
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
 int pick_bn(long long m_tiles, int Co) {
   const int sms = ctagan_num_sms();
   if (const char *env = getenv("CTAGAN_TC_BN")) {          // tuning override
@@ -693,6 +946,44 @@ int make_map_4d(CUtensorMap *map, const void *base, int N, int H, int W, int C, 
 int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, int w_taps, cudaStream_t st) {
   CUtensorMap mx, mw;
   int rc;
+  // ---- resident-A variant: the union of all tap windows fits in shared memory next to a weight ring ----
+  static int resa_mode = -1;
+  if (resa_mode < 0) { const char *e = getenv("CTAGAN_TC_RESA"); resa_mode = e ? atoi(e) : 0; }   // opt-in: see profiles/tc_tile_tuning_r1.md
+  if (p.mode == 0 && resa_mode > 0 && p.n_taps > 1) {
+    int max_shift = 0;
+    for (int t = 0; t < p.n_taps; ++t) { const int sft = p.tap_dh[t] * p.Wv + p.tap_dw[t]; if (sft > max_shift) max_shift = sft; }
+    const int R = TILE_M + max_shift;
+    ResAParams rp;
+    rp.n_box = (R + 255) / 256;
+    rp.rows_box = (((R + rp.n_box - 1) / rp.n_box) + 7) & ~7;
+    rp.chunks = (p.Ci + CHUNK_K - 1) / CHUNK_K;
+    rp.base_offset_mode = resa_mode == 3 ? 1 : 0;
+    const size_t a_bytes = (size_t)rp.chunks * rp.rows_box * rp.n_box * 128;
+    const long long m_tiles = (long long)N * p.tiles_per_img;
+    int bn = 64;
+    if (p.Co % 256 == 0 && m_tiles * (p.Co / 256) >= 2LL * ctagan_num_sms()) bn = 256;
+    else if (p.Co % 128 == 0 && m_tiles * (p.Co / 128) >= ctagan_num_sms()) bn = 128;
+    if (const char *env = getenv("CTAGAN_TC_BN")) { const int b = atoi(env); if ((b == 64 || b == 128 || b == 256) && p.Co % b == 0) bn = b; }
+    const size_t budget = 224 * 1024 - 1024 - 512;
+    const size_t stage_bytes = 32 * 1024;      // CPS chunks x BN rows x 128 B
+    if (rp.chunks <= 8 && rp.rows_box <= 256 && a_bytes + 2 * stage_bytes <= budget) {
+      size_t stages = (budget - a_bytes) / stage_bytes;
+      if (stages > 8) stages = 8;
+      rp.b_stages = (int)stages;
+      rc = make_map_2d(&mx, x, (uint64_t)N * Hi * Wi, (uint64_t)p.Ci, (uint32_t)rp.rows_box);
+      if (rc) return rc;
+      rc = make_map_w3d(&mw, wp, p.Co, w_taps, p.Ci, (uint32_t)bn);
+      if (rc) return rc;
+      dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
+      if (p.stat_total_ctas == 0) p.stat_total_ctas = grid.x * grid.y;
+      const size_t smem = a_bytes + stages * stage_bytes + 1024 + 512;
+      switch (bn) {
+        case 256: return launch_resA<256>(mx, mw, p, rp, grid, smem, st);
+        case 128: return launch_resA<128>(mx, mw, p, rp, grid, smem, st);
+        default: return launch_resA<64>(mx, mw, p, rp, grid, smem, st);
+      }
+    }
+  }
   if (p.mode == 0) {
     rc = make_map_2d(&mx, x, (uint64_t)N * Hi * Wi, (uint64_t)p.Ci, TILE_M);
   } else {

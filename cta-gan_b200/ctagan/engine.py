@@ -148,6 +148,42 @@ class ConvPrim:
         return ops.conv_wgrad(gy, gx, g, want_bias, _ENGINE["value"])
 
 
+_WGRAD_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_WGRAD_OVERLAP = {"value": True}
+
+
+def set_wgrad_overlap(flag: bool):
+    _WGRAD_OVERLAP["value"] = bool(flag)
+
+
+class _WgradLane:
+    """Weight gradients are leaves of the backward dependency chain (nothing downstream of a layer's dgrad needs them), so they
+    are enqueued on a side stream: the critical path of a backward pass is then norm-backward + dgrad per layer, and the
+    latency-bound batch-1 wgrad GEMMs (split-K + reduce) fill the SMs the main chain leaves idle."""
+
+    def __init__(self):
+        self.main = torch.cuda.current_stream()
+        self.side = None
+        if _WGRAD_OVERLAP["value"]:
+            key = self.main.cuda_stream
+            side = _WGRAD_STREAMS.get(key)
+            if side is None:
+                side = torch.cuda.Stream()
+                _WGRAD_STREAMS[key] = side
+            self.side = side
+
+    def run(self, fn):
+        if self.side is None:
+            return fn()
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            return fn()
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+
+
 def prepack_prims(prims, dtype):
     """Re-pack every stale weight copy of a network with one kernel launch."""
     import os
@@ -232,10 +268,12 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
     T = y.dtype
     grads: List[Optional[torch.Tensor]] = []
 
+    lane = _WgradLane()
+
     def wg(prim, gy, gx, bias=False, margin=0):
         if not need_dw:
             return None, None
-        return prim.wgrad(gy, gx, want_bias=bias, pad=(margin if margin else None), gy_margin=margin)
+        return lane.run(lambda: prim.wgrad(gy, gx, want_bias=bias, pad=(margin if margin else None), gy_margin=margin))
 
     bpool = ops.ZeroPool(2 * y.shape[0] * (64 + 128 + 256 + 512 * plan.n_blocks + 128 + 64), y.device)
     gy = ops.nchw_to_nhwc(dout, T)
@@ -273,6 +311,7 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
         dP0 = plan.head1.bprop(dr1, (P0.shape[1], P0.shape[2]))
         dx0 = ops.norm_act_pad_bwd(dP0, None, None, L.ACT_NONE, 3)
         dx = ops.nhwc_to_nchw(dx0)
+    lane.join()
     if need_dw:
         # biases in front of a non-affine InstanceNorm are mathematically dead: zero gradient
         z = lambda prim: None          # (None == no gradient: Adam leaves the dead parameter untouched)
@@ -328,22 +367,24 @@ def discriminator_backward(plan: DiscriminatorPlan, saved, dout: torch.Tensor, n
     c = plan.convs
     dy = ops.nchw_to_nhwc(dout, T)
     gw: List[Optional[torch.Tensor]] = [None] * 10
+    lane = _WgradLane()
     if need_dw:
-        gw[8], gw[9] = c[4].wgrad(dy, acts[3], want_bias=True)
+        gw[8], gw[9] = lane.run(lambda: c[4].wgrad(dy, acts[3], want_bias=True))
     da = c[4].bprop(dy, (acts[3].shape[1], acts[3].shape[2]))
     for i in (3, 2, 1):
         dr = ops.norm_act_pad_bwd(da, raws[i - 1], stats[i - 1], L.ACT_LRELU, 0)
         if need_dw:
-            gw[2 * i], _ = c[i].wgrad(dr, acts[i - 1])
+            gw[2 * i], _ = lane.run(lambda dr=dr, i=i: c[i].wgrad(dr, acts[i - 1]))
             gw[2 * i + 1] = None            # bias in front of InstanceNorm: mathematically dead
         da = c[i].bprop(dr, (acts[i - 1].shape[1], acts[i - 1].shape[2]))
     dy0 = ops.act_bwd(da, acts[0], L.ACT_LRELU)
     if need_dw:
-        gw[0], gw[1] = c[0].wgrad(dy0, x0, want_bias=True)
+        gw[0], gw[1] = lane.run(lambda: c[0].wgrad(dy0, x0, want_bias=True))
     dx = None
     if need_dx:
         dx0 = c[0].bprop(dy0, (x0.shape[1], x0.shape[2]))
         dx = ops.nhwc_to_nchw(dx0)
+    lane.join()
     return dx, gw
 
 
