@@ -164,6 +164,7 @@ class _WgradLane:
     def __init__(self):
         self.main = torch.cuda.current_stream()
         self.side = None
+        self.used = False
         if _WGRAD_OVERLAP["value"]:
             key = self.main.cuda_stream
             side = _WGRAD_STREAMS.get(key)
@@ -175,12 +176,14 @@ class _WgradLane:
     def run(self, fn):
         if self.side is None:
             return fn()
+        self.used = True
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
             return fn()
 
     def join(self):
-        if self.side is not None:
+        # (only when something was forked: waiting on a stream that never joined a CUDA-graph capture would invalidate the capture)
+        if self.side is not None and self.used:
             self.main.wait_stream(self.side)
 
 
