@@ -414,16 +414,18 @@ class _ResBlock:
         out = ops.norm_act_pad(rb, sb, L.ACT_NONE, 0, res=a, res_pad=0)
         return out, ((Pa, ra, sa, Tt, rb, sb) if save else None)
 
-    def backward(self, saved, G, pre_act=None, pre_act_kind=L.ACT_NONE):
+    def backward(self, saved, G, pre_act=None, pre_act_kind=L.ACT_NONE, lane=None):
         """G: grad w.r.t. the block output.  Returns (grad w.r.t. block input [through `pre_act_kind` of the producer when
         pre_act is given], [dW1, db1, dW2, db2])."""
         Pa, ra, sa, Tt, rb, sb = saved
-        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0)
-        dW2, _ = self.c2.wgrad(drb, Tt)
-        dT = self.c2.bprop(drb, (Tt.shape[1], Tt.shape[2]))
-        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1)
-        dW1, _ = self.c1.wgrad(dra, Pa)
-        dPa = self.c1.bprop(dra, (Pa.shape[1], Pa.shape[2]))
+        run = lane.run if lane is not None else (lambda f: f())
+        m = self.c2.K - 1                                                 # zero margin: dgrad becomes a VALID conv (tcgen05 form)
+        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0, out_pad=m)
+        dW2, _ = run(lambda: self.c2.wgrad(drb, Tt, pad=m, gy_margin=m))
+        dT = self.c2.bprop(drb, (Tt.shape[1], Tt.shape[2]), pad=m)
+        dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1, out_pad=m)
+        dW1, _ = run(lambda: self.c1.wgrad(dra, Pa, pad=m, gy_margin=m))
+        dPa = self.c1.bprop(dra, (Pa.shape[1], Pa.shape[2]), pad=m)
         Ga = ops.norm_act_pad_bwd(dPa, pre_act, None, pre_act_kind, 1, addend=G)
         return Ga, [dW1, None, dW2, None]      # biases in front of InstanceNorm are dead
 
@@ -509,19 +511,20 @@ def reg_forward(plan: RegPlan, img_a: torch.Tensor, img_b: torch.Tensor, save: b
 
 def reg_backward(plan: RegPlan, saved, dflow: torch.Tensor, need_da: bool, need_db: bool, in_channels=(1, 1)):
     downs, m_in, m1, ts_in, tsaved, t_out, m2, ups, x_last, rfsaved, rf, r1, T = saved
+    lane = _WgradLane()
     dfl = ops.nchw_to_nhwc(dflow, T)
-    dWo, dbo = plan.output.wgrad(dfl, r1, want_bias=True)
+    dWo, dbo = lane.run(lambda: plan.output.wgrad(dfl, r1, want_bias=True))
     dr1 = plan.output.bprop(dfl, (r1.shape[1], r1.shape[2]))
     dy = ops.act_bwd(dr1, r1, L.ACT_LRELU)
-    dWr1, dbr1 = plan.refine1.wgrad(dy, rf, want_bias=True)
+    dWr1, dbr1 = lane.run(lambda dy=dy: plan.refine1.wgrad(dy, rf, want_bias=True))
     Grf = plan.refine1.bprop(dy, (rf.shape[1], rf.shape[2]))
     # refine.0 res-block: its input is the LeakyReLU output of up_1 -> fold that activation's backward in
-    Gx, g_refine0 = plan.refine0.backward(rfsaved, Grf, pre_act=x_last, pre_act_kind=L.ACT_LRELU)
+    Gx, g_refine0 = plan.refine0.backward(rfsaved, Grf, pre_act=x_last, pre_act_kind=L.ACT_LRELU, lane=lane)
     up_grads = []
     skip_grads = []
     dyo = Gx  # already multiplied by lrelu'(x_last)
     for conv, (u, xo, C1) in zip(reversed(plan.up), reversed(ups)):
-        dW, db = conv.wgrad(dyo, u, want_bias=True)
+        dW, db = lane.run(lambda dyo=dyo, conv=conv, u=u: conv.wgrad(dyo, u, want_bias=True))
         du = conv.bprop(dyo, (u.shape[1], u.shape[2]))
         gx, gskip = ops.upsample2x_cat_bwd(du, C1)
         up_grads.append((dW, db))
@@ -536,17 +539,17 @@ def reg_backward(plan: RegPlan, saved, dflow: torch.Tensor, need_da: bool, need_
     up_grads.reverse()            # now in plan.up order
     # dyo is grad w.r.t. m2 (post-lrelu)
     dy = ops.act_bwd(dyo, m2, L.ACT_LRELU)
-    dWc2, dbc2 = plan.c2.wgrad(dy, t_out, want_bias=True)
+    dWc2, dbc2 = lane.run(lambda dy=dy: plan.c2.wgrad(dy, t_out, want_bias=True))
     Gt = plan.c2.bprop(dy, (t_out.shape[1], t_out.shape[2]))
     t_grads = []
     for i in (2, 1, 0):
         if i == 0:
-            Gt, gr = plan.t[i].backward(tsaved[i], Gt, pre_act=m1, pre_act_kind=L.ACT_LRELU)
+            Gt, gr = plan.t[i].backward(tsaved[i], Gt, pre_act=m1, pre_act_kind=L.ACT_LRELU, lane=lane)
         else:
-            Gt, gr = plan.t[i].backward(tsaved[i], Gt)
+            Gt, gr = plan.t[i].backward(tsaved[i], Gt, lane=lane)
         t_grads.append(gr)
     t_grads.reverse()
-    dWc1, dbc1 = plan.c1.wgrad(Gt, m_in, want_bias=True)
+    dWc1, dbc1 = lane.run(lambda Gt=Gt: plan.c1.wgrad(Gt, m_in, want_bias=True))
     Gp = plan.c1.bprop(Gt, (m_in.shape[1], m_in.shape[2]))      # grad w.r.t. pooled output of down_7
     down_grads = []
     # skip_grads was filled from up_1 (skip of down_1) to up_7 (skip of down_7): already in down-block order
@@ -554,8 +557,8 @@ def reg_backward(plan: RegPlan, saved, dflow: torch.Tensor, need_da: bool, need_
         conv, rb = plan.down[n]
         x_in, a, rsaved, sk = downs[n]
         Gsk = ops.maxpool2_bwd(Gp, sk, addend=skip_grads[n])
-        Ga, gr = rb.backward(rsaved, Gsk, pre_act=a, pre_act_kind=L.ACT_LRELU)
-        dW, db = conv.wgrad(Ga, x_in, want_bias=True)
+        Ga, gr = rb.backward(rsaved, Gsk, pre_act=a, pre_act_kind=L.ACT_LRELU, lane=lane)
+        dW, db = lane.run(lambda Ga=Ga, conv=conv, x_in=x_in: conv.wgrad(Ga, x_in, want_bias=True))
         down_grads.append((dW, db, gr))
         if n > 0:
             Gp = conv.bprop(Ga, (x_in.shape[1], x_in.shape[2]))
@@ -571,6 +574,7 @@ def reg_backward(plan: RegPlan, saved, dflow: torch.Tensor, need_da: bool, need_
             Ca = in_channels[0]
             da = gin[:, :Ca].contiguous() if need_da else None
             db_ = gin[:, Ca:].contiguous() if need_db else None
+    lane.join()
     grads: List[torch.Tensor] = []
     for dW, db, gr in down_grads:
         grads += [dW, db] + gr

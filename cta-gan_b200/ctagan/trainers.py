@@ -331,13 +331,20 @@ class Reg_Trainer(_TrainerBase):
     def checkpoint_nets(self):
         return {"netG_A2B_{st}.pth": self.netG_A2B, "R_A_{st}.pth": self.R_A, "netD_B_{st}.pth": self.netD_B}
 
+    def _side_stream(self):
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream()
+        return self._side
+
     def _adv_G(self, fake_B):
         return self.MSE_loss(self.netD_B(fake_B, freeze=True), self.target_real)
 
     def _loss_D(self, fake_B, real_B):
+        """fake and real slices go through D as ONE batch (InstanceNorm is per sample: same arithmetic, half the launches)."""
         c = self.config
-        return c[self.lam_adv] * self.MSE_loss(self.netD_B(fake_B), self.target_fake) + \
-            c[self.lam_adv] * self.MSE_loss(self.netD_B(real_B), self.target_real)
+        B = fake_B.shape[0]
+        pred = self.netD_B(torch.cat([fake_B, real_B], 0))
+        return c[self.lam_adv] * self.MSE_loss(pred[:B], self.target_fake) + c[self.lam_adv] * self.MSE_loss(pred[B:], self.target_real)
 
     def _extra_G_losses(self, SysRegist_A2B, tensors):
         return None
@@ -351,13 +358,20 @@ class Reg_Trainer(_TrainerBase):
         for net in (self.netG_A2B, self.R_A, self.netD_B):      # one re-pack launch per network (weights changed last step)
             net.prepack()
         fake_B = self.netG_A2B(real_A)
+        # two independent consumers of fake_B: the registration branch (Reg -> warp -> L1, smoothness) and the adversarial branch
+        cur = torch.cuda.current_stream()
+        side = self._side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            adv_loss = c[self.lam_adv] * self._adv_G(fake_B)
         Trans = self.R_A(fake_B, real_B)
         SysRegist_A2B = self.spatial_transform(fake_B, Trans)
         SR_loss = c[self.lam_corr] * self.L1_loss(SysRegist_A2B, real_B)
-        adv_loss = c[self.lam_adv] * self._adv_G(fake_B)
         SM_loss = c["Smooth_lamda"] * N.smooothing_loss(Trans)
-        toal_loss = SM_loss + adv_loss + SR_loss
         extra = self._extra_G_losses(SysRegist_A2B, tensors)
+        cur.wait_stream(side)
+        adv_loss.record_stream(cur)
+        toal_loss = SM_loss + adv_loss + SR_loss
         if extra is not None:
             toal_loss = toal_loss + extra
         toal_loss.backward()
