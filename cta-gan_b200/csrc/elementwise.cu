@@ -377,118 +377,6 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Single-launch InstanceNorm backward for planes that fit the L2/L1 comfortably: one CTA owns 8 channels of one image, reduces
-// (sum g, sum g*xhat) over all pixels (no atomics, no scratch, deterministic), then applies the formula in a second sweep over the
-// same (cache-hot) data and writes dx with its zero margin.  grid (C/8, N), 256 threads.
-// ---------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) norm_bwd_fused_kernel(const T *__restrict__ gout, const T *__restrict__ x,
-                                                             const float *__restrict__ stats, const T *__restrict__ addend,
-                                                             T *__restrict__ dx, int H, int W, int C, int pad, int act, int out_pad) {
-  constexpr int V = 8;
-  const int cv = blockIdx.x, n = blockIdx.y;
-  const int HW = H * W;
-  float mean[V], rstd[V];
-  load_stats<V>(stats + ((idx_t)n * C + cv * V) * 2, mean, rstd);
-  const int Wp = W + 2 * pad;
-  float s1[V], s2[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
-  constexpr int U = 4;
-  for (int p = threadIdx.x; p < HW; p += 256 * U) {
-    float g[U][V], xv[U][V];
-    int hh[U], ww[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pp = p + u * 256;
-      const bool ok = pp < HW;
-      const int pc = ok ? pp : p;
-      hh[u] = pc / W; ww[u] = pc - hh[u] * W;
-      load_vec<T, V>(gout + (((idx_t)n * (H + 2 * pad) + hh[u] + pad) * Wp + ww[u] + pad) * C + cv * V, g[u]);
-      load_vec<T, V>(x + ((idx_t)n * HW + pc) * C + cv * V, xv[u]);
-      if (addend) {
-        float av[V];
-        load_vec<T, V>(addend + ((idx_t)n * HW + pc) * C + cv * V, av);
-#pragma unroll
-        for (int i = 0; i < V; ++i) g[u][i] += av[i];
-      }
-      if (!ok) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) g[u][i] = 0.f;
-        hh[u] = -1;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (hh[u] >= 0 && fold_is_border(hh[u], ww[u], H, W, pad)) fold_extras<T, V>(gout, n, hh[u], ww[u], cv, H, W, C, pad, g[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (xv[u][i] - mean[i]) * rstd[i];
-        const float gg = g[u][i] * act_grad_from_sign(xh, act);
-        s1[i] += gg;
-        s2[i] = fmaf(gg, xh, s2[i]);
-      }
-  }
-  // block reduction of the 16 partial sums
-  __shared__ float red[8][2 * V];
-  __shared__ float tot[2 * V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    s1[i] = warp_sum(s1[i]);
-    s2[i] = warp_sum(s2[i]);
-  }
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      red[threadIdx.x >> 5][i] = s1[i];
-      red[threadIdx.x >> 5][V + i] = s2[i];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 2 * V) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    tot[threadIdx.x] = t / (float)HW;
-  }
-  __syncthreads();
-  float m1[V], m2[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) { m1[i] = tot[i]; m2[i] = tot[V + i]; }
-  // second sweep: apply, with the zero margin of out_pad pixels
-  const int Ho = H + 2 * out_pad, Wo = W + 2 * out_pad;
-  for (int op = threadIdx.x; op < Ho * Wo; op += 256) {
-    const int ho = op / Wo, wo = op - ho * Wo;
-    const int h = ho - out_pad, w = wo - out_pad;
-    float o[V];
-    if (h < 0 || h >= H || w < 0 || w >= W) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) o[i] = 0.f;
-    } else {
-      float g[V], xv[V];
-      folded_grad<T, V>(gout, n, h, w, cv, H, W, C, pad, g);
-      const idx_t idx = (((idx_t)n * H + h) * W + w) * C + cv * V;
-      if (addend) {
-        float av[V];
-        load_vec<T, V>(addend + idx, av);
-#pragma unroll
-        for (int i = 0; i < V; ++i) g[i] += av[i];
-      }
-      load_vec<T, V>(x + idx, xv);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (xv[i] - mean[i]) * rstd[i];
-        const float gg = g[i] * act_grad_from_sign(xh, act);
-        o[i] = rstd[i] * (gg - m1[i] - xh * m2[i]);
-      }
-    }
-    store_vec<T, V>(dx + (((idx_t)n * Ho + ho) * Wo + wo) * C + cv * V, o);
-  }
-}
-
 template <typename T, int V>
 __global__ void act_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ y, T *__restrict__ dx, idx_t nvec, int act) {
   for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (idx_t)gridDim.x * blockDim.x) {
@@ -834,14 +722,6 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
   CTAGAN_REQUIRE(!stats || acc, "norm_act_pad_bwd: acc scratch required with stats");
   CTAGAN_REQUIRE(act != CTAGAN_ACT_TANH, "norm_act_pad_bwd: tanh unsupported here (use act_bwd)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (stats && C % 8 == 0 && (int64_t)H * W <= 16384 && (int64_t)N * (C / 8) >= 16) {
-    dim3 grid(C / 8, N);
-    CTAGAN_DISPATCH_DTYPE(dtype, T, {
-      norm_bwd_fused_kernel<T><<<grid, 256, 0, st>>>((const T *)gout, (const T *)x, stats, (const T *)addend, (T *)dx, H, W, C, pad, act, out_pad);
-    });
-    CTAGAN_LAUNCH_OK();
-    return CTAGAN_OK;
-  }
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     int v = pick_vec<T>(C);
     if (stats) {
