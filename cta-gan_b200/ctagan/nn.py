@@ -100,11 +100,13 @@ class Generator(nn.Module):
         concurrently on side streams afterwards."""
         E.prepack_prims(self._get_plan().prims(), E.get_precision())
 
-    def forward(self, x):
+    def forward(self, x, params=None):
+        """`params` (extension): alternative leaf tensors aliasing this module's parameters (e.g. `p.detach().requires_grad_()`), so that
+        two passes of the network inside one autograd graph accumulate their gradients separately (see Cyc_Trainer.phase_G)."""
         if x.shape[2] % 4 or x.shape[3] % 4:
             raise ValueError("Generator needs H and W to be multiples of 4")
         plan = self._get_plan()
-        return _GeneratorFn.apply(plan, x, *plan.params)
+        return _GeneratorFn.apply(plan, x, *(plan.params if params is None else params))
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -227,18 +227,23 @@ class Cyc_Trainer(_TrainerBase):
         self.optimizer_G.zero_grad(set_to_none=True)
         for net in (self.netG_A2B, self.netG_B2A, self.netD_A, self.netD_B):
             net.prepack()
+        # Each generator is used once per chain.  autograd would sum the two gradient contributions of a parameter on ONE stream and make
+        # that stream wait for the other chain's producer, which serialises the chains; so the second use of each generator goes through
+        # twin leaves aliasing the same storage, and the two gradient sets are added once after the join (one multi-tensor kernel).
+        twins_B2A = [p.detach().requires_grad_() for p in self.netG_B2A.parameters()]
+        twins_A2B = [p.detach().requires_grad_() for p in self.netG_A2B.parameters()]
         sA, sB = self._side_streams()
         sA.wait_stream(cur); sB.wait_stream(cur)
         with torch.cuda.stream(sA):
             fake_B = self.netG_A2B(real_A)                                                 # CycTrainer.py:144-146
             loss_GAN_A2B = c["Adv_lamda"] * self.MSE_loss(self.netD_B(fake_B, freeze=True), self.target_real)
-            recovered_A = self.netG_B2A(fake_B)                                            # :153-154
+            recovered_A = self.netG_B2A(fake_B, params=twins_B2A)                          # :153-154
             loss_cycle_ABA = c["Cyc_lamda"] * self.L1_loss(recovered_A, real_A)
             loss_A = loss_GAN_A2B + loss_cycle_ABA
         with torch.cuda.stream(sB):
             fake_A = self.netG_B2A(real_B)                                                 # :148-150
             loss_GAN_B2A = c["Adv_lamda"] * self.MSE_loss(self.netD_A(fake_A, freeze=True), self.target_real)
-            recovered_B = self.netG_A2B(fake_A)                                            # :156-157
+            recovered_B = self.netG_A2B(fake_A, params=twins_A2B)                          # :156-157
             loss_cycle_BAB = c["Cyc_lamda"] * self.L1_loss(recovered_B, real_B)
             loss_B = loss_GAN_B2A + loss_cycle_BAB
         cur.wait_stream(sA); cur.wait_stream(sB)
@@ -246,6 +251,17 @@ class Cyc_Trainer(_TrainerBase):
             t.record_stream(cur)
         loss_Total = loss_A + loss_B                                                       # :160-162
         loss_Total.backward()
+        for net, twins in ((self.netG_A2B, twins_A2B), (self.netG_B2A, twins_B2A)):
+            own, extra = [], []
+            for p_, t_ in zip(net.parameters(), twins):
+                if t_.grad is None:
+                    continue
+                if p_.grad is None:
+                    p_.grad = t_.grad
+                else:
+                    own.append(p_.grad); extra.append(t_.grad)
+            if own:
+                torch._foreach_add_(own, extra)
         self._sync_G()
         self.optimizer_G.step()
         return fake_A.detach(), fake_B.detach(), loss_Total.detach()
