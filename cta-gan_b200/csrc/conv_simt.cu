@@ -263,41 +263,56 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, T *__restrict__
 }
 
 constexpr int PACK_MAX_ITEMS = 48;
+constexpr int PACK_TILE = 32;          // 32 output channels x 32 input channels x all taps per block
 struct PackTable {
   int n;
-  long long start[PACK_MAX_ITEMS + 1];      // prefix sums of element counts
+  int tile_start[PACK_MAX_ITEMS + 1];  // prefix sums of tile counts
   const float *w[PACK_MAX_ITEMS];
   void *wp[PACK_MAX_ITEMS];
   int O[PACK_MAX_ITEMS], I[PACK_MAX_ITEMS], KH[PACK_MAX_ITEMS], KW[PACK_MAX_ITEMS], mode[PACK_MAX_ITEMS];
 };
 
-// one launch re-packs every weight of a network (all layers x both layouts): the table rides in the kernel parameters
+// One launch re-packs every weight of a network (all layers x both layouts); the table rides in the kernel parameters.
+// Each block moves a 32(O) x 32(I) x taps tile through shared memory: reads are contiguous runs of 32*taps fp32 of the OIHW master
+// weights, writes are 32 consecutive elements of the packed layout (mode 0: [O][tap][I], mode 1: [I][flipped tap][O]).
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_constant__ PackTable t) {
-  const long long total = t.start[t.n];
-  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < total; gidx += (long long)gridDim.x * blockDim.x) {
-    int lo = 0, hi = t.n - 1;                  // binary search for the item holding gidx
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (t.start[mid] <= gidx) lo = mid; else hi = mid - 1;
+  extern __shared__ float tile[];        // [32 o][32 i * taps (+1 pad)]
+  int lo = 0, hi = t.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (t.tile_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const int it = lo;
+  const int O = t.O[it], I = t.I[it], taps = t.KH[it] * t.KW[it];
+  const int tiles_i = (I + PACK_TILE - 1) / PACK_TILE;
+  const int local = blockIdx.x - t.tile_start[it];
+  const int o0 = (local / tiles_i) * PACK_TILE, i0 = (local % tiles_i) * PACK_TILE;
+  const int no = min(PACK_TILE, O - o0), ni = min(PACK_TILE, I - i0);
+  const int row = ni * taps;             // contiguous fp32 per output channel in this tile
+  const int pitch = PACK_TILE * taps + 1;
+  const float *w = t.w[it];
+  for (int idx = threadIdx.x; idx < no * row; idx += 256) {
+    const int o = idx / row, r = idx - o * row;
+    tile[o * pitch + r] = w[((long long)(o0 + o) * I + i0) * taps + r];
+  }
+  __syncthreads();
+  T *dst = reinterpret_cast<T *>(t.wp[it]);
+  if (t.mode[it] == 0) {
+    // wp[o][tap][i]: consecutive threads -> consecutive i
+    for (int idx = threadIdx.x; idx < no * taps * ni; idx += 256) {
+      const int i = idx % ni;
+      const int r = idx / ni;
+      const int tap = r % taps, o = r / taps;
+      dst[((long long)(o0 + o) * taps + tap) * I + i0 + i] = from_f<T>(tile[o * pitch + i * taps + tap]);
     }
-    const int it = lo;
-    long long r = gidx - t.start[it];
-    const int O = t.O[it], I = t.I[it], KH = t.KH[it], KW = t.KW[it];
-    T *dst = reinterpret_cast<T *>(t.wp[it]);
-    const long long idx = r;
-    if (t.mode[it] == 0) {
-      const int i = (int)(r % I); r /= I;
-      const int kw = (int)(r % KW); r /= KW;
-      const int kh = (int)(r % KH); r /= KH;
-      const int o = (int)r;
-      dst[idx] = from_f<T>(t.w[it][(((long long)o * I + i) * KH + kh) * KW + kw]);
-    } else {
-      const int o = (int)(r % O); r /= O;
-      const int kw = (int)(r % KW); r /= KW;
-      const int kh = (int)(r % KH); r /= KH;
-      const int i = (int)r;
-      dst[idx] = from_f<T>(t.w[it][(((long long)o * I + i) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)]);
+  } else {
+    // wp[i][taps-1-tap][o]: consecutive threads -> consecutive o
+    for (int idx = threadIdx.x; idx < ni * taps * no; idx += 256) {
+      const int o = idx % no;
+      const int r = idx / no;
+      const int tap = r % taps, i = r / taps;
+      dst[((long long)(i0 + i) * taps + (taps - 1 - tap)) * O + o0 + o] = from_f<T>(tile[o * pitch + i * taps + tap]);
     }
   }
 }
@@ -355,19 +370,23 @@ extern "C" int ctagan_pack_weights_multi(const ctagan_pack_item *items, int n_it
   for (int base = 0; base < n_items; base += PACK_MAX_ITEMS) {
     PackTable t;
     t.n = n_items - base < PACK_MAX_ITEMS ? n_items - base : PACK_MAX_ITEMS;
-    t.start[0] = 0;
+    t.tile_start[0] = 0;
+    int max_taps = 1;
     for (int k = 0; k < t.n; ++k) {
       const ctagan_pack_item &it = items[base + k];
       CTAGAN_REQUIRE(it.w && it.wp && it.O > 0 && it.I > 0 && it.KH > 0 && it.KW > 0 && (it.mode == 0 || it.mode == 1),
                      "pack_weights_multi: bad item %d", base + k);
       t.w[k] = it.w; t.wp[k] = it.wp; t.O[k] = it.O; t.I[k] = it.I; t.KH[k] = it.KH; t.KW[k] = it.KW; t.mode[k] = it.mode;
-      t.start[k + 1] = t.start[k] + (long long)it.O * it.I * it.KH * it.KW;
+      const int tiles = ((it.O + PACK_TILE - 1) / PACK_TILE) * ((it.I + PACK_TILE - 1) / PACK_TILE);
+      t.tile_start[k + 1] = t.tile_start[k] + tiles;
+      if (it.KH * it.KW > max_taps) max_taps = it.KH * it.KW;
     }
-    const long long total = t.start[t.n];
-    long long blocks = (total + 1023) / 1024;
-    const long long cap = (long long)ctagan_num_sms() * 8;
-    if (blocks > cap) blocks = cap;
-    CTAGAN_DISPATCH_DTYPE(dtype, T, { pack_weights_multi_kernel<T><<<(int)blocks, 256, 0, st>>>(t); });
+    const size_t smem = (size_t)PACK_TILE * (PACK_TILE * max_taps + 1) * sizeof(float);
+    CTAGAN_REQUIRE(smem <= 200 * 1024, "pack_weights_multi: kernel window too large");
+    CTAGAN_DISPATCH_DTYPE(dtype, T, {
+      if (smem > 48 * 1024) CTAGAN_CUDA_OK(cudaFuncSetAttribute(pack_weights_multi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pack_weights_multi_kernel<T><<<t.tile_start[t.n], 256, smem, st>>>(t);
+    });
     CTAGAN_LAUNCH_OK();
   }
   return CTAGAN_OK;
