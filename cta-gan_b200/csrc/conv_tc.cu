@@ -1170,8 +1170,12 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
   pl.cb = (Wvld + pl.bkw - 1) / pl.bkw;
   pl.total_chunks = g->N * pl.rb * pl.cb;
   pl.tiles = g->KH * g->KW * ((g->Co + WG_M - 1) / WG_M) * ((g->Ci + pl.bnw - 1) / pl.bnw);
-  int splits = (ctagan_num_sms() + pl.tiles - 1) / pl.tiles;
-  const int max_splits = (pl.total_chunks + 3) / 4;         // at least 4 chunks (256 pixels) per CTA
+  static int split_div = 0;
+  if (!split_div) { const char *e = getenv("CTAGAN_WG_SPLIT_DIV"); split_div = e ? atoi(e) : 1; if (split_div < 1) split_div = 1; }
+  int splits = (ctagan_num_sms() / split_div + pl.tiles - 1) / pl.tiles;
+  // at least 32 chunks (2048 pixels) per CTA: measured on the batch-1 Cyc step, where the wgrads run on a side stream next to the
+  // backward chain, 2 splits (36 CTAs) beat 8 (144 CTAs) by 8% of the step; large batches still reach one CTA per SM
+  const int max_splits = (pl.total_chunks + 31) / 32;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   pl.cps = (pl.total_chunks + splits - 1) / splits;
