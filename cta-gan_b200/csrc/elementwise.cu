@@ -85,23 +85,25 @@ __global__ void __launch_bounds__(256) instnorm_partial_kernel(const T *__restri
     }
   }
   // combine pixel lanes through shared memory in fp64
-  __shared__ double sm[2][256];
+  // combine the pixel lanes in ONE shared-memory pass: every thread then owns one (channel, sum|sumsq) pair group and issues its
+  // atomics in parallel (the old per-channel loop serialised 16 block barriers and put all atomics on 32 threads)
+  __shared__ float sm[2][V][256];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    __syncthreads();
-    sm[0][threadIdx.x] = (pl < lanes) ? (double)s1[i] : 0.0;
-    sm[1][threadIdx.x] = (pl < lanes) ? (double)s2[i] : 0.0;
-    __syncthreads();
-    if (pl == 0) {
-      double a = 0.0, b = 0.0;
-      for (int l = 0; l < lanes; ++l) {
-        a += sm[0][l * CV + cv];
-        b += sm[1][l * CV + cv];
-      }
-      double *dst = acc + ((idx_t)n * C + cv * V + i) * 2;
-      atomicAdd(dst, a);
-      atomicAdd(dst + 1, b);
+    sm[0][i][threadIdx.x] = (pl < lanes) ? s1[i] : 0.f;
+    sm[1][i][threadIdx.x] = (pl < lanes) ? s2[i] : 0.f;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < CV * V; item += 256) {
+    const int ccv = item % CV, i = item / CV;
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      a += (double)sm[0][i][l * CV + ccv];
+      b += (double)sm[1][i][l * CV + ccv];
     }
+    double *dst = acc + ((idx_t)n * C + ccv * V + i) * 2;
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
   }
 }
 
@@ -297,23 +299,25 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
         }
     }
   }
-  __shared__ double sm[2][256];
+  // combine the pixel lanes in ONE shared-memory pass: every thread then owns one (channel, sum|sumsq) pair group and issues its
+  // atomics in parallel (the old per-channel loop serialised 16 block barriers and put all atomics on 32 threads)
+  __shared__ float sm[2][V][256];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    __syncthreads();
-    sm[0][threadIdx.x] = (pl < lanes) ? (double)s1[i] : 0.0;
-    sm[1][threadIdx.x] = (pl < lanes) ? (double)s2[i] : 0.0;
-    __syncthreads();
-    if (pl == 0) {
-      double a = 0.0, b = 0.0;
-      for (int l = 0; l < lanes; ++l) {
-        a += sm[0][l * CV + cv];
-        b += sm[1][l * CV + cv];
-      }
-      double *dst = acc + ((idx_t)n * C + cv * V + i) * 2;
-      atomicAdd(dst, a);
-      atomicAdd(dst + 1, b);
+    sm[0][i][threadIdx.x] = (pl < lanes) ? s1[i] : 0.f;
+    sm[1][i][threadIdx.x] = (pl < lanes) ? s2[i] : 0.f;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < CV * V; item += 256) {
+    const int ccv = item % CV, i = item / CV;
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      a += (double)sm[0][i][l * CV + ccv];
+      b += (double)sm[1][i][l * CV + ccv];
     }
+    double *dst = acc + ((idx_t)n * C + ccv * V + i) * 2;
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
   }
 }
 

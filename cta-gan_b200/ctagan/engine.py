@@ -42,9 +42,16 @@ def invalidate_weight_cache():
     _CACHE_EPOCH["value"] += 1
 
 
+_PTR_EPOCH: Dict[int, int] = {}
+
+
 def _after_optimizer_step(optimizer, args, kwargs):
-    # torch's fused Adam updates parameters without bumping their version counters: any optimizer step invalidates
-    invalidate_weight_cache()
+    # torch's fused Adam updates parameters without bumping their version counters: a step invalidates the packed copies of exactly the
+    # parameters this optimizer owns (keyed by storage address, so twin leaves aliasing a parameter are covered too)
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            k = p.data_ptr()
+            _PTR_EPOCH[k] = _PTR_EPOCH.get(k, 0) + 1
 
 
 try:    # global hook: every torch.optim step (also user-written loops around the drop-in modules) refreshes the packed weights
@@ -70,7 +77,7 @@ class ConvPrim:
 
     def packed(self, mode: int, dtype: torch.dtype) -> torch.Tensor:
         key = (mode, dtype)
-        ver = (self.w._version, self.w.data_ptr(), _CACHE_EPOCH["value"])
+        ver = self._version_key()
         hit = self._cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
@@ -84,9 +91,10 @@ class ConvPrim:
             self.packed(m, dtype)
 
     def _version_key(self):
-        return (self.w._version, self.w.data_ptr(), _CACHE_EPOCH["value"])
+        ptr = self.w.data_ptr()
+        return (self.w._version, ptr, _CACHE_EPOCH["value"], _PTR_EPOCH.get(ptr, 0))
 
-    def stale_entries(self, dtype: torch.dtype, modes=(0, 1)):
+    def stale_entries(self, dtype: torch.dtype, modes=(0, 1), force=False):
         """(w, destination buffer, mode) for every packed copy that is out of date; marks them fresh (the caller packs them all
         with ONE ctagan_pack_weights_multi launch).  Destination buffers persist, so CUDA graphs see stable pointers."""
         out = []
@@ -94,7 +102,7 @@ class ConvPrim:
         for m in modes:
             key = (m, dtype)
             hit = self._cache.get(key)
-            if hit is not None and hit[0] == ver:
+            if hit is not None and hit[0] == ver and not force:
                 continue
             if hit is not None and hit[1].dtype == dtype:
                 buf = hit[1]
@@ -145,10 +153,13 @@ class ConvPrim:
         assert Co == self.O and Ci == self.I
         p = self.p if pad is None else pad
         g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, self.K, self.s, 1, p, L.ACT_NONE, ops.dt(gy), gy_margin)
+        if _ACTIVE_LANE["value"] is not None:
+            _ACTIVE_LANE["value"].keep += (gy, gx)
         return ops.conv_wgrad(gy, gx, g, want_bias, _ENGINE["value"])
 
 
 _WGRAD_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_ACTIVE_LANE = {"value": None}
 _WGRAD_OVERLAP = {"value": True}
 
 
@@ -159,12 +170,17 @@ def set_wgrad_overlap(flag: bool):
 class _WgradLane:
     """Weight gradients are leaves of the backward dependency chain (nothing downstream of a layer's dgrad needs them), so they
     are enqueued on a side stream: the critical path of a backward pass is then norm-backward + dgrad per layer, and the
-    latency-bound batch-1 wgrad GEMMs (split-K + reduce) fill the SMs the main chain leaves idle."""
+    latency-bound batch-1 wgrad GEMMs (split-K + reduce) fill the SMs the main chain leaves idle.
+
+    The side stream reads tensors the main stream allocated (dy, the saved layer input).  The caching allocator would hand such a block
+    to the next main-stream allocation as soon as the main chain drops it -- while the lagging wgrad may still be reading it -- so the
+    lane keeps every wgrad operand alive until join() (record_stream is not an option under CUDA-graph capture)."""
 
     def __init__(self):
         self.main = torch.cuda.current_stream()
         self.side = None
         self.used = False
+        self.keep = []
         if _WGRAD_OVERLAP["value"]:
             key = self.main.cuda_stream
             side = _WGRAD_STREAMS.get(key)
@@ -178,25 +194,25 @@ class _WgradLane:
             return fn()
         self.used = True
         self.side.wait_stream(self.main)
-        with torch.cuda.stream(self.side):
-            return fn()
+        prev, _ACTIVE_LANE["value"] = _ACTIVE_LANE["value"], self
+        try:
+            with torch.cuda.stream(self.side):
+                return fn()
+        finally:
+            _ACTIVE_LANE["value"] = prev
 
     def join(self):
         # (only when something was forked: waiting on a stream that never joined a CUDA-graph capture would invalidate the capture)
         if self.side is not None and self.used:
             self.main.wait_stream(self.side)
+        self.keep = []
 
 
-def prepack_prims(prims, dtype):
-    """Re-pack every stale weight copy of a network with one kernel launch."""
-    import os
-    if os.environ.get("CTAGAN_PACK_MULTI", "1") == "0":
-        for prim in prims:
-            prim.prepack(dtype)
-        return
+def prepack_prims(prims, dtype, force=False):
+    """Re-pack every stale (force: every) weight copy of a network with one kernel launch, into the persistent pack buffers."""
     entries = []
     for prim in prims:
-        entries += prim.stale_entries(dtype)
+        entries += prim.stale_entries(dtype, force=force)
     if entries:
         ops.pack_weights_multi(entries, dtype)
 

@@ -7,8 +7,12 @@ reference keeps on the CPU (ReplayBuffer with Python `random`, trainer/utils.py:
 the Cyc step is two graphs (generator phase; both discriminator phases) around the buffer exchanges.  Inside each graph the two
 independent chains of the phase are forked onto two streams (see Cyc_Trainer.phase_G), i.e. parallel branches of the CUDA graph.
 
-Weight packing (fp32 master -> bf16 [O][kh][kw][I]) is part of the captured graphs: the packed-weight cache is invalidated
-right before capture, so every replay re-packs from the current master weights.
+Weight packing (fp32 master -> bf16 [O][kh][kw][I]) is part of the captured graphs.  Single-graph trainers invalidate the
+packed-weight cache right before capture, so every replay re-packs from the current master weights at its start.  The Cyc
+step instead re-packs each network right AFTER its optimizer step (forced, so the kernels are captured there): the generators
+on a third branch beside the discriminator phases, the discriminators at the end of their own branch -- the generator phase
+then starts on its convolutions at once.  Consequence: weights edited out of band between replays (e.g. load_state_dict) need
+`refresh_weights()` before the next Cyc replay.
 """
 from __future__ import annotations
 
@@ -39,6 +43,12 @@ class GraphedTrainer:
 
     def launches_per_step(self) -> int:
         return self._launches
+
+    def refresh_weights(self):
+        """Re-pack every network from its master weights now (after load_state_dict or any out-of-band edit between replays)."""
+        for m in self.t.__dict__.values():
+            if isinstance(m, torch.nn.Module) and hasattr(m, "prepack"):
+                m.prepack(force=True)
 
     # -- internals -------------------------------------------------------------------------------------------------------
     def _run(self, tensors, copy_inputs):
@@ -78,7 +88,10 @@ class GraphedTrainer:
                 t.step(tensors=static)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        E.invalidate_weight_cache()
+        if not self.is_cyc:
+            E.invalidate_weight_cache()
+        if self.is_cyc:
+            self.refresh_weights()
         n0 = ops.launch_count()
         if self.is_cyc:
             real_A, real_B = static

@@ -95,10 +95,11 @@ class Generator(nn.Module):
         self._plan = None
         return super()._apply(fn, *a, **k)
 
-    def prepack(self):
+    def prepack(self, force=False):
         """Pack the current weights (bf16 / re-laid-out copies) on the current stream; lets several passes of this network run
-        concurrently on side streams afterwards."""
-        E.prepack_prims(self._get_plan().prims(), E.get_precision())
+        concurrently on side streams afterwards.  `force` re-packs even copies the cache believes fresh (used where a trainer
+        knows the optimizer has just stepped, so that the pack kernels are captured in that position of a CUDA graph)."""
+        E.prepack_prims(self._get_plan().prims(), E.get_precision(), force)
 
     def forward(self, x, params=None):
         """`params` (extension): alternative leaf tensors aliasing this module's parameters (e.g. `p.detach().requires_grad_()`), so that
@@ -174,8 +175,8 @@ class _DiscBase(nn.Module):
         self._plan = None
         return super()._apply(fn, *a, **k)
 
-    def prepack(self):
-        E.prepack_prims(self._get_plan().prims(), E.get_precision())
+    def prepack(self, force=False):
+        E.prepack_prims(self._get_plan().prims(), E.get_precision(), force)
 
     def _run(self, x, sink=None, freeze=False):
         plan = self._get_plan()
@@ -269,9 +270,9 @@ class Discriminator_m(_DiscBase):
             self._plans[i] = plan
         return plan
 
-    def prepack(self):
+    def prepack(self, force=False):
         for i in range(self.num_D):
-            E.prepack_prims(self._scale_plan(i).prims(), E.get_precision())
+            E.prepack_prims(self._scale_plan(i).prims(), E.get_precision(), force)
 
     def forward(self, x, freeze=False):
         result = []
@@ -422,8 +423,8 @@ class Reg(nn.Module):
             self._plan = E.RegPlan(params)
         return self._plan
 
-    def prepack(self):
-        E.prepack_prims(self._get_plan().prims(), E.get_precision())
+    def prepack(self, force=False):
+        E.prepack_prims(self._get_plan().prims(), E.get_precision(), force)
 
     def forward(self, img_a, img_b, apply_on=None):
         plan = self._get_plan()

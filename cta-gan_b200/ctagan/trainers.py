@@ -218,15 +218,15 @@ class Cyc_Trainer(_TrainerBase):
     # replays each backward node on its forward stream, so the backward chains overlap the same way.  Same for the two D phases.
     def _side_streams(self):
         if not hasattr(self, "_streams"):
-            self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
-        return self._streams
+            self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+        return self._streams[:2]
 
     def phase_G(self, real_A, real_B):
         c = self.config
         cur = torch.cuda.current_stream()
         self.optimizer_G.zero_grad(set_to_none=True)
         for net in (self.netG_A2B, self.netG_B2A, self.netD_A, self.netD_B):
-            net.prepack()
+            net.prepack()                      # no-op in steady state: phase_DD re-packs every network right after its optimizer step
         # Each generator is used once per chain.  autograd would sum the two gradient contributions of a parameter on ONE stream and make
         # that stream wait for the other chain's producer, which serialises the chains; so the second use of each generator goes through
         # twin leaves aliasing the same storage, and the two gradient sets are added once after the join (one multi-tensor kernel).
@@ -279,6 +279,7 @@ class Cyc_Trainer(_TrainerBase):
         loss_D.backward()
         sync()
         opt.step()
+        netD.prepack(force=True)               # off the generator phase's critical path (it only reads the frozen discriminators)
         return loss_D.detach()
 
     def phase_DD(self, real_A, fake_A, real_B, fake_B):
@@ -286,12 +287,15 @@ class Cyc_Trainer(_TrainerBase):
         cur = torch.cuda.current_stream()
         self.netD_A.prepack(); self.netD_B.prepack()
         sA, sB = self._side_streams()
-        sA.wait_stream(cur); sB.wait_stream(cur)
+        sC = self._streams[2]
+        sA.wait_stream(cur); sB.wait_stream(cur); sC.wait_stream(cur)
+        with torch.cuda.stream(sC):            # the generators were just updated (phase_G): re-pack them beside the discriminator phases
+            self.netG_A2B.prepack(force=True); self.netG_B2A.prepack(force=True)
         with torch.cuda.stream(sA):
             loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, fake_A)
         with torch.cuda.stream(sB):
             loss_D_B = self.phase_D(self.netD_B, self.optimizer_D_B, self._sync_DB, real_B, fake_B)
-        cur.wait_stream(sA); cur.wait_stream(sB)
+        cur.wait_stream(sA); cur.wait_stream(sB); cur.wait_stream(sC)
         loss_D_A.record_stream(cur); loss_D_B.record_stream(cur)
         return loss_D_A, loss_D_B
 
