@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // C-ABI glue: error state, device checks and engine dispatch for the convolution entry points.
 #include <stdarg.h>
 #include "common.cuh"
@@ -35,6 +36,13 @@ int ctagan_num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+bool ctagan_pdl_enabled() {
+  // measured on the Cyc step (batch 1): trigger at kernel start 6.87 ms, trigger at the epilogue 6.16-6.21 ms, off 6.20-6.22 ms --
+  // the dependent-launch gap is not what bounds the chains, so the attribute stays opt-in
+  const char *e = getenv("CTAGAN_PDL");
+  return e && e[0] == '1';
 }
 
 extern "C" int ctagan_version(void) { return 100; }

@@ -1,5 +1,6 @@
 // Shared device/host helpers for libctagan (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -121,6 +122,34 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol).  At batch 1 a step is ~1000 dependent kernels of a few microseconds each, so the
+// launch gap between a kernel and its consumer is a large share of the chain.  Hot kernels therefore (a) signal
+// launch_dependents at their very top, so the consumer's CTAs are scheduled and run their prologue (barrier init, TMEM allocation,
+// index arithmetic) while this grid is still working, and (b) execute griddepcontrol.wait before their first global-memory access,
+// which blocks until the producer grid has completed and flushed.  Both instructions are no-ops for a normally launched kernel.
+// RULE: a kernel launched through launch_pdl() must call pdl_wait() before touching global memory.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool ctagan_pdl_enabled();     // env CTAGAN_PDL=1 (opt-in: measured neutral on the Cyc step, see capi.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = ctagan_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
 // number of SMs (B200: 148); cached

@@ -253,6 +253,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -305,6 +306,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
+    pdl_trigger();          // only the epilogue is left: let the split-K reduce be scheduled
 #pragma unroll 1
     for (int c = 0; c < BNW; c += 32) {
       uint32_t r[32];
@@ -332,6 +334,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
 
 // dw[co][ci][tap] = sum_s ws[s][co][tap][ci]     (also the [co][tap][ci] -> PyTorch OIHW transpose)
 __global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci) {
+  pdl_wait();
   const long long total = (long long)Co * ntaps * Ci;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(idx % Ci);
@@ -422,6 +425,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                          // producer grid complete + flushed: nothing above touches global memory
 
   if (warp == 0) {
     if (lane == 0) {
@@ -489,6 +493,10 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    // accumulator complete: from here on only the epilogue is left, so let the consumer's CTAs be scheduled now (they run their
+    // prologue and block in their own pdl_wait() until this grid has finished).  Triggering at kernel start instead made the
+    // step SLOWER: early-resident consumers held shared memory that the other streams' kernels needed.
+    pdl_trigger();
     __shared__ float stat_red[2][4][2][32];       // [chunk parity][epilogue warp][sum | sumsq][column]
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -907,7 +915,7 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
     const int ns = atoi(env);
     if (ns >= 1 && ns <= Cfg::STAGES) q.n_stages = ns;
   }
-  conv_tc_valid_kernel<BN, KCH><<<grid, 192, Cfg::SMEM_BYTES, st>>>(mx, mw, q);
+  CTAGAN_CUDA_OK(launch_pdl(conv_tc_valid_kernel<BN, KCH>, grid, dim3(192), Cfg::SMEM_BYTES, st, mx, mw, q));
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
@@ -1191,7 +1199,7 @@ int launch_wg(const CUtensorMap &my, const CUtensorMap &mx, const WgParams &p, d
     CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  conv_wgrad_tc_kernel<BNW><<<grid, 192, Cfg::SMEM_BYTES, st>>>(my, mx, p);
+  CTAGAN_CUDA_OK(launch_pdl(conv_wgrad_tc_kernel<BNW>, grid, dim3(192), Cfg::SMEM_BYTES, st, my, mx, p));
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
@@ -1237,7 +1245,7 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   const long long total = (long long)g->Co * p.ntaps * g->Ci;
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctagan_num_sms() * 8) blocks = ctagan_num_sms() * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>((const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci);
+  CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
   CTAGAN_LAUNCH_OK();
   if (db) {
     const long long pixels = (long long)g->N * g->Ho * g->Wo;

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__
                                                            const double *__restrict__ sums, float *__restrict__ stats_out,
                                                            const T *__restrict__ res, int res_pad, T *__restrict__ out, int N, int H,
                                                            int W, int C, int pad, int act) {
+  pdl_wait();
   const int CV = C / V;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const idx_t total = (idx_t)N * Hp * Wp * CV;
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
                                                               const float *__restrict__ stats, const T *__restrict__ addend,
                                                               double *__restrict__ acc, int H, int W, int C, int pad, int act,
                                                               int pix_per_block) {
+  pdl_wait();
   const int CV = C / V;
   const int n = blockIdx.y;
   const int lanes = 256 / CV > 0 ? 256 / CV : 1;
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
                                                              const float *__restrict__ stats, const double *__restrict__ acc,
                                                              const T *__restrict__ addend, T *__restrict__ dx,
                                                              int N, int H, int W, int C, int pad, int act, int out_pad) {
+  pdl_wait();
   const int CV = C / V;
   const int HW = H * W;
   const int Ho = H + 2 * out_pad, Wo = W + 2 * out_pad;
@@ -711,7 +714,7 @@ extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const doub
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C);
     const idx_t total = (idx_t)N * (H + 2 * pad) * (W + 2 * pad) * (C / v);
-    VEC_SWITCH(T, v, V, norm_act_pad_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)x, stats, sums, stats_out, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act));
+    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_act_pad_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)x, stats, sums, stats_out, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act)));
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
@@ -734,10 +737,10 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
       int ppb;
       const int chunks = reduce_chunks(N, H * W, C, v, ppb);
       dim3 grid(chunks, N);
-      VEC_SWITCH(T, v, V, norm_bwd_reduce_kernel<T, V><<<grid, 256, 0, st>>>((const T *)gout, (const T *)x, stats, (const T *)addend, acc, H, W, C, pad, act, ppb));
+      VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<T, V>, grid, dim3(256), 0, st, (const T *)gout, (const T *)x, stats, (const T *)addend, acc, H, W, C, pad, act, ppb)));
     }
     const idx_t total = (idx_t)N * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / v);
-    VEC_SWITCH(T, v, V, norm_bwd_apply_kernel<T, V><<<ew_blocks(total), 256, 0, st>>>((const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, N, H, W, C, pad, act, out_pad));
+    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, N, H, W, C, pad, act, out_pad)));
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
