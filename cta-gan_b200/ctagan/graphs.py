@@ -4,14 +4,15 @@ A Cyc step at batch 1 is ~1700 kernel launches for ~1.3 TFLOP: launch latency, n
 iteration body is therefore captured once (torch.cuda.CUDAGraph: all libctagan kernels, the NCCL gradient all-reduce and the
 capturable Adam updates are stream-ordered and allocation-free on replay) and replayed per step.  Host-side logic that the
 reference keeps on the CPU (ReplayBuffer with Python `random`, trainer/utils.py:120-140) stays on the host BETWEEN graphs:
-the Cyc step is two graphs (generator phase; both discriminator phases) around the buffer exchanges.  Inside each graph the two
-independent chains of the phase are forked onto two streams (see Cyc_Trainer.phase_G), i.e. parallel branches of the CUDA graph.
+but its random decisions do not depend on the data, so the host makes them before the replay and uploads them as an index tensor
+(replay.py); the Cyc step is then ONE graph whose branches are the two generator chains, the two discriminator updates (forked as
+soon as their fake exists, running beside the generator backward) and the weight-gradient lanes.
 
 Weight packing (fp32 master -> bf16 [O][kh][kw][I]) is part of the captured graphs.  Single-graph trainers invalidate the
 packed-weight cache right before capture, so every replay re-packs from the current master weights at its start.  The Cyc
-step instead re-packs each network right AFTER its optimizer step (forced, so the kernels are captured there): the generators
-on a third branch beside the discriminator phases, the discriminators at the end of their own branch -- the generator phase
-then starts on its convolutions at once.  Consequence: weights edited out of band between replays (e.g. load_state_dict) need
+step instead re-packs each network right AFTER its optimizer step (forced, so the kernels are captured there; the
+discriminators only once the generator backward, the last reader of their packed weights, is done) -- the next step then
+starts on its convolutions at once.  Consequence: weights edited out of band between replays (e.g. load_state_dict) need
 `refresh_weights()` before the next Cyc replay.
 """
 from __future__ import annotations
@@ -26,7 +27,7 @@ class GraphedTrainer:
     def __init__(self, trainer, enabled: bool = True, warmup: int = 3):
         self.t = trainer
         self.enabled = enabled
-        self.warmup = warmup
+        self.warmup = max(int(warmup), 1)
         self._graphs = None
         self._launches = 0
         self.is_cyc = hasattr(trainer, "phase_G")
@@ -64,13 +65,8 @@ class GraphedTrainer:
             self._capture(static)
         E.invalidate_weight_cache()          # eager users after us must not trust capture-time packed weights
         if self.is_cyc:
-            gG, gD = self._graphs
-            gG.replay()
-            fa = t.fake_A_buffer.push_and_pop(self._fake_A.clone())
-            fb = t.fake_B_buffer.push_and_pop(self._fake_B.clone())
-            self._sel_A.copy_(fa)
-            self._sel_B.copy_(fb)
-            gD.replay()
+            self._sel.copy_(t.plan_replay(static[0].shape[0]), non_blocking=True)   # this step's ReplayBuffer decisions (host RNG)
+            self._graphs[0].replay()
             t.last_losses = {"loss_G": self._loss_G, "loss_D_A": self._loss_DA, "loss_D_B": self._loss_DB}
         else:
             self._graphs[0].replay()
@@ -95,16 +91,15 @@ class GraphedTrainer:
         n0 = ops.launch_count()
         if self.is_cyc:
             real_A, real_B = static
-            gG = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gG):
-                self._fake_A, self._fake_B, self._loss_G = t.phase_G(real_A, real_B)
-            pool = gG.pool()
-            self._sel_A, self._sel_B = torch.empty_like(self._fake_A), torch.empty_like(self._fake_B)
-            self._sel_A.copy_(self._fake_A); self._sel_B.copy_(self._fake_B)
-            gD = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gD, pool=pool):
-                self._loss_DA, self._loss_DB = t.phase_DD(real_A, self._sel_A, real_B, self._sel_B)
-            self._graphs = (gG, gD)
+            B = real_A.shape[0]
+            # capture must not consume ReplayBuffer state or host RNG: it runs with "pass through" decisions on the scratch slot
+            scratch = t.fake_A_buffer.max_size
+            self._sel = torch.full((4, B), scratch, dtype=torch.int64, device=real_A.device)
+            assert t.fake_A_buffer.pool is not None and t.fake_B_buffer.pool is not None, "warm-up steps create the device pools"
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._loss_G, self._loss_DA, self._loss_DB = t.phase_all(real_A, real_B, self._sel)
+            self._graphs = (g,)
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

@@ -266,7 +266,7 @@ class Cyc_Trainer(_TrainerBase):
         self.optimizer_G.step()
         return fake_A.detach(), fake_B.detach(), loss_Total.detach()
 
-    def phase_D(self, netD, opt, sync, real, fake):
+    def phase_D(self, netD, opt, sync, real, fake, repack=True, step_after=None):
         """One discriminator update (:165-178 / :182-197).  real and fake go through the network as ONE batch: InstanceNorm is
         per sample, so this is the same arithmetic as the reference's two passes with half the kernel launches."""
         c = self.config
@@ -278,8 +278,11 @@ class Cyc_Trainer(_TrainerBase):
         loss_D = loss_real + loss_fake
         loss_D.backward()
         sync()
+        if step_after is not None:             # an event after which the master weights (biases are read in place) may change
+            torch.cuda.current_stream().wait_event(step_after)
         opt.step()
-        netD.prepack(force=True)               # off the generator phase's critical path (it only reads the frozen discriminators)
+        if repack:
+            netD.prepack(force=True)           # off the generator phase's critical path (it only reads the frozen discriminators)
         return loss_D.detach()
 
     def phase_DD(self, real_A, fake_A, real_B, fake_B):
@@ -299,7 +302,97 @@ class Cyc_Trainer(_TrainerBase):
         loss_D_A.record_stream(cur); loss_D_B.record_stream(cur)
         return loss_D_A, loss_D_B
 
+    # The whole iteration as ONE stream-ordered program.  The ReplayBuffer's random decisions do not depend on the data
+    # (replay.py), so the host makes them up front and the device applies them with index tensors; the discriminator updates
+    # then need nothing from the host and fork off as soon as their fake exists: they run beside the cycle forward and the
+    # generator backward (which only READS the packed discriminator weights) instead of after them.
+    def plan_replay(self, batch_size):
+        """Host half of the two push_and_pop calls (:170, :189), in the reference's order.  Returns one int64 CPU tensor [4, B]."""
+        sa, da = self.fake_A_buffer.plan(batch_size)
+        sb, db = self.fake_B_buffer.plan(batch_size)
+        return torch.tensor([sa, da, sb, db], dtype=torch.int64)
+
+    def phase_all(self, real_A, real_B, sel):
+        """sel: int64 device tensor [4, B] from plan_replay().  Returns (loss_G, loss_D_A, loss_D_B)."""
+        c = self.config
+        cur = torch.cuda.current_stream()
+        self.optimizer_G.zero_grad(set_to_none=True)
+        for net in (self.netG_A2B, self.netG_B2A, self.netD_A, self.netD_B):
+            net.prepack()                      # no-op in steady state: every network is re-packed right after its optimizer step
+        twins_B2A = [p.detach().requires_grad_() for p in self.netG_B2A.parameters()]      # see phase_G
+        twins_A2B = [p.detach().requires_grad_() for p in self.netG_A2B.parameters()]
+        sA, sB = self._side_streams()
+        if not hasattr(self, "_d_streams"):
+            self._d_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        sDA, sDB = self._d_streams
+        for s_ in (sA, sB, sDA, sDB):
+            s_.wait_stream(cur)
+        with torch.cuda.stream(sA):
+            fake_B = self.netG_A2B(real_A)                                                 # CycTrainer.py:144-146
+            ev_fake_B = torch.cuda.Event(); ev_fake_B.record(sA)
+            loss_GAN_A2B = c["Adv_lamda"] * self.MSE_loss(self.netD_B(fake_B, freeze=True), self.target_real)
+            ev_DB_read = torch.cuda.Event(); ev_DB_read.record(sA)
+            recovered_A = self.netG_B2A(fake_B, params=twins_B2A)                          # :153-154
+            loss_A = loss_GAN_A2B + c["Cyc_lamda"] * self.L1_loss(recovered_A, real_A)
+        with torch.cuda.stream(sB):
+            fake_A = self.netG_B2A(real_B)                                                 # :148-150
+            ev_fake_A = torch.cuda.Event(); ev_fake_A.record(sB)
+            loss_GAN_B2A = c["Adv_lamda"] * self.MSE_loss(self.netD_A(fake_A, freeze=True), self.target_real)
+            ev_DA_read = torch.cuda.Event(); ev_DA_read.record(sB)
+            recovered_B = self.netG_A2B(fake_A, params=twins_A2B)                          # :156-157
+            loss_B = loss_GAN_B2A + c["Cyc_lamda"] * self.L1_loss(recovered_B, real_B)
+        cur.wait_stream(sA); cur.wait_stream(sB)
+        for t in (loss_A, loss_B):
+            t.record_stream(cur)
+        loss_Total = loss_A + loss_B                                                       # :160-162
+        loss_Total.backward()
+        cur.wait_stream(sA); cur.wait_stream(sB)          # the backward nodes ran on their forward streams
+        ev_G_backward = torch.cuda.Event(); ev_G_backward.record(cur)
+        # The discriminator updates are ISSUED here -- after the generator backward in host order, because the backward looks the
+        # packed discriminator weights up when it runs and an optimizer step issued earlier would mark them stale -- but their
+        # streams only wait for the fakes, so on the device (and as CUDA-graph branches) they run beside the generator backward.
+        with torch.cuda.stream(sDA):                                                       # :165-178
+            sDA.wait_event(ev_fake_A)
+            pooled_A = self.fake_A_buffer.apply(fake_A, sel[0], sel[1])
+            loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, pooled_A, repack=False, step_after=ev_DA_read)
+            sDA.wait_event(ev_G_backward)      # the generator backward was the last reader of the packed discriminator weights
+            self.netD_A.prepack(force=True)
+        with torch.cuda.stream(sDB):                                                       # :182-197
+            sDB.wait_event(ev_fake_B)
+            pooled_B = self.fake_B_buffer.apply(fake_B, sel[2], sel[3])
+            loss_D_B = self.phase_D(self.netD_B, self.optimizer_D_B, self._sync_DB, real_B, pooled_B, repack=False, step_after=ev_DB_read)
+            sDB.wait_event(ev_G_backward)
+            self.netD_B.prepack(force=True)
+        for net, twins in ((self.netG_A2B, twins_A2B), (self.netG_B2A, twins_B2A)):
+            own, extra = [], []
+            for p_, t_ in zip(net.parameters(), twins):
+                if t_.grad is None:
+                    continue
+                if p_.grad is None:
+                    p_.grad = t_.grad
+                else:
+                    own.append(p_.grad); extra.append(t_.grad)
+            if own:
+                torch._foreach_add_(own, extra)
+        self._sync_G()
+        self.optimizer_G.step()
+        self.netG_A2B.prepack(force=True); self.netG_B2A.prepack(force=True)
+        cur.wait_stream(sDA); cur.wait_stream(sDB)
+        for t in (loss_D_A, loss_D_B, fake_A, fake_B):
+            t.record_stream(cur)
+        return loss_Total.detach(), loss_D_A, loss_D_B
+
     def step(self, batch=None, tensors=None):
+        real_A, real_B = tensors if tensors is not None else self.load_batch(batch)
+        sel = self.plan_replay(real_A.shape[0]).to(real_A.device, non_blocking=True)
+        loss_G, loss_D_A, loss_D_B = self.phase_all(real_A, real_B, sel)
+        self.step_count += 1
+        self.last_losses = {"loss_G": loss_G, "loss_D_A": loss_D_A, "loss_D_B": loss_D_B}
+        return self.last_losses
+
+    def step_two_phase(self, batch=None, tensors=None):
+        """The same iteration in the reference's serial order (generator phase, then both discriminator phases); kept as the
+        cross-check of the overlapped schedule."""
         real_A, real_B = tensors if tensors is not None else self.load_batch(batch)
         fake_A, fake_B, loss_G = self.phase_G(real_A, real_B)
         fake_A = self.fake_A_buffer.push_and_pop(fake_A)                                   # :170
