@@ -7,17 +7,17 @@ int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void
 int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
 // tcgen05 engine (conv_tc.cu): return CTAGAN_ERR_UNSUPPORTED when the geometry does not tile
 int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                          float *stat_out, cudaStream_t st);
+                          float *stat_out, cudaStream_t st, const ctagan_conv_groups *gr = nullptr);
 int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                         size_t workspace_bytes, cudaStream_t st);
-size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g);
+                         size_t workspace_bytes, cudaStream_t st, int n_groups = 1);
+size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g, int n_groups = 1);
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g);
 // degenerate (1-2 channel) convolutions (conv_small.cu)
 int ctagan_conv_small_kind(const ctagan_conv_geom *g);
 int ctagan_conv_gather_small(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
 int ctagan_conv_wgrad_thin_eligible(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
-int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g);
+int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups = 1);
 
 static thread_local char g_err[512] = "";
 
@@ -108,6 +108,42 @@ extern "C" int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine) 
   if (engine != 3 && ctagan_conv_small_kind(g)) return 4;
   if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return 2;
   return 1;
+}
+
+// ---- grouped launches: the batch is gr->groups consecutive image groups, group k convolved with the weights in slot gr->slot[k] of a
+// packed buffer [slots][Co][taps][Ci]; tcgen05 engine only (callers fall back to one launch per group for other geometries) ----
+extern "C" int ctagan_conv_gather_grouped_supported(const ctagan_conv_geom *g, const ctagan_conv_groups *gr) {
+  if (!g || !gr || gr->groups < 1 || gr->groups > CTAGAN_MAX_GROUPS || g->N % gr->groups) return 0;
+  return ctagan_conv_gather_tc_eligible(g) ? 1 : 0;
+}
+
+extern "C" int ctagan_conv_gather_grouped(const ctagan_conv_geom *g, const ctagan_conv_groups *gr, const void *x, const void *wp,
+                                          const float *bias, void *y, double *stat_acc, float *stats_out, void *stream) {
+  int rc = check_geom(g, "conv_gather_grouped");
+  if (rc) return rc;
+  CTAGAN_REQUIRE(gr && x && wp && y, "conv_gather_grouped: null pointer");
+  if (!ctagan_conv_gather_grouped_supported(g, gr)) {
+    ctagan_set_error("conv_gather_grouped: geometry / grouping not supported by the tcgen05 engine");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_acc, stat_acc ? stats_out : nullptr, (cudaStream_t)stream, gr);
+}
+
+extern "C" size_t ctagan_conv_wgrad_grouped_workspace_bytes(const ctagan_conv_geom *g, int groups) {
+  if (!g || groups < 1 || groups > CTAGAN_MAX_GROUPS) return 0;
+  return ctagan_conv_wgrad_tc_workspace(g, groups);
+}
+
+extern "C" int ctagan_conv_wgrad_grouped(const ctagan_conv_geom *g, int groups, const void *gy, const void *gx, float *dw, float *db,
+                                         void *workspace, size_t workspace_bytes, void *stream) {
+  int rc = check_geom(g, "conv_wgrad_grouped");
+  if (rc) return rc;
+  CTAGAN_REQUIRE(gy && gx && dw && groups >= 1 && groups <= CTAGAN_MAX_GROUPS, "conv_wgrad_grouped: bad arguments");
+  if (!ctagan_conv_wgrad_tc_eligible(g, groups)) {
+    ctagan_set_error("conv_wgrad_grouped: geometry / grouping not supported by the tcgen05 engine");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, (cudaStream_t)stream, groups);
 }
 
 extern "C" int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,

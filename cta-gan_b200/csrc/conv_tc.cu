@@ -51,6 +51,8 @@ struct TcParams {
   float *stat_out;             // optional [N][Co][2] (mean, rstd), written by the last CTA to finish (ticket right after stat_acc)
   int stat_n, stat_hw;         // images and pixels per (n,co) plane
   unsigned int stat_total_ctas;
+  int imgs_per_group;          // grouped launch: image n uses the weights (and bias) at row offset w_row_off[n / imgs_per_group]
+  int w_row_off[CTAGAN_MAX_GROUPS];
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -194,9 +196,10 @@ struct WgParams {
   int margin;                 // gy zero border that is skipped
   int rb, cb;                 // chunk grid per image (row blocks x col blocks)
   int bkh, bkw;               // chunk = bkh x bkw output pixels (= 64)
-  int total_chunks, chunks_per_split;
+  int total_chunks, chunks_per_split;   // chunks of ONE group (grouped launch: blockIdx.z = group, its images follow each other)
   int ci_tiles;
-  float *ws;                  // [splits][Co][ntaps][Ci] fp32 partials
+  int splits;
+  float *ws;                  // [groups][splits][Co][ntaps][Ci] fp32 partials
 };
 
 constexpr int WG_M = 128;       // Co tile
@@ -232,10 +235,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   const int co_t = t % co_tiles; t /= co_tiles;
   const int tap = t;
   const int kh = tap / p.KW, kw = tap - kh * p.KW;
-  const int split = blockIdx.y;
-  const int chunk0 = split * p.chunks_per_split;
-  const int chunk1 = min(p.total_chunks, chunk0 + p.chunks_per_split);
-  const int n_iters = chunk1 - chunk0;
+  const int split = blockIdx.y, grp = blockIdx.z;
+  const int chunk_lo = split * p.chunks_per_split;
+  const int n_iters = min(p.total_chunks, chunk_lo + p.chunks_per_split) - chunk_lo;
+  const int chunk0 = grp * p.total_chunks + chunk_lo;          // global chunk index: (image, row block, column block)
   const int co0 = co_t * WG_M, ci0 = ci_t * BNW;
 
   if (warp == 0 && lane == 0) {
@@ -300,7 +303,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;          // co within the tile
-    float *dst = p.ws + (((long long)split * p.Co + co0 + row) * p.ntaps + tap) * p.Ci + ci0;
+    float *dst = p.ws + ((((long long)grp * p.splits + split) * p.Co + co0 + row) * p.ntaps + tap) * p.Ci + ci0;
     const bool row_ok = co0 + row < p.Co;
     if (n_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
@@ -336,6 +339,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
 __global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci) {
   pdl_wait();
   const long long total = (long long)Co * ntaps * Ci;
+  ws += (long long)blockIdx.y * splits * total;       // grouped launch: one weight gradient per group
+  dw += (long long)blockIdx.y * total;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(idx % Ci);
     long long r = idx / Ci;
@@ -407,6 +412,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const int tile_i0 = (tile / p.tiles_w) * (TILE_M >> p.bw_log2);   // mode 1: tile origin in output positions
   const int tile_j0 = (tile % p.tiles_w) * BW;
   const int co0 = blockIdx.y * BN;
+  const int wrow0 = p.w_row_off[img / p.imgs_per_group] + co0;       // first row of this tile in the (grouped) packed-weight buffer
   const int groups = (p.Ci + CHUNK_K * KCH - 1) / (CHUNK_K * KCH);   // stages per tap (channel tail = TMA zero fill)
   const int NS = p.n_stages;
 
@@ -445,7 +451,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const int ch = (gk * KCH + k) * CHUNK_K;
             if (p.mode == 0) tma_load_2d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, row2d);
             else tma_load_4d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
-            tma_load_3d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, ch, wcol, co0);
+            tma_load_3d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, ch, wcol, wrow0);
           }
           if (++s == NS) { s = 0; ph ^= 1u; }
         }
@@ -543,7 +549,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
         if (p.bias) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += __ldg(p.bias + co0 + c + e);
+          for (int e = 0; e < 32; ++e) v[e] += __ldg(p.bias + wrow0 + c + e);
         }
         if (p.act != CTAGAN_ACT_NONE) {
 #pragma unroll
@@ -951,13 +957,14 @@ int pick_bn(long long m_tiles, int Co) {
 int make_map_4d(CUtensorMap *map, const void *base, int N, int H, int W, int C, int bw, int bh, int estr_hw);
 
 // launch one tcgen05 conv with the tap table already in p; x described by (mode 0) [rows][Ci] or (mode 1) [N][Hi][Wi][Ci]
-int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, int w_taps, cudaStream_t st) {
+int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, int w_taps, cudaStream_t st, int w_slots = 1) {
   CUtensorMap mx, mw;
   int rc;
+  if (p.imgs_per_group <= 0) { p.imgs_per_group = N; for (int k = 0; k < CTAGAN_MAX_GROUPS; ++k) p.w_row_off[k] = 0; }
   // ---- resident-A variant: the union of all tap windows fits in shared memory next to a weight ring ----
   static int resa_mode = -1;
   if (resa_mode < 0) { const char *e = getenv("CTAGAN_TC_RESA"); resa_mode = e ? atoi(e) : 0; }   // opt-in: see profiles/tc_tile_tuning_r1.md
-  if (p.mode == 0 && resa_mode > 0 && p.n_taps > 1) {
+  if (p.mode == 0 && resa_mode > 0 && p.n_taps > 1 && w_slots == 1) {
     int max_shift = 0;
     for (int t = 0; t < p.n_taps; ++t) { const int sft = p.tap_dh[t] * p.Wv + p.tap_dw[t]; if (sft > max_shift) max_shift = sft; }
     const int R = TILE_M + max_shift;
@@ -1000,7 +1007,7 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
   }
   if (rc) return rc;
   const int bn = pick_bn((long long)N * p.tiles_per_img, p.Co);
-  rc = make_map_w3d(&mw, wp, p.Co, w_taps, p.Ci, (uint32_t)bn);
+  rc = make_map_w3d(&mw, wp, p.Co * w_slots, w_taps, p.Ci, (uint32_t)bn);
   if (rc) return rc;
   dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
   if (p.stat_total_ctas == 0) p.stat_total_ctas = grid.x * grid.y;       // (phase-decomposed launches preset the sum over phases)
@@ -1048,7 +1055,7 @@ static int tc_gather_kind(const ctagan_conv_geom *g) {
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g) { return tc_gather_kind(g) != 0; }
 
 int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                          float *stat_out, cudaStream_t st) {
+                          float *stat_out, cudaStream_t st, const ctagan_conv_groups *gr) {
   const int kind = tc_gather_kind(g);
   if (!kind) {
     ctagan_set_error("conv_gather: geometry not supported by the tcgen05 engine (bf16, Ci%%64==0, Co%%64==0, stride<=2 / dil<=2)");
@@ -1063,6 +1070,16 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   p.out_H = g->Ho; p.out_W = g->Wo; p.sy = p.sx = 1; p.ay = p.ax = 0;
   p.act = g->act; p.bias = bias; p.out = (bf16 *)y; p.stat_acc = stat_acc; p.stat_out = stat_acc ? stat_out : nullptr;
   p.stat_n = g->N; p.stat_hw = g->Ho * g->Wo;
+  int w_slots = 1;
+  if (gr) {
+    CTAGAN_REQUIRE(gr->groups >= 1 && gr->groups <= CTAGAN_MAX_GROUPS && g->N % gr->groups == 0, "conv_gather(grouped): N must split evenly into 1..%d groups", CTAGAN_MAX_GROUPS);
+    p.imgs_per_group = g->N / gr->groups;
+    for (int k = 0; k < gr->groups; ++k) {
+      CTAGAN_REQUIRE(gr->slot[k] >= 0 && gr->slot[k] < CTAGAN_MAX_GROUPS, "conv_gather(grouped): bad weight slot");
+      p.w_row_off[k] = gr->slot[k] * g->Co;
+      if (gr->slot[k] + 1 > w_slots) w_slots = gr->slot[k] + 1;
+    }
+  }
   const int ntaps = g->KH * g->KW;
   const int w_taps = ntaps;
   if (kind == 1 || kind == 2) {
@@ -1085,7 +1102,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
       p.tiles_w = (g->Wo + BW - 1) / BW;
       p.tiles_per_img = p.tiles_w * ((g->Ho + BH - 1) / BH);
     }
-    return run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_taps, st);
+    return run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_taps, st, w_slots);
   }
   // kind 3: input dilation 2 (input gradient of a stride-2 conv == ConvTranspose2d forward).  Output pixel h = 2i + r reads
   // x[i + e - u] with weight tap kh' = 2u + a (a = (r + pad) & 1, e = (r + pad - a) / 2): one stride-1 launch per output parity.
@@ -1129,7 +1146,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
       const int BW = 1 << p.bw_log2, BH = TILE_M >> p.bw_log2;
       p.tiles_w = (p.Wov + BW - 1) / BW;
       p.tiles_per_img = p.tiles_w * ((p.Hov + BH - 1) / BH);
-      int rc = run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_taps, st);
+      int rc = run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_taps, st, w_slots);
       if (rc) return rc;
     }
   return CTAGAN_OK;
@@ -1162,7 +1179,7 @@ struct WgPlan {
   int bnw, bkw, bkh, rb, cb, total_chunks, splits, cps, tiles;
 };
 
-bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
+bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl, int n_groups = 1) {
   if (g->dtype != CTAGAN_BF16 || g->dil != 1) return false;
   if (g->stride > 2) return false;
   if (g->Co % 32 || g->Ci % 32) return false;              // tiles overhang with TMA zero fill, stores are masked
@@ -1176,11 +1193,11 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl) {
   pl.bkh = 64 / pl.bkw;
   pl.rb = (Hvld + pl.bkh - 1) / pl.bkh;
   pl.cb = (Wvld + pl.bkw - 1) / pl.bkw;
-  pl.total_chunks = g->N * pl.rb * pl.cb;
+  pl.total_chunks = (g->N / n_groups) * pl.rb * pl.cb;        // per group
   pl.tiles = g->KH * g->KW * ((g->Co + WG_M - 1) / WG_M) * ((g->Ci + pl.bnw - 1) / pl.bnw);
   static int split_div = 0;
   if (!split_div) { const char *e = getenv("CTAGAN_WG_SPLIT_DIV"); split_div = e ? atoi(e) : 1; if (split_div < 1) split_div = 1; }
-  int splits = (ctagan_num_sms() / split_div + pl.tiles - 1) / pl.tiles;
+  int splits = (ctagan_num_sms() / split_div + pl.tiles * n_groups - 1) / (pl.tiles * n_groups);
   // at least 32 chunks (2048 pixels) per CTA: measured on the batch-1 Cyc step, where the wgrads run on a side stream next to the
   // backward chain, 2 splits (36 CTAs) beat 8 (144 CTAs) by 8% of the step; large batches still reach one CTA per SM
   const int max_splits = (pl.total_chunks + 31) / 32;
@@ -1206,25 +1223,26 @@ int launch_wg(const CUtensorMap &my, const CUtensorMap &mx, const WgParams &p, d
 
 }  // namespace
 
-int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g) {
+int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups) {
   WgPlan pl;
-  return plan_wgrad(g, pl) ? 1 : 0;
+  return (n_groups >= 1 && g->N % n_groups == 0 && plan_wgrad(g, pl, n_groups)) ? 1 : 0;
 }
 
-size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g) {
+size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g, int n_groups) {
   WgPlan pl;
-  if (!plan_wgrad(g, pl)) return 0;
-  return (size_t)pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+  if (n_groups < 1 || g->N % n_groups || !plan_wgrad(g, pl, n_groups)) return 0;
+  return (size_t)n_groups * pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
 }
 
+// n_groups > 1: the batch is n_groups consecutive image groups and dw / db hold one gradient per group ([groups][Co][Ci][KH][KW])
 int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                         size_t workspace_bytes, cudaStream_t st) {
+                         size_t workspace_bytes, cudaStream_t st, int n_groups) {
   WgPlan pl;
-  if (!plan_wgrad(g, pl)) {
+  if (n_groups < 1 || g->N % n_groups || !plan_wgrad(g, pl, n_groups)) {
     ctagan_set_error("conv_wgrad: geometry not supported by the tcgen05 engine");
     return CTAGAN_ERR_UNSUPPORTED;
   }
-  const size_t need = (size_t)pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+  const size_t need = (size_t)n_groups * pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
   CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_wgrad(tc): workspace of %zu bytes required (got %zu)", need, workspace_bytes);
   CUtensorMap my, mx;
   int rc = make_map_4d(&my, gy, g->N, g->Ho, g->Wo, g->Co, pl.bkw, pl.bkh, 1);
@@ -1235,7 +1253,8 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   p.ntaps = g->KH * g->KW; p.KW = g->KW; p.Co = g->Co; p.Ci = g->Ci; p.stride = g->stride; p.pad = g->pad_h;
   p.margin = g->gy_margin; p.rb = pl.rb; p.cb = pl.cb; p.bkh = pl.bkh; p.bkw = pl.bkw;
   p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.ci_tiles = (g->Ci + pl.bnw - 1) / pl.bnw; p.ws = (float *)workspace;
-  dim3 grid((unsigned)pl.tiles, (unsigned)pl.splits);
+  p.splits = pl.splits;
+  dim3 grid((unsigned)pl.tiles, (unsigned)pl.splits, (unsigned)n_groups);
   switch (pl.bnw) {
     case 256: rc = launch_wg<256>(my, mx, p, grid, st); break;
     case 128: rc = launch_wg<128>(my, mx, p, grid, st); break;
@@ -1245,16 +1264,18 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   const long long total = (long long)g->Co * p.ntaps * g->Ci;
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctagan_num_sms() * 8) blocks = ctagan_num_sms() * 8;
-  CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
+  CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
   CTAGAN_LAUNCH_OK();
   if (db) {
-    const long long pixels = (long long)g->N * g->Ho * g->Wo;
+    const long long pixels = (long long)(g->N / n_groups) * g->Ho * g->Wo;
     long long blocks = (pixels + 511) / 512;
     if (blocks > 2LL * ctagan_num_sms()) blocks = 2LL * ctagan_num_sms();
     const long long ppb = (pixels + blocks - 1) / blocks;
-    CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
-    colsum_kernel<<<(int)((pixels + ppb - 1) / ppb), 256, 0, st>>>((const bf16 *)gy, db, pixels, g->Co, ppb);
-    CTAGAN_LAUNCH_OK();
+    CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co * n_groups, st));
+    for (int k = 0; k < n_groups; ++k) {
+      colsum_kernel<<<(int)((pixels + ppb - 1) / ppb), 256, 0, st>>>((const bf16 *)gy + (size_t)k * pixels * g->Co, db + (size_t)k * g->Co, pixels, g->Co, ppb);
+      CTAGAN_LAUNCH_OK();
+    }
   }
   return CTAGAN_OK;
 }

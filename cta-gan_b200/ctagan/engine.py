@@ -76,14 +76,11 @@ class ConvPrim:
         self._cache: Dict[Tuple[int, torch.dtype], Tuple[int, int, torch.Tensor]] = {}
 
     def packed(self, mode: int, dtype: torch.dtype) -> torch.Tensor:
-        key = (mode, dtype)
-        ver = self._version_key()
-        hit = self._cache.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
-        wp = ops.pack_weights(self.w.detach(), mode, dtype)
-        self._cache[key] = (ver, wp)
-        return wp
+        """The packed copy for `mode`, re-packed in place if stale (the buffer persists: CUDA graphs and grouped launches alias it)."""
+        entries = self.stale_entries(dtype, modes=(mode,))
+        if entries:
+            ops.pack_weights_multi(entries, dtype)
+        return self._cache[(mode, dtype)][1]
 
     def prepack(self, dtype: torch.dtype, modes=(0, 1)):
         """Materialise the packed copies on the CURRENT stream (call before forking work onto side streams)."""
@@ -208,6 +205,122 @@ class _WgradLane:
         self.keep = []
 
 
+class _PairStore:
+    """Packed-weight storage shared by ConvPrims of identical geometry: one buffer [G][...] per (mode, dtype) whose slices ARE the
+    prims' own cache buffers, so a grouped launch reaches every member's weights through one tensor map."""
+
+    def __init__(self, prims):
+        self.prims = list(prims)
+        self.bufs: Dict[Tuple[int, torch.dtype], torch.Tensor] = {}
+
+    def buffer(self, mode: int, dtype: torch.dtype) -> torch.Tensor:
+        key = (mode, dtype)
+        buf = self.bufs.get(key)
+        p0 = self.prims[0]
+        if buf is None:
+            shape = (p0.O, p0.K, p0.K, p0.I) if mode == 0 else (p0.I, p0.K, p0.K, p0.O)
+            buf = torch.empty((len(self.prims), *shape), dtype=dtype, device=p0.w.device)
+            self.bufs[key] = buf
+        for k, prim in enumerate(self.prims):                     # (re-)install the slices; a foreign buffer means "stale"
+            hit = prim._cache.get(key)
+            if hit is None or hit[1].data_ptr() != buf[k].data_ptr():
+                prim._cache[key] = (None, buf[k])
+        return buf
+
+
+_PAIR_STORES: Dict[Tuple[int, ...], _PairStore] = {}
+
+
+class GroupedPrim:
+    """G ConvPrims of identical geometry applied to G consecutive image groups of one batch: the ConvPrim interface, one launch per
+    layer where the tcgen05 engine can (ctagan_conv_gather_grouped / ctagan_conv_wgrad_grouped), one launch per group otherwise
+    (1-2 channel layers, live biases, fp32 validation mode).  Weight gradients come back stacked: dW[G][O][I][K][K]."""
+
+    def __init__(self, prims: Sequence[ConvPrim]):
+        p0 = prims[0]
+        assert all((q.O, q.I, q.K, q.s, q.p) == (p0.O, p0.I, p0.K, p0.s, p0.p) for q in prims)
+        self.prims = list(prims)
+        self.G = len(prims)
+        self.O, self.I, self.K, self.s, self.p, self.b = p0.O, p0.I, p0.K, p0.s, p0.p, p0.b
+        order = sorted(range(self.G), key=lambda k: id(prims[k]))
+        key = tuple(id(prims[k]) for k in order)
+        store = _PAIR_STORES.get(key)
+        if store is None:
+            store = _PAIR_STORES[key] = _PairStore([prims[k] for k in order])
+        self.store = store
+        self.slots = [0] * self.G
+        for s_, k in enumerate(order):
+            self.slots[k] = s_
+
+    def _packed(self, mode, dtype):
+        buf = self.store.buffer(mode, dtype)
+        entries = []
+        for prim in self.prims:
+            entries += prim.stale_entries(dtype, modes=(mode,))
+        if entries:
+            ops.pack_weights_multi(entries, dtype)
+        return buf
+
+    def _split(self, t):
+        B = t.shape[0] // self.G
+        return [t[k * B:(k + 1) * B] for k in range(self.G)]
+
+    def _ok(self, g):
+        return _ENGINE["value"] == L.ENGINE_AUTO and ops.conv_gather_grouped_supported(g, self.slots)
+
+    def fprop(self, x, act=L.ACT_NONE, use_bias=True, pad=None):
+        N, Hi, Wi, Ci = x.shape
+        p = self.p if pad is None else pad
+        Ho, Wo = (Hi + 2 * p - self.K) // self.s + 1, (Wi + 2 * p - self.K) // self.s + 1
+        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, self.O, self.K, self.s, 1, p, act, ops.dt(x))
+        if not (use_bias and self.b is not None) and self._ok(g):
+            return ops.conv_gather_grouped(x, self._packed(0, x.dtype), g, self.slots)
+        return torch.cat([q.fprop(xk, act, use_bias, pad) for q, xk in zip(self.prims, self._split(x))])
+
+    def fprop_stats(self, x, pool):
+        N, Hi, Wi, Ci = x.shape
+        Ho, Wo = (Hi + 2 * self.p - self.K) // self.s + 1, (Wi + 2 * self.p - self.K) // self.s + 1
+        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, self.O, self.K, self.s, 1, self.p, L.ACT_NONE, ops.dt(x))
+        if pool is not None and self._ok(g):
+            return ops.conv_gather_grouped(x, self._packed(0, x.dtype), g, self.slots, pool)
+        parts = [q.fprop_stats(xk, pool) for q, xk in zip(self.prims, self._split(x))]
+        return torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
+
+    def bprop(self, dy, out_hw, act=L.ACT_NONE, bias=None, pad=None):
+        N, Ho, Wo, Co = dy.shape
+        p = self.p if pad is None else pad
+        g = ops.make_geom(N, Ho, Wo, Co, out_hw[0], out_hw[1], self.I, self.K, 1, self.s, self.K - 1 - p, act, ops.dt(dy))
+        if bias is None and self._ok(g):
+            return ops.conv_gather_grouped(dy, self._packed(1, dy.dtype), g, self.slots)
+        return torch.cat([q.bprop(dk, out_hw, act, bias, pad) for q, dk in zip(self.prims, self._split(dy))])
+
+    def bprop_stats(self, dy, out_hw, pool):
+        N, Ho, Wo, Co = dy.shape
+        g = ops.make_geom(N, Ho, Wo, Co, out_hw[0], out_hw[1], self.I, self.K, 1, self.s, self.K - 1 - self.p, L.ACT_NONE, ops.dt(dy))
+        if pool is not None and self._ok(g):
+            return ops.conv_gather_grouped(dy, self._packed(1, dy.dtype), g, self.slots, pool)
+        parts = [q.bprop_stats(dk, out_hw, pool) for q, dk in zip(self.prims, self._split(dy))]
+        return torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
+
+    def wgrad(self, gy, gx, want_bias=False, pad=None, gy_margin=0):
+        N, Ho, Wo, Co = gy.shape
+        _, Hi, Wi, Ci = gx.shape
+        p = self.p if pad is None else pad
+        g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, self.K, self.s, 1, p, L.ACT_NONE, ops.dt(gy), gy_margin)
+        ws = ops.conv_wgrad_grouped_workspace(g, self.G) if _ENGINE["value"] == L.ENGINE_AUTO else 0
+        if ws:
+            if _ACTIVE_LANE["value"] is not None:
+                _ACTIVE_LANE["value"].keep += (gy, gx)
+            return ops.conv_wgrad_grouped(gy, gx, g, self.G, want_bias, ws)
+        parts = [q.wgrad(a, b, want_bias, pad, gy_margin) for q, a, b in zip(self.prims, self._split(gy), self._split(gx))]
+        return torch.stack([a for a, _ in parts]), (torch.stack([b for _, b in parts]) if want_bias else None)
+
+
+def split_group_grads(grads, G):
+    """Stacked per-layer gradients [G, ...] of a grouped plan -> flat list: all of member 0's gradients, then member 1's, ..."""
+    return [None if t is None else t[k] for k in range(G) for t in grads]
+
+
 def prepack_prims(prims, dtype, force=False):
     """Re-pack every stale (force: every) weight copy of a network with one kernel launch, into the persistent pack buffers."""
     entries = []
@@ -247,6 +360,21 @@ class GeneratorPlan:
         for c1, c2 in self.blocks:
             out += [c1, c2]
         return out + [self.tail0, self.tail3, self.tail7]
+
+
+class GroupedGeneratorPlan:
+    """G generators of the same architecture over G consecutive image groups (see GroupedPrim); parameter order = member 0, member 1.."""
+
+    def __init__(self, plans: Sequence[GeneratorPlan]):
+        self.plans = list(plans)
+        self.G = len(plans)
+        self.n_blocks = plans[0].n_blocks
+        grp = lambda name: GroupedPrim([getattr(p, name) for p in plans])
+        self.head1, self.head4, self.head7 = grp("head1"), grp("head4"), grp("head7")
+        self.blocks = [(GroupedPrim([p.blocks[i][0] for p in plans]), GroupedPrim([p.blocks[i][1] for p in plans]))
+                       for i in range(self.n_blocks)]
+        self.tail0, self.tail3, self.tail7 = grp("tail0"), grp("tail3"), grp("tail7")
+        self.params = [t for p in plans for t in p.params]
 
 
 def generator_forward(plan: GeneratorPlan, x_nchw: torch.Tensor, save: bool):
@@ -360,6 +488,14 @@ class DiscriminatorPlan:
 
     def prims(self):
         return list(self.convs)
+
+
+class GroupedDiscriminatorPlan:
+    def __init__(self, plans: Sequence[DiscriminatorPlan]):
+        self.plans = list(plans)
+        self.G = len(plans)
+        self.convs = [GroupedPrim([p.convs[i] for p in plans]) for i in range(len(plans[0].convs))]
+        self.params = [t for p in plans for t in p.params]
 
 
 def discriminator_forward(plan: DiscriminatorPlan, x_nchw: torch.Tensor, save: bool):

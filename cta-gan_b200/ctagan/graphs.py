@@ -98,7 +98,8 @@ class GraphedTrainer:
             assert t.fake_A_buffer.pool is not None and t.fake_B_buffer.pool is not None, "warm-up steps create the device pools"
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._loss_G, self._loss_DA, self._loss_DB = t.phase_all(real_A, real_B, self._sel)
+                fn = t.phase_all_grouped if t.config.get("cyc_schedule") == "grouped" else t.phase_all
+                self._loss_G, self._loss_DA, self._loss_DB = fn(real_A, real_B, self._sel)
             self._graphs = (g,)
         else:
             g = torch.cuda.CUDAGraph()

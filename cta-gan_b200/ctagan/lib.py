@@ -24,6 +24,13 @@ class ConvGeom(ctypes.Structure):
                 ("N", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "KH", "KW", "stride", "dil", "pad_h", "pad_w", "act", "dtype", "gy_margin")]
 
 
+MAX_GROUPS = 4
+
+
+class ConvGroups(ctypes.Structure):
+    _fields_ = [("groups", ctypes.c_int32), ("slot", ctypes.c_int32 * MAX_GROUPS)]
+
+
 class PackItem(ctypes.Structure):
     _fields_ = [("w", ctypes.c_void_p), ("wp", ctypes.c_void_p), ("O", ctypes.c_int32), ("I", ctypes.c_int32), ("KH", ctypes.c_int32),
                 ("KW", ctypes.c_int32), ("mode", ctypes.c_int32)]
@@ -34,6 +41,8 @@ def _ctype_of(decl: str):
     if "*" in d:
         if "ctagan_conv_geom" in d:
             return ctypes.POINTER(ConvGeom)
+        if "ctagan_conv_groups" in d:
+            return ctypes.POINTER(ConvGroups)
         if "ctagan_pack_item" in d:
             return ctypes.POINTER(PackItem)
         return ctypes.c_void_p

@@ -52,6 +52,8 @@ class _GeneratorFn(torch.autograd.Function):
         need_dw = any(ctx.needs_input_grad[2:])
         dx, grads = E.generator_backward(ctx.plan, ctx.saved, dout.contiguous(), need_dx, need_dw)
         ctx.saved = None
+        if isinstance(ctx.plan, E.GroupedGeneratorPlan):
+            grads = E.split_group_grads(grads, ctx.plan.G) if need_dw else [None] * len(ctx.plan.params)
         return (None, dx, *grads)
 
 
@@ -133,6 +135,8 @@ class _DiscriminatorFn(torch.autograd.Function):
         need_dw = any(ctx.needs_input_grad[3:])
         dx, gw = E.discriminator_backward(ctx.plan, ctx.saved, dout.contiguous(), need_dx, need_dw)
         ctx.saved = None
+        if isinstance(ctx.plan, E.GroupedDiscriminatorPlan):
+            gw = E.split_group_grads(gw, ctx.plan.G)
         return (None, None, dx, *gw)
 
 
@@ -201,6 +205,35 @@ class Discriminator(_DiscBase):
 
     def forward(self, x, freeze=False):
         return plane_mean(self._run(x, freeze=freeze))
+
+
+_GROUPED_PLANS = {}
+
+
+def _grouped_plan(nets, kind):
+    plans = [n._get_plan() for n in nets]
+    key = (kind, *[id(p) for p in plans])
+    hit = _GROUPED_PLANS.get(key)
+    if hit is None or any(a is not b for a, b in zip(hit.plans, plans)):
+        hit = (E.GroupedGeneratorPlan if kind == "G" else E.GroupedDiscriminatorPlan)(plans)
+        _GROUPED_PLANS[key] = hit
+    return hit
+
+
+def grouped_generators(nets, x):
+    """[nets[0](x[:B]); nets[1](x[B:2B]); ...] for Generators of the same architecture, one kernel launch per layer for all of them
+    (extension: the two generators of a CycleGAN iteration work on independent inputs at the same time, CycTrainer.py:144-157)."""
+    if x.shape[0] % len(nets) or x.shape[2] % 4 or x.shape[3] % 4:
+        raise ValueError("grouped_generators: batch must split evenly over the networks, H and W must be multiples of 4")
+    plan = _grouped_plan(nets, "G")
+    return _GeneratorFn.apply(plan, x, *plan.params)
+
+
+def grouped_discriminators(nets, x, freeze=False):
+    """The same for `Discriminator`s: returns the pooled predictions [N, 1] of nets[k] on the k-th image group."""
+    plan = _grouped_plan(nets, "D")
+    params = [p.detach() for p in plan.params] if freeze else plan.params
+    return plane_mean(_DiscriminatorFn.apply(plan, None, x, *params))
 
 
 class NLayerDiscriminator(_DiscBase):

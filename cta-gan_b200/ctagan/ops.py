@@ -96,6 +96,49 @@ def conv_gather_stats(x, wp, bias, g: L.ConvGeom, pool: "ZeroPool", engine=L.ENG
     return y, instnorm_stats(y)
 
 
+def _groups(slots) -> L.ConvGroups:
+    gr = L.ConvGroups()
+    gr.groups = len(slots)
+    for k, s in enumerate(slots):
+        gr.slot[k] = int(s)
+    return gr
+
+
+def conv_gather_grouped_supported(g: L.ConvGeom, slots) -> bool:
+    return bool(L.load().ctagan_conv_gather_grouped_supported(ctypes.byref(g), ctypes.byref(_groups(slots))))
+
+
+def conv_gather_grouped(x, wp, g: L.ConvGeom, slots, pool: "ZeroPool" = None):
+    """Grouped convolution (see ctagan_conv_gather_grouped): image group k uses slot slots[k] of the packed buffer wp[slots][...].
+    With a ZeroPool the InstanceNorm statistics come out of the epilogue: returns (y, stats), else y."""
+    _require_cuda(x, wp)
+    ensure_device()
+    y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
+    acc = stats = None
+    if pool is not None:
+        acc = pool.take(g.N * g.Co * 2 + 1)
+        stats = torch.empty((g.N, g.Co, 2), dtype=torch.float32, device=x.device)
+    _count(1)
+    L.check(L.load().ctagan_conv_gather_grouped(ctypes.byref(g), ctypes.byref(_groups(slots)), _p(x), _p(wp), None, _p(y), _p(acc), _p(stats),
+                                                _stream()))
+    return (y, stats) if pool is not None else y
+
+
+def conv_wgrad_grouped_workspace(g: L.ConvGeom, groups: int) -> int:
+    return int(L.load().ctagan_conv_wgrad_grouped_workspace_bytes(ctypes.byref(g), groups))
+
+
+def conv_wgrad_grouped(gy, gx, g: L.ConvGeom, groups: int, want_bias: bool, ws_bytes: int):
+    """One weight gradient per image group: returns (dw[groups,Co,Ci,KH,KW], db[groups,Co] or None)."""
+    _require_cuda(gy, gx)
+    dw = torch.empty((groups, g.Co, g.Ci, g.KH, g.KW), dtype=torch.float32, device=gy.device)
+    db = torch.empty((groups, g.Co), dtype=torch.float32, device=gy.device) if want_bias else None
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device)
+    _count(2)
+    L.check(L.load().ctagan_conv_wgrad_grouped(ctypes.byref(g), groups, _p(gy), _p(gx), _p(dw), _p(db), _p(ws), ws_bytes, _stream()))
+    return dw, db
+
+
 def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO):
     _require_cuda(gy, gx)
     dw = torch.empty((g.Co, g.Ci, g.KH, g.KW), dtype=torch.float32, device=gy.device)

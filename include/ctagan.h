@@ -78,6 +78,27 @@ int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const voi
 int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine);
 int ctagan_instnorm_finalize_sums(const double *acc, float *stats, int N, int HW, int C, void *stream);
 
+/* Grouped launches (tcgen05 engine only).  The batch is `groups` consecutive, equally sized image groups; group k is convolved
+ * with the weights in slot `slot[k]` of one packed buffer wp[slots][Co][taps][Ci] (bias[slots][Co]).  This is how the two generators
+ * (and the two discriminators) of a CycleGAN iteration -- same architecture, different weights, independent inputs
+ * (trainer/CycTrainer.py:144-157: netG_A2B(real_A) beside netG_B2A(real_B), then netG_B2A(fake_B) beside netG_A2B(fake_A)) -- run as
+ * ONE launch per layer: at batch 1 a single network fills only part of the chip and its kernels are latency-bound, so two
+ * problems per launch cost about the same time as one.  stat_acc / stats_out as in ctagan_conv_gather_stats (optional).
+ * CTAGAN_ERR_UNSUPPORTED when the geometry does not run on the tcgen05 engine (ask ctagan_conv_gather_grouped_supported first). */
+#define CTAGAN_MAX_GROUPS 4
+typedef struct {
+  int32_t groups;
+  int32_t slot[CTAGAN_MAX_GROUPS];
+} ctagan_conv_groups;
+int ctagan_conv_gather_grouped_supported(const ctagan_conv_geom *g, const ctagan_conv_groups *gr);
+int ctagan_conv_gather_grouped(const ctagan_conv_geom *g, const ctagan_conv_groups *gr, const void *x, const void *wp, const float *bias,
+                               void *y, double *stat_acc, float *stats_out, void *stream);
+/* one weight (and optional bias) gradient per group: dw[groups][Co][Ci][KH][KW], db[groups][Co]; workspace as for ctagan_conv_wgrad
+ * (0 bytes == unsupported geometry) */
+size_t ctagan_conv_wgrad_grouped_workspace_bytes(const ctagan_conv_geom *g, int groups);
+int ctagan_conv_wgrad_grouped(const ctagan_conv_geom *g, int groups, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
 /* Weight gradient (and optional bias gradient) of the same geometry:
  *   dw[a,b,kh,kw] (+)= sum_{n,oh,ow} gy[n,oh,ow,a] * gx[n,ih,iw,b],  db[a] = sum gy[n,oh,ow,a]
  * with (ih,iw) from (oh,ow,kh,kw) as above; g->Co == A (channels of gy), g->Ci == B (channels of gx); dw is fp32 in

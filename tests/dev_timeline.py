@@ -70,3 +70,10 @@ for sid in sids[:6]:
     # print a coarse trace: every 12th event with time and name
     for e in es[::max(1, len(es) // 28)]:
         print(f"   {(e['ts'] - t0) / 1e3:7.3f} ms  {e['dur']:6.1f} us  {fam(e)}")
+
+# full event list for offline inspection
+os.makedirs("gpurun_out", exist_ok=True)
+with open(f"gpurun_out/timeline_{wl}_events.csv", "w") as f:
+    f.write("start_us,dur_us,stream,name\n")
+    for e in ev:
+        f.write(f"{e['ts'] - t0:.1f},{e['dur']:.1f},{e['args'].get('stream')},{fam(e)}\n")

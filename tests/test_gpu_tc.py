@@ -110,3 +110,65 @@ def test_tc_fused_instancenorm_statistics(shape):
         yt, st = primT.bprop_stats(xt, (64, 64), pool)
         ytf = yt.float()
         assert maxrel(st[..., 1], (ytf.var((1, 2), unbiased=False) + 1e-5).rsqrt()) <= 2e-3
+
+
+GROUPED_CASES = [
+    # name, images per group, Ci, Co, H, W, K, stride, pad
+    ("res3x3_valid", 1, 256, 256, 66, 66, 3, 1, 0),
+    ("down_s2_b2", 2, 64, 128, 64, 64, 3, 2, 1),
+    ("disc_k4s1_odd", 2, 256, 512, 32, 32, 4, 1, 1),
+    ("reg_96to32", 1, 96, 32, 64, 64, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", GROUPED_CASES, ids=[c[0] for c in GROUPED_CASES])
+def test_grouped_launch_equals_one_launch_per_group(case):
+    """ctagan_conv_gather_grouped / ctagan_conv_wgrad_grouped (two weight sets, two image groups, one launch) against the ungrouped
+    entry points run per group -- both orders of the slots, since the cycle pass uses the pair in swapped order."""
+    from ctagan import engine as E, ops, lib as L
+    name, B, Ci, Co, H, W, K, s, p = case
+    g = torch.Generator().manual_seed(5)
+    prims = [E.ConvPrim((torch.randn(Co, Ci, K, K, generator=g) / (Ci * K * K) ** 0.5).cuda(), torch.randn(Co, generator=g).cuda(), s, p)
+             for _ in range(2)]
+    x = torch.randn(2 * B, H, W, Ci, generator=g).cuda().bfloat16()
+    for order in ((0, 1), (1, 0)):
+        members = [prims[k] for k in order]
+        gp = E.GroupedPrim(members)
+        pool = ops.ZeroPool(2 * 2 * B * Co + 8, x.device)
+        y, st = gp.fprop_stats(x, pool)
+        refs = [q.fprop_stats(xk, ops.ZeroPool(2 * B * Co + 8, x.device)) for q, xk in zip(members, (x[:B], x[B:]))]
+        y_ref, st_ref = torch.cat([a for a, _ in refs]), torch.cat([b for _, b in refs])
+        assert ops.launch_count() > 0
+        assert torch.equal(y, y_ref), (order, "fprop", maxrel(y.float(), y_ref.float()))
+        assert maxrel(st, st_ref) <= 1e-5, (order, "stats", maxrel(st, st_ref))
+        assert torch.equal(gp.fprop(x, use_bias=False), y_ref)
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6)).cuda().bfloat16()
+        dx = gp.bprop(dy, (H, W))
+        dx_ref = torch.cat([q.bprop(dk, (H, W)) for q, dk in zip(members, (dy[:B], dy[B:]))])
+        assert torch.equal(dx, dx_ref), (order, "dgrad", maxrel(dx.float(), dx_ref.float()))
+        dw, db = gp.wgrad(dy, x, want_bias=True)
+        for k, q in enumerate(members):
+            dwk, dbk = q.wgrad(dy[k * B:(k + 1) * B], x[k * B:(k + 1) * B], want_bias=True)
+            assert maxrel(dw[k], dwk) <= 1e-5, (order, "wgrad", k, maxrel(dw[k], dwk))
+            assert maxrel(db[k], dbk) <= 1e-5, (order, "bgrad", k)
+
+
+def test_grouped_cyc_schedule_matches_stream_schedule():
+    """bf16 Cyc iteration with the generators / discriminators run as grouped launches against the default two-stream schedule."""
+    import random
+    from oracle import restate as R
+    from trainer import Cyc_Trainer
+    from test_gpu_steps import _cfg, _close
+    out = {}
+    for sched in ("streams", "grouped"):
+        random.seed(42); torch.manual_seed(42)
+        tr = Cyc_Trainer(_cfg("CycleGan", 128, precision="bf16", cyc_schedule=sched))
+        out[sched] = []
+        for it in range(2):
+            rA, rB = R.synthetic_pair(1, 128, seed=700 + it, phantom=True)
+            out[sched].append({k: float(v) for k, v in tr.step({"A": rA, "B": rB}).items()})
+    import ctagan
+    ctagan.set_precision("bf16")
+    for it in range(2):
+        for k in out["streams"][it]:
+            assert _close(out["grouped"][it][k], out["streams"][it][k], 1e-3 if it == 0 else 3e-2), (it, k, out["grouped"][it][k], out["streams"][it][k])
