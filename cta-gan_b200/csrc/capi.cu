@@ -45,6 +45,23 @@ bool ctagan_pdl_enabled() {
   return e && e[0] == '1';
 }
 
+extern "C" int ctagan_stream_create(int priority, void **stream_out) {
+  CTAGAN_REQUIRE(stream_out, "stream_create: null pointer");
+  int lo = 0, hi = 0;
+  CTAGAN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (numerically largest)
+  int prio = priority < hi ? hi : (priority > lo ? lo : priority);
+  cudaStream_t st;
+  CTAGAN_CUDA_OK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio));
+  *stream_out = (void *)st;
+  return CTAGAN_OK;
+}
+
+extern "C" int ctagan_stream_destroy(void *stream) {
+  CTAGAN_REQUIRE(stream, "stream_destroy: null pointer");
+  CTAGAN_CUDA_OK(cudaStreamDestroy((cudaStream_t)stream));
+  return CTAGAN_OK;
+}
+
 extern "C" int ctagan_version(void) { return 100; }
 extern "C" const char *ctagan_last_error(void) { return g_err; }
 

@@ -11,6 +11,8 @@ trainer/reg.py:31-132, trainer/layers.py:71-104,156-183,216-300.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -182,7 +184,7 @@ class _WgradLane:
             key = self.main.cuda_stream
             side = _WGRAD_STREAMS.get(key)
             if side is None:
-                side = torch.cuda.Stream()
+                side = ops.named_stream(f"lane:{key}")
                 _WGRAD_STREAMS[key] = side
             self.side = side
 
@@ -200,9 +202,72 @@ class _WgradLane:
 
     def join(self):
         # (only when something was forked: waiting on a stream that never joined a CUDA-graph capture would invalidate the capture)
+        d = _DEFERRED["value"]
+        if d is not None:                 # the caller collects the weight gradients after the whole backward: nobody waits here
+            if self.side is not None and self.used:
+                d.lanes[(self.main.cuda_stream, self.side.cuda_stream)] = (self.main, self.side)
+                d.keep += self.keep
+            self.keep = []
+            return
         if self.side is not None and self.used:
             self.main.wait_stream(self.side)
         self.keep = []
+
+
+_DEFERRED = {"value": None}
+
+
+class deferred_weight_grads:
+    """`with deferred_weight_grads() as d: loss.backward(); d.flush()` -- inside the block the network Functions hand their weight
+    gradients to `d` instead of returning them to autograd, and their wgrad lanes are not joined at the end of each network's
+    backward.  The input-gradient chain (the critical path of the backward pass) then never waits for the lagging weight-gradient
+    lanes at network boundaries; flush() joins every lane once, on the current stream, and accumulates into `.grad` (`p.grad = g`
+    for the first contribution, one multi-tensor add for the others, e.g. the second use of a generator in the cycle pass)."""
+
+    def __init__(self):
+        self.items = []        # (leaf tensor, gradient)
+        self.lanes = {}
+        self.keep = []
+        self.flushed = False
+
+    def __enter__(self):
+        assert _DEFERRED["value"] is None, "deferred_weight_grads does not nest"
+        if os.environ.get("CTAGAN_DEFER", "1") != "0":
+            _DEFERRED["value"] = self
+        return self
+
+    def __exit__(self, *exc):
+        _DEFERRED["value"] = None
+        if exc[0] is None and not self.flushed:
+            self.flush()
+        return False
+
+    def take(self, leaves, grads, needs):
+        """Called by a Function's backward: keeps the gradients of the leaves that want one; returns what to hand to autograd."""
+        for leaf, g, need in zip(leaves, grads, needs):
+            if need and g is not None:
+                self.items.append((leaf, g))
+        return [None] * len(grads)
+
+    def flush(self):
+        cur = torch.cuda.current_stream()
+        for main, side in self.lanes.values():
+            cur.wait_stream(main)
+            cur.wait_stream(side)
+        own, extra = [], []
+        for leaf, g in self.items:
+            if leaf.grad is None:
+                leaf.grad = g
+            else:
+                own.append(leaf.grad); extra.append(g)
+        if own:
+            torch._foreach_add_(own, extra)
+        self.items, self.lanes, self.keep = [], {}, []
+        self.flushed = True
+
+
+def deferred():
+    return _DEFERRED["value"]
 
 
 class _PairStore:

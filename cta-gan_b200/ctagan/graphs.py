@@ -77,7 +77,7 @@ class GraphedTrainer:
     def _capture(self, static):
         t = self.t
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        side = ops.named_stream("graph.warmup")
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(self.warmup):                 # allocator / NCCL / optimizer-state warm-up, off the capture stream
@@ -98,8 +98,7 @@ class GraphedTrainer:
             assert t.fake_A_buffer.pool is not None and t.fake_B_buffer.pool is not None, "warm-up steps create the device pools"
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                fn = t.phase_all_grouped if t.config.get("cyc_schedule") == "grouped" else t.phase_all
-                self._loss_G, self._loss_DA, self._loss_DB = fn(real_A, real_B, self._sel)
+                self._loss_G, self._loss_DA, self._loss_DB = t.phase_fn()(real_A, real_B, self._sel)
             self._graphs = (g,)
         else:
             g = torch.cuda.CUDAGraph()

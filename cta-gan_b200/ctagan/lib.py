@@ -38,6 +38,8 @@ class PackItem(ctypes.Structure):
 
 def _ctype_of(decl: str):
     d = decl.strip()
+    if "**" in d:
+        return ctypes.POINTER(ctypes.c_void_p)
     if "*" in d:
         if "ctagan_conv_geom" in d:
             return ctypes.POINTER(ConvGeom)

@@ -44,6 +44,7 @@ class _GeneratorFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad)      # all False under torch.no_grad()
         out, saved = E.generator_forward(plan, x, save=need)
         ctx.plan, ctx.saved = plan, saved
+        ctx.leaves = params if need else None
         return out
 
     @staticmethod
@@ -54,6 +55,9 @@ class _GeneratorFn(torch.autograd.Function):
         ctx.saved = None
         if isinstance(ctx.plan, E.GroupedGeneratorPlan):
             grads = E.split_group_grads(grads, ctx.plan.G) if need_dw else [None] * len(ctx.plan.params)
+        if need_dw and E.deferred() is not None:
+            grads = E.deferred().take(ctx.leaves, grads, ctx.needs_input_grad[2:])
+        ctx.leaves = None
         return (None, dx, *grads)
 
 
@@ -127,6 +131,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         if sink is not None:
             sink.extend(acts)
         ctx.plan, ctx.saved = plan, saved
+        ctx.leaves = params if need else None
         return out
 
     @staticmethod
@@ -137,6 +142,9 @@ class _DiscriminatorFn(torch.autograd.Function):
         ctx.saved = None
         if isinstance(ctx.plan, E.GroupedDiscriminatorPlan):
             gw = E.split_group_grads(gw, ctx.plan.G)
+        if need_dw and E.deferred() is not None:
+            gw = E.deferred().take(ctx.leaves, gw, ctx.needs_input_grad[3:])
+        ctx.leaves = None
         return (None, None, dx, *gw)
 
 
@@ -359,6 +367,7 @@ class _RegFn(torch.autograd.Function):
         out, saved = E.reg_forward(plan, a, b, save=need)
         ctx.plan, ctx.saved = plan, saved
         ctx.in_channels = (a.shape[1], b.shape[1])
+        ctx.leaves = params if need else None
         return out
 
     @staticmethod
@@ -366,6 +375,9 @@ class _RegFn(torch.autograd.Function):
         da, db, grads = E.reg_backward(ctx.plan, ctx.saved, dflow.contiguous(), ctx.needs_input_grad[1], ctx.needs_input_grad[2],
                                        ctx.in_channels)
         ctx.saved = None
+        if E.deferred() is not None and any(ctx.needs_input_grad[3:]):
+            grads = E.deferred().take(ctx.leaves, grads, ctx.needs_input_grad[3:])
+        ctx.leaves = None
         return (None, da, db, *grads)
 
 

@@ -46,6 +46,23 @@ def ensure_device():
         _checked_devices.add(dev)
 
 
+_NAMED_STREAMS = {}
+
+
+def named_stream(name: str, priority: int = 0) -> "torch.cuda.Stream":
+    """The process-wide dedicated CUDA stream for a role (e.g. "cyc.chainA", "lane:<main stream>"): created once through
+    ctagan_stream_create, never taken from PyTorch's round-robin stream pool, so distinct roles are distinct CUDA streams."""
+    key = (torch.cuda.current_device(), name)
+    st = _NAMED_STREAMS.get(key)
+    if st is None:
+        ensure_device()
+        h = ctypes.c_void_p()
+        L.check(L.load().ctagan_stream_create(int(priority), ctypes.byref(h)))
+        st = torch.cuda.ExternalStream(h.value)
+        _NAMED_STREAMS[key] = st
+    return st
+
+
 def dt(t: torch.Tensor) -> int:
     return _DT[t.dtype]
 

@@ -41,6 +41,13 @@ const char *ctagan_last_error(void);
 /* 0 if device `dev` is compute capability 10.x, else CTAGAN_ERR_UNSUPPORTED (no other-arch fallback). */
 int ctagan_check_device(int dev);
 
+/* A dedicated CUDA stream (cudaStreamNonBlocking; priority: 0 = default, -1 = highest the device offers).  The host side uses
+ * these for the branches of an iteration (generator chains, discriminator updates, weight-gradient lanes) instead of streams
+ * from PyTorch's pool, which hands the same 32 streams out round-robin: two "different" streams of a long-lived process may be
+ * one CUDA stream, which silently serialises branches and entangles their memory reuse. */
+int ctagan_stream_create(int priority, void **stream_out);
+int ctagan_stream_destroy(void *stream);
+
 /*
  * One "gather convolution" geometry covers Conv2d fwd/dgrad and ConvTranspose2d fwd/dgrad:
  *   y[n,oh,ow,co] = act( bias[co] + sum_{kh,kw,ci} x[n,ih,iw,ci] * wp[co,kh,kw,ci] )
