@@ -284,7 +284,12 @@ def run_ours(args):
     peak_src = "measured burst (MEASURED_PEAKS.json)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s"
     ksec, kflops = time_dominant_kernel(args.precision, b, s)
     achieved = kflops / ksec / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+    # DRAM bytes per launch of this kernel from `ncu --set full` (profiles/ncu_full_conv_tc_valid_r1_n{1,8}.raw.csv: dram__bytes_read.sum
+    # + dram__bytes_write.sum, L2-warm as in the step): operands and output stay in the 126 MB L2; what the kernel moves is L2->SM traffic
+    # (l1tex__m_xbar2l1tex_read_bytes.sum = 78 MB at b=1, 469 MB at b=8).  Only the two profiled shapes have a figure.
+    traffic = {(1, 256): 234e3, (8, 256): 116e3}.get((b, s)) if args.precision == "bf16" else None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch (ncu --set full, L2-warm); L2->SM operand bytes per launch: 78e6 at b=1, 469e6 at b=8",
                 "kernel": "res-block 3x3 256->256 conv fprop (tcgen05 implicit GEMM M=%d N=256 K=2304), timed alone over CUDA-graph replays, L2-warm" % (b * (s // 4) ** 2),
                 "peak_source": peak_src,
                 "step_conv_tflops": GFLOP_PER_SLICE_256[args.workload] * (s / 256.0) ** 2 * b * args.steps / (ms_total * 1e-3) / 1e3}

@@ -1200,7 +1200,9 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl, int n_groups = 1) {
   int splits = (ctagan_num_sms() / split_div + pl.tiles * n_groups - 1) / (pl.tiles * n_groups);
   // at least 32 chunks (2048 pixels) per CTA: measured on the batch-1 Cyc step, where the wgrads run on a side stream next to the
   // backward chain, 2 splits (36 CTAs) beat 8 (144 CTAs) by 8% of the step; large batches still reach one CTA per SM
-  const int max_splits = (pl.total_chunks + 31) / 32;
+  static int min_chunks = 0;
+  if (!min_chunks) { const char *e = getenv("CTAGAN_WG_MIN_CHUNKS"); min_chunks = e ? atoi(e) : 32; if (min_chunks < 1) min_chunks = 32; }
+  const int max_splits = (pl.total_chunks + min_chunks - 1) / min_chunks;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   pl.cps = (pl.total_chunks + splits - 1) / splits;
