@@ -138,18 +138,31 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 bool ctagan_pdl_enabled();     // env CTAGAN_PDL=1 (opt-in: measured neutral on the Cyc step, see capi.cu)
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+inline cudaError_t launch_cluster_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x,
+                                      Args &&...args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = ctagan_pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {                      // thread-block cluster along x (CTA pairs of the cta_group::2 kernels)
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  return launch_cluster_pdl(kernel, grid, block, smem, st, 1u, std::forward<Args>(args)...);
 }
 
 // number of SMs (B200: 148); cached

@@ -127,6 +127,66 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): two SMs of one TPC run ONE 256 x BN MMA; each holds its own 128 A rows and HALF of the B rows ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address of this kernel's layout) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA loads of a pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *smem_dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *smem_dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *smem_dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -382,20 +442,25 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16 *__restrict__ gy
   }
 }
 
-template <int BN, int KCH>
+template <int BN, int KCH, bool PAIR = false>
 struct TcConfig {
   static constexpr int A_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB per chunk
-  static constexpr int B_BYTES = BN * CHUNK_K * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * CHUNK_K * 2;   // a CTA pair splits the BN weight rows between its two SMs
   static constexpr int STAGE_BYTES = KCH * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-template <int BN, int KCH>
+// PAIR = true: launched as clusters of two CTAs (consecutive blockIdx.x = two M tiles, same co0).  The pair executes
+// tcgen05.mma.cta_group::2 with M = 256: each SM stages its own 128 A rows and HALF of the BN weight rows, the leader (cluster rank 0)
+// issues the MMAs for both, each SM keeps its 128 x BN accumulator in its own TMEM and runs its own epilogue.  Per SM and 64-channel
+// chunk the L2->SM ingest falls from 16 KB + BN*128 B to 16 KB + BN*64 B -- the quantity that bounds this kernel.
+template <int BN, int KCH, bool PAIR = false>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
-  using Cfg = TcConfig<BN, KCH>;
+  using Cfg = TcConfig<BN, KCH, PAIR>;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -426,9 +491,13 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();        // both CTAs' barriers are initialised before either one's TMA / commit can touch them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                          // producer grid complete + flushed: nothing above touches global memory
@@ -445,21 +514,34 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t *b_dst = a_dst + KCH * Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (!PAIR) {
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < KCH; ++k) {
-            const int ch = (gk * KCH + k) * CHUNK_K;
-            if (p.mode == 0) tma_load_2d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, row2d);
-            else tma_load_4d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
-            tma_load_3d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, ch, wcol, wrow0);
+            for (int k = 0; k < KCH; ++k) {
+              const int ch = (gk * KCH + k) * CHUNK_K;
+              if (p.mode == 0) tma_load_2d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, row2d);
+              else tma_load_4d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
+              tma_load_3d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, ch, wcol, wrow0);
+            }
+          } else {
+            // both SMs' loads are counted on the leader's barrier: it expects the bytes of the whole pair
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+#pragma unroll
+            for (int k = 0; k < KCH; ++k) {
+              const int ch = (gk * KCH + k) * CHUNK_K;
+              if (p.mode == 0) tma_load_2d_pair(&map_x, lead_bar, a_dst + k * Cfg::A_BYTES, ch, row2d);
+              else tma_load_4d_pair(&map_x, lead_bar, a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
+              tma_load_3d_pair(&map_w, lead_bar, b_dst + k * Cfg::B_BYTES, ch, wcol, wrow0 + (int)rank * (BN / 2));
+            }
           }
           if (++s == NS) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+    if (lane == 0 && rank == 0) {     // (pair: the leader issues the MMAs of both SMs)
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, BN);
       const int n_iters = p.n_taps * groups;
       int s = 0;
       uint32_t ph = 0;
@@ -475,13 +557,18 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
           for (int kk = 0; kk < CHUNK_K / UMMA_K; ++kk) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (it > 0 || k > 0 || kk > 0) ? 1u : 0u);
+            const uint32_t acc = (it > 0 || k > 0 || kk > 0) ? 1u : 0u;
+            if (PAIR) umma_bf16_pair(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+            else umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
           }
         }
-        umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs retire (implies fence::before_thread_sync)
+        // frees the smem stage (in both SMs of a pair) when these MMAs retire (implies fence::before_thread_sync)
+        if (PAIR) umma_commit_pair(&empty_bar[s]);
+        else umma_commit(&empty_bar[s]);
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tmem_full_bar);     // accumulator complete
+      if (PAIR) umma_commit_pair(tmem_full_bar);     // accumulator complete
+      else umma_commit(tmem_full_bar);
     }
   } else {
     // ===== epilogue: warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31 =====
@@ -495,7 +582,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       i = tile_i0 + (row >> p.bw_log2); j = tile_j0 + (row & (BW - 1));
     }
     const int oi = i * p.sy + p.ay, oj = j * p.sx + p.ax;
-    const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W;
+    const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W && img < p.stat_n;
     bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -535,7 +622,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         stat_red[par][quarter][0][lane] = s1[0];
         stat_red[par][quarter][1][lane] = s2[0];
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && co0 + c + lane < p.Co) {
+        if (warp == 2 && co0 + c + lane < p.Co && img < p.stat_n) {     // (img == stat_n: the padding tile of an odd pair grid)
           const float a = stat_red[par][0][0][lane] + stat_red[par][1][0][lane] + stat_red[par][2][0][lane] + stat_red[par][3][0][lane];
           const float b = stat_red[par][0][1][lane] + stat_red[par][1][1][lane] + stat_red[par][2][1][lane] + stat_red[par][3][1][lane];
           double *dst = p.stat_acc + ((long long)img * p.Co + co0 + c + lane) * 2;
@@ -596,10 +683,12 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();        // the leader's MMAs wrote this SM's TMEM and read its shared memory: nobody leaves early
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -907,12 +996,12 @@ int make_map_w3d(CUtensorMap *map, const void *base, int O, int taps, int Ci, ui
   return CTAGAN_OK;
 }
 
-template <int BN, int KCH>
+template <int BN, int KCH, bool PAIR = false>
 int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, dim3 grid, cudaStream_t st) {
-  using Cfg = TcConfig<BN, KCH>;
+  using Cfg = TcConfig<BN, KCH, PAIR>;
   static bool configured = false;
   if (!configured) {
-    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_valid_kernel<BN, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_valid_kernel<BN, KCH, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   TcParams q = p;
@@ -921,7 +1010,7 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
     const int ns = atoi(env);
     if (ns >= 1 && ns <= Cfg::STAGES) q.n_stages = ns;
   }
-  CTAGAN_CUDA_OK(launch_pdl(conv_tc_valid_kernel<BN, KCH>, grid, dim3(192), Cfg::SMEM_BYTES, st, mx, mw, q));
+  CTAGAN_CUDA_OK(launch_cluster_pdl(conv_tc_valid_kernel<BN, KCH, PAIR>, grid, dim3(192), Cfg::SMEM_BYTES, st, PAIR ? 2u : 1u, mx, mw, q));
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
@@ -1006,11 +1095,24 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
     rc = make_map_4d(&mx, x, N, Hi, Wi, p.Ci, BW * p.stride, BH * p.stride, p.stride);
   }
   if (rc) return rc;
-  const int bn = pick_bn((long long)N * p.tiles_per_img, p.Co);
-  rc = make_map_w3d(&mw, wp, p.Co * w_slots, w_taps, p.Ci, (uint32_t)bn);
+  int bn = pick_bn((long long)N * p.tiles_per_img, p.Co);
+  // CTA pairs (cta_group::2, opt-in CTAGAN_TC_PAIR=1): 256 x BN tiles over two SMs; an odd tile count gets one fully masked padding tile
+  // MEASURED (profiles/tc_tile_tuning_r1.md): bit-identical results, no speed-up (N=8: 50.8 vs 49.9 us with fused statistics) -- at
+  // BN >= 128 the main loop already runs at ~86 % of the per-SM tensor peak; what is lost is SM under-use at b=1 and the
+  // non-overlapped epilogue + wave quantisation at b=8.  Kept opt-in as the base of a persistent 2-CTA kernel.
+  const char *pair_env = getenv("CTAGAN_TC_PAIR");
+  const int pair_mode = pair_env ? atoi(pair_env) : 0;
+  const bool pair = pair_mode > 0 && bn >= 128 && w_slots == 1 && p.Co % bn == 0 && p.stat_total_ctas == 0;
+  rc = make_map_w3d(&mw, wp, p.Co * w_slots, w_taps, p.Ci, (uint32_t)(pair ? bn / 2 : bn));
   if (rc) return rc;
   dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
+  if (pair && (grid.x & 1)) grid.x += 1;
   if (p.stat_total_ctas == 0) p.stat_total_ctas = grid.x * grid.y;       // (phase-decomposed launches preset the sum over phases)
+  if (pair) {
+    const bool k2 = (p.Ci % 128 == 0 && bn < 256);
+    if (bn == 256) return launch_tc<256, 1, true>(mx, mw, p, grid, st);
+    return k2 ? launch_tc<128, 2, true>(mx, mw, p, grid, st) : launch_tc<128, 1, true>(mx, mw, p, grid, st);
+  }
   int kch = (p.Ci % 128 == 0 && bn < 256) ? 2 : 1;      // BN=256 keeps 64-channel stages (4 of them fit; 2-chunk stages would leave 2)
   if (kch == 2) {
     switch (bn) {

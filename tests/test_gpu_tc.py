@@ -172,3 +172,20 @@ def test_grouped_cyc_schedule_matches_stream_schedule():
     for it in range(2):
         for k in out["streams"][it]:
             assert _close(out["grouped"][it][k], out["streams"][it][k], 1e-3 if it == 0 else 3e-2), (it, k, out["grouped"][it][k], out["streams"][it][k])
+
+
+@pytest.mark.parametrize("N", [1, 3, 8])
+def test_cta_pair_kernel_equals_single_cta_kernel(N, monkeypatch):
+    """cta_group::2 variant of the convolution (256 x BN tiles over two SMs, odd tile counts padded with a masked tile; opt-in
+    CTAGAN_TC_PAIR=1) against the default single-CTA kernel: same MMAs in the same order, so the result is bit-identical."""
+    from ctagan import engine as E, ops
+    g = torch.Generator().manual_seed(3)
+    prim = E.ConvPrim((torch.randn(256, 256, 3, 3, generator=g) / 48).cuda(), None, 1, 0)
+    x = torch.randn(N, 66, 66, 256, generator=g).cuda().bfloat16()
+    monkeypatch.delenv("CTAGAN_TC_PAIR", raising=False)
+    y0, s0 = prim.fprop_stats(x, ops.ZeroPool(2 * N * 256 + 8, x.device))
+    monkeypatch.setenv("CTAGAN_TC_PAIR", "1")
+    y1, s1 = prim.fprop_stats(x, ops.ZeroPool(2 * N * 256 + 8, x.device))
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+    assert maxrel(s1, s0) <= 1e-6
