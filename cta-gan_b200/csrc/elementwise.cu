@@ -2,6 +2,7 @@
 // reflection-pad and its backward, pooling, bilinear 2x upsample + concat, plane means, casts.
 // All are coalesced along the channel (innermost) dimension with 16-byte vectors when C allows it.
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 // All index arithmetic in this file is 32-bit (64-bit integer division costs ~100 instructions on the SM and dominated these
@@ -384,6 +385,149 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// InstanceNorm backward in ONE kernel: thread-block clusters + distributed shared memory.
+// The two-kernel form (reduce: few CTAs, fp64 atomics; apply: re-reads everything) costs ~20 us per layer at batch 1, more than the
+// input-gradient convolution next to it.  Here a cluster of NB_CL CTAs owns NB_CH channels of one image: every thread loads its
+// <= NB_PPT pixels ONCE (fold of the reflection-pad gradient, skip-connection addend, activation mask), keeps g and xhat in registers,
+// the per-channel sums are combined warp -> CTA (shared memory) -> cluster (each CTA reads its peers' partial sums through DSMEM),
+// and the same registers produce dx.  No accumulator, no memset, no atomics, one read of each operand.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NB_CL = 8;        // CTAs per cluster (portable maximum)
+constexpr int NB_CVG = 2;       // channel vectors (of 8 bf16) per CTA -> 16 channels per cluster
+constexpr int NB_LANES = 256 / NB_CVG;   // pixel lanes per CTA
+constexpr int NB_PPT = 4;       // pixels per thread held in registers
+
+__global__ void __launch_bounds__(256) norm_bwd_cluster_kernel(const bf16 *__restrict__ gout, const bf16 *__restrict__ x,
+                                                               const float *__restrict__ stats, const bf16 *__restrict__ addend,
+                                                               bf16 *__restrict__ dx, int H, int W, int C, int pad, int act, int out_pad) {
+  constexpr int V = 8;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  pdl_wait();
+  const int rank = (int)cluster.block_rank();
+  const int group = blockIdx.x / NB_CL;                 // channel group of this cluster
+  const int n = blockIdx.y;
+  const int cvl = threadIdx.x % NB_CVG, pl = threadIdx.x / NB_CVG;
+  const int cv = group * NB_CVG + cvl;
+  const int CV = C / V;
+  const int HW = H * W;
+  const int per_cta = (HW + NB_CL - 1) / NB_CL;
+  const int p0 = rank * per_cta, p1 = min(HW, p0 + per_cta);
+  const int Ho = H + 2 * out_pad, Wo = W + 2 * out_pad;
+
+  float mean[V], rstd[V];
+  load_stats<V>(stats + 2 * ((idx_t)n * C + cv * V), mean, rstd);
+  float gg[NB_PPT][V], xh[NB_PPT][V];
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < NB_PPT; ++k) {
+    const int pix = p0 + pl + k * NB_LANES;
+    if (pix < p1) {
+      const int h = pix / W, w = pix - h * W;
+      float g[V], xv[V];
+      folded_grad<bf16, V>(gout, n, h, w, cv, H, W, C, pad, g);
+      const idx_t idx = ((idx_t)n * HW + pix) * CV + cv;
+      if (addend) {
+        float av[V];
+        load_vec<bf16, V>(addend + idx * V, av);
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] += av[i];
+      }
+      load_vec<bf16, V>(x + idx * V, xv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float t = (xv[i] - mean[i]) * rstd[i];
+        const float q = g[i] * act_grad_from_sign(t, act);
+        xh[k][i] = t;
+        gg[k][i] = q;
+        s1[i] += q;
+        s2[i] = fmaf(q, t, s2[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) xh[k][i] = gg[k][i] = 0.f;
+    }
+  }
+  // warp: lanes with the same channel vector are NB_CVG apart
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+#pragma unroll
+    for (int o = NB_CVG; o < 32; o <<= 1) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+    }
+  }
+  __shared__ float warp_part[8][NB_CVG][2][V];
+  __shared__ float cta_part[NB_CVG][2][V];          // read by the peers through DSMEM
+  __shared__ float total[NB_CVG][2][V];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < NB_CVG) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      warp_part[warp][lane][0][i] = s1[i];
+      warp_part[warp][lane][1][i] = s2[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NB_CVG * 2 * V) {
+    const int c = threadIdx.x / (2 * V), q = (threadIdx.x / V) % 2, i = threadIdx.x % V;
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += warp_part[wv][c][q][i];
+    cta_part[c][q][i] = t;
+  }
+  cluster.sync();                                     // every CTA's partial sums are visible cluster-wide
+  if (threadIdx.x < NB_CVG * 2 * V) {
+    const int c = threadIdx.x / (2 * V), q = (threadIdx.x / V) % 2, i = threadIdx.x % V;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < NB_CL; ++r) {
+      const float *peer = cluster.map_shared_rank(&cta_part[0][0][0], r);
+      t += peer[(c * 2 + q) * V + i];
+    }
+    total[c][q][i] = t;
+  }
+  __syncthreads();
+  const float inv_hw = 1.f / (float)HW;
+  float m1[V], m2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    m1[i] = total[cvl][0][i] * inv_hw;
+    m2[i] = total[cvl][1][i] * inv_hw;
+  }
+#pragma unroll
+  for (int k = 0; k < NB_PPT; ++k) {
+    const int pix = p0 + pl + k * NB_LANES;
+    if (pix < p1) {
+      const int h = pix / W, w = pix - h * W;
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = rstd[i] * (gg[k][i] - m1[i] - xh[k][i] * m2[i]);
+      store_vec<bf16, V>(dx + ((((idx_t)n * Ho + h + out_pad) * Wo + w + out_pad) * CV + cv) * V, o);
+    }
+  }
+  if (out_pad > 0) {                                  // zero margin of the output (the dgrad convolution reads it as padding)
+    const int margin = Ho * Wo - HW;
+    float z[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) z[i] = 0.f;
+    for (int m = rank * NB_LANES + pl; m < margin; m += NB_CL * NB_LANES) {
+      // margin pixels in row-major order: full top rows, then left/right strips of the interior rows, then full bottom rows
+      int ho, wo;
+      const int top = out_pad * Wo, side = 2 * out_pad;
+      if (m < top) { ho = m / Wo; wo = m - ho * Wo; }
+      else if (m < top + H * side) { const int t = m - top; ho = out_pad + t / side; const int c2 = t % side; wo = c2 < out_pad ? c2 : W + c2; }
+      else { const int t = m - top - H * side; ho = out_pad + H + t / Wo; wo = t % Wo; }
+      store_vec<bf16, V>(dx + ((((idx_t)n * Ho + ho) * Wo + wo) * CV + cv) * V, z);
+    }
+  }
+  cluster.sync();                                     // no CTA may exit while a peer still reads its shared memory
+}
+
 template <typename T, int V>
 __global__ void act_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ y, T *__restrict__ dx, idx_t nvec, int act) {
   for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nvec; idx += (idx_t)gridDim.x * blockDim.x) {
@@ -729,6 +873,18 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
   CTAGAN_REQUIRE(!stats || acc, "norm_act_pad_bwd: acc scratch required with stats");
   CTAGAN_REQUIRE(act != CTAGAN_ACT_TANH, "norm_act_pad_bwd: tanh unsupported here (use act_bwd)");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // one-kernel cluster path (bf16, maps up to 64x64 per image: everything a thread needs fits in registers)
+    const char *e = getenv("CTAGAN_NORM_BWD_CLUSTER");
+    const bool want = !(e && e[0] == '0');
+    if (want && stats && dtype == CTAGAN_BF16 && C % (NB_CVG * 8) == 0 && (long long)H * W <= (long long)NB_CL * NB_LANES * NB_PPT) {
+      dim3 grid((unsigned)(C / (NB_CVG * 8) * NB_CL), (unsigned)N);
+      CTAGAN_CUDA_OK(launch_cluster_pdl(norm_bwd_cluster_kernel, grid, dim3(256), 0, st, (unsigned)NB_CL, (const bf16 *)gout, (const bf16 *)x, stats,
+                                        (const bf16 *)addend, (bf16 *)dx, H, W, C, pad, act, out_pad));
+      CTAGAN_LAUNCH_OK();
+      return CTAGAN_OK;
+    }
+  }
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     int v = pick_vec<T>(C);
     if (stats) {
