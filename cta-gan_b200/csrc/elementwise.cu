@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict__ gout, const T *__restrict__ x,
                                                              const float *__restrict__ stats, const double *__restrict__ acc,
-                                                             const T *__restrict__ addend, T *__restrict__ dx,
+                                                             const T *__restrict__ addend, T *__restrict__ dx, T *__restrict__ g_out,
                                                              int N, int H, int W, int C, int pad, int act, int out_pad) {
   pdl_wait();
   const int CV = C / V;
@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T *__restrict
 #pragma unroll
       for (int i = 0; i < V; ++i) g[i] += av[i];
     }
+    if (g_out) store_vec<T, V>(g_out + idx * V, g);
     if (stats) {
       float xv[V], mean[V], rstd[V], m1[V], m2[V];
       load_vec<T, V>(x + idx * V, xv);
@@ -401,7 +402,8 @@ constexpr int NB_PPT = 4;       // pixels per thread held in registers
 
 __global__ void __launch_bounds__(256) norm_bwd_cluster_kernel(const bf16 *__restrict__ gout, const bf16 *__restrict__ x,
                                                                const float *__restrict__ stats, const bf16 *__restrict__ addend,
-                                                               bf16 *__restrict__ dx, int H, int W, int C, int pad, int act, int out_pad) {
+                                                               bf16 *__restrict__ dx, bf16 *__restrict__ g_out, int H, int W, int C, int pad,
+                                                               int act, int out_pad) {
   constexpr int V = 8;
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(256) norm_bwd_cluster_kernel(const bf16 *__res
 #pragma unroll
         for (int i = 0; i < V; ++i) g[i] += av[i];
       }
+      if (g_out) store_vec<bf16, V>(g_out + idx * V, g);      // the folded (+ skip) gradient itself, for the next skip connection
       load_vec<bf16, V>(x + idx * V, xv);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
@@ -864,26 +867,33 @@ extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const doub
   return CTAGAN_OK;
 }
 
-extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
+static bool norm_bwd_uses_cluster(const float *stats, int H, int W, int C, int dtype) {
+  const char *e = getenv("CTAGAN_NORM_BWD_CLUSTER");
+  const bool want = !(e && e[0] == '0');
+  return want && stats && dtype == CTAGAN_BF16 && C % (NB_CVG * 8) == 0 && (long long)H * W <= (long long)NB_CL * NB_LANES * NB_PPT;
+}
+
+extern "C" int ctagan_norm_act_pad_bwd_launches(int has_stats, int H, int W, int C, int dtype) {
+  if (!has_stats) return 1;
+  return norm_bwd_uses_cluster((const float *)1, H, W, C, dtype) ? 1 : 2;
+}
+
+extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx, void *g_out,
                                        double *acc, int acc_is_zero, int N, int H, int W, int C, int pad, int act, int out_pad,
                                        int dtype, void *stream) {
   CTAGAN_REQUIRE(gout && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && out_pad >= 0, "norm_act_pad_bwd: bad arguments");
   CTAGAN_FITS32((int64_t)N * (H + 2 * pad + 2 * out_pad) * (W + 2 * pad + 2 * out_pad) * C);
   CTAGAN_REQUIRE(!(stats || act != CTAGAN_ACT_NONE) || x, "norm_act_pad_bwd: x required when stats/act given");
-  CTAGAN_REQUIRE(!stats || acc, "norm_act_pad_bwd: acc scratch required with stats");
+  CTAGAN_REQUIRE(!stats || acc || norm_bwd_uses_cluster(stats, H, W, C, dtype), "norm_act_pad_bwd: acc scratch required with stats");
   CTAGAN_REQUIRE(act != CTAGAN_ACT_TANH, "norm_act_pad_bwd: tanh unsupported here (use act_bwd)");
   cudaStream_t st = (cudaStream_t)stream;
-  {
+  if (norm_bwd_uses_cluster(stats, H, W, C, dtype)) {
     // one-kernel cluster path (bf16, maps up to 64x64 per image: everything a thread needs fits in registers)
-    const char *e = getenv("CTAGAN_NORM_BWD_CLUSTER");
-    const bool want = !(e && e[0] == '0');
-    if (want && stats && dtype == CTAGAN_BF16 && C % (NB_CVG * 8) == 0 && (long long)H * W <= (long long)NB_CL * NB_LANES * NB_PPT) {
-      dim3 grid((unsigned)(C / (NB_CVG * 8) * NB_CL), (unsigned)N);
-      CTAGAN_CUDA_OK(launch_cluster_pdl(norm_bwd_cluster_kernel, grid, dim3(256), 0, st, (unsigned)NB_CL, (const bf16 *)gout, (const bf16 *)x, stats,
-                                        (const bf16 *)addend, (bf16 *)dx, H, W, C, pad, act, out_pad));
-      CTAGAN_LAUNCH_OK();
-      return CTAGAN_OK;
-    }
+    dim3 grid((unsigned)(C / (NB_CVG * 8) * NB_CL), (unsigned)N);
+    CTAGAN_CUDA_OK(launch_cluster_pdl(norm_bwd_cluster_kernel, grid, dim3(256), 0, st, (unsigned)NB_CL, (const bf16 *)gout, (const bf16 *)x, stats,
+                                      (const bf16 *)addend, (bf16 *)dx, (bf16 *)g_out, H, W, C, pad, act, out_pad));
+    CTAGAN_LAUNCH_OK();
+    return CTAGAN_OK;
   }
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     int v = pick_vec<T>(C);
@@ -896,7 +906,7 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
       VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<T, V>, grid, dim3(256), 0, st, (const T *)gout, (const T *)x, stats, (const T *)addend, acc, H, W, C, pad, act, ppb)));
     }
     const idx_t total = (idx_t)N * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / v);
-    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, N, H, W, C, pad, act, out_pad)));
+    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, (T *)g_out, N, H, W, C, pad, act, out_pad)));
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;

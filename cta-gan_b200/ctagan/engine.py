@@ -499,18 +499,27 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
     G = plan.tail0.fprop(dr4, use_bias=False)
     dWt0, _ = wg(plan.tail0, X9, dr4)
     block_grads = []
+    # The gradient of a block's output has two consumers: the block's own second InstanceNorm and the skip connection.  It is
+    # G_k = fold(dXp_{k+1}) + G_{k+1}; instead of materialising it with a kernel of its own, the norm-backward launch of the next
+    # consumer folds dXp and adds the skip term itself and (when a further skip needs it) writes G_k as a second output.
+    dXp = None                                                            # not-yet-folded input gradient of the block processed last
     for (c1, c2), (Xk, ra, sa, Tt, rb, sb) in zip(reversed(plan.blocks), reversed(blocks)):
         m = c2.K - 1                                                      # zero margin: dgrad becomes a VALID conv
-        drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0, out_pad=m, pool=bpool)
+        if dXp is None:
+            drb = ops.norm_act_pad_bwd(G, rb, sb, L.ACT_NONE, 0, out_pad=m, pool=bpool)
+        else:
+            drb, G = ops.norm_act_pad_bwd(dXp, rb, sb, L.ACT_NONE, 1, addend=G, out_pad=m, pool=bpool, want_g=True)
         dW2, _ = wg(c2, drb, Tt, margin=m)
         dT = c2.bprop(drb, (Tt.shape[1], Tt.shape[2]), pad=m)
         dra = ops.norm_act_pad_bwd(dT, ra, sa, L.ACT_RELU, 1, out_pad=m, pool=bpool)
         dW1, _ = wg(c1, dra, Xk, margin=m)
         dXp = c1.bprop(dra, (Xk.shape[1], Xk.shape[2]), pad=m)
-        G = ops.norm_act_pad_bwd(dXp, None, None, L.ACT_NONE, 1, addend=G)
         block_grads.append((dW1, dW2))
     block_grads.reverse()
-    dr3 = ops.norm_act_pad_bwd(G, r3, s3, L.ACT_RELU, 0, pool=bpool)
+    if dXp is None:
+        dr3 = ops.norm_act_pad_bwd(G, r3, s3, L.ACT_RELU, 0, pool=bpool)
+    else:
+        dr3 = ops.norm_act_pad_bwd(dXp, r3, s3, L.ACT_RELU, 1, addend=G, pool=bpool)
     dWh7, _ = wg(plan.head7, dr3, A2)
     dA2 = plan.head7.bprop(dr3, (A2.shape[1], A2.shape[2]))
     dr2 = ops.norm_act_pad_bwd(dA2, r2, s2, L.ACT_RELU, 0, pool=bpool)

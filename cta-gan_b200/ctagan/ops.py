@@ -207,22 +207,26 @@ def norm_act_pad(x, stats, act, pad, res=None, res_pad=0):
     return out
 
 
-def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None, out_pad=0, pool=None):
+def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None, out_pad=0, pool=None, want_g=False):
+    """Backward of norm_act_pad (see ctagan_norm_act_pad_bwd).  want_g: also return fold(gout) + addend (the skip-connection gradient)."""
     N, Hp, Wp, C = gout.shape
     H, W = Hp - 2 * pad, Wp - 2 * pad
     if isinstance(stats, LazyStats):
         stats = stats.stats
     dx = torch.empty((N, H + 2 * out_pad, W + 2 * out_pad, C), dtype=gout.dtype, device=gout.device)
+    g_out = torch.empty((N, H, W, C), dtype=gout.dtype, device=gout.device) if want_g else None
+    lib = L.load()
+    launches = lib.ctagan_norm_act_pad_bwd_launches(int(stats is not None), H, W, C, dt(gout))
     acc, zeroed = None, 0
-    if stats is not None:
+    if stats is not None and launches == 2:
         if pool is not None:
             acc, zeroed = pool.take(N * C * 2), 1
         else:
             acc = torch.empty((N, C, 2), dtype=torch.float64, device=gout.device)
-    _count(2 if stats is not None else 1)
-    L.check(L.load().ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(acc), zeroed, N, H, W, C, pad, act,
-                                             out_pad, dt(gout), _stream()))
-    return dx
+    _count(launches)
+    L.check(lib.ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(g_out), _p(acc), zeroed, N, H, W, C, pad, act,
+                                        out_pad, dt(gout), _stream()))
+    return (dx, g_out) if want_g else dx
 
 
 def act_bwd(gy, y, act):

@@ -149,10 +149,16 @@ int ctagan_norm_act_pad(const void *x, const float *stats, const double *sums, f
  * The residual branch of the forward receives fold_reflect(gout) itself (call with stats=NULL, act=NONE).
  * dx is written as [N][H+2*out_pad][W+2*out_pad][C] with a zero margin of out_pad pixels: with out_pad = K-1-p the stride-1
  * input-gradient convolution that consumes it becomes a plain VALID convolution (the tcgen05 engine's native form).
- * acc: N*C*2 doubles scratch (only with stats); acc_is_zero != 0 promises it is already cleared (one memset per pass). */
-int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx,
+ * g_out (optional, [N][H][W][C]): also receives fold_reflect(gout) + addend, i.e. the gradient that continues along the skip
+ * connection of a residual block -- one launch then serves both consumers of a block's output gradient.
+ * acc: N*C*2 doubles scratch (only with stats); acc_is_zero != 0 promises it is already cleared (one memset per pass).
+ * bf16 maps of up to 64x64 pixels per image run as ONE kernel (thread-block clusters of 8 CTAs per 16 channels, per-channel sums
+ * combined through distributed shared memory, operands read once and kept in registers; acc is not used); otherwise two kernels
+ * (reduce with fp64 atomics into acc, then apply).  ctagan_norm_act_pad_bwd_launches tells which. */
+int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx, void *g_out,
                             double *acc, int acc_is_zero, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype,
                             void *stream);
+int ctagan_norm_act_pad_bwd_launches(int has_stats, int H, int W, int C, int dtype);
 
 /* Pointwise activation backward for conv-epilogue activations: dx = gy * act'(y) computed from the OUTPUT y
  * (relu/lrelu: sign(y); tanh: 1-y^2).  n elements. */

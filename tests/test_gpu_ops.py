@@ -132,6 +132,40 @@ def test_norm_act_pad_fwd_bwd(ct, cfg, dtype):
         assert maxrel(nchw(gres.float()), res.grad) <= tol
 
 
+@pytest.mark.parametrize("cfg", [(1, 256, 64, 64, 1, 2, "none"), (2, 64, 24, 20, 1, 0, "relu"), (1, 128, 70, 70, 1, 2, "lrelu"), (3, 32, 16, 16, 0, 1, "relu")])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_norm_bwd_skip_fusion_and_margin(ct, cfg, dtype):
+    """InstanceNorm backward with the reflection-pad fold, the skip-connection addend, the zero output margin and the second output
+    (the skip gradient itself) against autograd -- covers the one-kernel cluster/DSMEM path (bf16, <= 64x64) and the two-kernel path."""
+    ctagan, E, L, ops = ct
+    N, C, H, W, pad, out_pad, act = cfg
+    T = torch.float32 if dtype == "fp32" else torch.bfloat16
+    tol = TOL if dtype == "fp32" else 3e-2
+    actc = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU}[act]
+    g = torch.Generator().manual_seed(9)
+    rnd = lambda *sh: (torch.randn(*sh, generator=g).bfloat16().float() if dtype == "bf16" else torch.randn(*sh, generator=g))
+    x = rnd(N, C, H, W) * 1.5 + 0.3
+    x = (x.bfloat16().float() if dtype == "bf16" else x).requires_grad_(True)
+    gout = rnd(N, C, H + 2 * pad, W + 2 * pad)
+    skip = rnd(N, C, H, W)
+    y = F.instance_norm(x, eps=1e-5)
+    y = {"none": lambda t: t, "relu": F.relu, "lrelu": lambda t: F.leaky_relu(t, 0.2)}[act](y)
+    probe = torch.zeros(N, C, H, W, requires_grad=True)          # d(loss)/d(probe) = fold(gout) + skip
+    yp = F.pad(y + probe, (pad,) * 4, mode="reflect") if pad else y + probe
+    ((yp * gout).sum() + ((y + probe) * skip).sum()).backward()
+    xd = nhwc(x.detach()).cuda().to(T)
+    stats = ops.instnorm_stats(xd)
+    dx, gsk = ops.norm_act_pad_bwd(nhwc(gout).cuda().to(T), xd, stats, actc, pad, addend=nhwc(skip).cuda().to(T), out_pad=out_pad, want_g=True)
+    assert dx.shape == (N, H + 2 * out_pad, W + 2 * out_pad, C)
+    inner = dx[:, out_pad:out_pad + H, out_pad:out_pad + W]
+    assert maxrel(nchw(inner.float()), x.grad) <= tol, maxrel(nchw(inner.float()), x.grad)
+    assert maxrel(nchw(gsk.float()), probe.grad) <= tol
+    if out_pad:
+        border = dx.clone()
+        border[:, out_pad:out_pad + H, out_pad:out_pad + W] = 0
+        assert float(border.abs().max()) == 0.0
+
+
 def test_pool_upsample(ct):
     ctagan, E, L, ops = ct
     g = torch.Generator().manual_seed(9)
