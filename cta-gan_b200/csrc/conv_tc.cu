@@ -1144,10 +1144,15 @@ static int tc_gather_kind(const ctagan_conv_geom *g) {
   if (g->dtype != CTAGAN_BF16) return 0;
   if (g->Ci % 8 || g->Ci < 32 || g->Co % 32) return 0;       // 16-byte pixel rows; channel tails are TMA zero fill + masked stores
   if (g->KH * g->KW > MAX_TAPS) return 0;
-  if ((long long)g->N * g->Ho * g->Wo < 512) return 0;    // tiny maps: launch-latency bound either way -> CUDA-core kernel
+  // tiny maps are launch-latency bound either way, but the generic CUDA-core kernel needs ~65 us for a 64-channel 3x3 layer on
+  // 8 x 4 x 4 pixels (one thread per output, 576 dependent FMAs) where one masked tensor-core tile needs ~8 us
+  static int min_px = 0, min_wo = 0;
+  if (!min_px) { const char *e = getenv("CTAGAN_TC_MIN_PIXELS"); min_px = e ? atoi(e) : 32; if (min_px < 1) min_px = 1; }
+  if (!min_wo) { const char *e = getenv("CTAGAN_TC_MIN_WO"); min_wo = e ? atoi(e) : 2; if (min_wo < 1) min_wo = 1; }
+  if ((long long)g->N * g->Ho * g->Wo < min_px) return 0;
   if (g->dil == 1) {
     if (g->stride == 1 && g->pad_h == 0 && g->pad_w == 0 && g->Ho == g->Hi - g->KH + 1 && g->Wo == g->Wi - g->KW + 1) return 1;
-    if (g->stride <= 2 && g->Wo >= 16) return 2;
+    if (g->stride <= 2 && g->Wo >= min_wo) return 2;
     return 0;
   }
   if (g->dil == 2 && g->stride == 1 && g->Wo >= 32 && (g->Ho % 2 == 0) && (g->Wo % 2 == 0)) return 3;
@@ -1289,7 +1294,9 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl, int n_groups = 1) {
   const int m = g->gy_margin;
   const int Hvld = g->Ho - 2 * m, Wvld = g->Wo - 2 * m;
   if (Hvld <= 0 || Wvld <= 0) return false;
-  if ((long long)g->N * Hvld * Wvld < 512) return false;   // tiny maps stay on the CUDA-core kernel
+  static int min_px = 0;
+  if (!min_px) { const char *e = getenv("CTAGAN_WG_MIN_PIXELS"); min_px = e ? atoi(e) : 512; if (min_px < 1) min_px = 1; }
+  if ((long long)g->N * Hvld * Wvld < min_px) return false;   // tiny maps stay on the CUDA-core kernel
   pl.bnw = g->Ci > 128 ? 256 : (g->Ci > 64 ? 128 : 64);
   pl.bkw = Wvld >= 64 ? 64 : (Wvld > 16 ? 32 : 16);
   pl.bkh = 64 / pl.bkw;
