@@ -463,7 +463,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + p.n_stages * Cfg::STAGE_BYTES);   // (the ring may be shorter than Cfg::STAGES)
   uint64_t *empty_bar = full_bar + Cfg::STAGES;
   uint64_t *tmem_full_bar = empty_bar + Cfg::STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
@@ -1006,11 +1006,22 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
   }
   TcParams q = p;
   q.n_stages = Cfg::STAGES;
+  // Short-K tiles (few taps x few channel chunks, e.g. the 32-channel 3x3 layers of Reg: 9 stages per tile) on a grid of many waves are
+  // bound by the per-CTA prologue / epilogue, not by the ring depth: a ring that fits twice into an SM's shared memory lets two CTAs
+  // share the SM, so one CTA's main loop runs under the other's epilogue.
+  const int iters = p.n_taps * ((p.Ci + CHUNK_K * KCH - 1) / (CHUNK_K * KCH));
+  static int short_k = -1;
+  if (short_k < 0) { const char *e = getenv("CTAGAN_TC_SHORTK"); short_k = e ? atoi(e) : 20; }    // measured on the Reg step (b=8): off 18.05 ms, 12 -> 17.31 ms, 20 -> 17.21 ms
+  if (!PAIR && iters <= short_k && (long long)grid.x * grid.y >= 4LL * ctagan_num_sms()) {
+    const int fit = (110 * 1024) / Cfg::STAGE_BYTES;
+    if (fit >= 2 && fit < q.n_stages) q.n_stages = fit;
+  }
   if (const char *env = getenv("CTAGAN_TC_STAGES")) {
     const int ns = atoi(env);
     if (ns >= 1 && ns <= Cfg::STAGES) q.n_stages = ns;
   }
-  CTAGAN_CUDA_OK(launch_cluster_pdl(conv_tc_valid_kernel<BN, KCH, PAIR>, grid, dim3(192), Cfg::SMEM_BYTES, st, PAIR ? 2u : 1u, mx, mw, q));
+  const size_t smem_bytes = (size_t)q.n_stages * Cfg::STAGE_BYTES + 1024 + 256;
+  CTAGAN_CUDA_OK(launch_cluster_pdl(conv_tc_valid_kernel<BN, KCH, PAIR>, grid, dim3(192), smem_bytes, st, PAIR ? 2u : 1u, mx, mw, q));
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
