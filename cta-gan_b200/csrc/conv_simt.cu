@@ -269,6 +269,7 @@ struct PackTable {
   int tile_start[PACK_MAX_ITEMS + 1];  // prefix sums of tile counts
   const float *w[PACK_MAX_ITEMS];
   void *wp[PACK_MAX_ITEMS];
+  void *wp2[PACK_MAX_ITEMS];           // mode 2 (= both layouts from one read of the master weights): the mode-1 destination
   int O[PACK_MAX_ITEMS], I[PACK_MAX_ITEMS], KH[PACK_MAX_ITEMS], KW[PACK_MAX_ITEMS], mode[PACK_MAX_ITEMS];
 };
 
@@ -297,17 +298,20 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_co
     tile[o * pitch + r] = w[((long long)(o0 + o) * I + i0) * taps + r];
   }
   __syncthreads();
-  T *dst = reinterpret_cast<T *>(t.wp[it]);
-  if (t.mode[it] == 0) {
+  const int mode = t.mode[it];
+  if (mode == 0 || mode == 2) {
     // wp[o][tap][i]: consecutive threads -> consecutive i
+    T *dst = reinterpret_cast<T *>(t.wp[it]);
     for (int idx = threadIdx.x; idx < no * taps * ni; idx += 256) {
       const int i = idx % ni;
       const int r = idx / ni;
       const int tap = r % taps, o = r / taps;
       dst[((long long)(o0 + o) * taps + tap) * I + i0 + i] = from_f<T>(tile[o * pitch + i * taps + tap]);
     }
-  } else {
+  }
+  if (mode == 1 || mode == 2) {
     // wp[i][taps-1-tap][o]: consecutive threads -> consecutive o
+    T *dst = reinterpret_cast<T *>(mode == 2 ? t.wp2[it] : t.wp[it]);
     for (int idx = threadIdx.x; idx < ni * taps * no; idx += 256) {
       const int o = idx % no;
       const int r = idx / no;
@@ -367,27 +371,50 @@ extern "C" int ctagan_pack_weights(const float *w, void *wp, int O, int I, int K
 extern "C" int ctagan_pack_weights_multi(const ctagan_pack_item *items, int n_items, int dtype, void *stream) {
   CTAGAN_REQUIRE(items && n_items > 0, "pack_weights_multi: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  for (int base = 0; base < n_items; base += PACK_MAX_ITEMS) {
+  for (int k = 0; k < n_items; ++k) {
+    const ctagan_pack_item &it = items[k];
+    CTAGAN_REQUIRE(it.w && it.wp && it.O > 0 && it.I > 0 && it.KH > 0 && it.KW > 0 && (it.mode == 0 || it.mode == 1),
+                   "pack_weights_multi: bad item %d", k);
+  }
+  // One launch per shared-memory class (taps <= 9, <= 16, larger): the tile buffer is sized by the largest filter of a launch, and a
+  // single 7x7 layer in the list used to pin EVERY block to 200 KB (one block per SM).  A (mode 0, mode 1) pair of the same weight
+  // becomes one entry that reads the master weights once and writes both layouts.
+  const int class_taps[3] = {9, 16, 1 << 30};
+  for (int cls = 0; cls < 3; ++cls) {
     PackTable t;
-    t.n = n_items - base < PACK_MAX_ITEMS ? n_items - base : PACK_MAX_ITEMS;
+    t.n = 0;
     t.tile_start[0] = 0;
     int max_taps = 1;
-    for (int k = 0; k < t.n; ++k) {
-      const ctagan_pack_item &it = items[base + k];
-      CTAGAN_REQUIRE(it.w && it.wp && it.O > 0 && it.I > 0 && it.KH > 0 && it.KW > 0 && (it.mode == 0 || it.mode == 1),
-                     "pack_weights_multi: bad item %d", base + k);
-      t.w[k] = it.w; t.wp[k] = it.wp; t.O[k] = it.O; t.I[k] = it.I; t.KH[k] = it.KH; t.KW[k] = it.KW; t.mode[k] = it.mode;
+    auto flush = [&]() -> int {
+      if (t.n == 0) return CTAGAN_OK;
+      const size_t smem = (size_t)PACK_TILE * (PACK_TILE * max_taps + 1) * sizeof(float);
+      CTAGAN_REQUIRE(smem <= 200 * 1024, "pack_weights_multi: kernel window too large");
+      CTAGAN_DISPATCH_DTYPE(dtype, T, {
+        if (smem > 48 * 1024) CTAGAN_CUDA_OK(cudaFuncSetAttribute(pack_weights_multi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pack_weights_multi_kernel<T><<<t.tile_start[t.n], 256, smem, st>>>(t);
+      });
+      CTAGAN_LAUNCH_OK();
+      t.n = 0;
+      max_taps = 1;
+      return CTAGAN_OK;
+    };
+    for (int k = 0; k < n_items; ++k) {
+      const ctagan_pack_item &it = items[k];
+      const int taps = it.KH * it.KW;
+      if (taps > class_taps[cls] || (cls > 0 && taps <= class_taps[cls - 1])) continue;
+      const bool pair = k + 1 < n_items && it.mode == 0 && items[k + 1].mode == 1 && items[k + 1].w == it.w && items[k + 1].O == it.O &&
+                        items[k + 1].I == it.I && items[k + 1].KH == it.KH && items[k + 1].KW == it.KW;
+      const int e = t.n++;
+      t.w[e] = it.w; t.wp[e] = it.wp; t.wp2[e] = pair ? items[k + 1].wp : nullptr;
+      t.O[e] = it.O; t.I[e] = it.I; t.KH[e] = it.KH; t.KW[e] = it.KW; t.mode[e] = pair ? 2 : it.mode;
       const int tiles = ((it.O + PACK_TILE - 1) / PACK_TILE) * ((it.I + PACK_TILE - 1) / PACK_TILE);
-      t.tile_start[k + 1] = t.tile_start[k] + tiles;
-      if (it.KH * it.KW > max_taps) max_taps = it.KH * it.KW;
+      t.tile_start[e + 1] = t.tile_start[e] + tiles;
+      if (taps > max_taps) max_taps = taps;
+      if (pair) ++k;
+      if (t.n == PACK_MAX_ITEMS) { const int rc = flush(); if (rc) return rc; }
     }
-    const size_t smem = (size_t)PACK_TILE * (PACK_TILE * max_taps + 1) * sizeof(float);
-    CTAGAN_REQUIRE(smem <= 200 * 1024, "pack_weights_multi: kernel window too large");
-    CTAGAN_DISPATCH_DTYPE(dtype, T, {
-      if (smem > 48 * 1024) CTAGAN_CUDA_OK(cudaFuncSetAttribute(pack_weights_multi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      pack_weights_multi_kernel<T><<<t.tile_start[t.n], 256, smem, st>>>(t);
-    });
-    CTAGAN_LAUNCH_OK();
+    const int rc = flush();
+    if (rc) return rc;
   }
   return CTAGAN_OK;
 }

@@ -417,5 +417,11 @@ def pack_weights_multi(entries, dtype):
         O, I, KH, KW = w.shape
         arr[k] = L.PackItem(w.data_ptr(), wp.data_ptr(), O, I, KH, KW, mode)
     ensure_device()
-    _count((n + 47) // 48)
+    # one launch per shared-memory class of filter size (<= 9 taps, <= 16 taps, larger), 48 table entries each
+    per_class = {}
+    for w, _, _ in entries:
+        taps = w.shape[2] * w.shape[3]
+        c = 0 if taps <= 9 else (1 if taps <= 16 else 2)
+        per_class[c] = per_class.get(c, 0) + 1
+    _count(sum((v + 47) // 48 for v in per_class.values()))
     L.check(L.load().ctagan_pack_weights_multi(arr, n, _DT[dtype], _stream()))
