@@ -132,13 +132,17 @@ def test_norm_act_pad_fwd_bwd(ct, cfg, dtype):
         assert maxrel(nchw(gres.float()), res.grad) <= tol
 
 
-@pytest.mark.parametrize("cfg", [(1, 256, 64, 64, 1, 2, "none"), (2, 64, 24, 20, 1, 0, "relu"), (1, 128, 70, 70, 1, 2, "lrelu"), (3, 32, 16, 16, 0, 1, "relu")])
+@pytest.mark.parametrize("cfg", [(1, 256, 64, 64, 1, 2, "none"), (2, 64, 24, 20, 1, 0, "relu"), (1, 128, 70, 70, 1, 2, "lrelu"), (3, 32, 16, 16, 0, 1, "relu"),
+                                 (1, 128, 128, 128, 0, 0, "relu"), (2, 24, 100, 90, 1, 2, "none"), (1, 8, 132, 132, 0, 1, "relu")])
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_norm_bwd_skip_fusion_and_margin(ct, cfg, dtype):
+def test_norm_bwd_skip_fusion_and_margin(ct, cfg, dtype, monkeypatch):
     """InstanceNorm backward with the reflection-pad fold, the skip-connection addend, the zero output margin and the second output
-    (the skip gradient itself) against autograd -- covers the one-kernel cluster/DSMEM path (bf16, <= 64x64) and the two-kernel path."""
+    (the skip gradient itself) against autograd -- covers both one-kernel cluster/DSMEM variants (bf16, <= 64x64 and <= 128x128) and the
+    two-kernel path (fp32, larger maps)."""
     ctagan, E, L, ops = ct
     N, C, H, W, pad, out_pad, act = cfg
+    if H * W > 4096 and C % 16:
+        monkeypatch.setenv("CTAGAN_NORM_BWD_CLUSTER", "2")        # the opt-in 128x128 cluster variant
     T = torch.float32 if dtype == "fp32" else torch.bfloat16
     tol = TOL if dtype == "fp32" else 3e-2
     actc = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU}[act]
