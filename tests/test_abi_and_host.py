@@ -83,6 +83,25 @@ def test_replay_buffer_matches_reference(golden):
     assert picks == golden["replay.picks_seed5_size4"]
 
 
+def test_replay_buffer_plan_apply_equals_oracle_for_batches():
+    """The split ReplayBuffer (host decisions up front, index-tensor data movement) against the oracle's restatement of
+    trainer/utils.py:120-140 for batches > 1, where a later element of a call can receive an earlier one back."""
+    from oracle import restate as R
+    from trainer.utils import ReplayBuffer
+    g = torch.Generator().manual_seed(1)
+    batches = [torch.randn(3, 1, 4, 4, generator=g) for _ in range(12)]
+    random.seed(11); ref = R.ReplayBuffer(max_size=4)
+    want = [ref.push_and_pop(b) for b in batches]
+    random.seed(11); rb = ReplayBuffer(max_size=4)
+    got = []
+    for b in batches:
+        src, dst = rb.plan(b.shape[0])                              # (what the graphed trainer does: decisions first, data later)
+        got.append(rb.apply(b, torch.tensor(src), torch.tensor(dst)))
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert len(rb.data) == 4 and all(torch.equal(x, y) for x, y in zip(rb.data, ref.data))
+
+
 def test_yaml_configs_keep_reference_keys():
     from trainer.utils import get_config
     ref_keys = {"CycleGan": ["name", "noise_level", "port", "save_root", "image_save", "Adv_lamda", "Cyc_lamda", "Corr_lamda", "Smooth_lamda",
