@@ -1113,7 +1113,7 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
   // non-overlapped epilogue + wave quantisation at b=8.  Kept opt-in as the base of a persistent 2-CTA kernel.
   const char *pair_env = getenv("CTAGAN_TC_PAIR");
   const int pair_mode = pair_env ? atoi(pair_env) : 0;
-  const bool pair = pair_mode > 0 && bn >= 128 && w_slots == 1 && p.Co % bn == 0 && p.stat_total_ctas == 0;
+  const bool pair = pair_mode > 0 && (bn >= 128 || pair_mode == 2) && w_slots == 1 && p.Co % bn == 0 && p.stat_total_ctas == 0;
   rc = make_map_w3d(&mw, wp, p.Co * w_slots, w_taps, p.Ci, (uint32_t)(pair ? bn / 2 : bn));
   if (rc) return rc;
   dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
@@ -1122,6 +1122,7 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
   if (pair) {
     const bool k2 = (p.Ci % 128 == 0 && bn < 256);
     if (bn == 256) return launch_tc<256, 1, true>(mx, mw, p, grid, st);
+    if (bn == 64) return k2 ? launch_tc<64, 2, true>(mx, mw, p, grid, st) : launch_tc<64, 1, true>(mx, mw, p, grid, st);
     return k2 ? launch_tc<128, 2, true>(mx, mw, p, grid, st) : launch_tc<128, 1, true>(mx, mw, p, grid, st);
   }
   int kch = (p.Ci % 128 == 0 && bn < 256) ? 2 : 1;      // BN=256 keeps 64-channel stages (4 of them fit; 2-chunk stages would leave 2)
