@@ -77,11 +77,17 @@ class GradSync:
     def __call__(self):
         if self.world == 1:
             return
-        grads = [p.grad for p in self.params if p.grad is not None]
+        owners = [p for p in self.params if p.grad is not None]
+        grads = [p.grad for p in owners]
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(self.world)
-        torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)              # the division happens inside the collective
+        else:                                                        # gloo (CPU tests) has no AVG
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.div_(self.world)
+        # the averaged gradients stay in the flat buffer: .grad becomes a view of it (no copy back)
+        for p, c, g in zip(owners, flat.split([g.numel() for g in grads]), grads):
+            p.grad = c.view_as(g)
 
 
 class _TrainerBase:
