@@ -219,10 +219,11 @@ class Cyc_Trainer(_TrainerBase):
         return {"{st}.pth": self.netG_A2B, "netD_B_{st}.pth": self.netD_B, "netG_B2A_{st}.pth": self.netG_B2A,
                 "netD_A_{st}.pth": self.netD_A}
 
-    # The phases are separate methods so that they can be captured as CUDA graphs around the host-side ReplayBuffer.
-    # At batch 1 every kernel is latency-bound (132 CTAs for a few microseconds), so the two independent chains of the generator
+    # At batch 1 every kernel is latency-bound (66-132 CTAs for a few microseconds), so the two independent chains of the generator
     # phase (A: G_A2B(real_A) -> D_B -> G_B2A(fake_B);  B: G_B2A(real_B) -> D_A -> G_A2B(fake_A)) run on two streams; autograd
-    # replays each backward node on its forward stream, so the backward chains overlap the same way.  Same for the two D phases.
+    # replays each backward node on its forward stream, so the backward chains overlap the same way.
+    # phase_G / phase_DD / step_two_phase are the iteration in the reference's serial order (generator phase, host ReplayBuffer, both
+    # discriminator phases): the cross-check of phase_all, the overlapped one-program schedule that step() and the CUDA graph use.
     def _side_streams(self):
         if not hasattr(self, "_streams"):
             prio = int(os.environ.get("CTAGAN_CHAIN_PRIO", "-1"))      # the input-gradient chains outrank the wgrad lanes: 5.93 -> 5.77 ms
