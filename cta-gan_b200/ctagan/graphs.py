@@ -24,10 +24,14 @@ from . import ops
 
 
 class GraphedTrainer:
-    def __init__(self, trainer, enabled: bool = True, warmup: int = 3):
+    def __init__(self, trainer, enabled: bool = True, warmup: int = 3, replay_first: bool = True):
+        """warmup: eager iterations run before the capture (allocator / NCCL / optimizer-state warm-up; they are real training
+        iterations on the first batch).  replay_first=False makes the first call consist of exactly those eager iterations plus the
+        capture -- with warmup=1 every batch is then trained on exactly once (the epoch loop of trainer.train())."""
         self.t = trainer
         self.enabled = enabled
         self.warmup = max(int(warmup), 1)
+        self.replay_first = replay_first
         self._graphs = None
         self._launches = 0
         self.is_cyc = hasattr(trainer, "phase_G")
@@ -63,6 +67,8 @@ class GraphedTrainer:
                     dst.copy_(src, non_blocking=True)
         if self._graphs is None:
             self._capture(static)
+            if not self.replay_first:
+                return t.last_losses         # the eager warm-up iteration was this call's iteration; the capture itself executes nothing
         E.invalidate_weight_cache()          # eager users after us must not trust capture-time packed weights
         if self.is_cyc:
             self._sel.copy_(t.plan_replay(static[0].shape[0]), non_blocking=True)   # this step's ReplayBuffer decisions (host RNG)

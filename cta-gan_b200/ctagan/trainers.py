@@ -114,7 +114,17 @@ class _TrainerBase:
 
     # -- helpers -------------------------------------------------------------------------------------------------------
     def _adam(self, params, lr):
-        return torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), fused=True, capturable=True)
+        # lr lives in a device tensor: update_learning_rate() then also reaches the Adam kernels captured in a CUDA graph
+        return torch.optim.Adam(params, lr=torch.tensor(float(lr), dtype=torch.float32, device=self.device), betas=(0.5, 0.999), fused=True,
+                                capturable=True)
+
+    @staticmethod
+    def _set_lr(opt, lr):
+        for g in opt.param_groups:
+            if torch.is_tensor(g["lr"]):
+                g["lr"].fill_(float(lr))
+            else:
+                g["lr"] = lr
 
     def _alloc_inputs(self):
         c = self.config
@@ -148,13 +158,17 @@ class _TrainerBase:
             torch.save(net.state_dict(), os.path.join(c["save_root"], fname.format(st=str(epoch))))
 
     def train(self):
+        """The reference's epoch loop (CycTrainer.py:128-236 etc.).  Every iteration is a CUDA-graph replay (config `cuda_graphs`, default
+        true; the learning rates live in device tensors, so update_learning_rate() reaches the captured Adam kernels)."""
+        from .graphs import GraphedTrainer
         c = self.config
+        runner = GraphedTrainer(self, enabled=bool(c.get("cuda_graphs", True)), warmup=1, replay_first=False)
         for epoch in range(c["epoch"] + 1, c["n_epochs"] + 1 + c["decay_epoch"]):
             if epoch > c["n_epochs"]:
                 self.update_learning_rate()
             loader = self._loader()
             for i, batch in enumerate(loader):
-                self.step(batch)
+                runner.step_host(batch)
                 self._log(epoch, i, len(loader))
             self._save(epoch, self.checkpoint_nets())
 
@@ -211,8 +225,7 @@ class Cyc_Trainer(_TrainerBase):
         c = self.config
         lr = c["lr"] - c["lr"] / c["decay_epoch"]
         for opt in (self.optimizer_D_B, self.optimizer_G):          # optimizer_D_A is skipped, as in CycTrainer.py:117-126
-            for g in opt.param_groups:
-                g["lr"] = lr
+            self._set_lr(opt, lr)
         c["lr"] = lr
 
     def checkpoint_nets(self):
@@ -502,8 +515,7 @@ class Reg_Trainer(_TrainerBase):
         c = self.config
         lr = c["lr"] - c["lr"] / c["decay_epoch"]
         for opt in (self.optimizer_D_B, self.optimizer_R_A, self.optimizer_G):           # RegTrainer.py:150-161
-            for g in opt.param_groups:
-                g["lr"] = lr
+            self._set_lr(opt, lr)
         c["lr"] = lr
 
     def checkpoint_nets(self):
@@ -583,8 +595,7 @@ class Hd_Trainer_x1(Reg_Trainer):
         c = self.config
         lr = c["lr"] - c["lr"] / c["decay_epoch"]
         for opt in (self.optimizer_R_A, self.optimizer_G):
-            for g in opt.param_groups:
-                g["lr"] = lr
+            self._set_lr(opt, lr)
         for g in self.optimizer_D_B.param_groups:      # HdTrainer.py:163-164 writes a no-op key: D never decays
             g["lrd"] = c["lrd"] - c["lrd"] / c["decay_epoch"]
         c["lr"] = lr
@@ -645,8 +656,7 @@ class P2p_Trainer(_TrainerBase):
         c = self.config
         lr = c["lr"] - c["lr"] / c["decay_epoch"]
         for opt in (self.optimizer_D_B, self.optimizer_G):
-            for g in opt.param_groups:
-                g["lr"] = lr
+            self._set_lr(opt, lr)
         c["lr"] = lr
 
     def checkpoint_nets(self):

@@ -135,3 +135,21 @@ def test_cyc_overlapped_schedule_equals_serial_order():
             assert _close(fused[i][k], serial[i][k], tol[i]), ("fused", i, k, fused[i][k], serial[i][k])
             if graph[i] is not None:
                 assert _close(graph[i][k], serial[i][k], tol[i]), ("graph", i, k, graph[i][k], serial[i][k])
+
+
+def test_train_loop_runs_graphed_and_decays_lr():
+    """trainer.train(): the reference's epoch loop on CUDA-graph replays; the decayed learning rate must reach the captured Adam."""
+    from trainer import Cyc_Trainer
+    _seed(); tr = Cyc_Trainer(_cfg("CycleGan", 64, precision="bf16", n_epochs=1, decay_epoch=2, synthetic_batches=3, log_every=1000))
+    w0 = tr.netG_A2B.model_head[1].weight.detach().clone()
+    tr.train()                                        # epochs 1 (lr 1e-4), 2 (5e-5), 3 (2.5e-5): 3 batches each, every batch exactly once
+    assert tr.step_count == 9
+    lr = tr.optimizer_G.param_groups[0]["lr"]
+    assert torch.is_tensor(lr) and float(lr) == pytest.approx(2.5e-5), lr   # lr -= lr / decay_epoch, twice (CycTrainer.py:117-126)
+    assert float(tr.optimizer_D_A.param_groups[0]["lr"]) == pytest.approx(1e-4)     # optimizer_D_A never decays (CycTrainer.py:117-126)
+    w1 = tr.netG_A2B.model_head[1].weight.detach()
+    assert torch.isfinite(w1).all() and float((w1 - w0).abs().max()) > 1e-5
+    for v in tr.last_losses.values():
+        assert torch.isfinite(v).all()
+    import ctagan
+    ctagan.set_precision("bf16")
