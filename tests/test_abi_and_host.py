@@ -76,6 +76,25 @@ def test_state_dict_layouts_match_reference(golden):
         assert abs(float(v.double().sum()) - fp[k][1]) <= 1e-9 * max(1.0, fp[k][2]), k
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/ctagan.h is the drop-in boundary: it must compile as C99 (no C++ in the signatures) and its structs must have the
+    layout the ctypes binding assumes."""
+    import ctypes
+    import shutil
+    import subprocess
+    from ctagan import lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ctagan.h"\n#include <stdio.h>\nint main(void){ printf("%zu %zu %zu\\n", sizeof(ctagan_conv_geom), '
+                   'sizeof(ctagan_conv_groups), sizeof(ctagan_pack_item)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(lib.ConvGeom), ctypes.sizeof(lib.ConvGroups), ctypes.sizeof(lib.PackItem)]
+
+
 def test_replay_buffer_matches_reference(golden):
     from trainer.utils import ReplayBuffer
     random.seed(5); rb = ReplayBuffer(max_size=4)
