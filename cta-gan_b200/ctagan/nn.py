@@ -3,14 +3,12 @@ as the reference (Model/CycleGan.py, Model/HdGan.py, trainer/reg.py, trainer/tra
 forward/backward executed by the sm_100a kernels of libctagan.so through ctagan.engine."""
 from __future__ import annotations
 
-import functools
 from typing import List
 
 import torch
 import torch.nn as nn
 
 from . import engine as E
-from . import lib as L
 from . import ops
 
 

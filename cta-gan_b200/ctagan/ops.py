@@ -3,7 +3,7 @@ enqueues hand-written sm_100a kernels from libctagan.so on torch's current strea
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -13,9 +13,7 @@ from __future__ import annotations
 
 import itertools
 import os
-import random
-import time
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, Iterable
 
 import torch
 import torch.distributed as dist
