@@ -142,3 +142,39 @@ def test_trainer_package_exports():
         assert hasattr(trainer, n), n
     from trainer.transformer import Transformer_2D  # noqa: F401
     from trainer.utils import smooothing_loss  # noqa: F401
+
+
+def test_packed_weight_cache_is_invalidated_per_optimizer_and_keeps_its_buffers():
+    """Host bookkeeping of the packed (bf16 / re-laid-out) weight copies, no kernel involved: an optimizer step marks exactly its own
+    parameters stale (torch's fused Adam does not bump tensor versions, so a global post-step hook does it by storage address), in-place
+    edits do it through the version counter, `force` re-packs regardless, and the destination buffers persist (CUDA graphs and
+    grouped launches alias them)."""
+    from ctagan import engine as E
+    g = torch.Generator().manual_seed(0)
+    w1 = torch.nn.Parameter(torch.randn(8, 4, 3, 3, generator=g))
+    w2 = torch.nn.Parameter(torch.randn(8, 4, 3, 3, generator=g))
+    p1, p2 = E.ConvPrim(w1, None, 1, 1), E.ConvPrim(w2, None, 1, 1)
+    first = p1.stale_entries(torch.float32) + p2.stale_entries(torch.float32)
+    assert len(first) == 4                                                   # two layouts per weight
+    assert p1.stale_entries(torch.float32) == [] and p2.stale_entries(torch.float32) == []
+    bufs = {id(p): [p._cache[(m, torch.float32)][1].data_ptr() for m in (0, 1)] for p in (p1, p2)}
+    opt1 = torch.optim.SGD([w1], lr=0.1)
+    w1.grad = torch.ones_like(w1)
+    opt1.step()
+    assert len(p1.stale_entries(torch.float32)) == 2 and p2.stale_entries(torch.float32) == []
+    with torch.no_grad():
+        w2.add_(1.0)
+    assert len(p2.stale_entries(torch.float32)) == 2
+    assert len(p1.stale_entries(torch.float32, force=True)) == 2
+    E.invalidate_weight_cache()
+    assert len(p1.stale_entries(torch.float32)) == 2 and len(p2.stale_entries(torch.float32)) == 2
+    assert bufs == {id(p): [p._cache[(m, torch.float32)][1].data_ptr() for m in (0, 1)] for p in (p1, p2)}
+
+    # grouped launches: both orders of a pair share ONE store; slots follow the members, slices are the members' own cache buffers
+    ga, gb = E.GroupedPrim([p1, p2]), E.GroupedPrim([p2, p1])
+    assert ga.store is gb.store and ga.slots == list(reversed(gb.slots)) and sorted(ga.slots) == [0, 1]
+    buf = ga.store.buffer(0, torch.float32)
+    assert tuple(buf.shape) == (2, 8, 3, 3, 4)
+    assert p1._cache[(0, torch.float32)][1].data_ptr() == buf[ga.slots[0]].data_ptr()
+    assert p2._cache[(0, torch.float32)][1].data_ptr() == buf[ga.slots[1]].data_ptr()
+    assert len(p1.stale_entries(torch.float32, modes=(0,))) == 1             # re-homed copies are stale until re-packed
