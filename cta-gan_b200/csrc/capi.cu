@@ -4,10 +4,14 @@
 #include "common.cuh"
 
 int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
-int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
+int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                           size_t workspace_bytes, cudaStream_t st);
+size_t ctagan_conv_wgrad_simt_workspace(const ctagan_conv_geom *g);
 // tcgen05 engine (conv_tc.cu): return CTAGAN_ERR_UNSUPPORTED when the geometry does not tile
-int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                          float *stat_out, cudaStream_t st, const ctagan_conv_groups *gr = nullptr);
+int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, unsigned int *stat_ticket,
+                          void *stat_scratch, size_t stat_scratch_bytes, float *stat_out, cudaStream_t st,
+                          const ctagan_conv_groups *gr = nullptr);
+size_t ctagan_conv_gather_tc_stat_bytes(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
                          size_t workspace_bytes, cudaStream_t st, int n_groups = 1);
 size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g, int n_groups = 1);
@@ -16,7 +20,9 @@ int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g);
 int ctagan_conv_small_kind(const ctagan_conv_geom *g);
 int ctagan_conv_gather_small(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
 int ctagan_conv_wgrad_thin_eligible(const ctagan_conv_geom *g);
-int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st);
+int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                           size_t workspace_bytes, cudaStream_t st);
+size_t ctagan_conv_wgrad_thin_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups = 1);
 
 static thread_local char g_err[512] = "";
@@ -36,6 +42,24 @@ int ctagan_num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restrict__ part, float *__restrict__ out, int parts, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < parts; ++k) s += __ldcg(part + (long long)k * n + i);
+    out[i] = s;
+  }
+}
+}  // namespace
+
+int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8LL * ctagan_num_sms()) blocks = 8LL * ctagan_num_sms();
+  ordered_sum_kernel<<<(int)blocks, 256, 0, st>>>(part, out, parts, n);
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
 }
 
 bool ctagan_pdl_enabled() {
@@ -93,16 +117,18 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
   CTAGAN_REQUIRE(x && wp && y, "conv_gather: null pointer");
   CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_gather: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, st);
+  if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, 0, nullptr, st);
   if (engine != 3 && ctagan_conv_small_kind(g)) return ctagan_conv_gather_small(g, x, wp, bias, y, st);
-  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, st);
+  if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, 0, nullptr, st);
   return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
 }
 
 extern "C" size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine) {
-  if (!g || engine == 1 || engine == 3) return 0;
-  if (engine == 0 && ctagan_conv_wgrad_thin_eligible(g)) return 0;
-  return ctagan_conv_wgrad_tc_workspace(g);
+  if (!g) return 0;
+  if (engine == 2) return ctagan_conv_wgrad_tc_workspace(g);
+  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin_workspace(g);
+  if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc_workspace(g);
+  return ctagan_conv_wgrad_simt_workspace(g);
 }
 
 extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
@@ -113,9 +139,9 @@ extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, cons
   CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_wgrad: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == 2) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
-  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, st);
+  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, workspace, workspace_bytes, st);
   if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
-  return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, st);
+  return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, workspace, workspace_bytes, st);
 }
 
 // Which engine ctagan_conv_gather would run for this geometry: 1 CUDA-core generic, 2 tcgen05, 4 CUDA-core specialised (1-2 channels)
@@ -135,7 +161,8 @@ extern "C" int ctagan_conv_gather_grouped_supported(const ctagan_conv_geom *g, c
 }
 
 extern "C" int ctagan_conv_gather_grouped(const ctagan_conv_geom *g, const ctagan_conv_groups *gr, const void *x, const void *wp,
-                                          const float *bias, void *y, double *stat_acc, float *stats_out, void *stream) {
+                                          const float *bias, void *y, uint32_t *stat_tickets, void *stat_scratch, size_t stat_scratch_bytes,
+                                          float *stats_out, void *stream) {
   int rc = check_geom(g, "conv_gather_grouped");
   if (rc) return rc;
   CTAGAN_REQUIRE(gr && x && wp && y, "conv_gather_grouped: null pointer");
@@ -143,7 +170,7 @@ extern "C" int ctagan_conv_gather_grouped(const ctagan_conv_geom *g, const ctaga
     ctagan_set_error("conv_gather_grouped: geometry / grouping not supported by the tcgen05 engine");
     return CTAGAN_ERR_UNSUPPORTED;
   }
-  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_acc, stat_acc ? stats_out : nullptr, (cudaStream_t)stream, gr);
+  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_tickets, stat_scratch, stat_scratch_bytes, stats_out, (cudaStream_t)stream, gr);
 }
 
 extern "C" size_t ctagan_conv_wgrad_grouped_workspace_bytes(const ctagan_conv_geom *g, int groups) {
@@ -163,14 +190,20 @@ extern "C" int ctagan_conv_wgrad_grouped(const ctagan_conv_geom *g, int groups, 
   return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, (cudaStream_t)stream, groups);
 }
 
-extern "C" int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                                        float *stats_out, int engine, void *stream) {
+extern "C" size_t ctagan_conv_gather_stats_scratch_bytes(const ctagan_conv_geom *g, int engine) {
+  if (!g || ctagan_conv_gather_engine(g, engine) != 2) return 0;
+  return ctagan_conv_gather_tc_stat_bytes(g);
+}
+
+extern "C" int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y,
+                                        uint32_t *stat_tickets, void *stat_scratch, size_t stat_scratch_bytes, float *stats_out, int engine,
+                                        void *stream) {
   int rc = check_geom(g, "conv_gather_stats");
   if (rc) return rc;
-  CTAGAN_REQUIRE(x && wp && y && stat_acc, "conv_gather_stats: null pointer");
+  CTAGAN_REQUIRE(x && wp && y && stat_tickets && stat_scratch && stats_out, "conv_gather_stats: null pointer");
   if (ctagan_conv_gather_engine(g, engine) != 2) {
     ctagan_set_error("conv_gather_stats: fused statistics need the tcgen05 engine (use ctagan_conv_gather + ctagan_instnorm_stats)");
     return CTAGAN_ERR_UNSUPPORTED;
   }
-  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_acc, stats_out, (cudaStream_t)stream);
+  return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_tickets, stat_scratch, stat_scratch_bytes, stats_out, (cudaStream_t)stream);
 }

@@ -139,7 +139,11 @@ __global__ void __launch_bounds__(256) conv_gather_simt_kernel(ctagan_conv_geom 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ctagan_conv_geom g, const T *__restrict__ gy,
                                                               const T *__restrict__ gx, float *__restrict__ dw,
-                                                              float *__restrict__ db, int pixels_per_split, int use_atomics) {
+                                                              float *__restrict__ db, int pixels_per_split) {
+  // split-K: split z stores its partial sums in row z of dw[gridDim.z][Co*Ci*taps] / db[gridDim.z][Co] (the host points dw / db at the
+  // workspace and adds the rows in order with ctagan_ordered_sum when there is more than one split: no floating-point atomics)
+  dw += (long long)blockIdx.z * g.Co * g.Ci * g.KH * g.KW;
+  if (db != nullptr) db += (long long)blockIdx.z * g.Co;
   __shared__ __align__(16) float As[BK][BM + PADM];
   __shared__ __align__(16) float Bs[BK][BN + PADM];
   const int t = threadIdx.x;
@@ -230,13 +234,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ctagan_conv_geom g
       if (np >= NP) continue;
       const int tap = np / B, bb = np - tap * B;
       float *dst = dw + ((long long)a * B + bb) * ntaps + tap;
-      if (use_atomics) atomicAdd(dst, acc[i][j]);
-      else *dst = acc[i][j];
+      *dst = acc[i][j];
     }
   }
   if (db != nullptr && blockIdx.y == 0 && t < BM) {
     const int a = blockIdx.x * BM + t;
-    if (a < A) atomicAdd(db + a, colsum);
+    if (a < A) db[a] = colsum;
   }
 }
 
@@ -335,7 +338,7 @@ int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void
   return CTAGAN_OK;
 }
 
-int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st) {
+static int simt_wgrad_splits(const ctagan_conv_geom *g, int &pps) {
   const long long P = (long long)g->N * g->Ho * g->Wo;
   const int ntaps = g->KH * g->KW;
   const int gx_ = cdiv(g->Co, BM), gy_ = cdiv((long long)ntaps * g->Ci, BN);
@@ -345,17 +348,43 @@ int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void
   const int max_splits = (int)((P + 255) / 256);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  int pps = (int)((P + splits - 1) / splits);
+  pps = (int)((P + splits - 1) / splits);
   pps = ((pps + BK - 1) / BK) * BK;
-  splits = (int)((P + pps - 1) / pps);
-  const int use_atomics = splits > 1;
-  if (use_atomics) CTAGAN_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Co * g->Ci * ntaps, st));
-  if (db) CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
+  return (int)((P + pps - 1) / pps);
+}
+
+// scratch: split-K partial sums [splits][Co*Ci*taps] + [splits][Co] (nothing for a single split)
+size_t ctagan_conv_wgrad_simt_workspace(const ctagan_conv_geom *g) {
+  int pps;
+  const int splits = simt_wgrad_splits(g, pps);
+  return splits > 1 ? (size_t)splits * ((size_t)g->Co * g->Ci * g->KH * g->KW + g->Co) * sizeof(float) : 0;
+}
+
+int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+  const int ntaps = g->KH * g->KW;
+  const int gx_ = cdiv(g->Co, BM), gy_ = cdiv((long long)ntaps * g->Ci, BN);
+  int pps;
+  const int splits = simt_wgrad_splits(g, pps);
+  const long long dw_elems = (long long)g->Co * g->Ci * ntaps;
+  float *dw_dst = dw, *db_dst = db;
+  if (splits > 1) {
+    const size_t need = ctagan_conv_wgrad_simt_workspace(g);
+    CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_wgrad(simt): workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+    dw_dst = (float *)workspace;
+    db_dst = db ? dw_dst + (long long)splits * dw_elems : nullptr;
+  }
   dim3 grid(gx_, gy_, splits);
   CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
-    conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, pps, use_atomics);
+    conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw_dst, db_dst, pps);
   });
   CTAGAN_LAUNCH_OK();
+  if (splits > 1) {
+    int rc = ctagan_ordered_sum(dw_dst, dw, splits, dw_elems, st);
+    if (rc) return rc;
+    if (db) rc = ctagan_ordered_sum(db_dst, db, splits, g->Co, st);
+    return rc;
+  }
   return CTAGAN_OK;
 }
 

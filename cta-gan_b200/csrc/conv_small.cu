@@ -267,12 +267,38 @@ __global__ void __launch_bounds__(256) conv_fewin_tiled_kernel(ctagan_conv_geom 
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int THIN_MAXKW = 7;
 
+// db[s] (this block's share) = sum of gy over the block's slice of pixels, warps combined in warp order (256-thread blocks)
+template <typename T>
+__device__ __forceinline__ void thin_gy_bias(const ctagan_conv_geom &g, const T *__restrict__ gy, float *__restrict__ db, int SC) {
+  __shared__ float wsum[8];
+  const long long total = (long long)g.N * g.Ho * g.Wo;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = min(total, p0 + per);
+  for (int s = 0; s < SC; ++s) {
+    float t = 0.f;
+    for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) t += to_f(gy[p * SC + s]);
+    t = warp_sum(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += wsum[w];
+      db[s] = a;
+    }
+  }
+}
+
 // Register-window version: thread = (channel c, kernel row kh).  For U consecutive positions of the wide tensor it loads U wide
 // values and the (U-1)*STRIDE+KW thin values they touch once, then issues U*KW FMAs (>= 60% of the instruction stream).
 template <typename T, int KW, int STRIDE>
 __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(ctagan_conv_geom g, const T *__restrict__ gy, const T *__restrict__ gx,
-                                                              float *__restrict__ dw, float *__restrict__ db, int gy_thin,
+                                                              float *__restrict__ dw_part, float *__restrict__ db_part, int gy_thin,
                                                               int rows_per_block) {
+  // deterministic split reduction: block x stores its partial sums in row x of dw_part[gridDim.x][Co*Ci*taps] / db_part[gridDim.x][Co]
+  float *dw = dw_part + (long long)blockIdx.x * g.Co * g.Ci * g.KH * KW;
+  float *db = db_part ? db_part + (long long)blockIdx.x * g.Co : nullptr;
   constexpr int U = 8;
   constexpr int WIN = (U - 1) * STRIDE + KW;
   const int c = blockIdx.y * 64 + (threadIdx.x & 63);
@@ -330,23 +356,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(ctagan_conv_geom g
       for (int kw = 0; kw < KW; ++kw) {
         // dw is [A][B][KH][KW] with A = gy channels, B = gx channels
         const long long idx = gy_thin ? (((long long)s * C + c) * ntaps + kh * KW + kw) : (((long long)c * SC + s) * ntaps + kh * KW + kw);
-        atomicAdd(dw + idx, acc[kw]);
+        dw[idx] = acc[kw];
       }
     }
-    if (db && !gy_thin && kh == 0 && blockIdx.z == 0) atomicAdd(db + c, bsum);
+    if (db && !gy_thin && kh == 0 && blockIdx.z == 0) db[c] = bsum;
   }
   // bias gradient of the thin-gy case: db[sc] = sum of gy (first channel block / kernel-row group only)
-  if (db && gy_thin && blockIdx.y == 0 && blockIdx.z == 0) {
-    const long long total = (long long)g.N * g.Ho * g.Wo;
-    const long long per = (total + gridDim.x - 1) / gridDim.x;
-    const long long p0 = blockIdx.x * per, p1 = min(total, p0 + per);
-    for (int s = 0; s < SC; ++s) {
-      float t = 0.f;
-      for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) t += to_f(gy[p * SC + s]);
-      t = warp_sum(t);
-      if ((threadIdx.x & 31) == 0) atomicAdd(db + s, t);
-    }
-  }
+  if (db && gy_thin && blockIdx.y == 0 && blockIdx.z == 0) thin_gy_bias(g, gy, db, SC);
 }
 
 // Vectorised thin weight gradient for stride 1: thread = (8-channel slice, kernel row); one 16-byte load of the wide tensor and
@@ -354,9 +370,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(ctagan_conv_geom g
 // contiguous range of wide-tensor pixels; streams are combined in shared memory, blocks by fp32 atomics.
 template <typename T, int KW>
 __global__ void __launch_bounds__(256) conv_wgrad_thin_vec_kernel(ctagan_conv_geom g, const T *__restrict__ gy, const T *__restrict__ gx,
-                                                                  float *__restrict__ dw, float *__restrict__ db, int gy_thin,
+                                                                  float *__restrict__ dw_part, float *__restrict__ db_part, int gy_thin,
                                                                   long long pix_per_stream) {
+  // deterministic split reduction: block x stores its partial sums in row x of dw_part[gridDim.x][Co*Ci*taps] / db_part[gridDim.x][Co]
+  float *dw = dw_part + (long long)blockIdx.x * g.Co * g.Ci * g.KH * KW;
+  float *db = db_part ? db_part + (long long)blockIdx.x * g.Co : nullptr;
   __shared__ float red[64 * KW * 8];
+  __shared__ float redb[64];
   const int t = threadIdx.x;
   const int stream = t >> 6, cs = t & 7, kh = (t >> 3) & 7;
   const int C = gy_thin ? g.Ci : g.Co;            // wide channel count
@@ -404,19 +424,22 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_vec_kernel(ctagan_conv_ge
         if (++vw == VW) { vw = 0; if (++vh == VH) { vh = 0; ++n; } }
       }
     }
-    // combine the 4 streams of the block, then one atomic per output per block
-    for (int i = t; i < 64 * KW * 8; i += 256) red[i] = 0.f;
-    __syncthreads();
-    if (active) {
-      float *mine = red + (t & 63) * (KW * 8);
+    // combine the 4 streams of the block in stream order (plain read-modify-write, one stream at a time), then one store per output
+    float *mine = red + (t & 63) * (KW * 8);
+    for (int st_ = 0; st_ < 4; ++st_) {
+      if (stream == st_ && active) {
 #pragma unroll
-      for (int k = 0; k < KW; ++k)
+        for (int k = 0; k < KW; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(mine + k * 8 + e, acc[k][e]);
+          for (int e = 0; e < 8; ++e) mine[k * 8 + e] = (st_ == 0 ? 0.f : mine[k * 8 + e]) + acc[k][e];
+        if (kh == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) redb[cs * 8 + e] = (st_ == 0 ? 0.f : redb[cs * 8 + e]) + bsum[e];
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (stream == 0 && active) {
-      const float *mine = red + (t & 63) * (KW * 8);
 #pragma unroll
       for (int k = 0; k < KW; ++k)
 #pragma unroll
@@ -424,27 +447,17 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_vec_kernel(ctagan_conv_ge
           const int cc = c + e;
           // dw is [A][B][KH][KW] with A = gy channels, B = gx channels
           const long long idx = gy_thin ? (((long long)s * C + cc) * ntaps + kh * KW + k) : (((long long)cc * SC + s) * ntaps + kh * KW + k);
-          atomicAdd(dw + idx, mine[k * 8 + e]);
+          dw[idx] = mine[k * 8 + e];
         }
-    }
-    if (db && !gy_thin && s == 0 && kh == 0 && c < C) {
+      if (db && !gy_thin && s == 0 && kh == 0) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(db + c + e, bsum[e]);
+        for (int e = 0; e < 8; ++e) db[c + e] = redb[cs * 8 + e];
+      }
     }
     __syncthreads();
   }
   // bias gradient of the thin-gy case: db[sc] = sum of gy (first channel block only)
-  if (db && gy_thin && blockIdx.y == 0) {
-    const long long tot = (long long)g.N * g.Ho * g.Wo;
-    const long long per = (tot + gridDim.x - 1) / gridDim.x;
-    const long long q0 = blockIdx.x * per, q1 = min(tot, q0 + per);
-    for (int s = 0; s < SC; ++s) {
-      float tsum = 0.f;
-      for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) tsum += to_f(gy[q * SC + s]);
-      tsum = warp_sum(tsum);
-      if ((threadIdx.x & 31) == 0) atomicAdd(db + s, tsum);
-    }
-  }
+  if (db && gy_thin && blockIdx.y == 0) thin_gy_bias(g, gy, db, SC);
 }
 
 }  // namespace
@@ -514,28 +527,66 @@ int ctagan_conv_wgrad_thin_eligible(const ctagan_conv_geom *g) {
   return 0;
 }
 
-int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, cudaStream_t st) {
+namespace {
+struct ThinPlan {
+  bool vec;
+  int gy_thin, C;
+  dim3 grid;
+  long long pps;      // vec: pixels per stream
+  int rpb;            // row walker: rows per block
+};
+
+bool plan_thin(const ctagan_conv_geom *g, ThinPlan &pl) {
   const int kind = ctagan_conv_wgrad_thin_eligible(g);
-  if (!kind) {
-    ctagan_set_error("conv_wgrad_thin: geometry is not degenerate");
-    return CTAGAN_ERR_UNSUPPORTED;
-  }
-  const int gy_thin = kind == 2;
-  const int C = gy_thin ? g->Ci : g->Co;
-  const int VH = gy_thin ? g->Hi : g->Ho;
+  if (!kind) return false;
+  pl.gy_thin = kind == 2;
+  pl.C = pl.gy_thin ? g->Ci : g->Co;
+  const int VH = pl.gy_thin ? g->Hi : g->Ho;
   const long long rows = (long long)g->N * VH;
-  CTAGAN_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->Co * g->Ci * g->KH * g->KW, st));
-  if (db) CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co, st));
-  if (g->stride == 1 && C % 8 == 0 && g->KH <= 8 && (g->KW == 7 || g->KW == 4 || g->KW == 3 || g->KW == 1)) {
-    const int VW = gy_thin ? g->Wi : g->Wo;
+  pl.vec = g->stride == 1 && pl.C % 8 == 0 && g->KH <= 8 && (g->KW == 7 || g->KW == 4 || g->KW == 3 || g->KW == 1);
+  if (pl.vec) {
+    const int VW = pl.gy_thin ? g->Wi : g->Wo;
     const long long total = rows * VW;
-    const int chb = cdiv(C, 64);
+    const int chb = cdiv(pl.C, 64);
     long long blocks = (2LL * ctagan_num_sms() + chb - 1) / chb;
     if (blocks * 4 * 32 > total) blocks = (total + 127) / 128;       // at least 32 pixels per stream
     if (blocks < 1) blocks = 1;
-    const long long pps = (total + blocks * 4 - 1) / (blocks * 4);
-    dim3 grid((unsigned)((total + pps * 4 - 1) / (pps * 4)), chb);
-#define THINV_LAUNCH(KW_) conv_wgrad_thin_vec_kernel<T, KW_><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, gy_thin, pps)
+    pl.pps = (total + blocks * 4 - 1) / (blocks * 4);
+    pl.grid = dim3((unsigned)((total + pl.pps * 4 - 1) / (pl.pps * 4)), chb);
+    return true;
+  }
+  const int ch_blocks = cdiv(pl.C, 64), kh_blocks = cdiv(g->KH, 4);
+  long long want = (2LL * ctagan_num_sms()) / ((long long)ch_blocks * kh_blocks);
+  if (want < 1) want = 1;
+  if (want > rows) want = rows;
+  pl.rpb = (int)((rows + want - 1) / want);
+  pl.grid = dim3(cdiv(rows, pl.rpb), ch_blocks, kh_blocks);
+  return true;
+}
+}  // namespace
+
+// scratch: per-block partial sums [grid.x][Co*Ci*taps] + [grid.x][Co]
+size_t ctagan_conv_wgrad_thin_workspace(const ctagan_conv_geom *g) {
+  ThinPlan pl;
+  if (!plan_thin(g, pl)) return 0;
+  return (size_t)pl.grid.x * ((size_t)g->Co * g->Ci * g->KH * g->KW + g->Co) * sizeof(float);
+}
+
+int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+  ThinPlan pl;
+  if (!plan_thin(g, pl)) {
+    ctagan_set_error("conv_wgrad_thin: geometry is not degenerate");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  const size_t need = ctagan_conv_wgrad_thin_workspace(g);
+  CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_wgrad(thin): workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+  const long long dw_elems = (long long)g->Co * g->Ci * g->KH * g->KW;
+  float *dw_part = (float *)workspace;
+  float *db_part = db ? dw_part + (long long)pl.grid.x * dw_elems : nullptr;
+  const int gy_thin = pl.gy_thin;
+  if (pl.vec) {
+#define THINV_LAUNCH(KW_) conv_wgrad_thin_vec_kernel<T, KW_><<<pl.grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw_part, db_part, gy_thin, pl.pps)
     CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
       if (g->KW == 7) THINV_LAUNCH(7);
       else if (g->KW == 4) THINV_LAUNCH(4);
@@ -543,24 +594,20 @@ int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void
       else THINV_LAUNCH(1);
     });
 #undef THINV_LAUNCH
-    CTAGAN_LAUNCH_OK();
-    return CTAGAN_OK;
-  }
-  const int ch_blocks = cdiv(C, 64), kh_blocks = cdiv(g->KH, 4);
-  long long want = (2LL * ctagan_num_sms()) / ((long long)ch_blocks * kh_blocks);
-  if (want < 1) want = 1;
-  if (want > rows) want = rows;
-  const int rpb = (int)((rows + want - 1) / want);
-  dim3 grid(cdiv(rows, rpb), ch_blocks, kh_blocks);
-#define THIN_LAUNCH(KW_, S_) conv_wgrad_thin_kernel<T, KW_, S_><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw, db, gy_thin, rpb)
-  CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
-    if (g->KW == 7) THIN_LAUNCH(7, 1);
-    else if (g->KW == 4 && g->stride == 1) THIN_LAUNCH(4, 1);
-    else if (g->KW == 4) THIN_LAUNCH(4, 2);
-    else if (g->KW == 3) THIN_LAUNCH(3, 1);
-    else THIN_LAUNCH(1, 1);
-  });
+  } else {
+#define THIN_LAUNCH(KW_, S_) conv_wgrad_thin_kernel<T, KW_, S_><<<pl.grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw_part, db_part, gy_thin, pl.rpb)
+    CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
+      if (g->KW == 7) THIN_LAUNCH(7, 1);
+      else if (g->KW == 4 && g->stride == 1) THIN_LAUNCH(4, 1);
+      else if (g->KW == 4) THIN_LAUNCH(4, 2);
+      else if (g->KW == 3) THIN_LAUNCH(3, 1);
+      else THIN_LAUNCH(1, 1);
+    });
 #undef THIN_LAUNCH
+  }
   CTAGAN_LAUNCH_OK();
-  return CTAGAN_OK;
+  int rc = ctagan_ordered_sum(dw_part, dw, (int)pl.grid.x, dw_elems, st);
+  if (rc) return rc;
+  if (db) rc = ctagan_ordered_sum(db_part, db, (int)pl.grid.x, g->Co, st);
+  return rc;
 }

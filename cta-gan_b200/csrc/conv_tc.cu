@@ -47,10 +47,13 @@ struct TcParams {
   long long *prof;             // optional per-phase clock64 stamps of CTA 0 (developer probe)
   const float *bias;
   bf16 *out;
-  double *stat_acc;            // optional [N][Co][2]: per-(n,co) sum and sum of squares of the fp32 conv output (pre-zeroed by the caller)
-  float *stat_out;             // optional [N][Co][2] (mean, rstd), written by the last CTA to finish (ticket right after stat_acc)
-  int stat_n, stat_hw;         // images and pixels per (n,co) plane
-  unsigned int stat_total_ctas;
+  float *stat_part;            // optional [N][stat_parts][Co][2]: per-tile (sum, sum of squares) of the fp32 conv output over the tile's rows
+  unsigned int *stat_ticket;   // [N][stat_tpi], zero on entry (and again on exit): arrivals per (image, column tile)
+  float *stat_out;             // [N][Co][2] (mean, rstd), written by the last CTA of an (image, column tile)
+  int stat_hw;                 // pixels per (n,co) plane
+  int stat_parts;              // partial-sum slots per image (over all launches that feed these statistics)
+  int stat_part0;              // first slot of THIS launch (output-phase launches: phase index * tiles per image)
+  int stat_tpi;                // tickets per image (>= column tiles)
   int imgs_per_group;          // grouped launch: image n uses the weights (and bias) at row offset w_row_off[n / imgs_per_group]
   int w_row_off[CTAGAN_MAX_GROUPS];
 };
@@ -92,6 +95,22 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully converged warp (elect.sync): unlike `if (lane == 0)` the compiler knows that exactly one lane runs the
+// guarded code, so the TMA / tcgen05 instructions (uniform-datapath operands) are emitted straight instead of inside a
+// per-lane "waterfall" loop (ELECT + BRA.U.ANY around every UTCHMMA / UTMALDG).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *smem_dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
@@ -125,66 +144,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// ---- CTA pair (cta_group::2): two SMs of one TPC run ONE 256 x BN MMA; each holds its own 128 A rows and HALF of the B rows ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local_addr` (a shared::cta address of this kernel's layout) in the CTA of rank `rank`
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have retired
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-// TMA loads of a pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the LEADER's mbarrier
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *smem_dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *smem_dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *smem_dst, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -319,34 +278,36 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        int ch = chunk0 + it;
-        const int cbi = ch % p.cb; ch /= p.cb;
-        const int rbi = ch % p.rb;
-        const int n = ch / p.rb;
-        const int oh0 = p.margin + rbi * p.bkh, ow0 = p.margin + cbi * p.bkw;     // gy coordinates of the chunk origin
+    // TMA producer: converged warp, one elected lane issues (see elect_one)
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      int ch = chunk0 + it;
+      const int cbi = ch % p.cb; ch /= p.cb;
+      const int rbi = ch % p.rb;
+      const int n = ch / p.rb;
+      const int oh0 = p.margin + rbi * p.bkh, ow0 = p.margin + cbi * p.bkw;     // gy coordinates of the chunk origin
+      const int iw0 = ow0 * p.stride + kw - p.pad, ih0 = oh0 * p.stride + kh - p.pad;
+      if (elect_one()) {
         uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
         uint8_t *b_dst = a_dst + Cfg::A_BYTES;
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
 #pragma unroll
         for (int sl = 0; sl < WG_M / 64; ++sl) tma_load_4d(&map_gy, &full_bar[s], a_dst + sl * WG_SLAB, co0 + sl * 64, ow0, oh0, n);
-        const int iw0 = ow0 * p.stride + kw - p.pad, ih0 = oh0 * p.stride + kh - p.pad;
 #pragma unroll
         for (int sl = 0; sl < BNW / 64; ++sl) tma_load_4d(&map_gx, &full_bar[s], b_dst + sl * WG_SLAB, ci0 + sl * 64, iw0, ih0, n);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_mn(WG_M, BNW);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16_mn(WG_M, BNW);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
@@ -357,8 +318,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
           umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
+        if (it == n_iters - 1) umma_commit(tmem_full_bar);
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
@@ -413,8 +375,9 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restr
 }
 
 // db[c] = sum over pixels of gy[p][c]   (bias gradient, only when requested).  grid.x = pixel chunks; block = 8 pixel lanes x 32
-// channel pairs (C <= 64 per pass); partial sums go to db by fp32 atomics (db is zeroed by the caller).
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16 *__restrict__ gy, float *__restrict__ db, long long pixels, int C,
+// channel pairs (C <= 64 per pass).  Every block stores its partial sums in its own row of part[blocks][C]; ctagan_ordered_sum adds
+// the rows in block order (deterministic: no floating-point atomics).
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16 *__restrict__ gy, float *__restrict__ part, long long pixels, int C,
                                                      long long pix_per_block) {
   const int cp = threadIdx.x & 31, pl = threadIdx.x >> 5;      // channel pair, pixel lane
   const long long p0 = (long long)blockIdx.x * pix_per_block;
@@ -437,36 +400,156 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16 *__restrict__ gy
       float t = 0.f;
 #pragma unroll
       for (int l = 0; l < 8; ++l) t += sm[l][threadIdx.x];
-      atomicAdd(db + c0 + threadIdx.x, t);
+      part[(long long)blockIdx.x * C + c0 + threadIdx.x] = t;
     }
   }
 }
 
-template <int BN, int KCH, bool PAIR = false>
+template <int BN, int KCH>
 struct TcConfig {
   static constexpr int A_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB per chunk
-  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * CHUNK_K * 2;   // a CTA pair splits the BN weight rows between its two SMs
+  static constexpr int B_BYTES = BN * CHUNK_K * 2;
   static constexpr int STAGE_BYTES = KCH * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-// PAIR = true: launched as clusters of two CTAs (consecutive blockIdx.x = two M tiles, same co0).  The pair executes
-// tcgen05.mma.cta_group::2 with M = 256: each SM stages its own 128 A rows and HALF of the BN weight rows, the leader (cluster rank 0)
-// issues the MMAs for both, each SM keeps its 128 x BN accumulator in its own TMEM and runs its own epilogue.  Per SM and 64-channel
-// chunk the L2->SM ingest falls from 16 KB + BN*128 B to 16 KB + BN*64 B -- the quantity that bounds this kernel.
-template <int BN, int KCH, bool PAIR = false>
+// Epilogue of one 128 x BN accumulator tile (4 warps, warp w reads TMEM lanes 32*(w%4) .. +31): bias / activation / bf16 stores and,
+// optionally, the InstanceNorm statistics of the layer.
+//
+// Statistics are DETERMINISTIC: every CTA stores its per-column (sum, sum of squares) over its 128 rows into its own slot of
+// stat_part[N][parts][Co][2] (plain stores, fixed arithmetic order inside the tile), and the last CTA of an (image, column tile) to
+// arrive -- a ticket per (image, column tile) -- adds the slots in slot order in fp64 and writes (mean, rstd).  No floating-point
+// atomics anywhere: the same inputs give the same bits whatever the CTA schedule.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t tmem_acc, int warp, int lane, int img, int tile, int co0, int wrow0,
+                                            int co_tile, float (*stat_red)[4][2][32], unsigned int *ticket_s) {
+  const int quarter = warp & 3;
+  const int row = quarter * 32 + lane;
+  const int BW = 1 << p.bw_log2;
+  int i, j;
+  if (p.mode == 0) {
+    const int ql = tile * TILE_M + row;
+    i = ql / p.Wv; j = ql - i * p.Wv;
+  } else {
+    i = (tile / p.tiles_w) * (TILE_M >> p.bw_log2) + (row >> p.bw_log2);
+    j = (tile % p.tiles_w) * BW + (row & (BW - 1));
+  }
+  const int oi = i * p.sy + p.ay, oj = j * p.sx + p.ax;
+  const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W;
+  bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
+  float2 *part = p.stat_part ? reinterpret_cast<float2 *>(p.stat_part) + ((long long)img * p.stat_parts + p.stat_part0 + tile) * p.Co + co0
+                             : nullptr;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+    tmem_ld_wait();
+    if (part != nullptr) {
+      // column sums over the warp's 32 rows by a butterfly that halves the data per step (31 shuffles per quantity), then the 4
+      // epilogue warps are combined in shared memory in warp order
+      float s1[32], s2[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float t = valid ? __uint_as_float(r[e]) : 0.f;
+        s1[e] = t;
+        s2[e] = t * t;
+      }
+#pragma unroll
+      for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int q = 0; q < n / 2; ++q) {
+          const float keep1 = upper ? s1[q + n / 2] : s1[q], send1 = upper ? s1[q] : s1[q + n / 2];
+          const float keep2 = upper ? s2[q + n / 2] : s2[q], send2 = upper ? s2[q] : s2[q + n / 2];
+          s1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
+          s2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+        }
+      }
+      // lane l now holds the sums of column l
+      const int par = (c >> 5) & 1;
+      stat_red[par][quarter][0][lane] = s1[0];
+      stat_red[par][quarter][1][lane] = s2[0];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && co0 + c + lane < p.Co) {
+        const float a = (stat_red[par][0][0][lane] + stat_red[par][1][0][lane]) + (stat_red[par][2][0][lane] + stat_red[par][3][0][lane]);
+        const float b = (stat_red[par][0][1][lane] + stat_red[par][1][1][lane]) + (stat_red[par][2][1][lane] + stat_red[par][3][1][lane]);
+        part[c + lane] = make_float2(a, b);
+      }
+    }
+    if (valid && co0 + c < p.Co) {            // Co is a multiple of 32 here; tiles may overhang it
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+      if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] += __ldg(p.bias + wrow0 + c + e);
+      }
+      if (p.act != CTAGAN_ACT_NONE) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], p.act);
+      }
+      uint4 *dst = reinterpret_cast<uint4 *>(out_row + c);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * g + 0], v[8 * g + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * g + 2], v[8 * g + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * g + 4], v[8 * g + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * g + 6], v[8 * g + 7]);
+        pk.x = *reinterpret_cast<uint32_t *>(&h0);
+        pk.y = *reinterpret_cast<uint32_t *>(&h1);
+        pk.z = *reinterpret_cast<uint32_t *>(&h2);
+        pk.w = *reinterpret_cast<uint32_t *>(&h3);
+        dst[g] = pk;
+      }
+    }
+  }
+  // "last CTA finalises": once every CTA of this (image, column tile) has stored its partial sums, the last one adds them in slot
+  // order and turns them into (mean, rstd); it also re-arms the ticket (the buffer is zero again when the kernel ends)
+  if (part != nullptr) {
+    const int et = (int)threadIdx.x - 64;      // 0..127
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    unsigned int *ticket = p.stat_ticket + (long long)img * p.stat_tpi + co_tile;
+    if (et == 0) *ticket_s = atomicAdd(ticket, 1u);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (*ticket_s == (unsigned int)p.stat_parts - 1u) {
+      __threadfence();
+      const double inv = 1.0 / (double)p.stat_hw;
+      for (int col = et; col < BN; col += 128) {
+        if (co0 + col >= p.Co) break;
+        const float2 *src = reinterpret_cast<const float2 *>(p.stat_part) + (long long)img * p.stat_parts * p.Co + co0 + col;
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < p.stat_parts; ++k) {
+          const float2 v = __ldcg(src + (long long)k * p.Co);
+          s1 += (double)v.x;
+          s2 += (double)v.y;
+        }
+        const double m = s1 * inv;
+        double var = s2 * inv - m * m;
+        if (var < 0) var = 0;
+        *reinterpret_cast<float2 *>(p.stat_out + ((long long)img * p.Co + co0 + col) * 2) = make_float2((float)m, (float)(1.0 / sqrt(var + 1e-5)));
+      }
+      if (et == 0) *ticket = 0u;
+    }
+  }
+}
+
+template <int BN, int KCH>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
-  using Cfg = TcConfig<BN, KCH, PAIR>;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  using Cfg = TcConfig<BN, KCH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + p.n_stages * Cfg::STAGE_BYTES);   // (the ring may be shorter than Cfg::STAGES)
   uint64_t *empty_bar = full_bar + Cfg::STAGES;
   uint64_t *tmem_full_bar = empty_bar + Cfg::STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+  __shared__ float stat_red[2][4][2][32];       // [chunk parity][epilogue warp][sum | sumsq][column]
+  __shared__ unsigned int ticket_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.x / p.tiles_per_img;
@@ -491,63 +574,49 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
-    if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
-    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  if (PAIR) cluster_sync_all();        // both CTAs' barriers are initialised before either one's TMA / commit can touch them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                          // producer grid complete + flushed: nothing above touches global memory
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tap = 0; tap < p.n_taps; ++tap) {
-        const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], wcol = p.tap_w_col[tap];
-        const int row2d = (int)(q0 + dh * p.Wv + dw);
-        const int c1 = tile_j0 * p.stride + dw, c2 = tile_i0 * p.stride + dh;
-        for (int gk = 0; gk < groups; ++gk) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+    // ===== TMA producer: the whole warp walks the ring (coordinates stay warp-uniform), one elected lane issues =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tap = 0; tap < p.n_taps; ++tap) {
+      const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], wcol = p.tap_w_col[tap];
+      const int row2d = (int)(q0 + dh * p.Wv + dw);
+      const int c1 = tile_j0 * p.stride + dw, c2 = tile_i0 * p.stride + dh;
+      for (int gk = 0; gk < groups; ++gk) {
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (elect_one()) {
           uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t *b_dst = a_dst + KCH * Cfg::A_BYTES;
-          if (!PAIR) {
-            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < KCH; ++k) {
-              const int ch = (gk * KCH + k) * CHUNK_K;
-              if (p.mode == 0) tma_load_2d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, row2d);
-              else tma_load_4d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
-              tma_load_3d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, ch, wcol, wrow0);
-            }
-          } else {
-            // both SMs' loads are counted on the leader's barrier: it expects the bytes of the whole pair
-            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
-            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[s]), 0);
-#pragma unroll
-            for (int k = 0; k < KCH; ++k) {
-              const int ch = (gk * KCH + k) * CHUNK_K;
-              if (p.mode == 0) tma_load_2d_pair(&map_x, lead_bar, a_dst + k * Cfg::A_BYTES, ch, row2d);
-              else tma_load_4d_pair(&map_x, lead_bar, a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
-              tma_load_3d_pair(&map_w, lead_bar, b_dst + k * Cfg::B_BYTES, ch, wcol, wrow0 + (int)rank * (BN / 2));
-            }
+          for (int k = 0; k < KCH; ++k) {
+            const int ch = (gk * KCH + k) * CHUNK_K;
+            if (p.mode == 0) tma_load_2d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, row2d);
+            else tma_load_4d(&map_x, &full_bar[s], a_dst + k * Cfg::A_BYTES, ch, c1, c2, img);
+            tma_load_3d(&map_w, &full_bar[s], b_dst + k * Cfg::B_BYTES, ch, wcol, wrow0);
           }
-          if (++s == NS) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {     // (pair: the leader issues the MMAs of both SMs)
-      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, BN);
-      const int n_iters = p.n_taps * groups;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    // ===== MMA issuer: converged warp, one elected lane issues the tcgen05.mma / commit =====
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+    const int n_iters = p.n_taps * groups;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t b_addr = a_addr + KCH * Cfg::A_BYTES;
 #pragma unroll
@@ -557,373 +626,24 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
           for (int kk = 0; kk < CHUNK_K / UMMA_K; ++kk) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            const uint32_t acc = (it > 0 || k > 0 || kk > 0) ? 1u : 0u;
-            if (PAIR) umma_bf16_pair(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
-            else umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+            umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (it > 0 || k > 0 || kk > 0) ? 1u : 0u);
           }
         }
-        // frees the smem stage (in both SMs of a pair) when these MMAs retire (implies fence::before_thread_sync)
-        if (PAIR) umma_commit_pair(&empty_bar[s]);
-        else umma_commit(&empty_bar[s]);
-        if (++s == NS) { s = 0; ph ^= 1u; }
+        umma_commit(&empty_bar[s]);           // frees the smem stage when these MMAs retire (implies fence::before_thread_sync)
+        if (it == n_iters - 1) umma_commit(tmem_full_bar);     // accumulator complete
       }
-      if (PAIR) umma_commit_pair(tmem_full_bar);     // accumulator complete
-      else umma_commit(tmem_full_bar);
+      __syncwarp();
+      if (++s == NS) { s = 0; ph ^= 1u; }
     }
   } else {
-    // ===== epilogue: warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31 =====
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    int i, j;
-    if (p.mode == 0) {
-      const int ql = q_local0 + row;
-      i = ql / p.Wv; j = ql - i * p.Wv;
-    } else {
-      i = tile_i0 + (row >> p.bw_log2); j = tile_j0 + (row & (BW - 1));
-    }
-    const int oi = i * p.sy + p.ay, oj = j * p.sx + p.ax;
-    const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W && img < p.stat_n;
-    bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
+    // ===== epilogue: warps 2..5 =====
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     // accumulator complete: from here on only the epilogue is left, so let the consumer's CTAs be scheduled now (they run their
     // prologue and block in their own pdl_wait() until this grid has finished).  Triggering at kernel start instead made the
     // step SLOWER: early-resident consumers held shared memory that the other streams' kernels needed.
     pdl_trigger();
-    __shared__ float stat_red[2][4][2][32];       // [chunk parity][epilogue warp][sum | sumsq][column]
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      if (p.stat_acc != nullptr) {
-        // InstanceNorm statistics fused into the epilogue: column sums over the warp's 32 rows by a butterfly that halves the data per
-        // step (31 shuffles per quantity), the 4 epilogue warps are combined in shared memory, one fp64 atomic pair per column and CTA.
-        float s1[32], s2[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float t = valid ? __uint_as_float(r[e]) : 0.f;
-          s1[e] = t;
-          s2[e] = t * t;
-        }
-#pragma unroll
-        for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
-          const bool upper = (lane & step) != 0;
-#pragma unroll
-          for (int i = 0; i < n / 2; ++i) {
-            const float keep1 = upper ? s1[i + n / 2] : s1[i], send1 = upper ? s1[i] : s1[i + n / 2];
-            const float keep2 = upper ? s2[i + n / 2] : s2[i], send2 = upper ? s2[i] : s2[i + n / 2];
-            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
-            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
-          }
-        }
-        // lane l now holds the sums of column l
-        const int par = (c >> 5) & 1;
-        stat_red[par][quarter][0][lane] = s1[0];
-        stat_red[par][quarter][1][lane] = s2[0];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && co0 + c + lane < p.Co && img < p.stat_n) {     // (img == stat_n: the padding tile of an odd pair grid)
-          const float a = stat_red[par][0][0][lane] + stat_red[par][1][0][lane] + stat_red[par][2][0][lane] + stat_red[par][3][0][lane];
-          const float b = stat_red[par][0][1][lane] + stat_red[par][1][1][lane] + stat_red[par][2][1][lane] + stat_red[par][3][1][lane];
-          double *dst = p.stat_acc + ((long long)img * p.Co + co0 + c + lane) * 2;
-          atomicAdd(dst, (double)a);
-          atomicAdd(dst + 1, (double)b);
-        }
-      }
-      if (valid && co0 + c < p.Co) {            // Co is a multiple of 32 here; tiles may overhang it
-        float v[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-        if (p.bias) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += __ldg(p.bias + wrow0 + c + e);
-        }
-        if (p.act != CTAGAN_ACT_NONE) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], p.act);
-        }
-        uint4 *dst = reinterpret_cast<uint4 *>(out_row + c);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * g + 0], v[8 * g + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * g + 2], v[8 * g + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * g + 4], v[8 * g + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * g + 6], v[8 * g + 7]);
-          pk.x = *reinterpret_cast<uint32_t *>(&h0);
-          pk.y = *reinterpret_cast<uint32_t *>(&h1);
-          pk.z = *reinterpret_cast<uint32_t *>(&h2);
-          pk.w = *reinterpret_cast<uint32_t *>(&h3);
-          dst[g] = pk;
-        }
-      }
-    }
-  }
-  // "last CTA finalises": once every CTA of the layer has added its partial sums, the last one turns them into (mean, rstd)
-  if (p.stat_out != nullptr && warp >= 2) {
-    __shared__ unsigned int ticket_s;
-    __threadfence();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 64) {
-      unsigned int *ticket = reinterpret_cast<unsigned int *>(p.stat_acc + (long long)p.stat_n * p.Co * 2);
-      ticket_s = atomicAdd(ticket, 1u);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (ticket_s == p.stat_total_ctas - 1) {
-      __threadfence();
-      const double inv = 1.0 / (double)p.stat_hw;
-      for (int i = threadIdx.x - 64; i < p.stat_n * p.Co; i += 128) {
-        const double s1 = __ldcg(p.stat_acc + 2 * i), s2 = __ldcg(p.stat_acc + 2 * i + 1);
-        const double m = s1 * inv;
-        double var = s2 * inv - m * m;
-        if (var < 0) var = 0;
-        p.stat_out[2 * i] = (float)m;
-        p.stat_out[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
-      }
-    }
-  }
-  tc_fence_before();
-  if (PAIR) cluster_sync_all();        // the leader's MMAs wrote this SM's TMEM and read its shared memory: nobody leaves early
-  else __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
-    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Resident-A variant of the pitch-trick kernel.  The nine taps of a 3x3 filter read almost the same input rows: tap (kh,kw) is
-// the run [q0 + kh*Wv + kw, +128) of the flattened input.  So the CTA loads the union of those runs ONCE per 64-channel chunk
-// (R = 128 + (KH-1)*Wv + KW-1 rows, e.g. 262 instead of 9 x 128) and every tap's A operand is the same shared-memory block with
-// the descriptor start address shifted by (kh*Wv + kw) rows of 128 bytes.  Only the weights stream through the mbarrier ring.
-// L2->SM operand traffic per CTA drops from taps*(A+B) to A_union + taps*B  (3x3, 256 ch, BN=64: 864 KB -> 429 KB).
-// ---------------------------------------------------------------------------------------------------------------------
-struct ResAParams {
-  int rows_box;        // rows per TMA box of the resident block (multiple of 8, <= 256)
-  int n_box;           // boxes per chunk
-  int chunks;          // 64-channel chunks (<= 8)
-  int b_stages;
-  int base_offset_mode;  // 0: none, 1: descriptor base_offset = (row shift & 7)
-};
-
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr, uint32_t base_off) {
-  return make_kmajor_sw128_desc(smem_addr) | ((uint64_t)(base_off & 7u) << 49);
-}
-
-template <int BN>
-struct ResACfg {
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int B_BYTES = BN * CHUNK_K * 2;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
-conv_tc_resA_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p,
-                    const ResAParams rp) {
-  using Cfg = ResACfg<BN>;
-  constexpr int CPS = 256 / BN;             // chunks per weight stage
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int a_chunk_bytes = rp.rows_box * rp.n_box * 128;
-  uint8_t *b_ring = smem + rp.chunks * a_chunk_bytes;
-  uint64_t *a_full = reinterpret_cast<uint64_t *>(b_ring + rp.b_stages * (256 / BN) * Cfg::B_BYTES);
-  uint64_t *full_bar = a_full + 8;
-  uint64_t *empty_bar = full_bar + 8;
-  uint64_t *tmem_full_bar = empty_bar + 8;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x / p.tiles_per_img;
-  const int tile = blockIdx.x - img * p.tiles_per_img;
-  const int q_local0 = tile * TILE_M;
-  const long long q0 = (long long)img * p.Hv * p.Wv + q_local0;
-  const int BW = 1 << p.bw_log2;          // (mode 0 only: the 4-D addressing fields below are never used)
-  const int tile_i0 = 0, tile_j0 = 0;
-  const int co0 = blockIdx.y * BN;
-  const int NSB = rp.b_stages;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_x);
-    tma_prefetch_desc(&map_w);
-    for (int s = 0; s < 8; ++s) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // resident input block: one barrier per channel chunk so that the MMAs start as soon as chunk 0 has landed
-      for (int kc = 0; kc < rp.chunks; ++kc) {
-        mbar_expect_tx(&a_full[kc], (uint32_t)a_chunk_bytes);
-        for (int b = 0; b < rp.n_box; ++b)
-          tma_load_2d(&map_x, &a_full[kc], smem + kc * a_chunk_bytes + b * rp.rows_box * 128, kc * CHUNK_K, (int)(q0 + b * rp.rows_box));
-      }
-      // weight ring: one stage = CPS consecutive 64-channel chunks of one tap (always 32 KB = 512 tensor cycles of MMAs, which
-      // covers the ~500-700 cycles a single lane needs per stage for try_wait / expect_tx / TMA issue / commit)
-      int s = 0;
-      uint32_t ph = 0;
-      const int groups = (rp.chunks + CPS - 1) / CPS;
-      for (int tap = 0; tap < p.n_taps; ++tap)
-        for (int gk = 0; gk < groups; ++gk) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], CPS * Cfg::B_BYTES);
-#pragma unroll
-          for (int k = 0; k < CPS; ++k)
-            tma_load_3d(&map_w, &full_bar[s], b_ring + (s * CPS + k) * Cfg::B_BYTES, (gk * CPS + k) * CHUNK_K, p.tap_w_col[tap], co0);
-          if (++s == NSB) { s = 0; ph ^= 1u; }
-        }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
-      int s = 0;
-      uint32_t ph = 0;
-      bool first = true;
-      const int groups = (rp.chunks + CPS - 1) / CPS;
-      for (int tap = 0; tap < p.n_taps; ++tap) {
-        const uint32_t shift = (uint32_t)(p.tap_dh[tap] * p.Wv + p.tap_dw[tap]);        // rows of 128 bytes
-        for (int gk = 0; gk < groups; ++gk) {
-          if (tap == 0)
-            for (int k = 0; k < CPS; ++k)
-              if (gk * CPS + k < rp.chunks) mbar_wait(&a_full[gk * CPS + k], 0);
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < CPS; ++k) {
-            // the tap's A operand = the resident block shifted by `shift` rows: the 128B swizzle is a function of the absolute
-            // shared-memory address bits, so a start address that is not 1024-byte aligned needs no descriptor base offset (measured)
-            const uint32_t a_addr = smem_u32(smem + (gk * CPS + k) * a_chunk_bytes) + shift * 128u;
-            const uint64_t adesc = make_kmajor_sw128_desc_off(a_addr, rp.base_offset_mode ? shift : 0u);
-            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + (s * CPS + k) * Cfg::B_BYTES));
-#pragma unroll
-            for (int kk = 0; kk < CHUNK_K / UMMA_K; ++kk) {
-              umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (first && kk == 0) ? 0u : 1u);
-            }
-            first = false;
-          }
-          umma_commit(&empty_bar[s]);
-          if (++s == NSB) { s = 0; ph ^= 1u; }
-        }
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else {
-    // ===== epilogue: warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31 =====
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    int i, j;
-    if (p.mode == 0) {
-      const int ql = q_local0 + row;
-      i = ql / p.Wv; j = ql - i * p.Wv;
-    } else {
-      i = tile_i0 + (row >> p.bw_log2); j = tile_j0 + (row & (BW - 1));
-    }
-    const int oi = i * p.sy + p.ay, oj = j * p.sx + p.ax;
-    const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W;
-    bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    __shared__ float stat_red[2][4][2][32];       // [chunk parity][epilogue warp][sum | sumsq][column]
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      if (p.stat_acc != nullptr) {
-        // InstanceNorm statistics fused into the epilogue: column sums over the warp's 32 rows by a butterfly that halves the data per
-        // step (31 shuffles per quantity), the 4 epilogue warps are combined in shared memory, one fp64 atomic pair per column and CTA.
-        float s1[32], s2[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float t = valid ? __uint_as_float(r[e]) : 0.f;
-          s1[e] = t;
-          s2[e] = t * t;
-        }
-#pragma unroll
-        for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
-          const bool upper = (lane & step) != 0;
-#pragma unroll
-          for (int i = 0; i < n / 2; ++i) {
-            const float keep1 = upper ? s1[i + n / 2] : s1[i], send1 = upper ? s1[i] : s1[i + n / 2];
-            const float keep2 = upper ? s2[i + n / 2] : s2[i], send2 = upper ? s2[i] : s2[i + n / 2];
-            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
-            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
-          }
-        }
-        // lane l now holds the sums of column l
-        const int par = (c >> 5) & 1;
-        stat_red[par][quarter][0][lane] = s1[0];
-        stat_red[par][quarter][1][lane] = s2[0];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && co0 + c + lane < p.Co) {
-          const float a = stat_red[par][0][0][lane] + stat_red[par][1][0][lane] + stat_red[par][2][0][lane] + stat_red[par][3][0][lane];
-          const float b = stat_red[par][0][1][lane] + stat_red[par][1][1][lane] + stat_red[par][2][1][lane] + stat_red[par][3][1][lane];
-          double *dst = p.stat_acc + ((long long)img * p.Co + co0 + c + lane) * 2;
-          atomicAdd(dst, (double)a);
-          atomicAdd(dst + 1, (double)b);
-        }
-      }
-      if (valid && co0 + c < p.Co) {            // Co is a multiple of 32 here; tiles may overhang it
-        float v[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-        if (p.bias) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += __ldg(p.bias + co0 + c + e);
-        }
-        if (p.act != CTAGAN_ACT_NONE) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], p.act);
-        }
-        uint4 *dst = reinterpret_cast<uint4 *>(out_row + c);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * g + 0], v[8 * g + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * g + 2], v[8 * g + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * g + 4], v[8 * g + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * g + 6], v[8 * g + 7]);
-          pk.x = *reinterpret_cast<uint32_t *>(&h0);
-          pk.y = *reinterpret_cast<uint32_t *>(&h1);
-          pk.z = *reinterpret_cast<uint32_t *>(&h2);
-          pk.w = *reinterpret_cast<uint32_t *>(&h3);
-          dst[g] = pk;
-        }
-      }
-    }
-  }
-  // "last CTA finalises": once every CTA of the layer has added its partial sums, the last one turns them into (mean, rstd)
-  if (p.stat_out != nullptr && warp >= 2) {
-    __shared__ unsigned int ticket_s;
-    __threadfence();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 64) {
-      unsigned int *ticket = reinterpret_cast<unsigned int *>(p.stat_acc + (long long)p.stat_n * p.Co * 2);
-      ticket_s = atomicAdd(ticket, 1u);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (ticket_s == p.stat_total_ctas - 1) {
-      __threadfence();
-      const double inv = 1.0 / (double)p.stat_hw;
-      for (int i = threadIdx.x - 64; i < p.stat_n * p.Co; i += 128) {
-        const double s1 = __ldcg(p.stat_acc + 2 * i), s2 = __ldcg(p.stat_acc + 2 * i + 1);
-        const double m = s1 * inv;
-        double var = s2 * inv - m * m;
-        if (var < 0) var = 0;
-        p.stat_out[2 * i] = (float)m;
-        p.stat_out[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
-      }
-    }
+    tc_epilogue<BN>(p, tmem_base, warp, lane, img, tile, co0, wrow0, (int)blockIdx.y, stat_red, &ticket_s);
   }
   tc_fence_before();
   __syncthreads();
@@ -996,12 +716,12 @@ int make_map_w3d(CUtensorMap *map, const void *base, int O, int taps, int Ci, ui
   return CTAGAN_OK;
 }
 
-template <int BN, int KCH, bool PAIR = false>
+template <int BN, int KCH>
 int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, dim3 grid, cudaStream_t st) {
-  using Cfg = TcConfig<BN, KCH, PAIR>;
+  using Cfg = TcConfig<BN, KCH>;
   static bool configured = false;
   if (!configured) {
-    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_valid_kernel<BN, KCH, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_valid_kernel<BN, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   TcParams q = p;
@@ -1012,7 +732,7 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
   const int iters = p.n_taps * ((p.Ci + CHUNK_K * KCH - 1) / (CHUNK_K * KCH));
   static int short_k = -1;
   if (short_k < 0) { const char *e = getenv("CTAGAN_TC_SHORTK"); short_k = e ? atoi(e) : 20; }    // measured on the Reg step (b=8): off 18.05 ms, 12 -> 17.31 ms, 20 -> 17.21 ms
-  if (!PAIR && iters <= short_k && (long long)grid.x * grid.y >= 4LL * ctagan_num_sms()) {
+  if (iters <= short_k && (long long)grid.x * grid.y >= 4LL * ctagan_num_sms()) {
     const int fit = (110 * 1024) / Cfg::STAGE_BYTES;
     if (fit >= 2 && fit < q.n_stages) q.n_stages = fit;
   }
@@ -1021,19 +741,7 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
     if (ns >= 1 && ns <= Cfg::STAGES) q.n_stages = ns;
   }
   const size_t smem_bytes = (size_t)q.n_stages * Cfg::STAGE_BYTES + 1024 + 256;
-  CTAGAN_CUDA_OK(launch_cluster_pdl(conv_tc_valid_kernel<BN, KCH, PAIR>, grid, dim3(192), smem_bytes, st, PAIR ? 2u : 1u, mx, mw, q));
-  CTAGAN_LAUNCH_OK();
-  return CTAGAN_OK;
-}
-
-template <int BN>
-int launch_resA(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const ResAParams &rp, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_tc_resA_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    configured = true;
-  }
-  conv_tc_resA_kernel<BN><<<grid, 192, smem, st>>>(mx, mw, p, rp);
+  CTAGAN_CUDA_OK(launch_pdl(conv_tc_valid_kernel<BN, KCH>, grid, dim3(192), smem_bytes, st, mx, mw, q));
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
@@ -1061,44 +769,6 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
   CUtensorMap mx, mw;
   int rc;
   if (p.imgs_per_group <= 0) { p.imgs_per_group = N; for (int k = 0; k < CTAGAN_MAX_GROUPS; ++k) p.w_row_off[k] = 0; }
-  // ---- resident-A variant: the union of all tap windows fits in shared memory next to a weight ring ----
-  static int resa_mode = -1;
-  if (resa_mode < 0) { const char *e = getenv("CTAGAN_TC_RESA"); resa_mode = e ? atoi(e) : 0; }   // opt-in: see profiles/tc_tile_tuning_r1.md
-  if (p.mode == 0 && resa_mode > 0 && p.n_taps > 1 && w_slots == 1) {
-    int max_shift = 0;
-    for (int t = 0; t < p.n_taps; ++t) { const int sft = p.tap_dh[t] * p.Wv + p.tap_dw[t]; if (sft > max_shift) max_shift = sft; }
-    const int R = TILE_M + max_shift;
-    ResAParams rp;
-    rp.n_box = (R + 255) / 256;
-    rp.rows_box = (((R + rp.n_box - 1) / rp.n_box) + 7) & ~7;
-    rp.chunks = (p.Ci + CHUNK_K - 1) / CHUNK_K;
-    rp.base_offset_mode = resa_mode == 3 ? 1 : 0;
-    const size_t a_bytes = (size_t)rp.chunks * rp.rows_box * rp.n_box * 128;
-    const long long m_tiles = (long long)N * p.tiles_per_img;
-    int bn = 64;
-    if (p.Co % 256 == 0 && m_tiles * (p.Co / 256) >= 2LL * ctagan_num_sms()) bn = 256;
-    else if (p.Co % 128 == 0 && m_tiles * (p.Co / 128) >= ctagan_num_sms()) bn = 128;
-    if (const char *env = getenv("CTAGAN_TC_BN")) { const int b = atoi(env); if ((b == 64 || b == 128 || b == 256) && p.Co % b == 0) bn = b; }
-    const size_t budget = 224 * 1024 - 1024 - 512;
-    const size_t stage_bytes = 32 * 1024;      // CPS chunks x BN rows x 128 B
-    if (rp.chunks <= 8 && rp.rows_box <= 256 && a_bytes + 2 * stage_bytes <= budget) {
-      size_t stages = (budget - a_bytes) / stage_bytes;
-      if (stages > 8) stages = 8;
-      rp.b_stages = (int)stages;
-      rc = make_map_2d(&mx, x, (uint64_t)N * Hi * Wi, (uint64_t)p.Ci, (uint32_t)rp.rows_box);
-      if (rc) return rc;
-      rc = make_map_w3d(&mw, wp, p.Co, w_taps, p.Ci, (uint32_t)bn);
-      if (rc) return rc;
-      dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
-      if (p.stat_total_ctas == 0) p.stat_total_ctas = grid.x * grid.y;
-      const size_t smem = a_bytes + stages * stage_bytes + 1024 + 512;
-      switch (bn) {
-        case 256: return launch_resA<256>(mx, mw, p, rp, grid, smem, st);
-        case 128: return launch_resA<128>(mx, mw, p, rp, grid, smem, st);
-        default: return launch_resA<64>(mx, mw, p, rp, grid, smem, st);
-      }
-    }
-  }
   if (p.mode == 0) {
     rc = make_map_2d(&mx, x, (uint64_t)N * Hi * Wi, (uint64_t)p.Ci, TILE_M);
   } else {
@@ -1106,29 +776,14 @@ int run_tc(TcParams &p, const void *x, int N, int Hi, int Wi, const void *wp, in
     rc = make_map_4d(&mx, x, N, Hi, Wi, p.Ci, BW * p.stride, BH * p.stride, p.stride);
   }
   if (rc) return rc;
-  int bn = pick_bn((long long)N * p.tiles_per_img, p.Co);
-  // CTA pairs (cta_group::2, opt-in CTAGAN_TC_PAIR=1): 256 x BN tiles over two SMs; an odd tile count gets one fully masked padding tile
-  // MEASURED (profiles/tc_tile_tuning_r1.md): bit-identical results, no speed-up (N=8: 50.8 vs 49.9 us with fused statistics) -- at
-  // BN >= 128 the main loop already runs at ~86 % of the per-SM tensor peak; what is lost is SM under-use at b=1 and the
-  // non-overlapped epilogue + wave quantisation at b=8.  Kept opt-in as the base of a persistent 2-CTA kernel.
-  const char *pair_env = getenv("CTAGAN_TC_PAIR");
-  const int pair_mode = pair_env ? atoi(pair_env) : 0;
-  const bool pair = pair_mode > 0 && (bn >= 128 || pair_mode == 2) && w_slots == 1 && p.Co % bn == 0 && p.stat_total_ctas == 0;
-  rc = make_map_w3d(&mw, wp, p.Co * w_slots, w_taps, p.Ci, (uint32_t)(pair ? bn / 2 : bn));
+  const int bn = pick_bn((long long)N * p.tiles_per_img, p.Co);
+  rc = make_map_w3d(&mw, wp, p.Co * w_slots, w_taps, p.Ci, (uint32_t)bn);
   if (rc) return rc;
   dim3 grid((unsigned)(N * p.tiles_per_img), (unsigned)((p.Co + bn - 1) / bn));
-  if (pair && (grid.x & 1)) grid.x += 1;
-  if (p.stat_total_ctas == 0) p.stat_total_ctas = grid.x * grid.y;       // (phase-decomposed launches preset the sum over phases)
-  if (pair) {
-    const bool k2 = (p.Ci % 128 == 0 && bn < 256);
-    if (bn == 256) return launch_tc<256, 1, true>(mx, mw, p, grid, st);
-    if (bn == 64) return k2 ? launch_tc<64, 2, true>(mx, mw, p, grid, st) : launch_tc<64, 1, true>(mx, mw, p, grid, st);
-    return k2 ? launch_tc<128, 2, true>(mx, mw, p, grid, st) : launch_tc<128, 1, true>(mx, mw, p, grid, st);
-  }
-  int kch = (p.Ci % 128 == 0 && bn < 256) ? 2 : 1;      // BN=256 keeps 64-channel stages (4 of them fit; 2-chunk stages would leave 2)
+  CTAGAN_REQUIRE(p.stat_part == nullptr || (int)grid.y <= p.stat_tpi, "conv_gather(tc): ticket buffer too small");
+  const int kch = (p.Ci % 128 == 0 && bn < 256) ? 2 : 1;      // BN=256 keeps 64-channel stages (4 of them fit; 2-chunk stages would leave 2)
   if (kch == 2) {
     switch (bn) {
-      case 256: return launch_tc<256, 2>(mx, mw, p, grid, st);
       case 128: return launch_tc<128, 2>(mx, mw, p, grid, st);
       case 64: return launch_tc<64, 2>(mx, mw, p, grid, st);
     }
@@ -1173,11 +828,45 @@ static int tc_gather_kind(const ctagan_conv_geom *g) {
 
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g) { return tc_gather_kind(g) != 0; }
 
-int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                          float *stat_out, cudaStream_t st, const ctagan_conv_groups *gr) {
+// tiles per image of one launch, and the number of launches, for the statistics slots
+static void tc_tile_counts(const ctagan_conv_geom *g, int kind, int &tiles_per_img, int &launches) {
+  launches = 1;
+  if (kind == 1) {
+    tiles_per_img = (int)(((long long)g->Ho * g->Wi + TILE_M - 1) / TILE_M);
+  } else if (kind == 2) {
+    const int bwl = ceil_log2(g->Wo < 128 ? g->Wo : 128);
+    const int BW = 1 << bwl, BH = TILE_M >> bwl;
+    tiles_per_img = ((g->Wo + BW - 1) / BW) * ((g->Ho + BH - 1) / BH);
+  } else {
+    const int Hq = g->Ho / 2, Wq = g->Wo / 2;
+    const int bwl = ceil_log2(Wq < 128 ? Wq : 128);
+    const int BWq = 1 << bwl, BHq = TILE_M >> bwl;
+    tiles_per_img = ((Wq + BWq - 1) / BWq) * ((Hq + BHq - 1) / BHq);
+    launches = 0;
+    for (int rh = 0; rh < 2; ++rh)
+      for (int rw = 0; rw < 2; ++rw) {
+        int t = 0;
+        for (int kh = (rh + g->pad_h) & 1; kh < g->KH; kh += 2)
+          for (int kw = (rw + g->pad_w) & 1; kw < g->KW; kw += 2) ++t;
+        if (t) ++launches;
+      }
+  }
+}
+
+// scratch of the fused statistics: partial-sum slots [N][parts][Co][2] fp32 (0 when the geometry is not served by this engine)
+size_t ctagan_conv_gather_tc_stat_bytes(const ctagan_conv_geom *g) {
+  const int kind = tc_gather_kind(g);
+  if (!kind) return 0;
+  int tiles, launches;
+  tc_tile_counts(g, kind, tiles, launches);
+  return (size_t)g->N * tiles * launches * g->Co * 2 * sizeof(float);
+}
+
+int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, unsigned int *stat_ticket,
+                          void *stat_scratch, size_t stat_scratch_bytes, float *stat_out, cudaStream_t st, const ctagan_conv_groups *gr) {
   const int kind = tc_gather_kind(g);
   if (!kind) {
-    ctagan_set_error("conv_gather: geometry not supported by the tcgen05 engine (bf16, Ci%%64==0, Co%%64==0, stride<=2 / dil<=2)");
+    ctagan_set_error("conv_gather: geometry not supported by the tcgen05 engine (bf16, Ci%%8==0, Ci>=32, Co%%32==0, stride<=2 / dil<=2)");
     return CTAGAN_ERR_UNSUPPORTED;
   }
   CTAGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
@@ -1187,8 +876,18 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   memset(&p, 0, sizeof(p));
   p.Ci = g->Ci; p.Co = g->Co; p.stride = g->stride;
   p.out_H = g->Ho; p.out_W = g->Wo; p.sy = p.sx = 1; p.ay = p.ax = 0;
-  p.act = g->act; p.bias = bias; p.out = (bf16 *)y; p.stat_acc = stat_acc; p.stat_out = stat_acc ? stat_out : nullptr;
-  p.stat_n = g->N; p.stat_hw = g->Ho * g->Wo;
+  p.act = g->act; p.bias = bias; p.out = (bf16 *)y;
+  if (stat_out) {
+    int tiles, launches;
+    tc_tile_counts(g, kind, tiles, launches);
+    CTAGAN_REQUIRE(stat_ticket && stat_scratch && stat_scratch_bytes >= ctagan_conv_gather_tc_stat_bytes(g),
+                   "conv_gather_stats: ticket buffer and %zu bytes of scratch required", ctagan_conv_gather_tc_stat_bytes(g));
+    CTAGAN_REQUIRE((reinterpret_cast<uintptr_t>(stat_scratch) & 7) == 0 && (reinterpret_cast<uintptr_t>(stat_out) & 7) == 0,
+                   "conv_gather_stats: scratch / stats must be 8-byte aligned");
+    p.stat_part = (float *)stat_scratch; p.stat_ticket = stat_ticket; p.stat_out = stat_out;
+    p.stat_hw = g->Ho * g->Wo; p.stat_parts = tiles * launches; p.stat_part0 = 0;
+    p.stat_tpi = (g->Co + 31) / 32;
+  }
   int w_slots = 1;
   if (gr) {
     CTAGAN_REQUIRE(gr->groups >= 1 && gr->groups <= CTAGAN_MAX_GROUPS && g->N % gr->groups == 0, "conv_gather(grouped): N must split evenly into 1..%d groups", CTAGAN_MAX_GROUPS);
@@ -1225,23 +924,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
   }
   // kind 3: input dilation 2 (input gradient of a stride-2 conv == ConvTranspose2d forward).  Output pixel h = 2i + r reads
   // x[i + e - u] with weight tap kh' = 2u + a (a = (r + pad) & 1, e = (r + pad - a) / 2): one stride-1 launch per output parity.
-  if (p.stat_out) {
-    // all four output-parity launches add into the same sums: the ticket counts the CTAs of all of them
-    const int Hq = g->Ho / 2, Wq = g->Wo / 2;
-    const int bwl = ceil_log2(Wq < 128 ? Wq : 128);
-    const int BWq = 1 << bwl, BHq = TILE_M >> bwl;
-    const int tiles = ((Wq + BWq - 1) / BWq) * ((Hq + BHq - 1) / BHq);
-    const int bn = pick_bn((long long)g->N * tiles, g->Co);
-    int launches = 0;
-    for (int rh = 0; rh < 2; ++rh)
-      for (int rw = 0; rw < 2; ++rw) {
-        int t = 0;
-        for (int kh = (rh + g->pad_h) & 1; kh < g->KH; kh += 2)
-          for (int kw = (rw + g->pad_w) & 1; kw < g->KW; kw += 2) ++t;
-        if (t) ++launches;
-      }
-    p.stat_total_ctas = (unsigned)(launches * g->N * tiles * ((g->Co + bn - 1) / bn));
-  }
+  int phase = 0;       // statistics: every output-parity launch owns its own slots, the ticket counts the CTAs of all of them
   for (int rh = 0; rh < 2; ++rh)
     for (int rw = 0; rw < 2; ++rw) {
       const int ah = (rh + g->pad_h) & 1, eh = (rh + g->pad_h - ah) / 2;
@@ -1265,6 +948,8 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
       const int BW = 1 << p.bw_log2, BH = TILE_M >> p.bw_log2;
       p.tiles_w = (p.Wov + BW - 1) / BW;
       p.tiles_per_img = p.tiles_w * ((p.Hov + BH - 1) / BH);
+      p.stat_part0 = phase * p.tiles_per_img;
+      ++phase;
       int rc = run_tc(p, x, g->N, g->Hi, g->Wi, wp, w_taps, st, w_slots);
       if (rc) return rc;
     }
@@ -1351,10 +1036,16 @@ int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups) {
   return (n_groups >= 1 && g->N % n_groups == 0 && plan_wgrad(g, pl, n_groups)) ? 1 : 0;
 }
 
+// split-K partial sums [groups][splits][Co][taps][Ci] followed by the bias-gradient partial sums [groups][WG_DB_BLOCKS][Co]
+static size_t wg_split_bytes(const ctagan_conv_geom *g, const WgPlan &pl, int n_groups) {
+  return (size_t)n_groups * pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+}
+static int wg_db_blocks() { return 2 * ctagan_num_sms(); }
+
 size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g, int n_groups) {
   WgPlan pl;
   if (n_groups < 1 || g->N % n_groups || !plan_wgrad(g, pl, n_groups)) return 0;
-  return (size_t)n_groups * pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+  return wg_split_bytes(g, pl, n_groups) + (size_t)n_groups * wg_db_blocks() * g->Co * sizeof(float);
 }
 
 // n_groups > 1: the batch is n_groups consecutive image groups and dw / db hold one gradient per group ([groups][Co][Ci][KH][KW])
@@ -1365,7 +1056,7 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
     ctagan_set_error("conv_wgrad: geometry not supported by the tcgen05 engine");
     return CTAGAN_ERR_UNSUPPORTED;
   }
-  const size_t need = (size_t)n_groups * pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+  const size_t need = ctagan_conv_wgrad_tc_workspace(g, n_groups);
   CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_wgrad(tc): workspace of %zu bytes required (got %zu)", need, workspace_bytes);
   CUtensorMap my, mx;
   int rc = make_map_4d(&my, gy, g->N, g->Ho, g->Wo, g->Co, pl.bkw, pl.bkh, 1);
@@ -1392,12 +1083,16 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   if (db) {
     const long long pixels = (long long)(g->N / n_groups) * g->Ho * g->Wo;
     long long blocks = (pixels + 511) / 512;
-    if (blocks > 2LL * ctagan_num_sms()) blocks = 2LL * ctagan_num_sms();
+    if (blocks > wg_db_blocks()) blocks = wg_db_blocks();
     const long long ppb = (pixels + blocks - 1) / blocks;
-    CTAGAN_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)g->Co * n_groups, st));
+    const int nb = (int)((pixels + ppb - 1) / ppb);
+    float *part = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + wg_split_bytes(g, pl, n_groups));
     for (int k = 0; k < n_groups; ++k) {
-      colsum_kernel<<<(int)((pixels + ppb - 1) / ppb), 256, 0, st>>>((const bf16 *)gy + (size_t)k * pixels * g->Co, db + (size_t)k * g->Co, pixels, g->Co, ppb);
+      float *pk = part + (size_t)k * wg_db_blocks() * g->Co;
+      colsum_kernel<<<nb, 256, 0, st>>>((const bf16 *)gy + (size_t)k * pixels * g->Co, pk, pixels, g->Co, ppb);
       CTAGAN_LAUNCH_OK();
+      rc = ctagan_ordered_sum(pk, db + (size_t)k * g->Co, nb, g->Co, st);
+      if (rc) return rc;
     }
   }
   return CTAGAN_OK;

@@ -46,7 +46,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // InstanceNorm statistics.  Shifted sums (shift = first pixel of the plane) in fp32 per thread, fp64 across threads.
-// grid (chunks, N); block 256 = PL pixel lanes x CV channel vectors.
+// grid (chunks, N); block 256 = PL pixel lanes x CV channel vectors.  Every block stores its partial sums in its own row of
+// acc[N][chunks][C][2]; the finalize kernel adds the rows in chunk order (deterministic: no floating-point atomics).
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(256) instnorm_partial_kernel(const T *__restrict__ x, double *__restrict__ acc, int HW, int C,
@@ -102,56 +103,37 @@ __global__ void __launch_bounds__(256) instnorm_partial_kernel(const T *__restri
       a += (double)sm[0][i][l * CV + ccv];
       b += (double)sm[1][i][l * CV + ccv];
     }
-    double *dst = acc + ((idx_t)n * C + ccv * V + i) * 2;
-    atomicAdd(dst, a);
-    atomicAdd(dst + 1, b);
+    double *dst = acc + (((idx_t)n * gridDim.x + blockIdx.x) * C + ccv * V + i) * 2;
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 
 template <typename T>
 __global__ void instnorm_finalize_kernel(const T *__restrict__ x, const double *__restrict__ acc, float *__restrict__ stats, int N,
-                                         int HW, int C) {
+                                         int HW, int C, int chunks) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i - n * C;
   const double shift = (double)to_f(x[(idx_t)n * HW * C + c]);
-  const double m1 = acc[2 * i] / HW, m2 = acc[2 * i + 1] / HW;
+  double a1 = 0.0, a2 = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const double2 t = *reinterpret_cast<const double2 *>(acc + (((idx_t)n * chunks + k) * C + c) * 2);
+    a1 += t.x;
+    a2 += t.y;
+  }
+  const double m1 = a1 / HW, m2 = a2 / HW;
   double var = m2 - m1 * m1;
   if (var < 0) var = 0;
   stats[2 * i] = (float)(shift + m1);
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
 }
 
-// (sum, sum of squares) accumulated by the convolution epilogue -> (mean, rstd)
-__global__ void instnorm_finalize_sums_kernel(const double *__restrict__ acc, float *__restrict__ stats, int NC, int HW) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NC) return;
-  const double2 t = *reinterpret_cast<const double2 *>(acc + 2 * i);
-  const double m = t.x / HW;
-  double var = t.y / HW - m * m;
-  if (var < 0) var = 0;
-  *reinterpret_cast<float2 *>(stats + 2 * i) = make_float2((float)m, (float)(1.0 / sqrt(var + 1e-5)));
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // out[n,hp,wp,c] = act((x-mean)*rstd) + res ; gather form (one thread per output vector), reflect indices.
 // ---------------------------------------------------------------------------------------------------------------
-template <int V>
-__device__ __forceinline__ void stats_from_sums(const double *__restrict__ ap, float inv_hw, float (&mean)[V], float (&rstd)[V]) {
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const double2 t = *reinterpret_cast<const double2 *>(ap + 2 * i);
-    const double m = t.x * (double)inv_hw;
-    double var = t.y * (double)inv_hw - m * m;
-    if (var < 0) var = 0;
-    mean[i] = (float)m;
-    rstd[i] = rsqrtf((float)var + 1e-5f);
-  }
-}
-
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__ x, const float *__restrict__ stats,
-                                                           const double *__restrict__ sums, float *__restrict__ stats_out,
                                                            const T *__restrict__ res, int res_pad, T *__restrict__ out, int N, int H,
                                                            int W, int C, int pad, int act) {
   pdl_wait();
@@ -171,18 +153,6 @@ __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__
     if (stats) {
       float mean[V], rstd[V];
       load_stats<V>(stats + ((idx_t)n * C + cv * V) * 2, mean, rstd);
-#pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = (v[i] - mean[i]) * rstd[i];
-    } else if (sums) {
-      float mean[V], rstd[V];
-      stats_from_sums<V>(sums + ((idx_t)n * C + cv * V) * 2, 1.f / (float)(H * W), mean, rstd);
-      if (stats_out && hp == 0 && wp == 0) {     // one thread per (n, channel vector) publishes (mean, rstd) for the backward pass
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          stats_out[((idx_t)n * C + cv * V + i) * 2] = mean[i];
-          stats_out[((idx_t)n * C + cv * V + i) * 2 + 1] = rstd[i];
-        }
-      }
 #pragma unroll
       for (int i = 0; i < V; ++i) v[i] = (v[i] - mean[i]) * rstd[i];
     }
@@ -245,12 +215,14 @@ __device__ __forceinline__ float act_grad_from_sign(float pre, int act) {
   return 1.f;
 }
 
-// pass 1: per-(n,c) sums of g and g*xhat.  grid (chunks, N)
+// pass 1: per-(n,c) sums of g and g*xhat.  grid (chunks, N).  Deterministic: every block stores its partial sums in its own row of
+// part[N][chunks][C][2]; the last block of an image to arrive (ticket = the double at acc[N*C*2 + n], zero on entry and again on
+// exit) adds the rows in chunk order into acc[n][C][2].
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restrict__ gout, const T *__restrict__ x,
                                                               const float *__restrict__ stats, const T *__restrict__ addend,
-                                                              double *__restrict__ acc, int H, int W, int C, int pad, int act,
-                                                              int pix_per_block) {
+                                                              double *__restrict__ acc, double *__restrict__ part, int N, int H, int W,
+                                                              int C, int pad, int act, int pix_per_block) {
   pdl_wait();
   const int CV = C / V;
   const int n = blockIdx.y;
@@ -318,9 +290,26 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T *__restric
       a += (double)sm[0][i][l * CV + ccv];
       b += (double)sm[1][i][l * CV + ccv];
     }
-    double *dst = acc + ((idx_t)n * C + ccv * V + i) * 2;
-    atomicAdd(dst, a);
-    atomicAdd(dst + 1, b);
+    double *dst = part + (((idx_t)n * gridDim.x + blockIdx.x) * C + ccv * V + i) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+  __shared__ unsigned long long ticket_s;
+  __threadfence();
+  __syncthreads();
+  unsigned long long *ticket = reinterpret_cast<unsigned long long *>(acc + (idx_t)N * C * 2) + n;
+  if (threadIdx.x == 0) ticket_s = atomicAdd(ticket, 1ull);
+  __syncthreads();
+  if (ticket_s == (unsigned long long)gridDim.x - 1ull) {
+    __threadfence();
+    const int chunks = (int)gridDim.x;
+    for (int item = threadIdx.x; item < C * 2; item += 256) {
+      const double *src = part + (idx_t)n * chunks * C * 2 + item;
+      double t = 0.0;
+      for (int k = 0; k < chunks; ++k) t += __ldcg(src + (idx_t)k * C * 2);
+      acc[(idx_t)n * C * 2 + item] = t;
+    }
+    if (threadIdx.x == 0) *ticket = 0ull;
   }
 }
 
@@ -834,11 +823,29 @@ static int reduce_chunks(int N, int HW, int C, int v, int &pix_per_block) {
   return (int)((HW + pix_per_block - 1) / pix_per_block);
 }
 
+template <typename T>
+static int stats_vec(int C) {
+  int v = pick_vec<T>(C);
+  while (C / v > 256 && v < max_vec<T>()) v *= 2;
+  return v;
+}
+
+// doubles of scratch ctagan_instnorm_stats / the two-kernel ctagan_norm_act_pad_bwd need: one row of C*2 partial sums per block
+static size_t reduce_scratch_doubles(int N, int HW, int C, int dtype) {
+  int ppb;
+  const int v = dtype == CTAGAN_BF16 ? stats_vec<bf16>(C) : stats_vec<float>(C);
+  return (size_t)N * reduce_chunks(N, HW, C, v, ppb) * C * 2;
+}
+
+extern "C" size_t ctagan_instnorm_stats_scratch_doubles(int N, int HW, int C, int dtype) {
+  if (N <= 0 || HW <= 0 || C <= 0) return 0;
+  return reduce_scratch_doubles(N, HW, C, dtype);
+}
+
 extern "C" int ctagan_instnorm_stats(const void *x, float *stats, double *acc, int N, int HW, int C, int dtype, void *stream) {
   CTAGAN_REQUIRE(x && stats && acc && N > 0 && HW > 0 && C > 0, "instnorm_stats: bad arguments");
   CTAGAN_FITS32((int64_t)N * HW * C);
   cudaStream_t st = (cudaStream_t)stream;
-  CTAGAN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     int v = pick_vec<T>(C);
     while (C / v > 256) { CTAGAN_REQUIRE(v < max_vec<T>(), "instnorm_stats: C=%d too large", C); v *= 2; }
@@ -846,22 +853,21 @@ extern "C" int ctagan_instnorm_stats(const void *x, float *stats, double *acc, i
     const int chunks = reduce_chunks(N, HW, C, v, ppb);
     dim3 grid(chunks, N);
     VEC_SWITCH(T, v, V, instnorm_partial_kernel<T, V><<<grid, 256, 0, st>>>((const T *)x, acc, HW, C, ppb));
-    instnorm_finalize_kernel<T><<<cdiv((idx_t)N * C, 128), 128, 0, st>>>((const T *)x, acc, stats, N, HW, C);
+    instnorm_finalize_kernel<T><<<cdiv((idx_t)N * C, 128), 128, 0, st>>>((const T *)x, acc, stats, N, HW, C, chunks);
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
 
-extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const double *sums, float *stats_out, const void *res, int res_pad,
-                                   void *out, int N, int H, int W, int C, int pad, int act, int dtype, void *stream) {
-  CTAGAN_REQUIRE(!(stats && sums), "norm_act_pad: give either stats or sums");
+extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int res_pad, void *out, int N, int H, int W, int C,
+                                   int pad, int act, int dtype, void *stream) {
   CTAGAN_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && pad < H && pad < W, "norm_act_pad: bad arguments");
   CTAGAN_FITS32((int64_t)N * (H + 2 * pad) * (W + 2 * pad) * C);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C);
     const idx_t total = (idx_t)N * (H + 2 * pad) * (W + 2 * pad) * (C / v);
-    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_act_pad_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)x, stats, sums, stats_out, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act)));
+    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_act_pad_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)x, stats, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act)));
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
@@ -885,13 +891,18 @@ extern "C" int ctagan_norm_act_pad_bwd_launches(int has_stats, int H, int W, int
   return norm_bwd_uses_cluster((const float *)1, H, W, C, dtype) ? 1 : 2;
 }
 
+extern "C" size_t ctagan_norm_act_pad_bwd_scratch_doubles(int has_stats, int N, int H, int W, int C, int dtype) {
+  if (!has_stats || N <= 0 || H <= 0 || W <= 0 || C <= 0 || norm_bwd_uses_cluster((const float *)1, H, W, C, dtype)) return 0;
+  return reduce_scratch_doubles(N, H * W, C, dtype);
+}
+
 extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx, void *g_out,
-                                       double *acc, int acc_is_zero, int N, int H, int W, int C, int pad, int act, int out_pad,
-                                       int dtype, void *stream) {
+                                       double *acc, int acc_is_zero, double *scratch, int N, int H, int W, int C, int pad, int act,
+                                       int out_pad, int dtype, void *stream) {
   CTAGAN_REQUIRE(gout && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && out_pad >= 0, "norm_act_pad_bwd: bad arguments");
   CTAGAN_FITS32((int64_t)N * (H + 2 * pad + 2 * out_pad) * (W + 2 * pad + 2 * out_pad) * C);
   CTAGAN_REQUIRE(!(stats || act != CTAGAN_ACT_NONE) || x, "norm_act_pad_bwd: x required when stats/act given");
-  CTAGAN_REQUIRE(!stats || acc || norm_bwd_uses_cluster(stats, H, W, C, dtype), "norm_act_pad_bwd: acc scratch required with stats");
+  CTAGAN_REQUIRE(!stats || (acc && scratch) || norm_bwd_uses_cluster(stats, H, W, C, dtype), "norm_act_pad_bwd: acc and scratch required with stats");
   CTAGAN_REQUIRE(act != CTAGAN_ACT_TANH, "norm_act_pad_bwd: tanh unsupported here (use act_bwd)");
   cudaStream_t st = (cudaStream_t)stream;
   if (const int kind = norm_bwd_cluster_kind(stats, H, W, C, dtype)) {
@@ -912,11 +923,11 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
     int v = pick_vec<T>(C);
     if (stats) {
       while (C / v > 256) { CTAGAN_REQUIRE(v < max_vec<T>(), "norm_act_pad_bwd: C=%d too large", C); v *= 2; }
-      if (!acc_is_zero) CTAGAN_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
+      if (!acc_is_zero) CTAGAN_CUDA_OK(cudaMemsetAsync(acc + 2 * (size_t)N * C, 0, sizeof(double) * (size_t)N, st));     // the tickets
       int ppb;
       const int chunks = reduce_chunks(N, H * W, C, v, ppb);
       dim3 grid(chunks, N);
-      VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<T, V>, grid, dim3(256), 0, st, (const T *)gout, (const T *)x, stats, (const T *)addend, acc, H, W, C, pad, act, ppb)));
+      VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<T, V>, grid, dim3(256), 0, st, (const T *)gout, (const T *)x, stats, (const T *)addend, acc, scratch, N, H, W, C, pad, act, ppb)));
     }
     const idx_t total = (idx_t)N * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / v);
     VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)gout, (const T *)x, stats, acc, (const T *)addend, (T *)dx, (T *)g_out, N, H, W, C, pad, act, out_pad)));
@@ -1068,13 +1079,6 @@ extern "C" int ctagan_deinterleave2(const void *src, float *a, float *b, int64_t
   CTAGAN_FITS32(2 * n);
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, { deinterleave2_kernel<T><<<ew_blocks(n), 256, 0, st>>>((const T *)src, a, b, n); });
-  CTAGAN_LAUNCH_OK();
-  return CTAGAN_OK;
-}
-
-extern "C" int ctagan_instnorm_finalize_sums(const double *acc, float *stats, int N, int HW, int C, void *stream) {
-  CTAGAN_REQUIRE(acc && stats && N > 0 && HW > 0 && C > 0, "instnorm_finalize_sums: bad arguments");
-  instnorm_finalize_sums_kernel<<<cdiv((long long)N * C, 128), 128, 0, (cudaStream_t)stream>>>(acc, stats, N * C, HW);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }

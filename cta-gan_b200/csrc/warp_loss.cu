@@ -26,101 +26,275 @@ __device__ __forceinline__ float clip_coord(float c, int size, float &g) {
   return c;
 }
 
+// Tiling shared by the forward and backward kernels: a block of 256 threads owns WT_H x WT_W output pixels (4 consecutive columns per
+// thread: 16-byte loads of the flow / gout rows and 16-byte stores) and stages the source window
+// [i0 - HALO, i0 + WT_H + HALO] x [j0 - HALO, j0 + WT_W + HALO] of the current channel plane in shared memory with coalesced row
+// loads.  Registration flows are small (Reg is initialised to ~zero flow), so practically every bilinear tap is a shared-memory hit;
+// a tap outside the window (a displacement of more than HALO pixels) falls back to a global load, so any flow is handled.
+constexpr int WT_H = 16, WT_W = 64, WT_HALO = 8;
+constexpr int WS_H = WT_H + 2 * WT_HALO + 1, WS_W = WT_W + 2 * WT_HALO + 1;      // window extent incl. the +1 neighbour
+
+struct WarpTile {
+  int b, i0, j0;         // image, tile origin
+  int wi0, wj0;          // window origin in the image (may be negative: clipped on load)
+};
+
+__device__ __forceinline__ WarpTile warp_tile(int H, int W) {
+  const int tiles_w = (W + WT_W - 1) / WT_W, tiles_h = (H + WT_H - 1) / WT_H;
+  int t = blockIdx.x;
+  WarpTile wt;
+  wt.j0 = (t % tiles_w) * WT_W; t /= tiles_w;
+  wt.i0 = (t % tiles_h) * WT_H;
+  wt.b = t / tiles_h;
+  wt.wi0 = wt.i0 - WT_HALO; wt.wj0 = wt.j0 - WT_HALO;
+  return wt;
+}
+
+__device__ __forceinline__ void warp_load_window(const float *__restrict__ plane, float *__restrict__ win, const WarpTile &wt, int H, int W) {
+  for (int idx = threadIdx.x; idx < WS_H * WS_W; idx += blockDim.x) {
+    const int r = idx / WS_W, c = idx - r * WS_W;
+    const int y = wt.wi0 + r, x = wt.wj0 + c;
+    win[idx] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(plane + (long long)y * W + x) : 0.f;
+  }
+}
+
+__device__ __forceinline__ float warp_tap(const float *__restrict__ plane, const float *__restrict__ win, const WarpTile &wt, int y, int x,
+                                          int W) {
+  const int r = y - wt.wi0, c = x - wt.wj0;
+  if ((unsigned)r < (unsigned)WS_H && (unsigned)c < (unsigned)WS_W) return win[r * WS_W + c];
+  return __ldg(plane + (long long)y * W + x);
+}
+
 __global__ void __launch_bounds__(256) warp_fwd_kernel(const float *__restrict__ src, const float *__restrict__ flow,
                                                        float *__restrict__ out, int B, int C, int H, int W) {
-  const long long HW = (long long)H * W, total = (long long)B * HW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(idx / HW);
-    const int p = (int)(idx - (long long)b * HW);
-    const int i = p / W, j = p - i * W;
-    const float fy = __ldg(flow + ((long long)b * 2 + 0) * HW + p), fx = __ldg(flow + ((long long)b * 2 + 1) * HW + p);
-    float gdummy;
-    const float iy = clip_coord(ref_coord((float)i + fy, H), H, gdummy);
-    const float ix = clip_coord(ref_coord((float)j + fx, W), W, gdummy);
-    const float fy0 = floorf(iy), fx0 = floorf(ix);
-    const int y0 = (int)fy0, x0 = (int)fx0, y1 = y0 + 1, x1 = x0 + 1;
-    const float wnw = (fx0 + 1.f - ix) * (fy0 + 1.f - iy), wne = (ix - fx0) * (fy0 + 1.f - iy);
-    const float wsw = (fx0 + 1.f - ix) * (iy - fy0), wse = (ix - fx0) * (iy - fy0);
-    const bool x1ok = x1 < W, y1ok = y1 < H;  // x0,y0 are always in range after clipping
-    for (int c = 0; c < C; ++c) {
-      const float *s = src + ((long long)b * C + c) * HW;
-      float v = __ldg(s + (long long)y0 * W + x0) * wnw;
-      if (x1ok) v += __ldg(s + (long long)y0 * W + x1) * wne;
-      if (y1ok) v += __ldg(s + (long long)y1 * W + x0) * wsw;
-      if (x1ok && y1ok) v += __ldg(s + (long long)y1 * W + x1) * wse;
-      out[((long long)b * C + c) * HW + p] = v;
-    }
+  __shared__ float win[WS_H * WS_W];
+  const WarpTile wt = warp_tile(H, W);
+  const long long HW = (long long)H * W;
+  const int i = wt.i0 + (int)(threadIdx.x >> 4), j = wt.j0 + (int)(threadIdx.x & 15) * 4;
+  const bool row_ok = i < H;
+  const bool vec = row_ok && ((W & 3) == 0) && j + 3 < W;
+  float fy[4] = {0.f, 0.f, 0.f, 0.f}, fx[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long p = (long long)i * W + j;
+  if (vec) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(flow + ((long long)wt.b * 2 + 0) * HW + p));
+    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(flow + ((long long)wt.b * 2 + 1) * HW + p));
+    fy[0] = a.x; fy[1] = a.y; fy[2] = a.z; fy[3] = a.w;
+    fx[0] = c4.x; fx[1] = c4.y; fx[2] = c4.z; fx[3] = c4.w;
+  } else if (row_ok) {
+    for (int e = 0; e < 4; ++e)
+      if (j + e < W) {
+        fy[e] = __ldg(flow + ((long long)wt.b * 2 + 0) * HW + p + e);
+        fx[e] = __ldg(flow + ((long long)wt.b * 2 + 1) * HW + p + e);
+      }
   }
+  for (int c = 0; c < C; ++c) {
+    const float *plane = src + ((long long)wt.b * C + c) * HW;
+    __syncthreads();
+    warp_load_window(plane, win, wt, H, W);
+    __syncthreads();
+    if (!row_ok) continue;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o[e] = 0.f;
+      if (j + e >= W) continue;
+      float gdummy;
+      const float iy = clip_coord(ref_coord((float)i + fy[e], H), H, gdummy);
+      const float ix = clip_coord(ref_coord((float)(j + e) + fx[e], W), W, gdummy);
+      const float fy0 = floorf(iy), fx0 = floorf(ix);
+      const int y0 = (int)fy0, x0 = (int)fx0, y1 = y0 + 1, x1 = x0 + 1;
+      const float wnw = (fx0 + 1.f - ix) * (fy0 + 1.f - iy), wne = (ix - fx0) * (fy0 + 1.f - iy);
+      const float wsw = (fx0 + 1.f - ix) * (iy - fy0), wse = (ix - fx0) * (iy - fy0);
+      const bool x1ok = x1 < W, y1ok = y1 < H;  // x0,y0 are always in range after clipping
+      float v = warp_tap(plane, win, wt, y0, x0, W) * wnw;
+      if (x1ok) v += warp_tap(plane, win, wt, y0, x1, W) * wne;
+      if (y1ok) v += warp_tap(plane, win, wt, y1, x0, W) * wsw;
+      if (x1ok && y1ok) v += warp_tap(plane, win, wt, y1, x1, W) * wse;
+      o[e] = v;
+    }
+    float *dst = out + ((long long)wt.b * C + c) * HW + p;
+    if (vec) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      for (int e = 0; e < 4; ++e)
+        if (j + e < W) dst[e] = o[e];
+  }
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------------------
+// gsrc is a scatter-add (several output pixels sample the same source pixel).  Floating-point atomics would make the result depend on
+// the CTA schedule, so the contributions are accumulated in 64-bit FIXED POINT (integer addition is associative: any order gives the
+// same bits): scale = 2^(40 - e) with 2^e > max|gout| (found by warp_absmax_kernel), i.e. every product w*g (|w| <= 1) is below 2^40
+// and a source pixel can absorb 2^22 of them; the quantum is max|gout| * 2^-40, far below one fp32 ulp of any sum that matters.
+// Contributions that land inside the block's window go to a shared-memory tile first (one global atomic per touched pixel and block).
+__global__ void __launch_bounds__(256) warp_absmax_kernel(const float *__restrict__ g, unsigned int *__restrict__ out, long long n) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(g + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && !(m != m)) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bit patterns
+}
+
+__device__ __forceinline__ double warp_fixed_scale(unsigned int absmax_bits) {
+  if (absmax_bits == 0u) return 1.0;
+  const int e = (int)((absmax_bits >> 23) & 0xffu) - 127 + 1;       // max|gout| < 2^e   (denormals: e = -126)
+  return ldexp(1.0, 40 - e);
 }
 
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ src,
-                                                       const float *__restrict__ flow, float *__restrict__ gsrc,
-                                                       float *__restrict__ gflow, int B, int C, int H, int W) {
-  const long long HW = (long long)H * W, total = (long long)B * HW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(idx / HW);
-    const int p = (int)(idx - (long long)b * HW);
-    const int i = p / W, j = p - i * W;
-    const float fy = __ldg(flow + ((long long)b * 2 + 0) * HW + p), fx = __ldg(flow + ((long long)b * 2 + 1) * HW + p);
-    float gmy, gmx;
-    const float iy = clip_coord(ref_coord((float)i + fy, H), H, gmy);
-    const float ix = clip_coord(ref_coord((float)j + fx, W), W, gmx);
-    const float fy0 = floorf(iy), fx0 = floorf(ix);
-    const int y0 = (int)fy0, x0 = (int)fx0, y1 = y0 + 1, x1 = x0 + 1;
-    const float ax = fx0 + 1.f - ix, bx = ix - fx0, ay = fy0 + 1.f - iy, by = iy - fy0;
-    const bool x1ok = x1 < W, y1ok = y1 < H;
-    float gix = 0.f, giy = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const long long plane = ((long long)b * C + c) * HW;
-      const float g = __ldg(gout + plane + p);
-      const float *s = src + plane;
-      float *gs = gsrc ? gsrc + plane : nullptr;
-      {
-        const float v = __ldg(s + (long long)y0 * W + x0);
-        gix -= v * ay * g; giy -= v * ax * g;
-        if (gs) atomicAdd(gs + (long long)y0 * W + x0, ax * ay * g);
+                                                       const float *__restrict__ flow, long long *__restrict__ gacc,
+                                                       const unsigned int *__restrict__ absmax, float *__restrict__ gflow, int B, int C,
+                                                       int H, int W) {
+  __shared__ float win[WS_H * WS_W];
+  __shared__ long long gwin[WS_H * WS_W];
+  const WarpTile wt = warp_tile(H, W);
+  const long long HW = (long long)H * W;
+  const int i = wt.i0 + (int)(threadIdx.x >> 4), j = wt.j0 + (int)(threadIdx.x & 15) * 4;
+  const bool row_ok = i < H;
+  const bool vec = row_ok && ((W & 3) == 0) && j + 3 < W;
+  const double scale = gacc ? warp_fixed_scale(*absmax) : 1.0;
+  float fy[4] = {0.f, 0.f, 0.f, 0.f}, fx[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long p = (long long)i * W + j;
+  if (vec) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(flow + ((long long)wt.b * 2 + 0) * HW + p));
+    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(flow + ((long long)wt.b * 2 + 1) * HW + p));
+    fy[0] = a.x; fy[1] = a.y; fy[2] = a.z; fy[3] = a.w;
+    fx[0] = c4.x; fx[1] = c4.y; fx[2] = c4.z; fx[3] = c4.w;
+  } else if (row_ok) {
+    for (int e = 0; e < 4; ++e)
+      if (j + e < W) {
+        fy[e] = __ldg(flow + ((long long)wt.b * 2 + 0) * HW + p + e);
+        fx[e] = __ldg(flow + ((long long)wt.b * 2 + 1) * HW + p + e);
       }
-      if (x1ok) {
-        const float v = __ldg(s + (long long)y0 * W + x1);
-        gix += v * ay * g; giy -= v * bx * g;
-        if (gs) atomicAdd(gs + (long long)y0 * W + x1, bx * ay * g);
+  }
+  float gix[4] = {0.f, 0.f, 0.f, 0.f}, giy[4] = {0.f, 0.f, 0.f, 0.f}, gmx[4] = {0.f, 0.f, 0.f, 0.f}, gmy[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) {
+    const long long plane_off = ((long long)wt.b * C + c) * HW;
+    const float *plane = src + plane_off;
+    __syncthreads();
+    warp_load_window(plane, win, wt, H, W);
+    if (gacc)
+      for (int idx = threadIdx.x; idx < WS_H * WS_W; idx += blockDim.x) gwin[idx] = 0ll;
+    __syncthreads();
+    if (row_ok) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(gout + plane_off + p));
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (j + e < W) g[e] = __ldg(gout + plane_off + p + e);
       }
-      if (y1ok) {
-        const float v = __ldg(s + (long long)y1 * W + x0);
-        gix -= v * by * g; giy += v * ax * g;
-        if (gs) atomicAdd(gs + (long long)y1 * W + x0, ax * by * g);
-      }
-      if (x1ok && y1ok) {
-        const float v = __ldg(s + (long long)y1 * W + x1);
-        gix += v * by * g; giy += v * bx * g;
-        if (gs) atomicAdd(gs + (long long)y1 * W + x1, bx * by * g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (j + e >= W) continue;
+        const float iy = clip_coord(ref_coord((float)i + fy[e], H), H, gmy[e]);
+        const float ix = clip_coord(ref_coord((float)(j + e) + fx[e], W), W, gmx[e]);
+        const float fy0 = floorf(iy), fx0 = floorf(ix);
+        const int y0 = (int)fy0, x0 = (int)fx0, y1 = y0 + 1, x1 = x0 + 1;
+        const float ax = fx0 + 1.f - ix, bx = ix - fx0, ay = fy0 + 1.f - iy, by = iy - fy0;
+        const bool x1ok = x1 < W, y1ok = y1 < H;
+        const float ge = g[e];
+        auto scatter = [&](int y, int x, float v) {
+          if (!gacc) return;
+          const long long q = __double2ll_rn((double)v * scale);
+          if (q == 0ll) return;
+          const int r = y - wt.wi0, cc = x - wt.wj0;
+          if ((unsigned)r < (unsigned)WS_H && (unsigned)cc < (unsigned)WS_W)
+            atomicAdd(reinterpret_cast<unsigned long long *>(&gwin[r * WS_W + cc]), (unsigned long long)q);
+          else
+            atomicAdd(reinterpret_cast<unsigned long long *>(gacc + plane_off + (long long)y * W + x), (unsigned long long)q);
+        };
+        {
+          const float v = warp_tap(plane, win, wt, y0, x0, W);
+          gix[e] -= v * ay * ge; giy[e] -= v * ax * ge;
+          scatter(y0, x0, ax * ay * ge);
+        }
+        if (x1ok) {
+          const float v = warp_tap(plane, win, wt, y0, x1, W);
+          gix[e] += v * ay * ge; giy[e] -= v * bx * ge;
+          scatter(y0, x1, bx * ay * ge);
+        }
+        if (y1ok) {
+          const float v = warp_tap(plane, win, wt, y1, x0, W);
+          gix[e] -= v * by * ge; giy[e] += v * ax * ge;
+          scatter(y1, x0, ax * by * ge);
+        }
+        if (x1ok && y1ok) {
+          const float v = warp_tap(plane, win, wt, y1, x1, W);
+          gix[e] += v * by * ge; giy[e] += v * bx * ge;
+          scatter(y1, x1, bx * by * ge);
+        }
       }
     }
-    if (gflow) {
-      // ATen: grad_grid = gix * ((size-1)/2 * clip_grad); then autograd through 2*(x/(size-1) - 0.5): (g*2)/(size-1)
-      const float gx = gix * (gmx * ((float)(W - 1) / 2.f));
-      const float gy = giy * (gmy * ((float)(H - 1) / 2.f));
-      gflow[((long long)b * 2 + 0) * HW + p] = (gy * 2.f) / (float)(H - 1);
-      gflow[((long long)b * 2 + 1) * HW + p] = (gx * 2.f) / (float)(W - 1);
+    if (gacc) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < WS_H * WS_W; idx += blockDim.x) {
+        const long long q = gwin[idx];
+        if (q == 0ll) continue;
+        const int r = idx / WS_W, cc = idx - r * WS_W;
+        atomicAdd(reinterpret_cast<unsigned long long *>(gacc + plane_off + (long long)(wt.wi0 + r) * W + wt.wj0 + cc), (unsigned long long)q);
+      }
+    }
+  }
+  if (gflow && row_ok) {
+    // ATen: grad_grid = gix * ((size-1)/2 * clip_grad); then autograd through 2*(x/(size-1) - 0.5): (g*2)/(size-1)
+    float oy[4], ox[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gx = gix[e] * (gmx[e] * ((float)(W - 1) / 2.f));
+      const float gy = giy[e] * (gmy[e] * ((float)(H - 1) / 2.f));
+      oy[e] = (gy * 2.f) / (float)(H - 1);
+      ox[e] = (gx * 2.f) / (float)(W - 1);
+    }
+    float *dy = gflow + ((long long)wt.b * 2 + 0) * HW + p, *dx = gflow + ((long long)wt.b * 2 + 1) * HW + p;
+    if (vec) {
+      *reinterpret_cast<float4 *>(dy) = make_float4(oy[0], oy[1], oy[2], oy[3]);
+      *reinterpret_cast<float4 *>(dx) = make_float4(ox[0], ox[1], ox[2], ox[3]);
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (j + e < W) { dy[e] = oy[e]; dx[e] = ox[e]; }
     }
   }
 }
 
+// fixed point -> fp32
+__global__ void __launch_bounds__(256) warp_gsrc_finish_kernel(const long long *__restrict__ gacc, const unsigned int *__restrict__ absmax,
+                                                               float *__restrict__ gsrc, long long n) {
+  const double inv = 1.0 / warp_fixed_scale(*absmax);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    gsrc[i] = (float)((double)gacc[i] * inv);
+}
+
 // ---- block reduction + "last block finalises" -----------------------------------------------------------------
-// acc[0] = running sum, acc[1] = ticket counter (both zeroed by the host wrapper before launch).
+// acc[1] = ticket counter (zeroed by the host wrapper before launch), acc[2 + b] = partial sum of block b.  The last block to arrive
+// adds the partial sums in block order: deterministic (no floating-point atomics on the sum), one launch, no host sync.
 __device__ __forceinline__ void block_finish(double local, double *acc, float *loss, double scale) {
   __shared__ double sm[32];
+  __shared__ bool last;
   local = warp_sum_d(local);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
-    atomicAdd(acc, t);
+    acc[2 + blockIdx.x] = t;
     __threadfence();
     const double ticket = atomicAdd(acc + 1, 1.0);
-    if (ticket == (double)(gridDim.x - 1)) {
-      const double total = atomicAdd(acc, 0.0);
+    last = ticket == (double)(gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    // 256 threads: strided partial sums in a fixed pattern, then a fixed-order tree
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(acc + 2 + b);
+    t = warp_sum_d(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double total = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += sm[i];
       *loss = (float)(total * scale);
     }
   }
@@ -226,7 +400,8 @@ __global__ void masked_l1_bwd_kernel(const float *__restrict__ wv, const float *
 
 inline int red_blocks(long long n) {
   long long b = (n + 256 * 8 - 1) / (256 * 8);
-  const long long cap = (long long)ctagan_num_sms() * 4;
+  long long cap = (long long)ctagan_num_sms() * 4;
+  if (cap > CTAGAN_LOSS_ACC_DOUBLES - 2) cap = CTAGAN_LOSS_ACC_DOUBLES - 2;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -241,20 +416,47 @@ inline int ew_blocks2(long long n) {
 
 }  // namespace
 
+static int warp_tiles(int B, int H, int W) { return B * ((H + WT_H - 1) / WT_H) * ((W + WT_W - 1) / WT_W); }
+
 extern "C" int ctagan_warp_fwd(const float *src, const float *flow, float *out, int B, int C, int H, int W, void *stream) {
   CTAGAN_REQUIRE(src && flow && out && B > 0 && C > 0 && H > 1 && W > 1, "warp_fwd: bad arguments");
-  warp_fwd_kernel<<<ew_blocks2((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(src, flow, out, B, C, H, W);
+  CTAGAN_REQUIRE(((reinterpret_cast<uintptr_t>(flow) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "warp_fwd: flow / out must be 16-byte aligned");
+  warp_fwd_kernel<<<warp_tiles(B, H, W), 256, 0, (cudaStream_t)stream>>>(src, flow, out, B, C, H, W);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
 
-extern "C" int ctagan_warp_bwd(const float *gout, const float *src, const float *flow, float *gsrc, float *gflow, int B, int C, int H,
-                               int W, void *stream) {
+/* scratch of ctagan_warp_bwd when gsrc is wanted: the 64-bit fixed-point accumulator of the scatter-add + 16 bytes */
+extern "C" size_t ctagan_warp_bwd_workspace_bytes(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * C * H * W * sizeof(long long) + 16;
+}
+
+extern "C" int ctagan_warp_bwd(const float *gout, const float *src, const float *flow, float *gsrc, float *gflow, void *workspace,
+                               size_t workspace_bytes, int B, int C, int H, int W, void *stream) {
   CTAGAN_REQUIRE(gout && src && flow && (gsrc || gflow) && B > 0 && C > 0 && H > 1 && W > 1, "warp_bwd: bad arguments");
+  CTAGAN_REQUIRE(((reinterpret_cast<uintptr_t>(flow) | reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(gflow)) & 15) == 0,
+                 "warp_bwd: flow / gout / gflow must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (gsrc) CTAGAN_CUDA_OK(cudaMemsetAsync(gsrc, 0, sizeof(float) * (size_t)B * C * H * W, st));
-  warp_bwd_kernel<<<ew_blocks2((long long)B * H * W), 256, 0, st>>>(gout, src, flow, gsrc, gflow, B, C, H, W);
+  const long long n = (long long)B * C * H * W;
+  long long *gacc = nullptr;
+  unsigned int *absmax = nullptr;
+  if (gsrc) {
+    const size_t need = ctagan_warp_bwd_workspace_bytes(B, C, H, W);
+    CTAGAN_REQUIRE(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
+                   "warp_bwd: 8-byte aligned workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+    gacc = (long long *)workspace;
+    absmax = reinterpret_cast<unsigned int *>(gacc + n);
+    CTAGAN_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
+    warp_absmax_kernel<<<red_blocks(n), 256, 0, st>>>(gout, absmax, n);
+    CTAGAN_LAUNCH_OK();
+  }
+  warp_bwd_kernel<<<warp_tiles(B, H, W), 256, 0, st>>>(gout, src, flow, gacc, absmax, gflow, B, C, H, W);
   CTAGAN_LAUNCH_OK();
+  if (gsrc) {
+    warp_gsrc_finish_kernel<<<ew_blocks2(n), 256, 0, st>>>(gacc, absmax, gsrc, n);
+    CTAGAN_LAUNCH_OK();
+  }
   return CTAGAN_OK;
 }
 

@@ -69,7 +69,10 @@ class ResidualBlock(nn.Module):
                                         _Slot("instnorm"))
 
     def forward(self, x):
-        raise RuntimeError("ResidualBlock is executed by its Generator's fused schedule")
+        """x + IN(conv3(RP1(relu(IN(conv3(RP1(x)))))))  (Model/CycleGan.py:20-21).  Inside a Generator the block runs as part of the fused
+        schedule; called on its own it runs the same kernels through the single-layer functions below."""
+        c1, c2 = self.conv_block[1], self.conv_block[5]
+        return _to_nchw(_res_block(_to_nhwc(x), c1.weight, c1.bias, c2.weight, c2.bias))
 
 
 class Generator(nn.Module):
@@ -379,46 +382,239 @@ class _RegFn(torch.autograd.Function):
         return (None, da, db, *grads)
 
 
-class _ParamConv(nn.Module):
-    """trainer/layers.py:71-104 `Conv`: holds `conv2d` (+ optional `resnet_block`); arithmetic runs in the fused schedule."""
+# ---- single-layer autograd functions on internal NHWC tensors (the standalone forwards of trainer/layers.py's modules; the networks
+# themselves run the fused schedules of ctagan.engine) ----
 
-    def __init__(self, cin, cout, k, act, use_resnet=False):
-        super().__init__()
-        self.conv2d = nn.Conv2d(cin, cout, k, 1, (k - 1) // 2, bias=True)
-        self.resnet_block = _ResnetTransformer(cout, 1) if use_resnet else None
-        a = 0.2 if act == "leaky_relu" else 0.0
-        if act == "zeros":
-            nn.init.normal_(self.conv2d.weight, mean=0.0, std=1e-5)           # layers.py:44-45
+
+class _ToNHWCFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.nchw_to_nhwc(x, E.get_precision())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nhwc_to_nchw(g.contiguous())
+
+
+class _ToNCHWFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.dtype = x.dtype
+        return ops.nhwc_to_nchw(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nchw_to_nhwc(g.contiguous(), ctx.dtype)
+
+
+def _to_nhwc(x):
+    ops.ensure_device()
+    return _ToNHWCFn.apply(x)
+
+
+def _to_nchw(x):
+    return _ToNCHWFn.apply(x)
+
+
+_ACT_CODE = {None: E.L.ACT_NONE, "relu": E.L.ACT_RELU, "leaky_relu": E.L.ACT_LRELU, "tanh": E.L.ACT_TANH}
+
+
+class _ConvActFn(torch.autograd.Function):
+    """act(conv(x) + b) [or act(IN(conv(x))) with norm=True] for one Conv2d(stride, zero padding) on NHWC tensors."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, act, norm):
+        prim = E.ConvPrim(w.detach(), None if b is None else b.detach(), stride, pad)
+        if norm:
+            if act == E.L.ACT_TANH:
+                raise NotImplementedError("InstanceNorm followed by tanh")
+            pool = ops.ZeroPool(x.shape[0] * w.shape[0] + 8, x.device) if x.dtype == torch.bfloat16 else None
+            r, st = prim.fprop_stats(x, pool)                 # the bias in front of a non-affine InstanceNorm is dead
+            y = ops.norm_act_pad(r, st, act, 0)
+            ctx.saved = (x, r, st)
         else:
-            nn.init.kaiming_normal_(self.conv2d.weight, a=a, nonlinearity="relu" if act is None else act, mode="fan_in")
-        self.conv2d.bias.data.zero_()
+            y = prim.fprop(x, act=act, use_bias=b is not None)
+            ctx.saved = (x, y, None)
+        ctx.prim, ctx.act, ctx.norm, ctx.has_bias = prim, act, norm, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, r, st = ctx.saved
+        prim = ctx.prim
+        g = g.contiguous()
+        if ctx.norm:
+            dy = ops.norm_act_pad_bwd(g, r, st, ctx.act, 0)
+        else:
+            dy = ops.act_bwd(g, r, ctx.act) if ctx.act != E.L.ACT_NONE else g
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = prim.wgrad(dy, x, want_bias=ctx.has_bias and not ctx.norm)
+        if ctx.needs_input_grad[0]:
+            dx = prim.bprop(dy, (x.shape[1], x.shape[2]))
+        return dx, dw, (db if ctx.has_bias and not ctx.norm else None), None, None, None, None
 
 
-class _ResnetBlockParams(nn.Module):
-    """trainer/layers.py:243-300: conv_block indices 1 and 5 are the convolutions."""
+class _ResBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        rb = E._ResBlock(w1.detach(), b1, w2.detach(), b2)
+        out, saved = rb.forward(x, save=True)
+        ctx.rb, ctx.saved = rb, saved
+        return out
 
-    def __init__(self, dim):
+    @staticmethod
+    def backward(ctx, g):
+        gx, (dw1, _, dw2, _) = ctx.rb.backward(ctx.saved, g.contiguous())
+        ctx.saved = None
+        return gx, dw1, None, dw2, None
+
+
+def _res_block(x, w1, b1, w2, b2):
+    if x.shape[1] < 2 or x.shape[2] < 2:
+        raise ValueError("ReflectionPad2d(1) needs maps of at least 2x2")
+    return _ResBlockFn.apply(x, w1, b1, w2, b2)
+
+
+class _MaxPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.x = x
+        return ops.maxpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.maxpool2_bwd(g.contiguous(), ctx.x)
+
+
+def get_init_function(activation, init_function, **kwargs):
+    """trainer/layers.py:23-53 (same torch.nn.init calls, so the same random draws)."""
+    from functools import partial
+    a = 0.0
+    if activation == "leaky_relu":
+        a = 0.2 if "negative_slope" not in kwargs else kwargs["negative_slope"]
+    gain = 0.02 if "gain" not in kwargs else kwargs["gain"]
+    if isinstance(init_function, str):
+        if init_function == "kaiming":
+            activation = "relu" if activation is None else activation
+            return partial(nn.init.kaiming_normal_, a=a, nonlinearity=activation, mode="fan_in")
+        if init_function == "dirac":
+            return nn.init.dirac_
+        if init_function == "xavier":
+            activation = "relu" if activation is None else activation
+            return partial(nn.init.xavier_normal_, gain=nn.init.calculate_gain(nonlinearity=activation, param=a))
+        if init_function == "normal":
+            return partial(nn.init.normal_, mean=0.0, std=gain)
+        if init_function == "orthogonal":
+            return partial(nn.init.orthogonal_, gain=gain)
+        if init_function == "zeros":
+            return partial(nn.init.normal_, mean=0.0, std=1e-5)
+        raise ValueError(f"unknown init function {init_function!r}")
+    if init_function is None:
+        if activation in ("relu", "leaky_relu"):
+            return partial(nn.init.kaiming_normal_, a=a, nonlinearity=activation)
+        if activation in ("tanh", "sigmoid"):
+            return partial(nn.init.xavier_normal_, gain=nn.init.calculate_gain(nonlinearity=activation, param=a))
+        raise ValueError("init_func=None needs an activation")
+    return init_function
+
+
+class Conv(nn.Module):
+    """trainer/layers.py:71-104: Conv2d -> InstanceNorm (optional) -> activation -> ResnetTransformer (optional); same constructor,
+    sub-module names (`conv2d`, `resnet_block`) and initialisation draws as the reference."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, bias=True, activation="relu", init_func="kaiming",
+                 use_norm=False, use_resnet=False, **kwargs):
         super().__init__()
-        self.conv_block = nn.Sequential(_Slot("reflect1"), nn.Conv2d(dim, dim, 3, bias=True), _Slot("instnorm"), _Slot("relu"),
-                                        _Slot("reflect1"), nn.Conv2d(dim, dim, 3, bias=True), _Slot("instnorm"))
+        if activation not in _ACT_CODE:
+            raise NotImplementedError(f"activation {activation!r} is not on the hot path (relu / leaky_relu / tanh / None)")
+        if kwargs.get("negative_slope", 0.2) != 0.2:
+            raise NotImplementedError("LeakyReLU slopes other than 0.2")
+        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
+        self.resnet_block = ResnetTransformer(out_channels, 1, init_func) if use_resnet else None
+        self.use_norm, self.activation_name = bool(use_norm), activation
+        get_init_function(activation, init_func)(self.conv2d.weight)
+        if self.conv2d.bias is not None:
+            self.conv2d.bias.data.zero_()
+
+    def _forward_nhwc(self, x):
+        c = self.conv2d
+        x = _ConvActFn.apply(x, c.weight, c.bias, c.stride[0], c.padding[0], _ACT_CODE[self.activation_name], self.use_norm)
+        if self.resnet_block is not None:
+            x = self.resnet_block._forward_nhwc(x)
+        return x
+
+    def forward(self, x):
+        return _to_nchw(self._forward_nhwc(_to_nhwc(x)))
 
 
-class _ResnetTransformer(nn.Module):
-    """trainer/layers.py:216-240 (all convs are created first, then re-drawn kaiming(relu) in traversal order)."""
+class ResnetBlock(nn.Module):
+    """trainer/layers.py:243-300 (reflect padding, InstanceNorm, no dropout: the only configuration the reference builds).
+    conv_block indices 1 and 5 are the convolutions."""
 
-    def __init__(self, dim, n_blocks):
+    def __init__(self, dim, padding_type="reflect", norm_layer=None, use_dropout=False, use_bias=True):
         super().__init__()
-        self.model = nn.Sequential(*[_ResnetBlockParams(dim) for _ in range(n_blocks)])
+        if padding_type != "reflect" or use_dropout:
+            raise NotImplementedError("ResnetBlock: only padding_type='reflect' without dropout (trainer/layers.py:221-222)")
+        self.conv_block = nn.Sequential(_Slot("reflect1"), nn.Conv2d(dim, dim, 3, bias=use_bias), _Slot("instnorm"), _Slot("relu"),
+                                        _Slot("reflect1"), nn.Conv2d(dim, dim, 3, bias=use_bias), _Slot("instnorm"))
+
+    def _forward_nhwc(self, x):
+        c1, c2 = self.conv_block[1], self.conv_block[5]
+        return _res_block(x, c1.weight, c1.bias, c2.weight, c2.bias)
+
+    def forward(self, x):
+        return _to_nchw(self._forward_nhwc(_to_nhwc(x)))
+
+
+class ResnetTransformer(nn.Module):
+    """trainer/layers.py:216-240 (all convs are created first, then re-drawn with init_func('relu') in traversal order)."""
+
+    def __init__(self, dim, n_blocks, init_func="kaiming"):
+        super().__init__()
+        self.model = nn.Sequential(*[ResnetBlock(dim, "reflect", None, False, True) for _ in range(n_blocks)])
+        init_ = get_init_function("relu", init_func)
         for m in self.model.modules():
             if type(m) == nn.Conv2d:
-                nn.init.kaiming_normal_(m.weight, a=0.0, nonlinearity="relu", mode="fan_in")
-                m.bias.data.zero_()
+                init_(m.weight)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+
+    def _forward_nhwc(self, x):
+        for blk in self.model:
+            x = blk._forward_nhwc(x)
+        return x
+
+    def forward(self, x):
+        return _to_nchw(self._forward_nhwc(_to_nhwc(x)))
 
 
-class _DownBlockParams(nn.Module):
-    def __init__(self, cin, cout):
+class DownBlock(nn.Module):
+    """trainer/layers.py:156-183: conv_0 (+ conv_1 with refine) -> MaxPool2d(pool_size=2); returns (pooled, skip) with skip=True."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, bias=False, activation="relu", init_func="kaiming",
+                 use_norm=False, use_resnet=False, skip=True, refine=False, pool=True, pool_size=2, **kwargs):
         super().__init__()
-        self.conv_0 = _ParamConv(cin, cout, 3, "leaky_relu", use_resnet=True)
+        if pool and pool_size != 2:
+            raise NotImplementedError("DownBlock: MaxPool2d(2) only")
+        kwargs.pop("callback", None)
+        self.conv_0 = Conv(in_channels, out_channels, kernel_size, stride, padding, bias=bias, activation=activation, init_func=init_func,
+                           use_norm=use_norm, use_resnet=use_resnet, **kwargs)
+        self.conv_1 = None
+        if refine:
+            self.conv_1 = Conv(out_channels, out_channels, kernel_size, stride, padding, bias=bias, activation=activation,
+                               init_func=init_func, use_norm=use_norm, use_resnet=use_resnet, **kwargs)
+        self.skip, self.pool = skip, bool(pool)
+
+    def forward(self, x):
+        x = skip = self.conv_0._forward_nhwc(_to_nhwc(x))
+        if self.conv_1 is not None:
+            x = skip = self.conv_1._forward_nhwc(x)
+        if self.pool:
+            if x.shape[1] % 2 or x.shape[2] % 2:
+                raise ValueError("DownBlock: MaxPool2d(2) needs even H and W here")
+            x = _MaxPool2Fn.apply(x)
+        return (_to_nchw(x), _to_nchw(skip)) if self.skip else _to_nchw(x)
 
 
 class ResUnet(nn.Module):
@@ -429,19 +625,24 @@ class ResUnet(nn.Module):
         in_nf = nc_a + nc_b
         skip = {}
         for n, out_nf in enumerate(E.REG_NDF, start=1):
-            setattr(self, f"down_{n}", _DownBlockParams(in_nf, out_nf))
+            setattr(self, f"down_{n}", DownBlock(in_nf, out_nf, 3, 1, 1, bias=True, activation="leaky_relu", init_func=init_func,
+                                                 use_norm=False, use_resnet=True, skip=True, refine=False, pool=True))
             skip[n] = out_nf
             in_nf = out_nf
-        self.c1 = _ParamConv(in_nf, 2 * in_nf, 1, "leaky_relu")
-        self.t = _ResnetTransformer(2 * in_nf, 3)
-        self.c2 = _ParamConv(2 * in_nf, in_nf, 1, "leaky_relu")
+        self.c1 = Conv(in_nf, 2 * in_nf, 1, 1, 0, bias=True, activation="leaky_relu", init_func=init_func, use_norm=False, use_resnet=False)
+        self.t = ResnetTransformer(2 * in_nf, 3, init_func)
+        self.c2 = Conv(2 * in_nf, in_nf, 1, 1, 0, bias=True, activation="leaky_relu", init_func=init_func, use_norm=False, use_resnet=False)
         n = len(E.REG_NDF)
         for out_nf in E.REG_NUF:
-            setattr(self, f"up_{n}", _ParamConv(in_nf + skip[n], out_nf, 3, "leaky_relu"))
+            setattr(self, f"up_{n}", Conv(in_nf + skip[n], out_nf, 3, 1, 1, bias=True, activation="leaky_relu", init_func=init_func,
+                                          use_norm=False, use_resnet=False))
             in_nf = out_nf
             n -= 1
-        self.refine = nn.Sequential(_ResnetTransformer(in_nf, 1), _ParamConv(in_nf, in_nf, 1, "leaky_relu"))
-        self.output = _ParamConv(in_nf, 2, 3, "zeros" if init_to_identity else None)
+        self.refine = nn.Sequential(ResnetTransformer(in_nf, 1, init_func),
+                                    Conv(in_nf, in_nf, 1, 1, 0, bias=True, activation="leaky_relu", init_func=init_func, use_norm=False,
+                                         use_resnet=False))
+        self.output = Conv(in_nf, 2, 3, 1, 1, bias=True, activation=None, init_func="zeros" if init_to_identity else init_func,
+                           use_norm=False, use_resnet=False)
 
 
 class Reg(nn.Module):

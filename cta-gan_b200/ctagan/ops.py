@@ -82,32 +82,47 @@ def conv_gather(x, wp, bias, g: L.ConvGeom, engine=L.ENGINE_AUTO):
 
 
 class ZeroPool:
-    """One zero-filled fp64 buffer per network pass, handed out in slices: the accumulators of all fused-statistics convolutions of
-    the pass are cleared by a single memset instead of one per layer."""
+    """One zero-filled buffer per network pass, handed out in slices: the arrival tickets of all deterministic split reductions of the
+    pass (fused conv statistics, two-kernel norm backward) are cleared by a single memset instead of one per layer.  The kernels
+    re-arm their tickets, so a slice is zero again when its kernel has finished."""
 
     def __init__(self, n_doubles: int, device):
         self.buf = torch.zeros((max(n_doubles, 2),), dtype=torch.float64, device=device)
         self.off = 0
 
     def take(self, n: int):
-        if self.off + n > self.buf.numel():
-            return torch.zeros((n,), dtype=torch.float64, device=self.buf.device)
+        """n zeroed doubles, 16-byte aligned (the kernels read accumulator pairs as double2)."""
+        step = (n + 1) & ~1
+        if self.off + step > self.buf.numel():
+            return torch.zeros((step,), dtype=torch.float64, device=self.buf.device)[:n]
         out = self.buf[self.off:self.off + n]
-        self.off += n
+        self.off += step
         return out
+
+
+def _stat_buffers(g: L.ConvGeom, pool: "ZeroPool", scratch_bytes: int, device):
+    """(tickets, scratch, stats) of a fused-statistics convolution: N * ceil(Co/32) zeroed uint32 tickets from the pool, the per-tile
+    partial-sum slots (any content), the (mean, rstd) output."""
+    n_tickets = g.N * ((g.Co + 31) // 32)
+    tickets = pool.take((n_tickets + 1) // 2)
+    scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=device)
+    stats = torch.empty((g.N, g.Co, 2), dtype=torch.float32, device=device)
+    return tickets, scratch, stats
 
 
 def conv_gather_stats(x, wp, bias, g: L.ConvGeom, pool: "ZeroPool", engine=L.ENGINE_AUTO):
     """Convolution + InstanceNorm statistics.  Returns (y, stats[N][Co][2] = (mean, rstd)).  On the tcgen05 engine the sums come out
-    of the conv epilogue (no extra pass over y); otherwise conv followed by the shifted-sum statistics kernels."""
+    of the conv epilogue (no extra pass over y; per-tile partial sums added in tile order by the last CTA: deterministic); otherwise
+    conv followed by the shifted-sum statistics kernels."""
     lib = L.load()
     if pool is not None and lib.ctagan_conv_gather_engine(ctypes.byref(g), engine) == 2:
         ensure_device()
         y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
-        acc = pool.take(g.N * g.Co * 2 + 1)            # + the ticket of the in-kernel finalize
-        stats = torch.empty((g.N, g.Co, 2), dtype=torch.float32, device=x.device)
+        nbytes = int(lib.ctagan_conv_gather_stats_scratch_bytes(ctypes.byref(g), engine))
+        tickets, scratch, stats = _stat_buffers(g, pool, nbytes, x.device)
         _count(1)
-        L.check(lib.ctagan_conv_gather_stats(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(acc), _p(stats), engine, _stream()))
+        L.check(lib.ctagan_conv_gather_stats(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(tickets), _p(scratch), nbytes, _p(stats),
+                                             engine, _stream()))
         return y, stats
     y = conv_gather(x, wp, bias, g, engine)
     return y, instnorm_stats(y)
@@ -131,13 +146,14 @@ def conv_gather_grouped(x, wp, g: L.ConvGeom, slots, pool: "ZeroPool" = None):
     _require_cuda(x, wp)
     ensure_device()
     y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
-    acc = stats = None
+    tickets = scratch = stats = None
+    nbytes = 0
     if pool is not None:
-        acc = pool.take(g.N * g.Co * 2 + 1)
-        stats = torch.empty((g.N, g.Co, 2), dtype=torch.float32, device=x.device)
+        nbytes = int(L.load().ctagan_conv_gather_stats_scratch_bytes(ctypes.byref(g), L.ENGINE_AUTO))
+        tickets, scratch, stats = _stat_buffers(g, pool, nbytes, x.device)
     _count(1)
-    L.check(L.load().ctagan_conv_gather_grouped(ctypes.byref(g), ctypes.byref(_groups(slots)), _p(x), _p(wp), None, _p(y), _p(acc), _p(stats),
-                                                _stream()))
+    L.check(L.load().ctagan_conv_gather_grouped(ctypes.byref(g), ctypes.byref(_groups(slots)), _p(x), _p(wp), None, _p(y), _p(tickets),
+                                                _p(scratch), nbytes, _p(stats), _stream()))
     return (y, stats) if pool is not None else y
 
 
@@ -162,7 +178,7 @@ def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO):
     db = torch.empty((g.Co,), dtype=torch.float32, device=gy.device) if want_bias else None
     ws_bytes = L.load().ctagan_conv_wgrad_workspace_bytes(ctypes.byref(g), engine)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device) if ws_bytes else None
-    _count(2 if ws_bytes else 1)
+    _count(3 if ws_bytes and want_bias else (2 if ws_bytes else 1))
     L.check(L.load().ctagan_conv_wgrad(ctypes.byref(g), _p(gy), _p(gx), _p(dw), _p(db), _p(ws), ws_bytes, engine, _stream()))
     return dw, db
 
@@ -180,30 +196,18 @@ def pack_weights(w: torch.Tensor, mode: int, dtype: torch.dtype):
 def instnorm_stats(x):
     N, H, W, C = x.shape
     stats = torch.empty((N, C, 2), dtype=torch.float32, device=x.device)
-    acc = torch.empty((N, C, 2), dtype=torch.float64, device=x.device)
+    n_acc = int(L.load().ctagan_instnorm_stats_scratch_doubles(N, H * W, C, dt(x)))
+    acc = torch.empty((n_acc,), dtype=torch.float64, device=x.device)
     _count(2)
     L.check(L.load().ctagan_instnorm_stats(_p(x), _p(stats), _p(acc), N, H * W, C, dt(x), _stream()))
     return stats
-
-
-class LazyStats:
-    """(sum, sum of squares) accumulated by a conv epilogue; the first norm_act_pad that consumes it publishes fp32 (mean, rstd)."""
-
-    def __init__(self, sums, N, C):
-        self.sums = sums
-        self.stats = torch.empty((N, C, 2), dtype=torch.float32, device=sums.device)
 
 
 def norm_act_pad(x, stats, act, pad, res=None, res_pad=0):
     N, H, W, C = x.shape
     out = torch.empty((N, H + 2 * pad, W + 2 * pad, C), dtype=x.dtype, device=x.device)
     _count(1)
-    if isinstance(stats, LazyStats):
-        L.check(L.load().ctagan_norm_act_pad(_p(x), None, _p(stats.sums), _p(stats.stats), _p(res), res_pad, _p(out), N, H, W, C, pad, act,
-                                             dt(x), _stream()))
-    else:
-        L.check(L.load().ctagan_norm_act_pad(_p(x), _p(stats), None, None, _p(res), res_pad, _p(out), N, H, W, C, pad, act, dt(x),
-                                             _stream()))
+    L.check(L.load().ctagan_norm_act_pad(_p(x), _p(stats), _p(res), res_pad, _p(out), N, H, W, C, pad, act, dt(x), _stream()))
     return out
 
 
@@ -211,21 +215,21 @@ def norm_act_pad_bwd(gout, x, stats, act, pad, addend=None, out_pad=0, pool=None
     """Backward of norm_act_pad (see ctagan_norm_act_pad_bwd).  want_g: also return fold(gout) + addend (the skip-connection gradient)."""
     N, Hp, Wp, C = gout.shape
     H, W = Hp - 2 * pad, Wp - 2 * pad
-    if isinstance(stats, LazyStats):
-        stats = stats.stats
     dx = torch.empty((N, H + 2 * out_pad, W + 2 * out_pad, C), dtype=gout.dtype, device=gout.device)
     g_out = torch.empty((N, H, W, C), dtype=gout.dtype, device=gout.device) if want_g else None
     lib = L.load()
     launches = lib.ctagan_norm_act_pad_bwd_launches(int(stats is not None), H, W, C, dt(gout))
-    acc, zeroed = None, 0
+    acc, scratch, zeroed = None, None, 0
     if stats is not None and launches == 2:
         if pool is not None:
-            acc, zeroed = pool.take(N * C * 2), 1
+            acc, zeroed = pool.take(N * C * 2 + N), 1
         else:
-            acc = torch.empty((N, C, 2), dtype=torch.float64, device=gout.device)
+            acc = torch.empty((N * C * 2 + N,), dtype=torch.float64, device=gout.device)
+        n_scr = int(lib.ctagan_norm_act_pad_bwd_scratch_doubles(1, N, H, W, C, dt(gout)))
+        scratch = torch.empty((n_scr,), dtype=torch.float64, device=gout.device)
     _count(launches)
-    L.check(lib.ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(g_out), _p(acc), zeroed, N, H, W, C, pad, act,
-                                        out_pad, dt(gout), _stream()))
+    L.check(lib.ctagan_norm_act_pad_bwd(_p(gout), _p(x), _p(stats), _p(addend), _p(dx), _p(g_out), _p(acc), zeroed, _p(scratch), N, H, W, C,
+                                        pad, act, out_pad, dt(gout), _stream()))
     return (dx, g_out) if want_g else dx
 
 
@@ -321,13 +325,19 @@ def warp_bwd(gout, src, flow, need_src=True, need_flow=True):
     B, C, H, W = src.shape
     gsrc = torch.empty_like(src) if need_src else None
     gflow = torch.empty_like(flow) if need_flow else None
-    _count(1)
-    L.check(L.load().ctagan_warp_bwd(_p(gout), _p(src), _p(flow), _p(gsrc), _p(gflow), B, C, H, W, _stream()))
+    ws_bytes = int(L.load().ctagan_warp_bwd_workspace_bytes(B, C, H, W)) if need_src else 0
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=src.device) if ws_bytes else None
+    _count(3 if need_src else 1)
+    L.check(L.load().ctagan_warp_bwd(_p(gout), _p(src), _p(flow), _p(gsrc), _p(gflow), _p(ws), ws_bytes, B, C, H, W, _stream()))
     return gsrc, gflow
 
 
+LOSS_ACC_DOUBLES = 1024        # CTAGAN_LOSS_ACC_DOUBLES
+
+
 def _scalar_out(ref):
-    return torch.empty((), dtype=torch.float32, device=ref.device), torch.empty((2,), dtype=torch.float64, device=ref.device)
+    return (torch.empty((), dtype=torch.float32, device=ref.device),
+            torch.empty((LOSS_ACC_DOUBLES,), dtype=torch.float64, device=ref.device))
 
 
 def l1_fwd(a, b):

@@ -75,22 +75,23 @@ int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp,
                        int engine, void *stream);
 
 /* ctagan_conv_gather with the InstanceNorm statistics fused into the epilogue (tcgen05 engine only; CTAGAN_ERR_UNSUPPORTED
- * otherwise -- query with ctagan_conv_gather_engine): stat_acc[N][Co][2] (fp64, PRE-ZEROED by the caller) receives the per-(n,co)
- * sum and sum of squares of the fp32 convolution output.  stat_acc must hold N*Co*2 + 1 doubles, all zero: the extra one is the
- * ticket of the "last CTA finalises" step that writes stats_out[N][Co][2] = (mean, rstd) (optional; without it use
- * ctagan_instnorm_finalize_sums or pass the sums to ctagan_norm_act_pad). */
-int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, double *stat_acc,
-                             float *stats_out, int engine, void *stream);
+ * otherwise -- query with ctagan_conv_gather_engine).  stats_out[N][Co][2] receives (mean, rstd) of the fp32 convolution output.
+ * The reduction is DETERMINISTIC: every CTA stores the column sums of its tile in its own slot of stat_scratch
+ * (ctagan_conv_gather_stats_scratch_bytes bytes, any content, 8-byte aligned) and the last CTA of an (image, column tile) to arrive
+ * adds the slots in tile order; stat_tickets counts the arrivals: N * ceil(Co/32) uint32, ZERO on entry (zero again on return). */
+size_t ctagan_conv_gather_stats_scratch_bytes(const ctagan_conv_geom *g, int engine);
+int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, uint32_t *stat_tickets,
+                             void *stat_scratch, size_t stat_scratch_bytes, float *stats_out, int engine, void *stream);
 /* engine ctagan_conv_gather would use: 1 CUDA-core generic, 2 tcgen05, 4 CUDA-core specialised (1-2 channel layers) */
 int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine);
-int ctagan_instnorm_finalize_sums(const double *acc, float *stats, int N, int HW, int C, void *stream);
 
 /* Grouped launches (tcgen05 engine only).  The batch is `groups` consecutive, equally sized image groups; group k is convolved
  * with the weights in slot `slot[k]` of one packed buffer wp[slots][Co][taps][Ci] (bias[slots][Co]).  This is how the two generators
  * (and the two discriminators) of a CycleGAN iteration -- same architecture, different weights, independent inputs
  * (trainer/CycTrainer.py:144-157: netG_A2B(real_A) beside netG_B2A(real_B), then netG_B2A(fake_B) beside netG_A2B(fake_A)) -- run as
  * ONE launch per layer: at batch 1 a single network fills only part of the chip and its kernels are latency-bound, so two
- * problems per launch cost about the same time as one.  stat_acc / stats_out as in ctagan_conv_gather_stats (optional).
+ * problems per launch cost about the same time as one.  stat_tickets / stat_scratch / stats_out as in ctagan_conv_gather_stats
+ * (all NULL / 0: no statistics).
  * CTAGAN_ERR_UNSUPPORTED when the geometry does not run on the tcgen05 engine (ask ctagan_conv_gather_grouped_supported first). */
 #define CTAGAN_MAX_GROUPS 4
 typedef struct {
@@ -99,7 +100,7 @@ typedef struct {
 } ctagan_conv_groups;
 int ctagan_conv_gather_grouped_supported(const ctagan_conv_geom *g, const ctagan_conv_groups *gr);
 int ctagan_conv_gather_grouped(const ctagan_conv_geom *g, const ctagan_conv_groups *gr, const void *x, const void *wp, const float *bias,
-                               void *y, double *stat_acc, float *stats_out, void *stream);
+                               void *y, uint32_t *stat_tickets, void *stat_scratch, size_t stat_scratch_bytes, float *stats_out, void *stream);
 /* one weight (and optional bias) gradient per group: dw[groups][Co][Ci][KH][KW], db[groups][Co]; workspace as for ctagan_conv_wgrad
  * (0 bytes == unsupported geometry) */
 size_t ctagan_conv_wgrad_grouped_workspace_bytes(const ctagan_conv_geom *g, int groups);
@@ -113,7 +114,9 @@ int ctagan_conv_wgrad_grouped(const ctagan_conv_geom *g, int groups, const void 
  * Replaces the weight-gradient half of cudnn/ATen convolution_backward for the layers cited above. */
 int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db,
                       void *workspace, size_t workspace_bytes, int engine, void *stream);
-/* Scratch bytes ctagan_conv_wgrad needs for this geometry/engine (split-K partial sums of the tcgen05 engine; 0 for CUDA-core). */
+/* Scratch bytes ctagan_conv_wgrad needs for this geometry/engine: the per-CTA / per-split partial sums of every engine's split
+ * reduction (each CTA stores its partial result in its own row, a second kernel adds the rows in order: no floating-point atomics,
+ * the same inputs give the same bits). */
 size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine);
 
 /* fp32 master weights W[O][I][KH][KW] -> packed `dtype` weights.
@@ -130,17 +133,17 @@ typedef struct {
 int ctagan_pack_weights_multi(const ctagan_pack_item *items, int n_items, int dtype, void *stream);
 
 /* InstanceNorm2d statistics (affine=False, eps=1e-5, biased variance; Model/CycleGan.py:12,16,29,37,52,82,86,90,
- * trainer/layers.py:14): x[N][HW][C] -> stats[N][C][2] = (mean, rstd) fp32.  acc: caller scratch, N*C*2 doubles. */
+ * trainer/layers.py:14): x[N][HW][C] -> stats[N][C][2] = (mean, rstd) fp32.  acc: caller scratch of
+ * ctagan_instnorm_stats_scratch_doubles doubles (per-block partial sums, added in block order). */
+size_t ctagan_instnorm_stats_scratch_doubles(int N, int HW, int C, int dtype);
 int ctagan_instnorm_stats(const void *x, float *stats, double *acc, int N, int HW, int C, int dtype, void *stream);
 
 /* Fused InstanceNorm-apply + activation + residual add + reflection pad (one pass):
  *   out[n,hp,wp,c] = act((x[n,h,w,c]-mean)*rstd) + res[n,h+res_pad,w+res_pad,c],  (h,w) = reflect(hp-pad, wp-pad)
  * stats==NULL: no normalisation; res==NULL: no residual.  res has spatial size (H+2*res_pad, W+2*res_pad).
- * Instead of `stats` the fp64 (sum, sum of squares) accumulator of ctagan_conv_gather_stats may be passed as `sums`: mean/rstd are then
- * derived on the fly (no finalize launch) and, if stats_out != NULL, published there as fp32 (mean, rstd) for the backward pass.
  * Replaces InstanceNorm2d+ReLU/LeakyReLU+ReflectionPad2d+residual add (Model/CycleGan.py:10-21,27-30). */
-int ctagan_norm_act_pad(const void *x, const float *stats, const double *sums, float *stats_out, const void *res, int res_pad,
-                        void *out, int N, int H, int W, int C, int pad, int act, int dtype, void *stream);
+int ctagan_norm_act_pad(const void *x, const float *stats, const void *res, int res_pad, void *out, int N, int H, int W, int C, int pad,
+                        int act, int dtype, void *stream);
 
 /* Backward of the above.  gout is the gradient w.r.t. `out` (padded, size H+2*pad); x is the saved raw conv output
  * (or, when stats==NULL, any tensor with the sign of the pre-activation, e.g. the post-activation output).
@@ -151,13 +154,16 @@ int ctagan_norm_act_pad(const void *x, const float *stats, const double *sums, f
  * input-gradient convolution that consumes it becomes a plain VALID convolution (the tcgen05 engine's native form).
  * g_out (optional, [N][H][W][C]): also receives fold_reflect(gout) + addend, i.e. the gradient that continues along the skip
  * connection of a residual block -- one launch then serves both consumers of a block's output gradient.
- * acc: N*C*2 doubles scratch (only with stats); acc_is_zero != 0 promises it is already cleared (one memset per pass).
  * bf16 maps of up to 64x64 pixels per image run as ONE kernel (thread-block clusters of 8 CTAs per 16 channels, per-channel sums
- * combined through distributed shared memory, operands read once and kept in registers; acc is not used); otherwise two kernels
- * (reduce with fp64 atomics into acc, then apply).  ctagan_norm_act_pad_bwd_launches tells which. */
+ * combined through distributed shared memory, operands read once and kept in registers; acc / scratch are not used); otherwise two
+ * kernels: reduce (every block stores its partial sums in its own row of `scratch`,
+ * ctagan_norm_act_pad_bwd_scratch_doubles doubles; the last block of an image adds the rows in order into acc), then apply.
+ * acc: N*C*2 + N doubles (only with stats); the last N are the arrival tickets and must be ZERO on entry (they are zero again on
+ * return): acc_is_zero != 0 promises that, otherwise they are cleared here.  ctagan_norm_act_pad_bwd_launches tells which path runs. */
+size_t ctagan_norm_act_pad_bwd_scratch_doubles(int has_stats, int N, int H, int W, int C, int dtype);
 int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const float *stats, const void *addend, void *dx, void *g_out,
-                            double *acc, int acc_is_zero, int N, int H, int W, int C, int pad, int act, int out_pad, int dtype,
-                            void *stream);
+                            double *acc, int acc_is_zero, double *scratch, int N, int H, int W, int C, int pad, int act, int out_pad,
+                            int dtype, void *stream);
 int ctagan_norm_act_pad_bwd_launches(int has_stats, int H, int W, int C, int dtype);
 
 /* Pointwise activation backward for conv-epilogue activations: dx = gy * act'(y) computed from the OUTPUT y
@@ -179,14 +185,20 @@ int ctagan_copy_channels(const void *src, void *dst, int64_t pixels, int C, int 
                          int dtype, void *stream);
 
 /* Transformer_2D.forward (trainer/transformer.py:11-31): bilinear grid_sample(align_corners=True, padding_mode="border") of
- * src[B][C][H][W] at (i + flow[b,0,i,j], j + flow[b,1,i,j]); fp32 in/out (module boundary).  bwd produces gsrc AND gflow. */
+ * src[B][C][H][W] at (i + flow[b,0,i,j], j + flow[b,1,i,j]); fp32 in/out (module boundary).  bwd produces gsrc AND gflow (either
+ * may be NULL).  A block stages the source window of its 16x64 output tile (+-8 pixels) in shared memory; rows move as 16-byte
+ * vectors (flow / out / gout / gflow 16-byte aligned).  gsrc is a scatter-add: it is accumulated in 64-bit fixed point (scaled by
+ * max|gout|), so it does not depend on the order of the additions; workspace: ctagan_warp_bwd_workspace_bytes (only with gsrc). */
 int ctagan_warp_fwd(const float *src, const float *flow, float *out, int B, int C, int H, int W, void *stream);
-int ctagan_warp_bwd(const float *gout, const float *src, const float *flow, float *gsrc, float *gflow, int B, int C, int H, int W,
-                    void *stream);
+size_t ctagan_warp_bwd_workspace_bytes(int B, int C, int H, int W);
+int ctagan_warp_bwd(const float *gout, const float *src, const float *flow, float *gsrc, float *gflow, void *workspace,
+                    size_t workspace_bytes, int B, int C, int H, int W, void *stream);
 
-/* Fused single-pass losses; `loss` is one fp32 on the device, acc a 4-double scratch.  fp32 tensors.
+/* Fused single-pass losses; `loss` is one fp32 on the device, acc a scratch of CTAGAN_LOSS_ACC_DOUBLES doubles (ticket + one partial
+ * sum per block, added in block order by the last block to arrive: deterministic, one launch, no host sync).  fp32 tensors.
  * l1: torch.nn.L1Loss (CycTrainer.py:77);  mse_const: torch.nn.MSELoss vs a broadcast constant (CycTrainer.py:76,83-84);
  * smooth: smooothing_loss (trainer/utils.py:165-173);  masked_l1: HdTrainer.py:726-735. */
+#define CTAGAN_LOSS_ACC_DOUBLES 1024
 int ctagan_l1_fwd(const float *a, const float *b, float *loss, double *acc, int64_t n, void *stream);
 int ctagan_l1_bwd(const float *a, const float *b, const float *gloss, float *ga, int64_t n, void *stream);
 int ctagan_mse_const_fwd(const float *p, float target, float *loss, double *acc, int64_t n, void *stream);

@@ -17,3 +17,19 @@ def pytest_configure(config):
 def golden():
     import torch
     return torch.load(os.path.join(ROOT, "tests", "golden", "golden_v1.pt"), weights_only=False)
+
+
+_ORDER = ["test_abi_and_host", "test_oracle", "test_ddp", "test_gpu_ops", "test_gpu_tc", "test_gpu_determinism", "test_gpu_modules",
+          "test_gpu_bf16", "test_gpu_steps", "test_gpu_curves"]
+
+
+def pytest_collection_modifyitems(config, items):
+    """Kernel-level tests first (ops, tcgen05 engine, determinism), whole modules next, training iterations last: under `-x` a
+    failure high in the stack can then never hide the state of the layers below it."""
+    def rank(item):
+        name = item.fspath.basename
+        for k, prefix in enumerate(_ORDER):
+            if name.startswith(prefix):
+                return k
+        return len(_ORDER)
+    items.sort(key=rank)          # stable: keeps the order inside a file

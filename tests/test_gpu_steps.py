@@ -35,8 +35,15 @@ def test_cyc_step_matches_reference_losses(golden):
         out = tr.step({"A": rA, "B": rB})
         for k in ("loss_G", "loss_D_A", "loss_D_B"):
             assert _close(float(out[k]), ref[k], 2e-3 if it else 2e-4), (it, k, float(out[k]), ref[k])
+    # the UPDATE itself, not closeness to the initial weights.  Two Adam steps move every weight by ~lr * sign(gradient) each (the
+    # first steps of Adam are sign-like), so the comparison is element-wise: all but the few near-zero-gradient elements, where the
+    # 1e-4 gradient noise of the fp32 mode can flip a sign, must agree to 5 % of the step size.
     w = tr.netG_A2B.model_head[1].weight.detach().cpu()
-    assert (w - golden["cyc_step.G_A2B_head_w_after2"]).abs().max() <= 2.5e-4      # two Adam steps of lr 1e-4 each
+    _seed(); w0 = R.init_generator(1, 1)["model_head.1.weight"]
+    upd, upd_ref = w - w0, golden["cyc_step.G_A2B_head_w_after2"] - w0
+    assert float(upd_ref.abs().max()) > 1e-4 and float(upd.abs().max()) > 1e-4
+    agree = float(((upd - upd_ref).abs() <= 0.05 * 2e-4).float().mean())
+    assert agree >= 0.97, agree
 
 
 def test_reg_step_matches_oracle():
@@ -87,7 +94,8 @@ def test_bf16_cyc_step_runs_and_tracks(golden):
 
 
 def _run_cyc(mode, steps, size=64, precision="fp32"):
-    """Losses of `steps` Cyc iterations with a 2-slot ReplayBuffer (so the swap path is exercised after two steps)."""
+    """`steps` Cyc iterations with a 2-slot ReplayBuffer (so the swap path is exercised from the third push on).  Returns, per
+    iteration, the losses and a copy of EVERY parameter of the four networks after the iteration."""
     from oracle import restate as R
     from trainer import Cyc_Trainer
     from ctagan.graphs import GraphedTrainer
@@ -97,44 +105,42 @@ def _run_cyc(mode, steps, size=64, precision="fp32"):
     tr.fake_A_buffer, tr.fake_B_buffer = ReplayBuffer(2), ReplayBuffer(2)
     batches = [R.synthetic_pair(1, size, seed=500 + i, phantom=True) for i in range(steps)]
     random.seed(7)
+    nets = (tr.netG_A2B, tr.netG_B2A, tr.netD_A, tr.netD_B)
+
+    def snap(losses):
+        torch.cuda.synchronize()
+        return ({k: float(v) for k, v in losses.items()}, [p.detach().clone() for n in nets for p in n.parameters()])
+
     out = []
     if mode == "graph":
-        g = GraphedTrainer(tr, warmup=1)
-        for i, (a, b) in enumerate(batches):
-            if i == 0:
-                continue                      # the graphed trainer's first call = 1 eager warm-up step + 1 replay on the same batch
-            if i == 1:
-                a, b = batches[0]
-                l = g.step_device((a.cuda(), b.cuda()))
-                out.append(None)
-            else:
-                l = g.step_device((a.cuda(), b.cuda()))
-            out.append({k: float(v) for k, v in l.items()})
+        g = GraphedTrainer(tr, warmup=1, replay_first=False)       # first call = the eager warm-up iteration + the capture
+        for a, b in batches:
+            out.append(snap(g.step_device((a.cuda(), b.cuda()))))
     else:
         fn = tr.step if mode == "fused" else tr.step_two_phase
-        for i, (a, b) in enumerate(batches):
-            if i == 1:
-                a, b = batches[0]
-            out.append({k: float(v) for k, v in fn({"A": a, "B": b}).items()})
+        for a, b in batches:
+            out.append(snap(fn({"A": a, "B": b})))
     ctagan.set_precision("bf16")
     return out
 
 
-def test_cyc_overlapped_schedule_equals_serial_order():
-    """The one-program schedule (device-side ReplayBuffer moves, discriminator updates beside the generator backward) must compute what
-    the reference's serial order computes -- including the buffer's random swaps, which start at step 2 here -- eagerly and as a
-    CUDA graph.  Float atomics in the thin weight-gradient kernels make two runs of the SAME schedule differ in the last bits, and
-    Adam turns that into ~1e-4 by step 2 and ~1e-3 by step 3 (measured serial-vs-serial), hence the growing tolerance; a wrong
-    swap or a missed dependency shows up as tens of percent."""
-    tol = [1e-5, 1e-5, 3e-3, 4e-2]        # (step 3 exceeded 1.5e-2 once in ~10 suite runs: chaos, not a schedule error)
-    serial = _run_cyc("two_phase", 4)
-    fused = _run_cyc("fused", 4)
-    graph = _run_cyc("graph", 4)
-    for i in range(4):
-        for k in serial[i]:
-            assert _close(fused[i][k], serial[i][k], tol[i]), ("fused", i, k, fused[i][k], serial[i][k])
-            if graph[i] is not None:
-                assert _close(graph[i][k], serial[i][k], tol[i]), ("graph", i, k, graph[i][k], serial[i][k])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cyc_overlapped_schedule_equals_serial_order(precision):
+    """The one-program schedule (device-side ReplayBuffer moves, discriminator updates beside the generator backward, weight-gradient
+    lanes, deferred gradient collection) must compute what the reference's serial order computes -- including the buffer's random
+    swaps -- eagerly and as a CUDA graph.  The library is bit-reproducible (tests/test_gpu_determinism.py) and the three schedules run
+    the same kernels on the same operands, so the comparison is EXACT: after every iteration every parameter of the four networks
+    (i.e. every gradient that went through Adam) and every loss must be bit-identical.  A missed dependency or a wrong swap
+    cannot hide behind a tolerance."""
+    serial = _run_cyc("two_phase", 4, precision=precision)
+    fused = _run_cyc("fused", 4, precision=precision)
+    graph = _run_cyc("graph", 4, precision=precision)
+    for name, run in (("fused", fused), ("graph", graph)):
+        for i in range(4):
+            assert run[i][0] == serial[i][0], (name, i, run[i][0], serial[i][0])
+            bad = [k for k, (p, q) in enumerate(zip(run[i][1], serial[i][1])) if not torch.equal(p, q)]
+            assert not bad, (name, "iteration", i, "parameters", bad[:8],
+                             float((run[i][1][bad[0]] - serial[i][1][bad[0]]).abs().max()))
 
 
 def test_train_loop_runs_graphed_and_decays_lr():

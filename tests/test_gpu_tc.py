@@ -101,7 +101,7 @@ def test_tc_fused_instancenorm_statistics(shape):
     Ho, Wo = (H + 2 * p - K) // s + 1, (W + 2 * p - K) // s + 1
     pool = ops.ZeroPool(2 * N * Co + 1, x.device)
     y, stats = prim.fprop_stats(x, pool)
-    assert y.shape == (N, Ho, Wo, Co) and pool.off == 2 * N * Co + 1      # the fused (tcgen05) path was taken
+    assert y.shape == (N, Ho, Wo, Co) and pool.off > 0      # the fused (tcgen05) path was taken (tickets came from the pool)
     yf = y.float()
     mean = yf.mean((1, 2)); var = yf.var((1, 2), unbiased=False)
     assert float((stats[..., 0] - mean).abs().max()) <= 2e-3 * float(var.sqrt().max())
@@ -145,7 +145,7 @@ def test_grouped_launch_equals_one_launch_per_group(case):
         y_ref, st_ref = torch.cat([a for a, _ in refs]), torch.cat([b for _, b in refs])
         assert ops.launch_count() > 0
         assert torch.equal(y, y_ref), (order, "fprop", maxrel(y.float(), y_ref.float()))
-        assert maxrel(st, st_ref) <= 1e-5, (order, "stats", maxrel(st, st_ref))
+        assert torch.equal(st, st_ref), (order, "stats", maxrel(st, st_ref))
         assert torch.equal(gp.fprop(x, use_bias=False), y_ref)
         dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6)).cuda().bfloat16()
         dx = gp.bprop(dy, (H, W))
@@ -154,7 +154,7 @@ def test_grouped_launch_equals_one_launch_per_group(case):
         dw, db = gp.wgrad(dy, x, want_bias=True)
         for k, q in enumerate(members):
             dwk, dbk = q.wgrad(dy[k * B:(k + 1) * B], x[k * B:(k + 1) * B], want_bias=True)
-            assert maxrel(dw[k], dwk) <= 1e-5, (order, "wgrad", k, maxrel(dw[k], dwk))
+            assert maxrel(dw[k], dwk) <= 1e-5, (order, "wgrad", k, maxrel(dw[k], dwk))      # (the split-K counts differ)
             assert maxrel(db[k], dbk) <= 1e-5, (order, "bgrad", k)
 
 
@@ -180,17 +180,18 @@ def test_grouped_cyc_schedule_matches_stream_schedule():
 
 
 @pytest.mark.parametrize("N", [1, 3, 8])
-def test_cta_pair_kernel_equals_single_cta_kernel(N, monkeypatch):
-    """cta_group::2 variant of the convolution (256 x BN tiles over two SMs, odd tile counts padded with a masked tile; opt-in
-    CTAGAN_TC_PAIR=1) against the default single-CTA kernel: same MMAs in the same order, so the result is bit-identical."""
+def test_fused_statistics_are_bit_reproducible(N):
+    """The statistics epilogue has no floating-point atomics (per-tile partial sums, added in tile order by the last CTA): the
+    same launch gives the same bits every time, and the ticket buffer is zero again afterwards."""
     from ctagan import engine as E, ops
     g = torch.Generator().manual_seed(3)
     prim = E.ConvPrim((torch.randn(256, 256, 3, 3, generator=g) / 48).cuda(), None, 1, 0)
     x = torch.randn(N, 66, 66, 256, generator=g).cuda().bfloat16()
-    monkeypatch.delenv("CTAGAN_TC_PAIR", raising=False)
-    y0, s0 = prim.fprop_stats(x, ops.ZeroPool(2 * N * 256 + 8, x.device))
-    monkeypatch.setenv("CTAGAN_TC_PAIR", "1")
-    y1, s1 = prim.fprop_stats(x, ops.ZeroPool(2 * N * 256 + 8, x.device))
-    torch.cuda.synchronize()
-    assert torch.equal(y0, y1)
-    assert maxrel(s1, s0) <= 1e-6
+    pool = ops.ZeroPool(64, x.device)
+    y0, s0 = prim.fprop_stats(x, pool)
+    for _ in range(5):
+        pool.off = 0                                  # the same ticket slice again: the kernel must have re-armed it
+        y1, s1 = prim.fprop_stats(x, pool)
+        torch.cuda.synchronize()
+        assert torch.equal(y0, y1) and torch.equal(s0, s1)
+    assert float(pool.buf.abs().max()) == 0.0
