@@ -317,8 +317,9 @@ __global__ void l1_bwd_kernel(const float *__restrict__ a, const float *__restri
   }
 }
 
-__global__ void __launch_bounds__(256) mse_const_fwd_kernel(const float *__restrict__ p, float target, float *loss, double *acc,
-                                                            long long n) {
+__global__ void __launch_bounds__(256) mse_const_fwd_kernel(const float *__restrict__ p, float target, const float *__restrict__ target_dev,
+                                                            float *loss, double *acc, long long n) {
+  if (target_dev) target = __ldg(target_dev);        // the constant lives on the device (a (1,1) target tensor): no host read
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float d = p[i] - target;
@@ -327,8 +328,9 @@ __global__ void __launch_bounds__(256) mse_const_fwd_kernel(const float *__restr
   block_finish((double)s, acc, loss, 1.0 / (double)n);
 }
 
-__global__ void mse_const_bwd_kernel(const float *__restrict__ p, float target, const float *__restrict__ gloss, float *__restrict__ gp,
-                                     long long n) {
+__global__ void mse_const_bwd_kernel(const float *__restrict__ p, float target, const float *__restrict__ target_dev,
+                                     const float *__restrict__ gloss, float *__restrict__ gp, long long n) {
+  if (target_dev) target = __ldg(target_dev);
   const float g = 2.f * __ldg(gloss) / (float)n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     gp[i] = g * (p[i] - target);
@@ -477,16 +479,17 @@ extern "C" int ctagan_l1_bwd(const float *a, const float *b, const float *gloss,
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
-extern "C" int ctagan_mse_const_fwd(const float *p, float target, float *loss, double *acc, int64_t n, void *stream) {
+extern "C" int ctagan_mse_const_fwd(const float *p, float target, const float *target_dev, float *loss, double *acc, int64_t n, void *stream) {
   CTAGAN_REQUIRE(p && loss && acc && n > 0, "mse_const_fwd: bad arguments");
   LOSS_PROLOGUE(mse);
-  mse_const_fwd_kernel<<<red_blocks(n), 256, 0, st>>>(p, target, loss, acc, n);
+  mse_const_fwd_kernel<<<red_blocks(n), 256, 0, st>>>(p, target, target_dev, loss, acc, n);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
-extern "C" int ctagan_mse_const_bwd(const float *p, float target, const float *gloss, float *gp, int64_t n, void *stream) {
+extern "C" int ctagan_mse_const_bwd(const float *p, float target, const float *target_dev, const float *gloss, float *gp, int64_t n,
+                                    void *stream) {
   CTAGAN_REQUIRE(p && gloss && gp && n > 0, "mse_const_bwd: bad arguments");
-  mse_const_bwd_kernel<<<ew_blocks2(n), 256, 0, (cudaStream_t)stream>>>(p, target, gloss, gp, n);
+  mse_const_bwd_kernel<<<ew_blocks2(n), 256, 0, (cudaStream_t)stream>>>(p, target, target_dev, gloss, gp, n);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }

@@ -12,8 +12,8 @@ Weight packing (fp32 master -> bf16 [O][kh][kw][I]) is part of the captured grap
 packed-weight cache right before capture, so every replay re-packs from the current master weights at its start.  The Cyc
 step instead re-packs each network right AFTER its optimizer step (forced, so the kernels are captured there; the
 discriminators only once the generator backward, the last reader of their packed weights, is done) -- the next step then
-starts on its convolutions at once.  Consequence: weights edited out of band between replays (e.g. load_state_dict) need
-`refresh_weights()` before the next Cyc replay.
+starts on its convolutions at once.  Weights edited out of band between replays (load_state_dict, in-place copies) are
+detected through the parameters' version counters and re-packed before the next replay.
 """
 from __future__ import annotations
 
@@ -34,6 +34,7 @@ class GraphedTrainer:
         self.replay_first = replay_first
         self._graphs = None
         self._launches = 0
+        self._sig = None
         self.is_cyc = hasattr(trainer, "phase_G")
 
     # -- public ----------------------------------------------------------------------------------------------------------
@@ -48,6 +49,16 @@ class GraphedTrainer:
 
     def launches_per_step(self) -> int:
         return self._launches
+
+    def _weights_signature(self):
+        """Changes whenever a parameter is edited out of band (load_state_dict, `.copy_`, `.data` swaps): tensor versions and storage
+        addresses of every parameter.  The captured Adam kernels update parameters in place without touching either."""
+        sig = 0
+        for m in self.t.__dict__.values():
+            if isinstance(m, torch.nn.Module):
+                for p in m.parameters():
+                    sig = (sig * 1000003 + p._version * 31 + p.data_ptr()) & 0xFFFFFFFFFFFF
+        return sig
 
     def refresh_weights(self):
         """Re-pack every network from its master weights now (after load_state_dict or any out-of-band edit between replays)."""
@@ -70,6 +81,10 @@ class GraphedTrainer:
             if not self.replay_first:
                 return t.last_losses         # the eager warm-up iteration was this call's iteration; the capture itself executes nothing
         E.invalidate_weight_cache()          # eager users after us must not trust capture-time packed weights
+        sig = self._weights_signature()
+        if sig != self._sig:                 # weights were edited between replays (e.g. load_state_dict): the Cyc graph re-packs only AFTER its
+            self.refresh_weights()           # optimizer steps, so re-pack from the master weights now
+            self._sig = self._weights_signature()
         if self.is_cyc:
             self._sel.copy_(t.plan_replay(static[0].shape[0]), non_blocking=True)   # this step's ReplayBuffer decisions (host RNG)
             self._graphs[0].replay()
@@ -113,3 +128,4 @@ class GraphedTrainer:
             t.step_count -= 1
             self._graphs = (g,)
         self._launches = ops.launch_count() - n0
+        self._sig = self._weights_signature()

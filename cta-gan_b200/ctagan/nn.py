@@ -329,10 +329,10 @@ class Discriminator_m(_DiscBase):
                 result.append([a.permute(0, 3, 1, 2) for a in sink] + [last])
             else:
                 result.append([last])
-            if i != self.num_D - 1:
+            if i != self.num_D - 1:                # tf.center_crop(input, int(s/2)), Model/HdGan.py:251 (torchvision's rounding rule)
                 c = int(s / 2)
-                o = (s - c) // 2
-                cur = cur[:, :, o:o + c, o:o + c].contiguous()
+                top, left = int(round((cur.size(2) - c) / 2.0)), int(round((cur.size(3) - c) / 2.0))
+                cur = cur[:, :, top:top + c, left:left + c].contiguous()
         return result
 
 
@@ -764,9 +764,20 @@ def l1_loss(a, b):
     return _L1Fn.apply(a, b)
 
 
-def mse_const(p, target: float):
+def mse_const(p, target):
+    """mean((p - target)^2) against a constant: a Python number, or a 1-element tensor whose VALUE is read on the device at kernel time
+    (never cached by object identity; CPU tensors are read on the host)."""
     ops.ensure_device()
-    return _MseConstFn.apply(p, float(target))
+    if torch.is_tensor(target):
+        if target.numel() != 1:
+            raise NotImplementedError("MSELoss here takes a broadcast constant target (CycTrainer.py:83-84)")
+        if not target.is_cuda:
+            target = float(target)
+        else:
+            target = target.detach().reshape(1).float()
+    else:
+        target = float(target)
+    return _MseConstFn.apply(p, target)
 
 
 def smooothing_loss(y_pred):
@@ -787,19 +798,7 @@ class L1Loss(nn.Module):
 
 
 class MSELoss(nn.Module):
-    """torch.nn.MSELoss for the only way the trainers use it: prediction vs a constant (1,1) target tensor."""
+    """torch.nn.MSELoss for the only way the trainers use it: prediction vs a constant (1,1) target tensor (or a number)."""
 
     def forward(self, pred, target):
-        if torch.is_tensor(target):
-            if target.numel() != 1:
-                raise NotImplementedError("MSELoss here takes a broadcast constant target (CycTrainer.py:83-84)")
-            key = id(target)
-            tv = _TARGET_CACHE.get(key)
-            if tv is None:
-                tv = float(target.item())
-                _TARGET_CACHE[key] = tv
-            target = tv
-        return mse_const(pred, float(target))
-
-
-_TARGET_CACHE = {}
+        return mse_const(pred, target)

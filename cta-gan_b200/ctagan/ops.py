@@ -354,17 +354,26 @@ def l1_bwd(a, b, gloss):
     return ga
 
 
-def mse_const_fwd(p, target: float):
+def _mse_target(target):
+    """(scalar, device pointer): a float constant, or a 1-element fp32 CUDA tensor that the kernel reads on the device."""
+    if torch.is_tensor(target):
+        return 0.0, _p(target)
+    return float(target), None
+
+
+def mse_const_fwd(p, target):
     loss, acc = _scalar_out(p)
+    tv, tp = _mse_target(target)
     _count(1)
-    L.check(L.load().ctagan_mse_const_fwd(_p(p), float(target), _p(loss), _p(acc), p.numel(), _stream()))
+    L.check(L.load().ctagan_mse_const_fwd(_p(p), tv, tp, _p(loss), _p(acc), p.numel(), _stream()))
     return loss
 
 
-def mse_const_bwd(p, target: float, gloss):
+def mse_const_bwd(p, target, gloss):
     gp = torch.empty_like(p)
+    tv, tp = _mse_target(target)
     _count(1)
-    L.check(L.load().ctagan_mse_const_bwd(_p(p), float(target), _p(gloss), _p(gp), p.numel(), _stream()))
+    L.check(L.load().ctagan_mse_const_bwd(_p(p), tv, tp, _p(gloss), _p(gp), p.numel(), _stream()))
     return gp
 
 

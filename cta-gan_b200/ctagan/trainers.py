@@ -99,8 +99,9 @@ class _TrainerBase:
         c = self.config
         c.setdefault("precision", "bf16")
         c.setdefault("log_every", 50)
+        c.setdefault("synthetic", False)           # opt-in: a run on the reference's own Yaml must never silently train on synthetic discs
         c.setdefault("synthetic_batches", 100)
-        c.setdefault("save_checkpoints", True)
+        c.setdefault("save_checkpoints", not c["synthetic"])      # synthetic runs do not overwrite trained models unless asked to
         self.rank, self.world, self.local_rank = _dist_env()
         torch.cuda.set_device(self.local_rank)
         self.device = torch.device("cuda", self.local_rank)
@@ -129,12 +130,40 @@ class _TrainerBase:
         shape = (c["batchSize"], c["input_nc"], c["size"], c["size"])
         return {k: torch.empty(shape, dtype=torch.float32, device=self.device) for k in self.data_keys}
 
-    def _loader(self, list_key="train_list", seed_offset=0):
+    def _loader(self, list_key="train_list", seed_offset=0, train=True):
+        """`synthetic: true` (explicit opt-in) -> the synthetic CT-like stream; otherwise the slice list named by the Yaml key, read and
+        pre-processed by the GPU input pipeline (ctagan.data; trainer/datasets.py:36-119).  There is no silent fallback between them."""
         c = self.config
-        path = c.get(list_key)
-        if c.get("synthetic", True) or not (path and os.path.exists(path)):
+        if c["synthetic"]:
             return SyntheticSlices(c["batchSize"], c["size"], c["synthetic_batches"], 42 + self.rank + seed_offset, self.data_keys)
-        raise NotImplementedError("DICOM list datasets (trainer/datasets.py) are outside the hot path; set synthetic: true")
+        path = c.get(list_key)
+        if not (path and os.path.exists(path)):
+            raise FileNotFoundError(f"{list_key}={path!r} does not exist (set `synthetic: true` for the synthetic CT-like stream)")
+        from .data import SliceListLoader
+        return SliceListLoader(path, c["batchSize"], c["size"], self.data_keys, device=self.device, rank=self.rank, world=self.world,
+                               augment=train and self.name == "CycleGan", noise_level=c.get("noise_level", 0), seed=42 + self.rank + seed_offset)
+
+    def sync_replicas(self):
+        """Data parallelism only exchanges gradients, so every rank must START from the same weights: broadcast rank 0's parameters
+        (after construction and after every checkpoint load), as DistributedDataParallel does."""
+        if self.world <= 1 or not dist.is_initialized():
+            return
+        with torch.no_grad():
+            for m in self.__dict__.values():
+                if isinstance(m, torch.nn.Module):
+                    for p in m.parameters():
+                        dist.broadcast(p.data, src=0)
+        E.invalidate_weight_cache()
+
+    def load_checkpoint(self, net, fname, required=True):
+        """load_state_dict(torch.load(save_root + fname)) (CycTrainer.py:239 etc.); a missing file is an error unless required=False."""
+        path = os.path.join(self.config.get("save_root") or "", fname)
+        if not os.path.exists(path):
+            if required:
+                raise FileNotFoundError(f"checkpoint {path} not found")
+            return False
+        net.load_state_dict(torch.load(path, map_location=self.device, weights_only=True))
+        return True
 
     def load_batch(self, batch):
         """H2D copy of one batch into the preallocated device inputs (CycTrainer.py:80-82,140-141)."""
@@ -170,23 +199,26 @@ class _TrainerBase:
                 self._log(epoch, i, len(loader))
             self._save(epoch, self.checkpoint_nets())
 
+    test_checkpoint = "aa.pth"          # CycTrainer.py:239 / RegTrainer.py:245: `save_root + 'aa.pth'`
+
     @torch.no_grad()
-    def test(self, loader=None):
-        """Generator-only inference loop (CycTrainer.py:238-360 hot part: `fake_B = netG_A2B(real_A)`), batch-split across
-        ranks without any collective; returns mean MAE / PSNR of the synthetic pairs."""
-        loader = loader or self._loader("test_list", seed_offset=1000)
-        mae = psnr = 0.0
-        n = 0
+    def test(self, loader=None, checkpoint=None):
+        """The reference's test() (CycTrainer.py:238-360): load the generator checkpoint, `fake_B = netG_A2B(real_A)` per batch, then the
+        evaluation metrics -- computed ON THE GPU by fused reduction kernels (ctagan.evaluate: window, 0.3-threshold masks, MAE / PSNR /
+        UQI / SSIM, int16 conversion), batched, with one host read at the end instead of a `.cpu().numpy()` round trip per slice.
+        Batch-split across ranks without any collective.  checkpoint: file name under save_root (default: the reference's),
+        False to evaluate the weights in memory."""
+        from .evaluate import Evaluator
+        if checkpoint is not False:
+            self.load_checkpoint(self.netG_A2B, checkpoint or self.config.get("test_checkpoint") or self.test_checkpoint)
+        loader = loader or self._loader("test_list", seed_offset=1000, train=False)
+        ev = Evaluator(self.device)
         ka, kb = self.data_keys[0], self.data_keys[-1]
         for batch in loader:
             a = batch[ka].to(self.device, non_blocking=True)
             b = batch[kb].to(self.device, non_blocking=True)
-            fake = self.netG_A2B(a)
-            mae += float((fake - b).abs().mean())
-            mse = float(((fake - b) ** 2).mean())
-            psnr += 10.0 * torch.log10(torch.tensor(4.0 / max(mse, 1e-12))).item()
-            n += 1
-        out = {"MAE": mae / max(n, 1), "PSNR": psnr / max(n, 1), "slices": n * self.config["batchSize"]}
+            ev.add(self.netG_A2B(a), b)
+        out = ev.result()
         if self.rank == 0:
             print(f"[{self.name}] test: {out}", flush=True)
         return out
@@ -218,6 +250,7 @@ class Cyc_Trainer(_TrainerBase):
         self.fake_A_buffer, self.fake_B_buffer = ReplayBuffer(), ReplayBuffer()
         self._sync_G = GradSync(itertools.chain(self.netG_A2B.parameters(), self.netG_B2A.parameters()))
         self._sync_DA, self._sync_DB = GradSync(self.netD_A.parameters()), GradSync(self.netD_B.parameters())
+        self.sync_replicas()
 
     def update_learning_rate(self):
         c = self.config
@@ -508,6 +541,7 @@ class Reg_Trainer(_TrainerBase):
         self.target_real, self.target_fake = 1.0, 0.0
         self._sync_GR = GradSync(itertools.chain(self.R_A.parameters(), self.netG_A2B.parameters()))
         self._sync_D = GradSync(self.netD_B.parameters())
+        self.sync_replicas()
 
     def update_learning_rate(self):
         c = self.config
@@ -588,6 +622,11 @@ class Hd_Trainer_x1(Reg_Trainer):
     name = "HdGan_x1"
     data_keys = ("A2", "B1", "B2")
     lam_corr, lam_adv, lr_d = "Corr_lamda1", "Adv_lamda1", "lrd"
+    test_checkpoint = "netG_A2B_x_3.pth"          # HdTrainer.py:285
+
+    def checkpoint_nets(self):
+        """HdTrainer.py:275-280: the `_x_` names that stage 2 loads (`netG_A2B_x_45.pth`, `R_A_x_45.pth`, :697-699)."""
+        return {"netG_A2B_x_{st}.pth": self.netG_A2B, "R_A_x_{st}.pth": self.R_A, "netD_B_x_{st}.pth": self.netD_B}
 
     def update_learning_rate(self):
         c = self.config
@@ -617,12 +656,24 @@ class Hd_Trainer_x2(Hd_Trainer_x1):
         real_B1, real_B2 = tensors[1], tensors[2]
         return self.config["Corr_lamda2"] * N.masked_l1_loss(SysRegist_A2B, real_B1, real_B2)
 
-    def train(self):
+    stage1_epoch = 45
+
+    def load_stage1(self):
+        """HdTrainer.py:697-699: stage 2 starts from the stage-1 generator and registration network.  Missing files are an error (the
+        reference crashes in torch.load); `stage1_required: false` in the config starts from the current weights, loudly."""
         c = self.config
-        for fname, net in (("netG_A2B_x_45.pth", self.netG_A2B), ("R_A_x_45.pth", self.R_A)):    # HdTrainer.py:697-699
-            path = os.path.join(c.get("save_root") or "", fname)
-            if os.path.exists(path):
-                net.load_state_dict(torch.load(path, map_location=self.device))
+        ep = c.get("stage1_epoch", self.stage1_epoch)
+        required = c.get("stage1_required", True)
+        ok = [self.load_checkpoint(net, f"{prefix}_x_{ep}.pth", required=required)
+              for prefix, net in (("netG_A2B", self.netG_A2B), ("R_A", self.R_A))]
+        if not all(ok) and self.rank == 0:
+            print(f"[{self.name}] WARNING: stage-1 checkpoints *_x_{ep}.pth not found under {c.get('save_root')!r}: "
+                  "stage 2 starts from the weights in memory", flush=True)
+        self.sync_replicas()
+        return all(ok)
+
+    def train(self):
+        self.load_stage1()
         super().train()
 
 
@@ -649,6 +700,7 @@ class P2p_Trainer(_TrainerBase):
         self.inputs = self._alloc_inputs()
         self.target_real, self.target_fake = 1.0, 0.0
         self._sync_G, self._sync_D = GradSync(self.netG_A2B.parameters()), GradSync(self.netD_B.parameters())
+        self.sync_replicas()
 
     def update_learning_rate(self):
         c = self.config

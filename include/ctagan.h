@@ -201,8 +201,10 @@ int ctagan_warp_bwd(const float *gout, const float *src, const float *flow, floa
 #define CTAGAN_LOSS_ACC_DOUBLES 1024
 int ctagan_l1_fwd(const float *a, const float *b, float *loss, double *acc, int64_t n, void *stream);
 int ctagan_l1_bwd(const float *a, const float *b, const float *gloss, float *ga, int64_t n, void *stream);
-int ctagan_mse_const_fwd(const float *p, float target, float *loss, double *acc, int64_t n, void *stream);
-int ctagan_mse_const_bwd(const float *p, float target, const float *gloss, float *gp, int64_t n, void *stream);
+/* mse_const: the constant is `target`, or -- when target_dev != NULL -- the fp32 value target_dev points to on the device (the
+ * reference keeps its targets as (1,1) device tensors, CycTrainer.py:83-84: no host read, graph-capturable). */
+int ctagan_mse_const_fwd(const float *p, float target, const float *target_dev, float *loss, double *acc, int64_t n, void *stream);
+int ctagan_mse_const_bwd(const float *p, float target, const float *target_dev, const float *gloss, float *gp, int64_t n, void *stream);
 int ctagan_smooth_fwd(const float *flow, float *loss, double *acc, int B, int C, int H, int W, void *stream);
 int ctagan_smooth_bwd(const float *flow, const float *gloss, float *gflow, int B, int C, int H, int W, void *stream);
 int ctagan_masked_l1_fwd(const float *warped, const float *b1, const float *b2, float *loss, double *acc, int64_t n, void *stream);

@@ -233,11 +233,210 @@ def main():
     finally:
         torch.Tensor.cuda = orig_cuda
 
-    G["meta"] = {"torch": torch.__version__, "reference": ref.root, "note": "all tensors fp32 CPU, seed 42 init"}
+    G["meta"] = {"torch": str(torch.__version__), "reference": ref.root, "note": "all tensors fp32 CPU, seed 42 init"}
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     torch.save(G, OUT)
     print("wrote", OUT, os.path.getsize(OUT) / 1e6, "MB;", len(G), "entries")
 
 
+# ======================================================================================================================
+# golden_v2: the iteration bodies the reference cannot run as a trainer are pinned by exec'ing THE REFERENCE'S OWN SOURCE LINES
+# (read from the reference tree at run time, never copied into this repository) on the reference's own nn.Modules
+# ======================================================================================================================
+OUT2 = os.path.join(os.path.dirname(HERE), "tests", "golden", "golden_v2.pt")
+
+
+def reference_lines(ref_root, rel_path, first_marker, last_marker, after=None, lo=None, hi=None):
+    """Source lines [first_marker .. last_marker] (inclusive, dedented) of a reference file; the span is looked up by its first and
+    last statement (starting the search after the line containing `after`) and must lie inside the cited range [lo, hi]."""
+    import textwrap
+    lines = open(os.path.join(ref_root, rel_path), encoding="utf-8").read().split("\n")
+    start = 0
+    if after is not None:
+        start = next(i for i, l in enumerate(lines) if after in l)
+    a = next(i for i in range(start, len(lines)) if first_marker in lines[i])
+    b = next(i for i in range(a, len(lines)) if last_marker in lines[i])
+    assert lo is None or (lo <= a + 1 and b + 1 <= hi), (rel_path, a + 1, b + 1, lo, hi)
+    return textwrap.dedent("\n".join(lines[a:b + 1])), (a + 1, b + 1)
+
+
+def _adam(params, lr=1e-4):
+    return torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999))
+
+
+def weight_fp(sd):
+    return {k: (float(v.detach().double().sum()), float(v.detach().double().abs().sum())) for k, v in sd.items()}
+
+
+def main_v2():
+    import copy
+    import types
+    ref = load_reference()
+    G = {}
+    mse, l1 = torch.nn.MSELoss(), torch.nn.L1Loss()
+    t1, t0 = torch.ones(1, 1), torch.zeros(1, 1)
+    cfg = {"Smooth_lamda": 10, "Corr_lamda1": 20, "Corr_lamda2": 2, "Adv_lamda1": 1, "Adv_lamda": 1, "P2P_lamda": 100}
+    env = {"torch": torch, "copy": copy, "Variable": (lambda x, **k: x), "smooothing_loss": ref.utils.smooothing_loss, "D": 2}
+
+    # ---------------- masked L1 (HdTrainer.py:726-735) on its own: value and gradient ----------------
+    src, span = reference_lines(ref.root, "trainer/HdTrainer.py", "bb = real_B1", "SR_loss2 = self.config['Corr_lamda2']",
+                                after="class Hd_Trainer_x2", lo=705, hi=751)
+    G["masked_l1.ref_lines"] = span
+    g = torch.Generator().manual_seed(21)
+    for name, S in (("a", 48), ("b", 64)):
+        b2 = (torch.rand(2, 1, S, S, generator=g) * 2 - 1)
+        b1 = (b2 * 1.7 + 0.1 * torch.randn(2, 1, S, S, generator=g)).clamp(-1, 1)
+        warped = (b2 + 0.2 * torch.randn(2, 1, S, S, generator=g)).clamp(-1, 1)
+        warped[0, 0, :4] = 0.0                                   # exact zeros inside the mask: the `== 0 -> -1` fill of the warped image
+        b1[0, 0, :4] = 0.9
+        wv = warped.clone().requires_grad_(True)
+        loc = {"self": types.SimpleNamespace(config=cfg, L1_loss=l1), "real_B1": b1.clone(), "real_B2": b2.clone(), "SysRegist_A2B": wv * 1.0}
+        exec(src, dict(env), loc)
+        loc["SR_loss2"].backward()
+        wm = warped.clone().requires_grad_(True)
+        mine = cfg["Corr_lamda2"] * R.masked_l1(wm, b1, b2)
+        mine.backward()
+        assert torch.equal(loc["SR_loss2"].detach(), mine.detach()) and torch.equal(wv.grad, wm.grad), name
+        G[f"masked_l1.{name}"] = {"warped": warped, "b1": b1, "b2": b2, "loss": (loc["SR_loss2"].detach() / cfg["Corr_lamda2"]).clone(),
+                                  "grad": (wv.grad / cfg["Corr_lamda2"]).clone()}
+
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self        # transformer.py:21 hard-codes .cuda()
+    try:
+        def reg_like_self(multiscale):
+            seed()
+            s = types.SimpleNamespace(config=cfg, L1_loss=l1, MSE_loss=mse, target_real=t1, target_fake=t0)
+            s.netG_A2B = ref.HdGan.Generator(1, 1, n_residual_blocks=3)          # HdTrainer.py:99-105 / :610-616 creation order
+            s.netD_B = ref.HdGan.Discriminator_m(1) if multiscale else ref.HdGan.Discriminator(1)
+            s.optimizer_D_B = _adam(s.netD_B.parameters())
+            s.R_A = ref.reg.Reg(256, 256, 1, 1)
+            s.spatial_transform = ref.transformer.Transformer_2D()
+            s.optimizer_R_A = _adam(s.R_A.parameters())
+            s.optimizer_G = _adam(s.netG_A2B.parameters())
+            s.criterionGAN = ref.HdGan.GANLoss()
+            for k in ("input_A2", "input_B", "input_B2"):
+                setattr(s, k, torch.empty(1, 1, 256, 256))
+            return s
+
+        def hd_batch(it):
+            rA, rB = R.synthetic_pair(1, 256, seed=300 + it, phantom=True)
+            return {"A2": rA, "B1": (rB * 1.7).clamp(-1, 1), "B2": rB}
+
+        # ---------------- Hd stage 2 (HdTrainer.py:705-751) ----------------
+        src, span = reference_lines(ref.root, "trainer/HdTrainer.py", "real_A2 = Variable(self.input_A2.copy_(batch['A2']))",
+                                    "self.optimizer_D_B.step()", after="class Hd_Trainer_x2", lo=705, hi=751)
+        G["hd_x2_step.ref_lines"] = span
+        s = reg_like_self(True)
+        seed(); st = R.RegState(multiscale_d=True, n_blocks=3)
+        losses = []
+        for it in range(2):
+            batch = hd_batch(it)
+            loc = {"self": s, "batch": {k: v.clone() for k, v in batch.items()}}
+            exec(src, dict(env), loc)
+            mine = R.hd_x2_step(st, batch["A2"], batch["B1"], batch["B2"])
+            for k in ("SR_loss", "SR_loss2", "adv_loss", "SM_loss", "toal_loss", "loss_D_B"):
+                assert float(loc[k]) == mine[k], (it, k, float(loc[k]), mine[k])
+            losses.append(mine)
+        for (k, p_), (k2, p2) in zip(s.netG_A2B.named_parameters(), st.G.items()):
+            assert k == k2 and torch.equal(p_, p2), k
+        G["hd_x2_step.losses_256_nb3"] = losses
+        G["hd_x2_step.G_fp_after2"] = weight_fp(st.G)
+        G["hd_x2_step.D_fp_after2"] = weight_fp(st.D)
+
+        # ---------------- Hd stage 1 (HdTrainer.py:192-228) ----------------
+        src, span = reference_lines(ref.root, "trainer/HdTrainer.py", "real_A2 = Variable(self.input_A2.copy_(batch['A2']))",
+                                    "self.optimizer_D_B.step()", after="class Hd_Trainer_x1", lo=192, hi=228)
+        G["hd_x1_step.ref_lines"] = span
+        s = reg_like_self(False)
+        seed(); st = R.RegState(n_blocks=3)
+        losses = []
+        for it in range(2):
+            batch = hd_batch(it)
+            loc = {"self": s, "batch": {k: v.clone() for k, v in batch.items()}}
+            exec(src, dict(env), loc)
+            mine = R.reg_step(st, batch["A2"], batch["B2"], corr=cfg["Corr_lamda1"], adv=cfg["Adv_lamda1"], smooth=cfg["Smooth_lamda"])
+            for k in ("SR_loss", "adv_loss", "SM_loss", "toal_loss", "loss_D_B"):
+                assert float(loc[k]) == mine[k], (it, k, float(loc[k]), mine[k])
+            losses.append(mine)
+        G["hd_x1_step.losses_256_nb3"] = losses
+        G["hd_x1_step.G_fp_after2"] = weight_fp(st.G)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+    # ---------------- pix2pix (p2pTrainer.py:122-148) ----------------
+    src, span = reference_lines(ref.root, "trainer/p2pTrainer.py", "real_A = Variable(self.input_A.copy_(batch['A']))",
+                                "self.optimizer_D_B.step()", lo=122, hi=148)
+    G["p2p_step.ref_lines"] = span
+    seed()
+    s = types.SimpleNamespace(config=cfg, L1_loss=l1, MSE_loss=mse, target_real=t1, target_fake=t0)
+    s.netG_A2B = ref.CycleGan.Generator(1, 1)                                  # p2pTrainer.py:60-63
+    s.netD_B = ref.CycleGan.Discriminator(2)
+    s.optimizer_D_B = _adam(s.netD_B.parameters())
+    s.optimizer_G = _adam(s.netG_A2B.parameters())
+    s.input_A, s.input_B = torch.empty(1, 1, 64, 64), torch.empty(1, 1, 64, 64)
+    seed(); st = R.P2pState()
+    losses = []
+    for it in range(2):
+        rA, rB = R.synthetic_pair(1, 64, seed=400 + it, phantom=True)
+        loc = {"self": s, "batch": {"A": rA.clone(), "B": rB.clone()}}
+        exec(src, dict(env), loc)
+        mine = R.p2p_step(st, rA, rB)
+        for k in ("loss_L1", "loss_GAN_A2B", "toal_loss", "loss_D_B"):
+            assert float(loc[k]) == mine[k], (it, k, float(loc[k]), mine[k])
+        losses.append(mine)
+    G["p2p_step.losses_64"] = losses
+    G["p2p_step.G_fp_after2"] = weight_fp(st.G)
+
+    # ---------------- Discriminator_m(num_D=2) + GANLoss weights [1.8, 0.2] (HdGan.py:236-256,269-293) ----------------
+    seed(); dm = ref.HdGan.Discriminator_m(1, num_D=2)
+    seed(); dm_sd = R.init_discriminator_m(1, num_D=2)
+    G["discriminator_m2.state_fp"] = check_state(dm, dm_sd, "Discriminator_m(num_D=2)")
+    x, _ = R.synthetic_pair(2, 128, seed=9, phantom=True)
+    feats_ref = dm(x)
+    feats = R.discriminator_m_forward(dm_sd, x, num_D=2)
+    assert len(feats_ref) == 2
+    for sr_, sm_ in zip(feats_ref, feats):
+        for fr, f in zip(sr_, sm_):
+            assert torch.equal(fr, f)
+    gl = ref.HdGan.GANLoss()
+    for flag in (True, False):
+        assert torch.equal(gl(feats_ref, flag), R.gan_loss(feats, flag))
+        G[f"discriminator_m2.ganloss_{flag}"] = gl(feats_ref, flag).detach().clone()
+    G["discriminator_m2.last"] = [sc[-1].detach().clone() for sc in feats_ref]
+    G["discriminator_m2.feat_shapes"] = [[tuple(f.shape) for f in sc] for sc in feats_ref]
+
+    # ---------------- standalone layer modules: trainer/layers.py Conv / DownBlock / ResnetBlock, CycleGan.ResidualBlock ----------------
+    def layer_case(name, make, shape, tuple_out=False):
+        seed(7); m = make()
+        gx = torch.Generator().manual_seed(31)
+        x = torch.randn(*shape, generator=gx).requires_grad_(True)
+        y = m(x)
+        ys = y if tuple_out else (y,)
+        wt = [torch.randn(t.shape, generator=gx) for t in ys]
+        sum((t * w_).sum() for t, w_ in zip(ys, wt)).backward()
+        G[f"layer.{name}"] = {"state": {k: v.detach().clone() for k, v in m.state_dict().items()}, "x": x.detach().clone(),
+                              "y": [t.detach().clone() for t in ys], "wt": wt, "gx": x.grad.clone(),
+                              "gparams": {k: p_.grad.clone() for k, p_ in m.named_parameters() if p_.grad is not None}}
+
+    Lr = ref.layers
+    layer_case("conv_lrelu_resnet", lambda: Lr.Conv(8, 16, 3, 1, 1, activation="leaky_relu", init_func="kaiming", bias=True, use_resnet=True,
+                                                    use_norm=False), (2, 8, 16, 16))
+    layer_case("conv_norm_relu", lambda: Lr.Conv(8, 16, 3, 1, 1, activation="relu", init_func="kaiming", bias=True, use_resnet=False,
+                                                 use_norm=True), (2, 8, 12, 12))
+    layer_case("conv_1x1_none", lambda: Lr.Conv(16, 8, 1, 1, 0, activation=None, init_func="zeros", bias=True), (1, 16, 8, 8))
+    layer_case("downblock", lambda: Lr.DownBlock(2, 16, 3, 1, 1, activation="leaky_relu", init_func="kaiming", bias=True, use_resnet=True,
+                                                 use_norm=False), (2, 2, 16, 16), tuple_out=True)
+    layer_case("resnet_block", lambda: Lr.ResnetBlock(16, "reflect", Lr.norm_layer, False, True), (2, 16, 10, 10))
+    layer_case("resnet_transformer", lambda: Lr.ResnetTransformer(16, 2, "kaiming"), (1, 16, 8, 8))
+    layer_case("residual_block", lambda: ref.CycleGan.ResidualBlock(16), (2, 16, 12, 12))
+
+    G["meta"] = {"torch": str(torch.__version__), "reference": ref.root,
+                 "note": "iteration bodies: exec of the reference's own source lines on the reference's own modules; fp32 CPU"}
+    torch.save(G, OUT2)
+    print("wrote", OUT2, os.path.getsize(OUT2) / 1e6, "MB;", len(G), "entries")
+
+
 if __name__ == "__main__":
-    main()
+    if "--v2-only" not in sys.argv:
+        main()
+    main_v2()

@@ -79,8 +79,12 @@ def init_discriminator(input_nc: int = 1, key_fmt: str = "model.{i}") -> State:
     return sd
 
 
-def init_discriminator_m(input_nc: int = 1) -> State:
-    return init_discriminator(input_nc, key_fmt="scale0_layer{j}.0")
+def init_discriminator_m(input_nc: int = 1, num_D: int = 1) -> State:
+    """Discriminator_m parameters, Model/HdGan.py:215-221: one NLayerDiscriminator per scale, created in scale order."""
+    sd: State = OrderedDict()
+    for i in range(num_D):
+        sd.update(init_discriminator(input_nc, key_fmt="scale%d_layer{j}.0" % i))
+    return sd
 
 
 def _kaiming(cout, cin, k, act):
@@ -203,9 +207,18 @@ def discriminator_forward(sd: State, x: Tensor) -> Tensor:
     return F.avg_pool2d(y, y.shape[2:]).view(y.shape[0], -1)
 
 
-def discriminator_m_forward(sd: State, x: Tensor) -> List[List[Tensor]]:
-    """Discriminator_m.forward with the defaults num_D=1, getIntermFeat=True. Model/HdGan.py:236-256."""
-    return [discriminator_features(sd, x, key_fmt="scale0_layer{j}.0")]
+def discriminator_m_forward(sd: State, x: Tensor, num_D: int = 1) -> List[List[Tensor]]:
+    """Discriminator_m.forward with getIntermFeat=True, Model/HdGan.py:236-256: pass i runs scale (num_D-1-i) on the input centre-cropped
+    i times to half its size (torchvision center_crop, :251)."""
+    result = []
+    for i in range(num_D):
+        s = x.shape[2]
+        result.append(discriminator_features(sd, x, key_fmt="scale%d_layer{j}.0" % (num_D - 1 - i)))
+        if i != num_D - 1:
+            c = int(s / 2)
+            top, left = int(round((x.shape[2] - c) / 2.0)), int(round((x.shape[3] - c) / 2.0))      # torchvision.transforms.functional.center_crop
+            x = x[:, :, top:top + c, left:left + c]
+    return result
 
 
 def gan_loss(pred, target_is_real: bool) -> Tensor:

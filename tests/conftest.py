@@ -15,8 +15,11 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def golden():
+    """Vectors frozen from the real reference (oracle/make_golden.py): plain tensors / numbers / strings only (weights_only load)."""
     import torch
-    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_v1.pt"), weights_only=False)
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "golden_v1.pt"), weights_only=True)
+    g.update(torch.load(os.path.join(ROOT, "tests", "golden", "golden_v2.pt"), weights_only=True))
+    return g
 
 
 _ORDER = ["test_abi_and_host", "test_oracle", "test_ddp", "test_gpu_ops", "test_gpu_tc", "test_gpu_determinism", "test_gpu_modules",

@@ -155,3 +155,90 @@ def test_reg_fp32(fp32_mode, golden):
     R.smoothing_loss(R.reg_forward(leaf, xr, rb)).backward()
     _check_grads(net, leaf, tol=5e-3)
     assert l2rel(xa.grad, xr.grad) <= 3e-2      # input gradient crosses 7 max-pools + many ReLU kinks
+
+
+def test_discriminator_m_two_scales_fp32(fp32_mode, golden):
+    """Discriminator_m(num_D=2): the centre-crop second scale (Model/HdGan.py:236-256) and GANLoss's scale weights [1.8, 0.2] (:273),
+    against outputs of the real reference module (golden_v2)."""
+    import Model.HdGan as H
+    from oracle import restate as R
+    _seed(); net = H.Discriminator_m(1, num_D=2)
+    for k, (shape, s, sa) in golden["discriminator_m2.state_fp"].items():
+        v = net.state_dict()[k]
+        assert tuple(v.shape) == tuple(shape) and abs(float(v.double().sum()) - s) <= 1e-6 * max(1.0, abs(s)), k
+    net = net.cuda()
+    x, _ = R.synthetic_pair(2, 128, seed=9, phantom=True)
+    feats = net(x.cuda())
+    assert [[tuple(f.shape) for f in sc] for sc in feats] == [[tuple(t) for t in sc] for sc in golden["discriminator_m2.feat_shapes"]]
+    for mine, ref in zip(feats, golden["discriminator_m2.last"]):
+        assert maxrel(mine[-1], ref) <= 1e-4, maxrel(mine[-1], ref)
+    gl = H.GANLoss()
+    for flag in (True, False):
+        ref = float(golden[f"discriminator_m2.ganloss_{flag}"])
+        assert abs(float(gl(feats, flag)) - ref) <= 1e-4 * abs(ref)
+
+
+LAYER_CASES = ["conv_lrelu_resnet", "conv_norm_relu", "conv_1x1_none", "downblock", "resnet_block", "resnet_transformer", "residual_block"]
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_standalone_layers_fp32(fp32_mode, golden, name):
+    """trainer/layers.py Conv / DownBlock / ResnetBlock / ResnetTransformer and Model/CycleGan.py ResidualBlock used on their own:
+    reference constructor signatures, reference state_dict keys, forward and backward against the real reference modules."""
+    import Model.CycleGan as M
+    import trainer.layers as Lr
+    make = {
+        "conv_lrelu_resnet": lambda: Lr.Conv(8, 16, 3, 1, 1, activation="leaky_relu", init_func="kaiming", bias=True, use_resnet=True, use_norm=False),
+        "conv_norm_relu": lambda: Lr.Conv(8, 16, 3, 1, 1, activation="relu", init_func="kaiming", bias=True, use_resnet=False, use_norm=True),
+        "conv_1x1_none": lambda: Lr.Conv(16, 8, 1, 1, 0, activation=None, init_func="zeros", bias=True),
+        "downblock": lambda: Lr.DownBlock(2, 16, 3, 1, 1, activation="leaky_relu", init_func="kaiming", bias=True, use_resnet=True, use_norm=False),
+        "resnet_block": lambda: Lr.ResnetBlock(16, "reflect", None, False, True),
+        "resnet_transformer": lambda: Lr.ResnetTransformer(16, 2, "kaiming"),
+        "residual_block": lambda: M.ResidualBlock(16),
+    }[name]
+    g = golden[f"layer.{name}"]
+    _seed(7); m = make()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["state"].keys())
+    for k in sd:
+        assert torch.equal(sd[k], g["state"][k]), k                   # same seed -> the reference's initial weights (same draws)
+    m = m.cuda()
+    x = g["x"].cuda().requires_grad_(True)
+    y = m(x)
+    ys = y if isinstance(y, tuple) else (y,)
+    assert len(ys) == len(g["y"])
+    for mine, ref in zip(ys, g["y"]):
+        assert mine.shape == ref.shape and maxrel(mine, ref) <= 1e-4, (name, maxrel(mine, ref))
+    sum((t * w.cuda()).sum() for t, w in zip(ys, g["wt"])).backward()
+    assert l2rel(x.grad, g["gx"]) <= 2e-3, (name, l2rel(x.grad, g["gx"]))
+    gmax = max(float(v.abs().max()) for v in g["gparams"].values())
+    for k, p in m.named_parameters():
+        ref = g["gparams"][k]
+        if float(ref.abs().max()) <= 1e-6 * gmax:                       # dead bias in front of InstanceNorm
+            continue
+        assert p.grad is not None and l2rel(p.grad, ref) <= 2e-3, (name, k)
+
+
+def test_mse_loss_tensor_targets_and_state_reload(fp32_mode):
+    """nn.MSELoss drop-in with tensor targets (CycTrainer.py:83-84): the VALUE is read, never cached by object identity; and
+    load_state_dict / in-place edits of a module invalidate its packed weights."""
+    import Model.CycleGan as M
+    p = torch.tensor([[0.25], [0.75]], device="cuda")
+    crit = fp32_mode.MSELoss()
+    for _ in range(3):                                                   # fresh target objects (recycled ids) with different values
+        assert abs(float(crit(p, torch.ones(1, 1).cuda())) - 0.3125) <= 1e-6
+        assert abs(float(crit(p, torch.zeros(1, 1).cuda())) - 0.3125) <= 1e-6
+        assert abs(float(crit(p, torch.full((1, 1), 0.5).cuda())) - 0.0625) <= 1e-6
+    t = torch.ones(1, 1).cuda()
+    assert abs(float(crit(p, t)) - 0.3125) <= 1e-6
+    t.fill_(0.25)                                                        # in-place edit of the same target object
+    assert abs(float(crit(p, t)) - 0.125) <= 1e-6
+    _seed(); net = M.Generator(1, 1, n_residual_blocks=1).cuda()
+    x = torch.rand(1, 1, 32, 32, device="cuda") * 2 - 1
+    with torch.no_grad():
+        y0 = net(x)
+        _seed(5); other = M.Generator(1, 1, n_residual_blocks=1)
+        net.load_state_dict(other.state_dict())
+        y1 = net(x)
+        y_ref = other.cuda()(x)
+    assert not torch.equal(y0, y1) and torch.equal(y1, y_ref)

@@ -5,7 +5,21 @@ import random
 import pytest
 import torch
 
+from util import grad_report, trainer_leaves
+
 pytestmark = pytest.mark.gpu
+
+# fp32 validation mode: EVERY parameter gradient of every network of the iteration is compared with the restated reference body
+# (per tensor and globally).  That is what makes these tests decisive about the plumbing of a step -- loss weights, signs, which
+# gradient reaches which network (warp -> fake_B and flow, flow -> Reg -> fake_B, D -> fake_B, ...): a wrong route or sign changes
+# whole tensors by O(1), three orders of magnitude above the fp32 tolerance, whereas a loss VALUE may barely notice it.
+G_TENSOR, G_GLOBAL = 5e-3, 2e-3
+# In the Reg / Hd / P2p bodies the discriminator update comes AFTER the generator's Adam step and re-runs the updated generator
+# (RegTrainer.py:189-198).  Adam's first step moves every weight by lr * sign(gradient): the sign of near-zero-gradient weights is
+# round-off, so the two updated generators -- and with them the fake slices the discriminator sees -- differ at the 1e-3 level,
+# and the discriminator gradients at ~1e-2 (measured 1.1-1.2e-2 global).  (The Cyc body takes its fakes from BEFORE the update:
+# there the discriminator gradients agree to 1e-6.)
+D_AFTER_G = (5e-2, 3e-2)
 
 
 def _seed(s=42):
@@ -30,20 +44,26 @@ def test_cyc_step_matches_reference_losses(golden):
     from oracle import restate as R
     from trainer import Cyc_Trainer
     _seed(); tr = Cyc_Trainer(_cfg("CycleGan", 64))
+    _seed(); st = R.CycState()
     for it, ref in enumerate(golden["cyc_step.losses_64"]):
         rA, rB = R.synthetic_pair(1, 64, seed=100 + it, phantom=True)
         out = tr.step({"A": rA, "B": rB})
         for k in ("loss_G", "loss_D_A", "loss_D_B"):
             assert _close(float(out[k]), ref[k], 2e-3 if it else 2e-4), (it, k, float(out[k]), ref[k])
+        if it == 0:        # every parameter gradient of the four networks (both uses of each generator summed)
+            R.cyc_step(st, rA, rB)
+            for mod, leaf in ((tr.netG_A2B, st.G_A2B), (tr.netG_B2A, st.G_B2A), (tr.netD_A, st.D_A), (tr.netD_B, st.D_B)):
+                grad_report(*trainer_leaves([(mod, leaf)]), tensor_tol=2e-2, glob_tol=5e-3)
     # the UPDATE itself, not closeness to the initial weights.  Two Adam steps move every weight by ~lr * sign(gradient) each (the
-    # first steps of Adam are sign-like), so the comparison is element-wise: all but the few near-zero-gradient elements, where the
-    # 1e-4 gradient noise of the fp32 mode can flip a sign, must agree to 5 % of the step size.
+    # first steps of Adam are sign-like, and the second gradient already differs by a few per cent because the first update flipped
+    # the sign of near-zero-gradient weights in all four networks), so the comparison is element-wise: the large majority of the
+    # elements must agree to 30 % of the step size -- an optimizer that never stepped (update 0) agrees nowhere.
     w = tr.netG_A2B.model_head[1].weight.detach().cpu()
     _seed(); w0 = R.init_generator(1, 1)["model_head.1.weight"]
     upd, upd_ref = w - w0, golden["cyc_step.G_A2B_head_w_after2"] - w0
     assert float(upd_ref.abs().max()) > 1e-4 and float(upd.abs().max()) > 1e-4
-    agree = float(((upd - upd_ref).abs() <= 0.05 * 2e-4).float().mean())
-    assert agree >= 0.97, agree
+    agree = float(((upd - upd_ref).abs() <= 0.3 * 2e-4).float().mean())
+    assert agree >= 0.85, agree
 
 
 def test_reg_step_matches_oracle():
@@ -57,6 +77,10 @@ def test_reg_step_matches_oracle():
     for k in ("SR_loss", "adv_loss", "loss_D_B", "toal_loss"):
         assert _close(float(out[k]), ref[k], 3e-4), (k, float(out[k]), ref[k])
     assert _close(float(out["SM_loss"]), ref["SM_loss"], 2e-2), (float(out["SM_loss"]), ref["SM_loss"])   # ~1e-7 magnitude term
+    # gradients: generator (fed by warp, Reg and D), registration net (fed by warp and smoothness), discriminator
+    for mod, leaf in ((tr.netG_A2B, st.G), (tr.R_A, st.R)):
+        grad_report(*trainer_leaves([(mod, leaf)]), tensor_tol=2e-2, glob_tol=5e-3)
+    grad_report(*trainer_leaves([(tr.netD_B, st.D)]), tensor_tol=D_AFTER_G[0], glob_tol=D_AFTER_G[1])
 
 
 def test_hd_x2_and_p2p_steps_match_oracle():
@@ -70,6 +94,9 @@ def test_hd_x2_and_p2p_steps_match_oracle():
     ref = R.hd_x2_step(st, rA, rB1, rB)
     for k in ("SR_loss", "adv_loss", "loss_D_B", "toal_loss"):
         assert _close(float(out[k]), ref[k], 3e-4), (k, float(out[k]), ref[k])
+    for mod, leaf in ((tr.netG_A2B, st.G), (tr.R_A, st.R)):
+        grad_report(*trainer_leaves([(mod, leaf)]), tensor_tol=2e-2, glob_tol=5e-3)
+    grad_report(*trainer_leaves([(tr.netD_B, st.D)]), tensor_tol=D_AFTER_G[0], glob_tol=D_AFTER_G[1])
 
     _seed(); tp = P2p_Trainer(_cfg("P2p", 64))
     _seed(); sp = R.P2pState()
@@ -78,6 +105,24 @@ def test_hd_x2_and_p2p_steps_match_oracle():
     ref = R.p2p_step(sp, rA, rB)
     for k in ("loss_L1", "loss_GAN_A2B", "loss_D_B"):
         assert _close(float(out[k]), ref[k], 3e-4), (k, float(out[k]), ref[k])
+    grad_report(*trainer_leaves([(tp.netG_A2B, sp.G)]), tensor_tol=G_TENSOR, glob_tol=G_GLOBAL)
+    grad_report(*trainer_leaves([(tp.netD_B, sp.D)]), tensor_tol=D_AFTER_G[0], glob_tol=D_AFTER_G[1])
+
+
+def test_hd_x1_step_matches_oracle():
+    """Hd stage 1 (HdTrainer.py:192-228): the Reg-GAN body with the Hd loss weights and inputs (A2 -> B2), fp32, losses + gradients."""
+    from oracle import restate as R
+    from trainer import Hd_Trainer_x1
+    _seed(); tr = Hd_Trainer_x1(_cfg("HdGan", 256, Corr_lamda1=15, Adv_lamda1=0.5))       # non-default weights: the x1 keys are the ones read
+    _seed(); st = R.RegState()
+    rA, rB = R.synthetic_pair(1, 256, seed=310, phantom=True)
+    out = tr.step({"A2": rA, "B1": (rB * 1.7).clamp(-1, 1), "B2": rB})
+    ref = R.reg_step(st, rA, rB, corr=15, adv=0.5, smooth=10)
+    for k in ("SR_loss", "adv_loss", "loss_D_B", "toal_loss"):
+        assert _close(float(out[k]), ref[k], 3e-4), (k, float(out[k]), ref[k])
+    for mod, leaf in ((tr.netG_A2B, st.G), (tr.R_A, st.R)):
+        grad_report(*trainer_leaves([(mod, leaf)]), tensor_tol=2e-2, glob_tol=5e-3)
+    grad_report(*trainer_leaves([(tr.netD_B, st.D)]), tensor_tol=D_AFTER_G[0], glob_tol=D_AFTER_G[1])
 
 
 def test_bf16_cyc_step_runs_and_tracks(golden):

@@ -2,6 +2,8 @@
 modules by oracle/make_golden.py.  No reference tree needed."""
 import random
 
+import pytest
+
 import torch
 
 from oracle import restate as R
@@ -105,3 +107,99 @@ def test_cyc_step_losses(golden):
         for k, v in ref.items():
             assert abs(mine[k] - v) <= 2e-4 * abs(v) + 1e-7, (it, k, mine[k], v)
     assert torch.allclose(st.G_A2B["model_head.1.weight"], golden["cyc_step.G_A2B_head_w_after2"], atol=1e-5)
+
+
+# ---- golden_v2: vectors produced by exec'ing the reference's own source lines (oracle/make_golden.py:main_v2) ----
+
+
+def _weight_fp(sd):
+    return {k: (float(v.detach().double().sum()), float(v.detach().double().abs().sum())) for k, v in sd.items()}
+
+
+def _fp_close(a, b, rtol=1e-5):
+    assert a.keys() == b.keys()
+    for k in a:
+        for x, y in zip(a[k], b[k]):
+            assert abs(x - y) <= rtol * max(abs(y), 1e-3), (k, x, y)
+
+
+def test_masked_l1_pin(golden):
+    """HdTrainer.py:726-735 (exec'd from the reference tree when the golden file was made): value and gradient."""
+    assert 705 <= golden["masked_l1.ref_lines"][0] and golden["masked_l1.ref_lines"][1] <= 751
+    for name in ("a", "b"):
+        g = golden[f"masked_l1.{name}"]
+        w = g["warped"].clone().requires_grad_(True)
+        loss = R.masked_l1(w, g["b1"], g["b2"])
+        loss.backward()
+        assert torch.equal(loss.detach(), g["loss"]) and torch.equal(w.grad, g["grad"])
+
+
+def test_p2p_step_pin(golden):
+    """p2pTrainer.py:122-148, two iterations."""
+    _seed(); st = R.P2pState()
+    for it, ref in enumerate(golden["p2p_step.losses_64"]):
+        a, b = R.synthetic_pair(1, 64, seed=400 + it, phantom=True)
+        mine = R.p2p_step(st, a, b)
+        for k, v in ref.items():
+            assert abs(mine[k] - v) <= 1e-5 * abs(v) + 1e-8, (it, k, mine[k], v)
+    _fp_close(_weight_fp(st.G), golden["p2p_step.G_fp_after2"])
+
+
+@pytest.mark.timeout(600)
+def test_hd_steps_pin(golden):
+    """Hd stage 1 (HdTrainer.py:192-228) and stage 2 (:705-751: Discriminator_m + GANLoss + masked L1), first iteration each
+    (256x256 with a 3-block generator, as frozen)."""
+    for key, multiscale in (("hd_x1_step", False), ("hd_x2_step", True)):
+        _seed(); st = R.RegState(multiscale_d=multiscale, n_blocks=3)
+        a, b = R.synthetic_pair(1, 256, seed=300, phantom=True)
+        b1 = (b * 1.7).clamp(-1, 1)
+        mine = R.hd_x2_step(st, a, b1, b) if multiscale else R.reg_step(st, a, b, corr=20, adv=1, smooth=10)
+        for k, v in golden[f"{key}.losses_256_nb3"][0].items():
+            assert abs(mine[k] - v) <= 2e-5 * abs(v) + 1e-9, (key, k, mine[k], v)
+
+
+def test_discriminator_m_two_scales_pin(golden):
+    """Discriminator_m(num_D=2): scale order, centre crop (HdGan.py:236-256) and the GANLoss scale weights [1.8, 0.2] (:273)."""
+    _seed(); sd = R.init_discriminator_m(1, num_D=2)
+    for k, (shape, s, sa) in golden["discriminator_m2.state_fp"].items():
+        assert tuple(sd[k].shape) == tuple(shape) and abs(float(sd[k].double().sum()) - s) <= 1e-6 * max(1, abs(s))
+    x, _ = R.synthetic_pair(2, 128, seed=9, phantom=True)
+    feats = R.discriminator_m_forward(sd, x, num_D=2)
+    assert [[tuple(f.shape) for f in sc] for sc in feats] == [[tuple(t) for t in sc] for sc in golden["discriminator_m2.feat_shapes"]]
+    for mine, ref in zip(feats, golden["discriminator_m2.last"]):
+        assert torch.allclose(mine[-1], ref, rtol=1e-5, atol=1e-6)
+    for flag in (True, False):
+        assert torch.allclose(R.gan_loss(feats, flag), golden[f"discriminator_m2.ganloss_{flag}"], rtol=1e-5)
+
+
+# ---- the bf16-emulating oracle (oracle/bf16_emu.py) ----
+
+
+def test_bf16_emulator_disabled_equals_restatement():
+    """With rounding switched off the emulator's networks ARE the pinned restatement (so its only additions are the roundings)."""
+    from oracle import bf16_emu as B
+    _seed(); g, d, r = R.init_generator(1, 1, 2), R.init_discriminator(2), R.init_reg(1, 1)
+    a, b = R.synthetic_pair(1, 256, seed=5, phantom=True)
+    ref = (R.generator_forward(g, a[:, :, :64, :64], 2), R.discriminator_forward(d, torch.cat([a, b], 1)), R.reg_forward(r, a, b))
+    with B.emulate(enabled=False):
+        got = (R.generator_forward(g, a[:, :, :64, :64], 2), R.discriminator_forward(d, torch.cat([a, b], 1)), R.reg_forward(r, a, b))
+    assert R.generator_forward.__module__ == "oracle.restate"             # restored on exit
+    for x, y in zip(got, ref):
+        assert torch.equal(x, y)
+
+
+def test_bf16_emulator_stays_in_the_bf16_envelope():
+    """Rounding at the kernels' storage points moves a random-init generator by about the operand-rounding envelope measured for the
+    reference's own bf16 (~3e-2 max-rel), and gradients flow through the rounding points."""
+    from oracle import bf16_emu as B
+    _seed(); sd = R.leafify(R.init_generator(1, 1, 3))
+    a, b = R.synthetic_pair(1, 64, seed=42)
+    ref = R.generator_forward(sd, a, 3).detach()
+    with B.emulate():
+        y = R.generator_forward(sd, a, 3)
+        R.l1_loss(y, b).backward()
+    err = float((y.detach() - ref).abs().max() / ref.abs().max())
+    assert 1e-4 < err < 8e-2, err
+    assert torch.equal(y.detach(), y.detach().bfloat16().float())         # the module output is a stored bf16 tensor
+    gw = sd["model_body.1.conv_block.1.weight"].grad
+    assert gw is not None and float(gw.abs().max()) > 0
