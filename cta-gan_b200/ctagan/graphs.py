@@ -105,6 +105,7 @@ class GraphedTrainer:
                 t.step(tensors=static)
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        warm_losses = {k: v.detach().clone() for k, v in t.last_losses.items()}      # the capture below re-binds last_losses to graph outputs
         if not self.is_cyc:
             E.invalidate_weight_cache()
         if self.is_cyc:
@@ -129,3 +130,4 @@ class GraphedTrainer:
             self._graphs = (g,)
         self._launches = ops.launch_count() - n0
         self._sig = self._weights_signature()
+        t.last_losses = warm_losses          # what the caller of a replay_first=False first call sees: the eager iteration's losses
