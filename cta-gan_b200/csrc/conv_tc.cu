@@ -410,7 +410,7 @@ struct TcConfig {
   static constexpr int A_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB per chunk
   static constexpr int B_BYTES = BN * CHUNK_K * 2;
   static constexpr int STAGE_BYTES = KCH * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 6 ? 6 : (196 * 1024) / STAGE_BYTES;     // (+ ~25 KB of static epilogue buffers)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
@@ -422,9 +422,23 @@ struct TcConfig {
 // stat_part[N][parts][Co][2] (plain stores, fixed arithmetic order inside the tile), and the last CTA of an (image, column tile) to
 // arrive -- a ticket per (image, column tile) -- adds the slots in slot order in fp64 and writes (mean, rstd).  No floating-point
 // atomics anywhere: the same inputs give the same bits whatever the CTA schedule.
+//
+// Column sums inside the tile: a thread holds 32 columns of ONE row, the sums run over rows.  Each warp transposes its 32 x 32 block
+// through a private, bank-conflict-free shared-memory tile (row pitch 33 words: 32 STS + 32 LDS per thread and chunk, against 62
+// shuffles + 124 selects of a register butterfly), lane l then owns column l of the chunk; the per-warp results wait in shared memory
+// and the four warps are combined ONCE per tile (one barrier per tile, not one per 32-column chunk).
+constexpr int EPI_PITCH = 33;
+
+template <int BN>
+struct EpiSmem {
+  float xpose[4][32 * EPI_PITCH];     // per-warp transpose tile
+  float part[4][BN][2];               // per-warp column sums of the tile: [warp][column][sum | sumsq]
+  unsigned int ticket;
+};
+
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t tmem_acc, int warp, int lane, int img, int tile, int co0, int wrow0,
-                                            int co_tile, float (*stat_red)[4][2][32], unsigned int *ticket_s) {
+                                            int co_tile, EpiSmem<BN> &es) {
   const int quarter = warp & 3;
   const int row = quarter * 32 + lane;
   const int BW = 1 << p.bw_log2;
@@ -439,44 +453,27 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t tmem_acc
   const int oi = i * p.sy + p.ay, oj = j * p.sx + p.ax;
   const bool valid = (i < p.Hov) && (j < p.Wov) && oi >= 0 && oi < p.out_H && oj >= 0 && oj < p.out_W;
   bf16 *out_row = p.out + (((long long)img * p.out_H + oi) * p.out_W + oj) * p.Co + co0;
-  float2 *part = p.stat_part ? reinterpret_cast<float2 *>(p.stat_part) + ((long long)img * p.stat_parts + p.stat_part0 + tile) * p.Co + co0
-                             : nullptr;
+  const bool stats = p.stat_part != nullptr;
+  float *xp = es.xpose[quarter];
 #pragma unroll 1
   for (int c = 0; c < BN; c += 32) {
     uint32_t r[32];
     tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
     tmem_ld_wait();
-    if (part != nullptr) {
-      // column sums over the warp's 32 rows by a butterfly that halves the data per step (31 shuffles per quantity), then the 4
-      // epilogue warps are combined in shared memory in warp order
-      float s1[32], s2[32];
+    if (stats) {
+      __syncwarp();                                  // the previous chunk's column reads are done
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float t = valid ? __uint_as_float(r[e]) : 0.f;
-        s1[e] = t;
-        s2[e] = t * t;
-      }
+      for (int e = 0; e < 32; ++e) xp[lane * EPI_PITCH + e] = valid ? __uint_as_float(r[e]) : 0.f;
+      __syncwarp();
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int step = 16, n = 32; step >= 1; step >>= 1, n >>= 1) {
-        const bool upper = (lane & step) != 0;
-#pragma unroll
-        for (int q = 0; q < n / 2; ++q) {
-          const float keep1 = upper ? s1[q + n / 2] : s1[q], send1 = upper ? s1[q] : s1[q + n / 2];
-          const float keep2 = upper ? s2[q + n / 2] : s2[q], send2 = upper ? s2[q] : s2[q + n / 2];
-          s1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
-          s2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
-        }
+      for (int k = 0; k < 32; ++k) {                 // rows of the warp in order: fixed summation order
+        const float t = xp[k * EPI_PITCH + lane];
+        s1 += t;
+        s2 = fmaf(t, t, s2);
       }
-      // lane l now holds the sums of column l
-      const int par = (c >> 5) & 1;
-      stat_red[par][quarter][0][lane] = s1[0];
-      stat_red[par][quarter][1][lane] = s2[0];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2 && co0 + c + lane < p.Co) {
-        const float a = (stat_red[par][0][0][lane] + stat_red[par][1][0][lane]) + (stat_red[par][2][0][lane] + stat_red[par][3][0][lane]);
-        const float b = (stat_red[par][0][1][lane] + stat_red[par][1][1][lane]) + (stat_red[par][2][1][lane] + stat_red[par][3][1][lane]);
-        part[c + lane] = make_float2(a, b);
-      }
+      es.part[quarter][c + lane][0] = s1;
+      es.part[quarter][c + lane][1] = s2;
     }
     if (valid && co0 + c < p.Co) {            // Co is a multiple of 32 here; tiles may overhang it
       float v[32];
@@ -506,35 +503,63 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t tmem_acc
       }
     }
   }
-  // "last CTA finalises": once every CTA of this (image, column tile) has stored its partial sums, the last one adds them in slot
-  // order and turns them into (mean, rstd); it also re-arms the ticket (the buffer is zero again when the kernel ends)
-  if (part != nullptr) {
-    const int et = (int)threadIdx.x - 64;      // 0..127
+  if (!stats) return;
+  // combine the four warps (in warp order) and store this tile's slot; then "last CTA finalises": once every CTA of this (image,
+  // column tile) has stored its slot, the last one adds the slots in slot order and turns them into (mean, rstd); it also re-arms
+  // the ticket (the buffer is zero again when the kernel ends)
+  const int et = (int)threadIdx.x - 64;      // 0..127
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  float2 *slot = reinterpret_cast<float2 *>(p.stat_part) + ((long long)img * p.stat_parts + p.stat_part0 + tile) * p.Co + co0;
+#pragma unroll
+  for (int col = et; col < BN; col += 128) {
+    if (co0 + col < p.Co) {
+      const float a = (es.part[0][col][0] + es.part[1][col][0]) + (es.part[2][col][0] + es.part[3][col][0]);
+      const float b = (es.part[0][col][1] + es.part[1][col][1]) + (es.part[2][col][1] + es.part[3][col][1]);
+      slot[col] = make_float2(a, b);
+    }
+  }
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  unsigned int *ticket = p.stat_ticket + (long long)img * p.stat_tpi + co_tile;
+  if (et == 0) es.ticket = atomicAdd(ticket, 1u);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (es.ticket == (unsigned int)p.stat_parts - 1u) {
     __threadfence();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    unsigned int *ticket = p.stat_ticket + (long long)img * p.stat_tpi + co_tile;
-    if (et == 0) *ticket_s = atomicAdd(ticket, 1u);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (*ticket_s == (unsigned int)p.stat_parts - 1u) {
-      __threadfence();
-      const double inv = 1.0 / (double)p.stat_hw;
-      for (int col = et; col < BN; col += 128) {
-        if (co0 + col >= p.Co) break;
-        const float2 *src = reinterpret_cast<const float2 *>(p.stat_part) + (long long)img * p.stat_parts * p.Co + co0 + col;
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < p.stat_parts; ++k) {
-          const float2 v = __ldcg(src + (long long)k * p.Co);
-          s1 += (double)v.x;
-          s2 += (double)v.y;
+    const double inv = 1.0 / (double)p.stat_hw;
+    const float2 *base = reinterpret_cast<const float2 *>(p.stat_part) + (long long)img * p.stat_parts * p.Co + co0;
+    constexpr int NC = (BN + 127) / 128;         // columns per thread
+    double s1[NC], s2[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) s1[q] = s2[q] = 0.0;
+    // many independent loads in flight (the slots are L2 lines written by other SMs); the additions stay in slot order
+    for (int k0 = 0; k0 < p.stat_parts; k0 += 16) {
+      float2 v[NC][16];
+#pragma unroll
+      for (int q = 0; q < NC; ++q)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int col = et + q * 128;
+          v[q][u] = (k0 + u < p.stat_parts && col < BN && co0 + col < p.Co) ? __ldcg(base + (long long)(k0 + u) * p.Co + col) : make_float2(0.f, 0.f);
         }
-        const double m = s1 * inv;
-        double var = s2 * inv - m * m;
+#pragma unroll
+      for (int q = 0; q < NC; ++q)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          s1[q] += (double)v[q][u].x;
+          s2[q] += (double)v[q][u].y;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      const int col = et + q * 128;
+      if (col < BN && co0 + col < p.Co) {
+        const double m = s1[q] * inv;
+        double var = s2[q] * inv - m * m;
         if (var < 0) var = 0;
         *reinterpret_cast<float2 *>(p.stat_out + ((long long)img * p.Co + co0 + col) * 2) = make_float2((float)m, (float)(1.0 / sqrt(var + 1e-5)));
       }
-      if (et == 0) *ticket = 0u;
     }
+    if (et == 0) *ticket = 0u;
   }
 }
 
@@ -548,8 +573,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   uint64_t *empty_bar = full_bar + Cfg::STAGES;
   uint64_t *tmem_full_bar = empty_bar + Cfg::STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
-  __shared__ float stat_red[2][4][2][32];       // [chunk parity][epilogue warp][sum | sumsq][column]
-  __shared__ unsigned int ticket_s;
+  __shared__ EpiSmem<BN> epi;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.x / p.tiles_per_img;
@@ -643,7 +667,7 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     // prologue and block in their own pdl_wait() until this grid has finished).  Triggering at kernel start instead made the
     // step SLOWER: early-resident consumers held shared memory that the other streams' kernels needed.
     pdl_trigger();
-    tc_epilogue<BN>(p, tmem_base, warp, lane, img, tile, co0, wrow0, (int)blockIdx.y, stat_red, &ticket_s);
+    tc_epilogue<BN>(p, tmem_base, warp, lane, img, tile, co0, wrow0, (int)blockIdx.y, epi);
   }
   tc_fence_before();
   __syncthreads();
@@ -733,7 +757,7 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
   static int short_k = -1;
   if (short_k < 0) { const char *e = getenv("CTAGAN_TC_SHORTK"); short_k = e ? atoi(e) : 20; }    // measured on the Reg step (b=8): off 18.05 ms, 12 -> 17.31 ms, 20 -> 17.21 ms
   if (iters <= short_k && (long long)grid.x * grid.y >= 4LL * ctagan_num_sms()) {
-    const int fit = (110 * 1024) / Cfg::STAGE_BYTES;
+    const int fit = (int)((113 * 1024 - sizeof(EpiSmem<BN>) - 2048) / Cfg::STAGE_BYTES);
     if (fit >= 2 && fit < q.n_stages) q.n_stages = fit;
   }
   if (const char *env = getenv("CTAGAN_TC_STAGES")) {

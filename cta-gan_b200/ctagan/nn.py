@@ -113,6 +113,13 @@ class Generator(nn.Module):
         two passes of the network inside one autograd graph accumulate their gradients separately (see Cyc_Trainer.phase_G)."""
         if x.shape[2] % 4 or x.shape[3] % 4:
             raise ValueError("Generator needs H and W to be multiples of 4")
+        # the kernels index with 32 bits: the largest activation (64 channels at full resolution, reflection-padded by 3) must stay below
+        # 2^31 elements.  Every op of the network is per sample (InstanceNorm statistics are per (n, c)), so a larger batch -- the
+        # 128- and 256-slice points of the inference sweep at 512^2 -- is run in chunks with identical results.
+        per_sample = 64 * (x.shape[2] + 6) * (x.shape[3] + 6)
+        if x.shape[0] * per_sample >= 2 ** 31:
+            chunk = max(1, (2 ** 31 - 1) // per_sample)
+            return torch.cat([self.forward(xc, params) for xc in x.split(chunk)])
         plan = self._get_plan()
         return _GeneratorFn.apply(plan, x, *(plan.params if params is None else params))
 

@@ -289,7 +289,7 @@ def reg_forward(sd: State, img_a: Tensor, img_b: Tensor) -> Tensor:
 def warp(src: Tensor, flow: Tensor) -> Tensor:
     """Transformer_2D.forward, trainer/transformer.py:12-29, without the hard `.cuda()` at :21."""
     b, _, h, w = flow.shape
-    grids = torch.meshgrid([torch.arange(0, h), torch.arange(0, w)], indexing="ij")
+    grids = torch.meshgrid([torch.arange(0, h, device=flow.device), torch.arange(0, w, device=flow.device)], indexing="ij")
     grid = torch.stack(grids).to(flow.dtype).repeat(b, 1, 1, 1)
     new_locs = grid + flow
     shape = (h, w)

@@ -1,6 +1,6 @@
 """Developer probe (not a pytest): tcgen05 conv engines vs the CUDA-core engine + graph-replay kernel timing."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import _ctagan_path  # noqa
 import torch
 from ctagan import engine as E, lib as L, ops
