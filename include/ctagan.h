@@ -223,6 +223,32 @@ int ctagan_nhwc_to_nchw(const void *src, float *dst, int N, int C, int64_t HW, i
 int ctagan_interleave2(const float *a, const float *b, void *dst, int64_t n, int dtype, void *stream);
 int ctagan_deinterleave2(const void *src, float *a, float *b, int64_t n, int dtype, void *stream);
 
+/* ---- f1: input pipeline on the GPU (batched; the reference does this per slice on the CPU inside its DataLoader worker) ----
+ * hu_to_unit: read_dicom (trainer/datasets.py:74-82) and the raw half of read_ori_w (:62-65): v = raw + add, negative -> 0,
+ *   (v / 4095 - 0.5) / 0.5 (double arithmetic, stored fp32).  add = 0 for stored pixel values, 1024 for HU (SimpleITK reads HU).
+ * hu_window: the display-window half of read_ori_w (:45-56; centre 50 / width 400 there): trunc((hu - win_min) * 255 / (win_max -
+ *   win_min)) clipped to [0, 255], / 255, (x - 0.5) / 0.5.
+ * resize_nearest: Resize (trainer/utils.py:13-30) = F.interpolate(size) with the default 'nearest' mode, [B][Hs][Ws] -> [B][Hd][Wd].
+ * affine_nearest: the resampling of RandomAffine(fillcolor=-1) (trainer/CycTrainer.py:91-95): PIL's nearest-neighbour affine transform in
+ *   16.16 fixed point; inv_matrix[B][6] (device, fp64) holds the inverse affine matrix (a, b, c, d, e, f) of every slice, the random
+ *   parameters themselves are drawn on the host exactly as torchvision draws them. */
+int ctagan_hu_to_unit(const int16_t *raw, float *out, int64_t n, int add, void *stream);
+int ctagan_hu_window(const int16_t *hu, float *out, int64_t n, double center, double width, void *stream);
+int ctagan_resize_nearest(const float *src, float *dst, int B, int Hs, int Ws, int Hd, int Wd, void *stream);
+int ctagan_affine_nearest(const float *src, float *dst, int B, int H, int W, const double *inv_matrix, float fill, void *stream);
+
+/* ---- f2: evaluation metrics of test() on the GPU (trainer/CycTrainer.py:286-330, :362-398), batched, no host round trip per slice ----
+ * fake / real: [B][H][W] fp32 in [-1, 1].  Per slice: the display window (to_windowdata, :34-57, centre wc / width ww), the
+ * 0.3-threshold masks, and for both image pairs the reference compares (the thresholded windowed pair and the masked raw pair)
+ * MAE, PSNR, SSIM (skimage compare_ssim defaults: 7x7 uniform window, sample covariance, data range 2) and UQI:
+ *   out[B][8] = (MAEw, PSNRw, SSIMw, UQIw, MAE, PSNR, SSIM, UQI), fp64.  Deterministic (ordered partial sums).
+ * scratch: ctagan_eval_metrics_scratch_doubles doubles.  LPIPS (a third-party network) is not computed.
+ * to_dicom_i16: (x + 1) * 0.5 * 4095 truncated to int16, the pixel data written back to DICOM (:337-341). */
+size_t ctagan_eval_metrics_scratch_doubles(int B, int H, int W);
+int ctagan_eval_metrics(const float *fake, const float *real, double *out, double *scratch, int B, int H, int W, double wc, double ww,
+                        void *stream);
+int ctagan_to_dicom_i16(const float *x, int16_t *out, int64_t n, void *stream);
+
 /* dtype conversion (fp32 <-> activation dtype), n elements. */
 int ctagan_cast(const void *src, int src_dtype, void *dst, int dst_dtype, int64_t n, void *stream);
 

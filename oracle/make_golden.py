@@ -436,7 +436,95 @@ def main_v2():
     print("wrote", OUT2, os.path.getsize(OUT2) / 1e6, "MB;", len(G), "entries")
 
 
+# ======================================================================================================================
+# golden_v3: the data-side / evaluation-side arithmetic (oracle/restate_eval.py) pinned against the reference's own source lines, PIL and torch
+# ======================================================================================================================
+OUT3 = os.path.join(os.path.dirname(HERE), "tests", "golden", "golden_v3.pt")
+
+
+def main_v3():
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms.functional as TF
+    from oracle import restate_eval as RE
+    ref = load_reference()
+    G = {}
+    rng = np.random.default_rng(7)
+    # to_windowdata (CycTrainer.py:34-57) and the metric methods (:362-398): exec the reference's lines
+    src_w, span_w = reference_lines(ref.root, "trainer/CycTrainer.py", "def to_windowdata(image,WC,WW):", "return image", lo=34, hi=57)
+    src_m, span_m = reference_lines(ref.root, "trainer/CycTrainer.py", "def PSNR(self, fake, real):", "return UQI", lo=362, hi=398)
+    env = {"np": np}
+    exec(src_w, env)
+    exec(src_m, env)
+    G["eval.ref_lines"] = {"to_windowdata": span_w, "metrics": span_m}
+    src_b, span_b = reference_lines(ref.root, "trainer/CycTrainer.py", "b = to_windowdata(real_B, WC, WW)", "fake_B[fake_B==0]=-1", lo=286, hi=320)
+    # keep only the image-building statements of that span (the metric calls in between need skimage / lpips)
+    keep = [ln for ln in src_b.split("\n") if not any(t in ln for t in ("self.", "measure.", "loss_fn", "+=", "LPIPSw", "#"))]
+    src_b = "\n".join(keep)
+    cases = {}
+    for name, (H, W) in {"a": (64, 80), "b": (96, 96)}.items():
+        yy, xx = np.mgrid[0:H, 0:W]
+        disc = ((yy - H / 2) ** 2 + (xx - W / 2) ** 2) <= (0.4 * min(H, W)) ** 2
+        real = np.where(disc, rng.uniform(-0.55, -0.35, (H, W)), -1.0).astype(np.float32)       # soft tissue ~ 0..400 HU inside, air outside
+        vessels = rng.uniform(0, 1, (H, W)) > 0.9
+        real = np.where(disc & vessels, real + 0.12, real).astype(np.float32)
+        fake = (real + rng.normal(0, 0.03, (H, W))).astype(np.float32).clip(-1, 1)
+        WC, WW = 40.0, 400.0
+        loc = {"real_B": real.copy(), "fake_B": fake.copy(), "WC": WC, "WW": WW}
+        exec(src_b, dict(env), loc)
+        c, b, fm, rm = RE.eval_images(fake.copy(), real.copy(), WC, WW)
+        for mine, key in ((c, "c"), (b, "b"), (fm, "fake_B"), (rm, "real_B")):
+            assert np.array_equal(mine, loc[key]), (name, key)
+        assert np.array_equal(RE.to_windowdata(real.copy().astype(np.float64), WC, WW), env["to_windowdata"](real.copy().astype(np.float64), WC, WW))
+        vals = {}
+        for tag, (f_, r_) in {"w": (c, b), "raw": (fm, rm)}.items():
+            for fn in ("MAE", "PSNR", "UQI"):
+                v_ref = float(env[fn](None, f_, r_)); v = float(getattr(RE, fn)(f_, r_))
+                assert v == v_ref, (name, tag, fn, v, v_ref)
+                vals[f"{fn}_{tag}"] = v_ref
+            vals[f"SSIM_{tag}"] = float(RE.SSIM(f_, r_))
+        cases[name] = {"fake": torch.from_numpy(fake), "real": torch.from_numpy(real), "WC": WC, "WW": WW, "metrics": vals,
+                       "int16": torch.from_numpy(RE.to_dicom_int16(fake))}
+    # an all-air slice: the "no valid pixel" branches of MAE / PSNR
+    air = np.full((40, 40), -1.0, np.float32)
+    c, b, fm, rm = RE.eval_images(air.copy(), air.copy(), 40.0, 400.0)
+    assert float(env["MAE"](None, fm, rm)) == float(RE.MAE(fm, rm)) and float(env["PSNR"](None, fm, rm)) == float(RE.PSNR(fm, rm))
+    G["eval.cases"] = cases
+    # read_dicom / read_ori_w arithmetic (datasets.py:74-82, 45-65) on synthetic stored pixel values
+    src_d, span_d = reference_lines(ref.root, "trainer/datasets.py", "image2[image2<0]=0", "image2 = (image2 - 0.5)/0.5", after="def read_dicom", lo=74, hi=82)
+    raw = rng.integers(-50, 4096, (32, 48)).astype(np.int16)
+    loc = {"image2": raw.astype(np.int64)}
+    exec(src_d, {"np": np}, loc)
+    assert np.array_equal(loc["image2"], RE.read_dicom_norm(raw))
+    src_o, span_o = reference_lines(ref.root, "trainer/datasets.py", "center =50", "image1 = (image1 - 0.5)/0.5", after="def read_ori_w", lo=36, hi=71)
+    hu = rng.integers(-1100, 3000, (32, 48)).astype(np.int16)
+    loc = {"data1": hu.astype(np.int64)}
+    exec(src_o, {"np": np}, loc)
+    assert np.array_equal(loc["image1"], RE.window_image(hu.astype(np.float64), 50, 400))
+    G["data.ref_lines"] = {"read_dicom": span_d, "read_ori_w": span_o}
+    G["data.raw"] = torch.from_numpy(raw); G["data.raw_norm"] = torch.from_numpy(RE.read_dicom_norm(raw).astype(np.float32))
+    G["data.hu"] = torch.from_numpy(hu); G["data.hu_window"] = torch.from_numpy(RE.window_image(hu.astype(np.float64), 50, 400).astype(np.float32))
+    # RandomAffine resampling against PIL, Resize against torch
+    img = rng.standard_normal((97, 131)).astype(np.float32)
+    aff = []
+    for angle, tr, sc in ((1.0, (2, -1), 1.02), (-7.5, (5, 3), 0.9), (0.3, (0, 0), 1.0), (33.0, (-20, 11), 1.3)):
+        m = TF._get_inverse_affine_matrix((131 * 0.5, 97 * 0.5), angle, list(tr), sc, [0.0, 0.0])
+        pil = np.asarray(Image.fromarray(img, mode="F").transform((131, 97), Image.AFFINE, m, resample=Image.NEAREST, fillcolor=-1))
+        assert np.array_equal(pil, RE.affine_nearest(img, m, -1.0))
+        aff.append({"m": torch.tensor(m, dtype=torch.float64), "out": torch.from_numpy(pil.copy()), "angle": angle, "translate": tr, "scale": sc})
+    G["data.affine_src"] = torch.from_numpy(img); G["data.affine"] = aff
+    x = torch.from_numpy(img)[None, None]
+    G["data.resize"] = {(h, w): torch.nn.functional.interpolate(x, size=[h, w])[0, 0].clone() for h, w in ((64, 64), (200, 257), (97, 131))}
+    G["meta"] = {"torch": str(torch.__version__), "note": "eval/data arithmetic: reference source lines exec'd; affine vs PIL " + Image.__version__}
+    torch.save(G, OUT3)
+    print("wrote", OUT3, os.path.getsize(OUT3) / 1e6, "MB;", len(G), "entries")
+
+
 if __name__ == "__main__":
-    if "--v2-only" not in sys.argv:
-        main()
-    main_v2()
+    if "--v3-only" in sys.argv:
+        main_v3()
+    else:
+        if "--v2-only" not in sys.argv:
+            main()
+        main_v2()
+        main_v3()

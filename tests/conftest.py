@@ -19,10 +19,11 @@ def golden():
     import torch
     g = torch.load(os.path.join(ROOT, "tests", "golden", "golden_v1.pt"), weights_only=True)
     g.update(torch.load(os.path.join(ROOT, "tests", "golden", "golden_v2.pt"), weights_only=True))
+    g.update(torch.load(os.path.join(ROOT, "tests", "golden", "golden_v3.pt"), weights_only=True))
     return g
 
 
-_ORDER = ["test_abi_and_host", "test_oracle", "test_ddp", "test_gpu_ops", "test_gpu_tc", "test_gpu_determinism", "test_gpu_modules",
+_ORDER = ["test_abi_and_host", "test_oracle", "test_ddp", "test_gpu_ops", "test_gpu_tc", "test_gpu_data_eval", "test_gpu_determinism", "test_gpu_modules",
           "test_gpu_bf16", "test_gpu_steps", "test_gpu_curves"]
 
 

@@ -203,3 +203,22 @@ def test_bf16_emulator_stays_in_the_bf16_envelope():
     assert torch.equal(y.detach(), y.detach().bfloat16().float())         # the module output is a stored bf16 tensor
     gw = sd["model_body.1.conv_block.1.weight"].grad
     assert gw is not None and float(gw.abs().max()) > 0
+
+
+# ---- golden_v3: data-side / evaluation-side arithmetic (oracle/restate_eval.py) ----
+
+
+def test_eval_and_data_restatement_pins(golden):
+    import numpy as np
+    from oracle import restate_eval as RE
+    for name, case in golden["eval.cases"].items():
+        vals = RE.slice_metrics(case["fake"].numpy(), case["real"].numpy(), case["WC"], case["WW"])
+        ref = case["metrics"]
+        order = ("MAE_w", "PSNR_w", "SSIM_w", "UQI_w", "MAE_raw", "PSNR_raw", "SSIM_raw", "UQI_raw")
+        for v, k in zip(vals, order):
+            assert abs(float(v) - ref[k]) <= 1e-12 * max(1.0, abs(ref[k])), (name, k, v, ref[k])
+        assert np.array_equal(RE.to_dicom_int16(case["fake"].numpy()), case["int16"].numpy())
+    assert np.array_equal(RE.read_dicom_norm(golden["data.raw"].numpy()).astype(np.float32), golden["data.raw_norm"].numpy())
+    assert np.array_equal(RE.window_image(golden["data.hu"].numpy().astype(np.float64), 50, 400).astype(np.float32), golden["data.hu_window"].numpy())
+    for a in golden["data.affine"]:
+        assert np.array_equal(RE.affine_nearest(golden["data.affine_src"].numpy(), a["m"].tolist(), -1.0), a["out"].numpy())
