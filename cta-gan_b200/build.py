@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "ctagan", "libctagan.so")
-SOURCES = ["capi.cu", "conv_simt.cu", "conv_small.cu", "conv_tc.cu", "data_eval.cu", "elementwise.cu", "warp_loss.cu"]
+SOURCES = ["capi.cu", "conv_simt.cu", "conv_small.cu", "conv_tc.cu", "data_eval.cu", "elementwise.cu", "optim.cu", "warp_loss.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-diag-suppress", "20281", "-Xptxas", "-v" if os.environ.get("CTAGAN_PTXAS_V") else "-O3"]

@@ -5,7 +5,7 @@
 
 int ctagan_conv_gather_simt(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
 int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                           size_t workspace_bytes, cudaStream_t st);
+                           size_t workspace_bytes, cudaStream_t st, int accumulate = 0);
 size_t ctagan_conv_wgrad_simt_workspace(const ctagan_conv_geom *g);
 // tcgen05 engine (conv_tc.cu): return CTAGAN_ERR_UNSUPPORTED when the geometry does not tile
 int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, unsigned int *stat_ticket,
@@ -13,7 +13,7 @@ int ctagan_conv_gather_tc(const ctagan_conv_geom *g, const void *x, const void *
                           const ctagan_conv_groups *gr = nullptr);
 size_t ctagan_conv_gather_tc_stat_bytes(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                         size_t workspace_bytes, cudaStream_t st, int n_groups = 1);
+                         size_t workspace_bytes, cudaStream_t st, int n_groups = 1, int accumulate = 0);
 size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g, int n_groups = 1);
 int ctagan_conv_gather_tc_eligible(const ctagan_conv_geom *g);
 // degenerate (1-2 channel) convolutions (conv_small.cu)
@@ -21,7 +21,7 @@ int ctagan_conv_small_kind(const ctagan_conv_geom *g);
 int ctagan_conv_gather_small(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, cudaStream_t st);
 int ctagan_conv_wgrad_thin_eligible(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                           size_t workspace_bytes, cudaStream_t st);
+                           size_t workspace_bytes, cudaStream_t st, int accumulate = 0);
 size_t ctagan_conv_wgrad_thin_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups = 1);
 
@@ -45,19 +45,20 @@ int ctagan_num_sms() {
 }
 
 namespace {
-__global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restrict__ part, float *__restrict__ out, int parts, long long n) {
+__global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restrict__ part, float *__restrict__ out, int parts, long long n,
+                                                          int accumulate) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < parts; ++k) s += __ldcg(part + (long long)k * n + i);
-    out[i] = s;
+    out[i] = accumulate ? out[i] + s : s;
   }
 }
 }  // namespace
 
-int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st) {
+int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st, int accumulate) {
   long long blocks = (n + 255) / 256;
   if (blocks > 8LL * ctagan_num_sms()) blocks = 8LL * ctagan_num_sms();
-  ordered_sum_kernel<<<(int)blocks, 256, 0, st>>>(part, out, parts, n);
+  ordered_sum_kernel<<<(int)blocks, 256, 0, st>>>(part, out, parts, n, accumulate);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
@@ -132,16 +133,16 @@ extern "C" size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, i
 }
 
 extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                                 size_t workspace_bytes, int engine, void *stream) {
+                                 size_t workspace_bytes, int engine, int accumulate, void *stream) {
   int rc = check_geom(g, "conv_wgrad");
   if (rc) return rc;
   CTAGAN_REQUIRE(gy && gx && dw, "conv_wgrad: null pointer");
   CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_wgrad: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == 2) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
-  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, workspace, workspace_bytes, st);
-  if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st);
-  return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, workspace, workspace_bytes, st);
+  if (engine == 2) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st, 1, accumulate);
+  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, workspace, workspace_bytes, st, accumulate);
+  if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st, 1, accumulate);
+  return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, workspace, workspace_bytes, st, accumulate);
 }
 
 // Which engine ctagan_conv_gather would run for this geometry: 1 CUDA-core generic, 2 tcgen05, 4 CUDA-core specialised (1-2 channels)

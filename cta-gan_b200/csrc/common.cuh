@@ -168,6 +168,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // number of SMs (B200: 148); cached
 int ctagan_num_sms();
 
-// out[i] = part[0][i] + part[1][i] + ... + part[parts-1][i]  (i < n), added in row order: the deterministic second half of every
-// split reduction of the library (each CTA stores its partial result in its own row; no floating-point atomics)
-int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st);
+// out[i] = (accumulate ? out[i] : 0) + part[0][i] + part[1][i] + ... + part[parts-1][i]  (i < n), added in row order: the deterministic
+// second half of every split reduction of the library (each CTA stores its partial result in its own row; no floating-point atomics)
+int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st, int accumulate = 0);

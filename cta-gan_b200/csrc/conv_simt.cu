@@ -357,18 +357,19 @@ static int simt_wgrad_splits(const ctagan_conv_geom *g, int &pps) {
 size_t ctagan_conv_wgrad_simt_workspace(const ctagan_conv_geom *g) {
   int pps;
   const int splits = simt_wgrad_splits(g, pps);
-  return splits > 1 ? (size_t)splits * ((size_t)g->Co * g->Ci * g->KH * g->KW + g->Co) * sizeof(float) : 0;
+  return (size_t)splits * ((size_t)g->Co * g->Ci * g->KH * g->KW + g->Co) * sizeof(float);      // (a single split goes direct unless it accumulates)
 }
 
 int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                           size_t workspace_bytes, cudaStream_t st) {
+                           size_t workspace_bytes, cudaStream_t st, int accumulate) {
   const int ntaps = g->KH * g->KW;
   const int gx_ = cdiv(g->Co, BM), gy_ = cdiv((long long)ntaps * g->Ci, BN);
   int pps;
   const int splits = simt_wgrad_splits(g, pps);
   const long long dw_elems = (long long)g->Co * g->Ci * ntaps;
   float *dw_dst = dw, *db_dst = db;
-  if (splits > 1) {
+  const bool staged = splits > 1 || accumulate;
+  if (staged) {
     const size_t need = ctagan_conv_wgrad_simt_workspace(g);
     CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_wgrad(simt): workspace of %zu bytes required (got %zu)", need, workspace_bytes);
     dw_dst = (float *)workspace;
@@ -379,10 +380,10 @@ int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void
     conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw_dst, db_dst, pps);
   });
   CTAGAN_LAUNCH_OK();
-  if (splits > 1) {
-    int rc = ctagan_ordered_sum(dw_dst, dw, splits, dw_elems, st);
+  if (staged) {
+    int rc = ctagan_ordered_sum(dw_dst, dw, splits, dw_elems, st, accumulate);
     if (rc) return rc;
-    if (db) rc = ctagan_ordered_sum(db_dst, db, splits, g->Co, st);
+    if (db) rc = ctagan_ordered_sum(db_dst, db, splits, g->Co, st, accumulate);
     return rc;
   }
   return CTAGAN_OK;

@@ -573,7 +573,7 @@ size_t ctagan_conv_wgrad_thin_workspace(const ctagan_conv_geom *g) {
 }
 
 int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                           size_t workspace_bytes, cudaStream_t st) {
+                           size_t workspace_bytes, cudaStream_t st, int accumulate) {
   ThinPlan pl;
   if (!plan_thin(g, pl)) {
     ctagan_set_error("conv_wgrad_thin: geometry is not degenerate");
@@ -606,8 +606,8 @@ int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void
 #undef THIN_LAUNCH
   }
   CTAGAN_LAUNCH_OK();
-  int rc = ctagan_ordered_sum(dw_part, dw, (int)pl.grid.x, dw_elems, st);
+  int rc = ctagan_ordered_sum(dw_part, dw, (int)pl.grid.x, dw_elems, st, accumulate);
   if (rc) return rc;
-  if (db) rc = ctagan_ordered_sum(db_part, db, (int)pl.grid.x, g->Co, st);
+  if (db) rc = ctagan_ordered_sum(db_part, db, (int)pl.grid.x, g->Co, st, accumulate);
   return rc;
 }

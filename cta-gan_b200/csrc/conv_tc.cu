@@ -358,7 +358,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
 }
 
 // dw[co][ci][tap] = sum_s ws[s][co][tap][ci]     (also the [co][tap][ci] -> PyTorch OIHW transpose)
-__global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci) {
+__global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci, int accumulate) {
   pdl_wait();
   const long long total = (long long)Co * ntaps * Ci;
   ws += (long long)blockIdx.y * splits * total;       // grouped launch: one weight gradient per group
@@ -370,7 +370,8 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restr
     const int co = (int)(r / ntaps);
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += ws[(long long)k * total + idx];
-    dw[((long long)co * Ci + ci) * ntaps + tap] = s;
+    float *dst = dw + ((long long)co * Ci + ci) * ntaps + tap;
+    *dst = accumulate ? *dst + s : s;
   }
 }
 
@@ -1074,7 +1075,7 @@ size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g, int n_groups) {
 
 // n_groups > 1: the batch is n_groups consecutive image groups and dw / db hold one gradient per group ([groups][Co][Ci][KH][KW])
 int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
-                         size_t workspace_bytes, cudaStream_t st, int n_groups) {
+                         size_t workspace_bytes, cudaStream_t st, int n_groups, int accumulate) {
   WgPlan pl;
   if (n_groups < 1 || g->N % n_groups || !plan_wgrad(g, pl, n_groups)) {
     ctagan_set_error("conv_wgrad: geometry not supported by the tcgen05 engine");
@@ -1102,7 +1103,7 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   const long long total = (long long)g->Co * p.ntaps * g->Ci;
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctagan_num_sms() * 8) blocks = ctagan_num_sms() * 8;
-  CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
+  CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci, accumulate));
   CTAGAN_LAUNCH_OK();
   if (db) {
     const long long pixels = (long long)(g->N / n_groups) * g->Ho * g->Wo;
@@ -1115,7 +1116,7 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
       float *pk = part + (size_t)k * wg_db_blocks() * g->Co;
       colsum_kernel<<<nb, 256, 0, st>>>((const bf16 *)gy + (size_t)k * pixels * g->Co, pk, pixels, g->Co, ppb);
       CTAGAN_LAUNCH_OK();
-      rc = ctagan_ordered_sum(pk, db + (size_t)k * g->Co, nb, g->Co, st);
+      rc = ctagan_ordered_sum(pk, db + (size_t)k * g->Co, nb, g->Co, st, accumulate);
       if (rc) return rc;
     }
   }

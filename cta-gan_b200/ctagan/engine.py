@@ -76,6 +76,37 @@ class ConvPrim:
         self.O, self.I, self.K, _ = weight.shape
         self.s, self.p = stride, pad
         self._cache: Dict[Tuple[int, torch.dtype], Tuple[int, int, torch.Tensor]] = {}
+        # persistent gradient buffers (slices of an optimiser's flat gradient bucket, ctagan.optim.FusedAdam): the weight-gradient
+        # kernels write there directly; the first use of the layer in a step overwrites, a second use accumulates
+        self.grad_w: Optional[torch.Tensor] = None
+        self.grad_b: Optional[torch.Tensor] = None
+        self.grad_writes = 0
+        self.grad_event = None
+
+    def attach_grads(self, grad_w, grad_b):
+        self.grad_w, self.grad_b, self.grad_writes, self.grad_event = grad_w, grad_b, 0, None
+
+    def mark_packed(self, dtype: torch.dtype):
+        """The optimiser kernel has just re-packed both copies of `dtype` from the updated master weights: every other cached copy is
+        stale, these two are fresh."""
+        ptr = self.w.data_ptr()
+        _PTR_EPOCH[ptr] = _PTR_EPOCH.get(ptr, 0) + 1
+        ver = self._version_key()
+        for m in (0, 1):
+            hit = self._cache.get((m, dtype))
+            if hit is not None:
+                self._cache[(m, dtype)] = (ver, hit[1])
+
+    def packed_buffers(self, dtype: torch.dtype):
+        """(mode-0 buffer, mode-1 buffer), allocated if need be (contents unspecified until packed)."""
+        out = []
+        for m in (0, 1):
+            hit = self._cache.get((m, dtype))
+            if hit is None or hit[1].dtype != dtype:
+                shape = (self.O, self.K, self.K, self.I) if m == 0 else (self.I, self.K, self.K, self.O)
+                self._cache[(m, dtype)] = (None, torch.empty(shape, dtype=dtype, device=self.w.device))
+            out.append(self._cache[(m, dtype)][1])
+        return out
 
     def packed(self, mode: int, dtype: torch.dtype) -> torch.Tensor:
         """The packed copy for `mode`, re-packed in place if stale (the buffer persists: CUDA graphs and grouped launches alias it)."""
@@ -154,7 +185,19 @@ class ConvPrim:
         g = ops.make_geom(N, Hi, Wi, Ci, Ho, Wo, Co, self.K, self.s, 1, p, L.ACT_NONE, ops.dt(gy), gy_margin)
         if _ACTIVE_LANE["value"] is not None:
             _ACTIVE_LANE["value"].keep += (gy, gx)
-        return ops.conv_wgrad(gy, gx, g, want_bias, _ENGINE["value"])
+        if self.grad_w is None:
+            return ops.conv_wgrad(gy, gx, g, want_bias, _ENGINE["value"])
+        # gradient bucket: the first writer of the step overwrites and leaves an event, a later one (the other use of this network,
+        # possibly on another stream) waits for it and accumulates
+        acc = self.grad_writes > 0
+        if acc and self.grad_event is not None:
+            torch.cuda.current_stream().wait_event(self.grad_event)
+        out = ops.conv_wgrad(gy, gx, g, want_bias and self.grad_b is not None, _ENGINE["value"], out_w=self.grad_w,
+                             out_b=self.grad_b if want_bias else None, accumulate=acc)
+        self.grad_writes += 1
+        self.grad_event = torch.cuda.Event()
+        self.grad_event.record()
+        return out
 
 
 _WGRAD_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
@@ -243,9 +286,10 @@ class deferred_weight_grads:
         return False
 
     def take(self, leaves, grads, needs):
-        """Called by a Function's backward: keeps the gradients of the leaves that want one; returns what to hand to autograd."""
+        """Called by a Function's backward: keeps the gradients of the leaves that want one; returns what to hand to autograd.
+        Gradients that the kernels have already written into the leaf's persistent gradient buffer are done."""
         for leaf, g, need in zip(leaves, grads, needs):
-            if need and g is not None:
+            if need and g is not None and not grad_in_place(leaf, g):
                 self.items.append((leaf, g))
         return [None] * len(grads)
 
@@ -268,6 +312,16 @@ class deferred_weight_grads:
 
 def deferred():
     return _DEFERRED["value"]
+
+
+def grad_in_place(leaf, g) -> bool:
+    """True when `g` IS the leaf's persistent gradient buffer (the weight-gradient kernel wrote there): nothing to hand to autograd."""
+    return leaf.grad is not None and g is not None and g.data_ptr() == leaf.grad.data_ptr()
+
+
+def strip_in_place(leaves, grads):
+    """Gradients for autograd: None for the ones already in place in their leaf's gradient buffer."""
+    return [None if (g is None or grad_in_place(leaf, g)) else g for leaf, g in zip(leaves, grads)]
 
 
 class _PairStore:

@@ -36,6 +36,11 @@ class PackItem(ctypes.Structure):
                 ("KW", ctypes.c_int32), ("mode", ctypes.c_int32)]
 
 
+class AdamItem(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p), ("wp0", ctypes.c_void_p),
+                ("wp1", ctypes.c_void_p), ("O", ctypes.c_int32), ("I", ctypes.c_int32), ("KH", ctypes.c_int32), ("KW", ctypes.c_int32)]
+
+
 def _ctype_of(decl: str):
     d = decl.strip()
     if "**" in d:
@@ -47,6 +52,8 @@ def _ctype_of(decl: str):
             return ctypes.POINTER(ConvGroups)
         if "ctagan_pack_item" in d:
             return ctypes.POINTER(PackItem)
+        if "ctagan_adam_item" in d:
+            return ctypes.c_void_p          # host array or device pointer, depending on the entry point
         return ctypes.c_void_p
     base = d.split()[0] if d.split()[0] != "const" else d.split()[1]
     return {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float,

@@ -55,6 +55,8 @@ class _GeneratorFn(torch.autograd.Function):
             grads = E.split_group_grads(grads, ctx.plan.G) if need_dw else [None] * len(ctx.plan.params)
         if need_dw and E.deferred() is not None:
             grads = E.deferred().take(ctx.leaves, grads, ctx.needs_input_grad[2:])
+        elif need_dw:
+            grads = E.strip_in_place(ctx.leaves, grads)
         ctx.leaves = None
         return (None, dx, *grads)
 
@@ -152,6 +154,8 @@ class _DiscriminatorFn(torch.autograd.Function):
             gw = E.split_group_grads(gw, ctx.plan.G)
         if need_dw and E.deferred() is not None:
             gw = E.deferred().take(ctx.leaves, gw, ctx.needs_input_grad[3:])
+        elif need_dw:
+            gw = E.strip_in_place(ctx.leaves, gw)
         ctx.leaves = None
         return (None, None, dx, *gw)
 
@@ -385,6 +389,8 @@ class _RegFn(torch.autograd.Function):
         ctx.saved = None
         if E.deferred() is not None and any(ctx.needs_input_grad[3:]):
             grads = E.deferred().take(ctx.leaves, grads, ctx.needs_input_grad[3:])
+        elif any(ctx.needs_input_grad[3:]):
+            grads = E.strip_in_place(ctx.leaves, grads)
         ctx.leaves = None
         return (None, da, db, *grads)
 

@@ -1,0 +1,145 @@
+"""Optimiser of the training iterations: torch.optim.Adam(lr, betas=(0.5, 0.999)) of the reference trainers
+(CycTrainer.py:67-73, RegTrainer.py:97-101, HdTrainer.py:101-105, p2pTrainer.py:62-63) as ONE kernel launch per parameter group.
+
+* Gradients live in one flat fp32 bucket per optimiser.  Every parameter's `.grad` is a persistent view into it, and the
+  weight-gradient kernels write there directly (ConvPrim.attach_grads): no per-step gradient allocation, no `zero_grad` pass (the
+  first use of a layer in a step overwrites its slice, a second use accumulates), no flatten copy before the data-parallel
+  all-reduce -- the bucket IS the all-reduce buffer.
+* `step()` launches `ctagan_adam_pack_multi`: Adam with the arithmetic of PyTorch's fused kernel (bit-identical, see
+  tests/test_gpu_optim.py) on weights, gradients and both moments read once, plus both packed bf16 layouts of every convolution
+  weight written from the same tile.  The learning rate and the step counter live on the device, so the launch is captured in the
+  iteration's CUDA graph and `update_learning_rate()` reaches it.
+
+Parameters that never receive a gradient (the biases in front of a non-affine InstanceNorm: mathematically dead) keep a zero
+gradient slice: Adam leaves them untouched, exactly like torch.optim.Adam skipping `grad is None`."""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, List, Sequence
+
+import torch
+
+from . import engine as E
+from . import lib as L
+from . import ops
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _prims_of(nets) -> dict:
+    """{id(weight parameter): ConvPrim} of the given networks' plans."""
+    out = {}
+    for net in nets:
+        plans = []
+        if hasattr(net, "_scale_plan"):
+            plans = [net._scale_plan(i) for i in range(net.num_D)]
+        elif hasattr(net, "_get_plan"):
+            plans = [net._get_plan()]
+        for plan in plans:
+            for prim in plan.prims():
+                out[id(prim.w)] = prim
+    return out
+
+
+class FusedAdam:
+    """Adam over `params` (the reference's betas; eps 1e-8; no weight decay).  nets: the networks owning the parameters -- their
+    ConvPrims get their gradient slices attached and their packed weights refreshed by the optimiser kernel."""
+
+    def __init__(self, params: Iterable[torch.Tensor], lr: float, nets: Sequence[torch.nn.Module], betas=(0.5, 0.999), eps=1e-8):
+        self.params: List[torch.Tensor] = [p for p in params]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self.params)
+        dev = self.params[0].device
+        self.device = dev
+        self.betas, self.eps = betas, eps
+        self.lr = torch.tensor(float(lr), dtype=torch.float32, device=dev)
+        self.param_groups = [{"params": self.params, "lr": self.lr, "betas": betas, "eps": eps}]      # torch.optim surface the trainers use
+        self.step_count = torch.zeros((), dtype=torch.float32, device=dev)
+        self.ticket = torch.zeros((1,), dtype=torch.int32, device=dev)
+        sizes = [p.numel() for p in self.params]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + ((n + 3) & ~3))                   # 16-byte aligned slices
+        self.grad_flat = torch.zeros((offs[-1],), dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.grad_flat)
+        self.exp_avg_sq = torch.zeros_like(self.grad_flat)
+        self.views = [self.grad_flat[o:o + n].view_as(p) for p, o, n in zip(self.params, offs, sizes)]
+        self._offs, self._sizes = offs, sizes
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        # attach the gradient slices to the ConvPrims (weight + its bias)
+        self.nets = list(nets)
+        self._bind_prims()
+        self._table_key = None
+        self._dtype = None
+
+    def _bind_prims(self):
+        prims = _prims_of(self.nets)
+        self._plans = [self._plans_of(net) for net in self.nets]
+        by_id = {id(p): v for p, v in zip(self.params, self.views)}
+        self.prims = []
+        for p in self.params:
+            prim = prims.get(id(p))
+            if prim is not None:
+                prim.attach_grads(by_id[id(p)], by_id.get(id(prim.b)) if prim.b is not None else None)
+                self.prims.append(prim)
+        self._prim_of = {id(prim.w): prim for prim in self.prims}
+
+    @staticmethod
+    def _plans_of(net):
+        if hasattr(net, "_scale_plan"):
+            return [net._scale_plan(i) for i in range(net.num_D)]
+        return [net._get_plan()] if hasattr(net, "_get_plan") else []
+
+    # ---- torch.optim surface -----------------------------------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = True):
+        """Start of a backward pass: nothing is cleared (the first weight-gradient kernel of each layer overwrites its slice);
+        the per-step write counters are re-armed."""
+        if any(p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in zip(self.params, self.views)):
+            for p, v in zip(self.params, self.views):                # someone replaced .grad (e.g. a foreign zero_grad): re-attach
+                p.grad = v
+        cur = [self._plans_of(net) for net in self.nets]
+        if any(a is not b for pa, pb in zip(cur, self._plans) for a, b in zip(pa, pb)):
+            self._bind_prims()            # a network rebuilt its plan (e.g. after .to()): attach the gradient slices to the new ConvPrims
+            self._table_key = None
+        for prim in self.prims:
+            prim.grad_writes, prim.grad_event = 0, None
+
+    def _build_table(self, dtype):
+        lib = L.load()
+        n = len(self.params)
+        items = (L.AdamItem * n)()
+        for k, (p, o, sz) in enumerate(zip(self.params, self._offs, self._sizes)):
+            prim = self._prim_of.get(id(p))
+            wp0 = wp1 = None
+            if prim is not None:
+                b0, b1 = prim.packed_buffers(dtype)
+                wp0, wp1 = b0.data_ptr(), b1.data_ptr()
+                O, I, KH, KW = p.shape
+            else:
+                O, I, KH, KW = p.numel(), 1, 1, 1
+            items[k] = L.AdamItem(p.data_ptr(), self.grad_flat[o:].data_ptr(), self.exp_avg[o:].data_ptr(), self.exp_avg_sq[o:].data_ptr(),
+                                  wp0, wp1, O, I, KH, KW)
+        tiles = (ctypes.c_int * (n + 1))()
+        L.check(lib.ctagan_adam_pack_tiles(ctypes.cast(items, ctypes.c_void_p), n, tiles))
+        self._smem = int(lib.ctagan_adam_pack_smem_bytes(ctypes.cast(items, ctypes.c_void_p), n))
+        raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
+        self._items_dev = raw.to(self.device)
+        self._tiles_dev = torch.tensor(list(tiles), dtype=torch.int32).to(self.device)
+        self._n, self._total = n, int(tiles[n])
+        self._dtype = dtype
+
+    def step(self):
+        dtype = E.get_precision()
+        key = (dtype, tuple(p.data_ptr() for p in self.params))
+        if key != self._table_key:            # first step, or parameters were re-allocated / the precision changed: rebuild (outside captures)
+            self._build_table(dtype)
+            self._table_key = key
+        ops.ensure_device()
+        ops._count(1)
+        L.check(L.load().ctagan_adam_pack_multi(ctypes.c_void_p(self._items_dev.data_ptr()), ctypes.c_void_p(self._tiles_dev.data_ptr()), self._n,
+                                                self._total, self._smem, ctypes.c_void_p(self.lr.data_ptr()),
+                                                ctypes.c_void_p(self.step_count.data_ptr()), ctypes.c_void_p(self.ticket.data_ptr()),
+                                                float(self.betas[0]), float(self.betas[1]), float(self.eps), _DT[dtype],
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for prim in self.prims:
+            prim.mark_packed(dtype)

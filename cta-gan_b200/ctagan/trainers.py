@@ -65,24 +65,47 @@ class SyntheticSlices:
 
 
 class GradSync:
-    """Data-parallel gradient averaging: one flat NCCL all-reduce per optimiser group (weak scaling over slices; every op
-    on the path is per-sample, so N ranks x b slices == 1 rank x N*b slices up to reduction order)."""
+    """Data-parallel gradient averaging (weak scaling over slices; every op on the path is per-sample, so N ranks x b slices ==
+    1 rank x N*b slices up to reduction order).  With the fused optimiser the gradients already live in one flat bucket per optimiser
+    group, which IS the NCCL buffer: no flatten copy.  The bucket is reduced in chunks of ~`chunk_mb` on a communication stream, so
+    that a chunk's all-reduce runs under the next chunk's wait / the optimiser kernels of other groups, and the training stream only
+    waits for the last event."""
 
-    def __init__(self, params: Iterable[torch.Tensor]):
-        self.params = [p for p in params]
+    def __init__(self, source, chunk_mb: float = 24.0):
+        self.opt = source if hasattr(source, "grad_flat") else None
+        self.params = None if self.opt is not None else [p for p in source]
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.chunk = int(chunk_mb * (1 << 20) / 4)
+        self._comm = None
 
-    def __call__(self):
-        if self.world == 1:
-            return
-        owners = [p for p in self.params if p.grad is not None]
-        grads = [p.grad for p in owners]
-        flat = torch.cat([g.reshape(-1) for g in grads])
+    def _all_reduce(self, flat):
         if dist.get_backend() == "nccl":
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)              # the division happens inside the collective
         else:                                                        # gloo (CPU tests) has no AVG
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
             flat.div_(self.world)
+
+    def __call__(self):
+        if self.world == 1:
+            return
+        if self.opt is not None:
+            flat = self.opt.grad_flat
+            if not flat.is_cuda:
+                self._all_reduce(flat)
+                return
+            if self._comm is None:
+                self._comm = ops.named_stream("ddp.comm")
+            cur = torch.cuda.current_stream()
+            self._comm.wait_stream(cur)
+            with torch.cuda.stream(self._comm):
+                for o in range(0, flat.numel(), self.chunk):
+                    self._all_reduce(flat[o:o + self.chunk])
+            cur.wait_stream(self._comm)
+            return
+        owners = [p for p in self.params if p.grad is not None]
+        grads = [p.grad for p in owners]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        self._all_reduce(flat)
         # the averaged gradients stay in the flat buffer: .grad becomes a view of it (no copy back)
         for p, c, g in zip(owners, flat.split([g.numel() for g in grads]), grads):
             p.grad = c.view_as(g)
@@ -112,10 +135,21 @@ class _TrainerBase:
         self.last_losses: Dict[str, torch.Tensor] = {}
 
     # -- helpers -------------------------------------------------------------------------------------------------------
-    def _adam(self, params, lr):
-        # lr lives in a device tensor: update_learning_rate() then also reaches the Adam kernels captured in a CUDA graph
+    def _adam(self, params, lr, nets):
+        """Adam(betas=(0.5, 0.999)) of the reference.  Default: ctagan.optim.FusedAdam (one kernel per group: update + both packed bf16
+        weight layouts, gradients in a flat bucket the weight-gradient kernels write into).  `fused_optimizer: false` (and the grouped
+        Cyc schedule) fall back to torch.optim.Adam(fused, capturable).  Either way the learning rate lives in a device tensor, so
+        update_learning_rate() also reaches the kernels captured in a CUDA graph."""
+        c = self.config
+        if c.get("fused_optimizer", True) and (c.get("cyc_schedule") or os.environ.get("CTAGAN_CYC_SCHEDULE", "streams")) != "grouped":
+            from .optim import FusedAdam
+            return FusedAdam(params, float(lr), nets)
         return torch.optim.Adam(params, lr=torch.tensor(float(lr), dtype=torch.float32, device=self.device), betas=(0.5, 0.999), fused=True,
                                 capturable=True)
+
+    @staticmethod
+    def _fused(opt):
+        return hasattr(opt, "grad_flat")
 
     @staticmethod
     def _set_lr(opt, lr):
@@ -238,18 +272,20 @@ class Cyc_Trainer(_TrainerBase):
         dev = self.device
         self.netG_A2B = N.Generator(c["input_nc"], c["output_nc"]).to(dev)            # CycTrainer.py:64-71 creation order
         self.netD_B = N.Discriminator(c["input_nc"]).to(dev)
-        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c["lr"])
+        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c["lr"], [self.netD_B])
         self.netG_B2A = N.Generator(c["input_nc"], c["output_nc"]).to(dev)
         self.netD_A = N.Discriminator(c["input_nc"]).to(dev)
-        self.optimizer_G = self._adam(itertools.chain(self.netG_A2B.parameters(), self.netG_B2A.parameters()), c["lr"])
-        self.optimizer_D_A = self._adam(self.netD_A.parameters(), c["lr"])
+        self.optimizer_G = self._adam(itertools.chain(self.netG_A2B.parameters(), self.netG_B2A.parameters()), c["lr"], [self.netG_A2B, self.netG_B2A])
+        self.optimizer_D_A = self._adam(self.netD_A.parameters(), c["lr"], [self.netD_A])
         self.MSE_loss, self.L1_loss = N.MSELoss(), N.L1Loss()
         self.inputs = self._alloc_inputs()
         self.target_real, self.target_fake = 1.0, 0.0
         from .replay import ReplayBuffer
         self.fake_A_buffer, self.fake_B_buffer = ReplayBuffer(), ReplayBuffer()
-        self._sync_G = GradSync(itertools.chain(self.netG_A2B.parameters(), self.netG_B2A.parameters()))
-        self._sync_DA, self._sync_DB = GradSync(self.netD_A.parameters()), GradSync(self.netD_B.parameters())
+        def sync(opt, params):
+            return GradSync(opt if self._fused(opt) else params)
+        self._sync_G = sync(self.optimizer_G, itertools.chain(self.netG_A2B.parameters(), self.netG_B2A.parameters()))
+        self._sync_DA, self._sync_DB = sync(self.optimizer_D_A, self.netD_A.parameters()), sync(self.optimizer_D_B, self.netD_B.parameters())
         self.sync_replicas()
 
     def update_learning_rate(self):
@@ -283,8 +319,10 @@ class Cyc_Trainer(_TrainerBase):
         # Each generator is used once per chain.  autograd would sum the two gradient contributions of a parameter on ONE stream and make
         # that stream wait for the other chain's producer, which serialises the chains; so the second use of each generator goes through
         # twin leaves aliasing the same storage, and the two gradient sets are added once after the join (one multi-tensor kernel).
-        twins_B2A = [p.detach().requires_grad_() for p in self.netG_B2A.parameters()]
-        twins_A2B = [p.detach().requires_grad_() for p in self.netG_A2B.parameters()]
+        # (with the fused optimiser the weight-gradient kernels accumulate the second use in place: no twins needed)
+        fused = self._fused(self.optimizer_G)
+        twins_B2A = None if fused else [p.detach().requires_grad_() for p in self.netG_B2A.parameters()]
+        twins_A2B = None if fused else [p.detach().requires_grad_() for p in self.netG_A2B.parameters()]
         sA, sB = self._side_streams()
         sA.wait_stream(cur); sB.wait_stream(cur)
         with torch.cuda.stream(sA):
@@ -304,7 +342,7 @@ class Cyc_Trainer(_TrainerBase):
             t.record_stream(cur)
         loss_Total = loss_A + loss_B                                                       # :160-162
         loss_Total.backward()
-        for net, twins in ((self.netG_A2B, twins_A2B), (self.netG_B2A, twins_B2A)):
+        for net, twins in (() if fused else ((self.netG_A2B, twins_A2B), (self.netG_B2A, twins_B2A))):
             own, extra = [], []
             for p_, t_ in zip(net.parameters(), twins):
                 if t_.grad is None:
@@ -319,7 +357,7 @@ class Cyc_Trainer(_TrainerBase):
         self.optimizer_G.step()
         return fake_A.detach(), fake_B.detach(), loss_Total.detach()
 
-    def phase_D(self, netD, opt, sync, real, fake, repack=True, step_after=None):
+    def phase_D(self, netD, opt, sync, real, fake, repack=True, step_after=None, packed_after=None):
         """One discriminator update (:165-178 / :182-197).  real and fake go through the network as ONE batch: InstanceNorm is
         per sample, so this is the same arithmetic as the reference's two passes with half the kernel launches."""
         c = self.config
@@ -333,8 +371,10 @@ class Cyc_Trainer(_TrainerBase):
         sync()
         if step_after is not None:             # an event after which the master weights (biases are read in place) may change
             torch.cuda.current_stream().wait_event(step_after)
+        if packed_after is not None and self._fused(opt):      # the fused step rewrites the PACKED weights too: wait for their last reader
+            torch.cuda.current_stream().wait_event(packed_after)
         opt.step()
-        if repack:
+        if repack and not self._fused(opt):
             netD.prepack(force=True)           # off the generator phase's critical path (it only reads the frozen discriminators)
         return loss_D.detach()
 
@@ -346,7 +386,8 @@ class Cyc_Trainer(_TrainerBase):
         sC = self._streams[2]
         sA.wait_stream(cur); sB.wait_stream(cur); sC.wait_stream(cur)
         with torch.cuda.stream(sC):            # the generators were just updated (phase_G): re-pack them beside the discriminator phases
-            self.netG_A2B.prepack(force=True); self.netG_B2A.prepack(force=True)
+            if not self._fused(self.optimizer_G):
+                self.netG_A2B.prepack(force=True); self.netG_B2A.prepack(force=True)
         with torch.cuda.stream(sA):
             loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, fake_A)
         with torch.cuda.stream(sB):
@@ -410,18 +451,23 @@ class Cyc_Trainer(_TrainerBase):
         with torch.cuda.stream(sDA):                                                       # :165-178
             sDA.wait_event(ev_fake_A)
             pooled_A = self.fake_A_buffer.apply(fake_A, sel[0], sel[1])
-            loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, pooled_A, repack=False, step_after=ev_DA_read)
-            sDA.wait_event(ev_G_backward)      # the generator backward was the last reader of the packed discriminator weights
-            self.netD_A.prepack(force=True)
+            loss_D_A = self.phase_D(self.netD_A, self.optimizer_D_A, self._sync_DA, real_A, pooled_A, repack=False, step_after=ev_DA_read,
+                                    packed_after=ev_G_backward)
+            if not self._fused(self.optimizer_D_A):
+                sDA.wait_event(ev_G_backward)  # the generator backward was the last reader of the packed discriminator weights
+                self.netD_A.prepack(force=True)
         with torch.cuda.stream(sDB):                                                       # :182-197
             sDB.wait_event(ev_fake_B)
             pooled_B = self.fake_B_buffer.apply(fake_B, sel[2], sel[3])
-            loss_D_B = self.phase_D(self.netD_B, self.optimizer_D_B, self._sync_DB, real_B, pooled_B, repack=False, step_after=ev_DB_read)
-            sDB.wait_event(ev_G_backward)
-            self.netD_B.prepack(force=True)
+            loss_D_B = self.phase_D(self.netD_B, self.optimizer_D_B, self._sync_DB, real_B, pooled_B, repack=False, step_after=ev_DB_read,
+                                    packed_after=ev_G_backward)
+            if not self._fused(self.optimizer_D_B):
+                sDB.wait_event(ev_G_backward)
+                self.netD_B.prepack(force=True)
         self._sync_G()
         self.optimizer_G.step()
-        self.netG_A2B.prepack(force=True); self.netG_B2A.prepack(force=True)
+        if not self._fused(self.optimizer_G):
+            self.netG_A2B.prepack(force=True); self.netG_B2A.prepack(force=True)
         cur.wait_stream(sDA); cur.wait_stream(sDB)
         for t in (loss_D_A, loss_D_B, fake_A, fake_B):
             t.record_stream(cur)
@@ -530,17 +576,22 @@ class Reg_Trainer(_TrainerBase):
         dev = self.device
         self.netG_A2B = N.Generator(c["input_nc"], c["output_nc"]).to(dev)              # RegTrainer.py:94-101
         self.netD_B = self._make_D().to(dev)
-        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c[self.lr_d])
+        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c[self.lr_d], [self.netD_B])
         self.R_A = N.Reg(c["size"], c["size"], c["input_nc"], c["input_nc"]).to(dev)
         self.spatial_transform = N.Transformer_2D().to(dev)
-        self.optimizer_R_A = self._adam(self.R_A.parameters(), c["lr"])
-        self.optimizer_G = self._adam(self.netG_A2B.parameters(), c["lr"])
+        self.optimizer_R_A = self._adam(self.R_A.parameters(), c["lr"], [self.R_A])
+        self.optimizer_G = self._adam(self.netG_A2B.parameters(), c["lr"], [self.netG_A2B])
         self.MSE_loss, self.L1_loss = N.MSELoss(), N.L1Loss()
         self.criterionGAN = N.GANLoss()
         self.inputs = self._alloc_inputs()
         self.target_real, self.target_fake = 1.0, 0.0
-        self._sync_GR = GradSync(itertools.chain(self.R_A.parameters(), self.netG_A2B.parameters()))
-        self._sync_D = GradSync(self.netD_B.parameters())
+        if self._fused(self.optimizer_G):
+            sr, sg = GradSync(self.optimizer_R_A), GradSync(self.optimizer_G)
+            self._sync_GR = lambda: (sr(), sg())
+            self._sync_D = GradSync(self.optimizer_D_B)
+        else:
+            self._sync_GR = GradSync(itertools.chain(self.R_A.parameters(), self.netG_A2B.parameters()))
+            self._sync_D = GradSync(self.netD_B.parameters())
         self.sync_replicas()
 
     def update_learning_rate(self):
@@ -694,12 +745,14 @@ class P2p_Trainer(_TrainerBase):
         dev = self.device
         self.netG_A2B = N.Generator(c["input_nc"], c["output_nc"]).to(dev)               # p2pTrainer.py:60-63
         self.netD_B = N.Discriminator(c["input_nc"] * 2).to(dev)
-        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c["lr"])
-        self.optimizer_G = self._adam(self.netG_A2B.parameters(), c["lr"])
+        self.optimizer_D_B = self._adam(self.netD_B.parameters(), c["lr"], [self.netD_B])
+        self.optimizer_G = self._adam(self.netG_A2B.parameters(), c["lr"], [self.netG_A2B])
         self.MSE_loss, self.L1_loss = N.MSELoss(), N.L1Loss()
         self.inputs = self._alloc_inputs()
         self.target_real, self.target_fake = 1.0, 0.0
-        self._sync_G, self._sync_D = GradSync(self.netG_A2B.parameters()), GradSync(self.netD_B.parameters())
+        fz = self._fused(self.optimizer_G)
+        self._sync_G = GradSync(self.optimizer_G if fz else self.netG_A2B.parameters())
+        self._sync_D = GradSync(self.optimizer_D_B if fz else self.netD_B.parameters())
         self.sync_replicas()
 
     def update_learning_rate(self):

@@ -110,10 +110,12 @@ int ctagan_conv_wgrad_grouped(const ctagan_conv_geom *g, int groups, const void 
 /* Weight gradient (and optional bias gradient) of the same geometry:
  *   dw[a,b,kh,kw] (+)= sum_{n,oh,ow} gy[n,oh,ow,a] * gx[n,ih,iw,b],  db[a] = sum gy[n,oh,ow,a]
  * with (ih,iw) from (oh,ow,kh,kw) as above; g->Co == A (channels of gy), g->Ci == B (channels of gx); dw is fp32 in
- * PyTorch's [A][B][KH][KW] order and is OVERWRITTEN (db too, may be NULL).  Conv2d: gy=dy, gx=x.  ConvTranspose2d: gy=x, gx=dy.
+ * PyTorch's [A][B][KH][KW] order and is OVERWRITTEN (db too, may be NULL) -- or, with accumulate != 0, ADDED TO (the second use of a
+ * network inside one backward pass, e.g. the cycle pass of CycTrainer.py:153-157, lands in the same gradient buffer as the first:
+ * what autograd's AccumulateGrad does, without a temporary and an add kernel).  Conv2d: gy=dy, gx=x.  ConvTranspose2d: gy=x, gx=dy.
  * Replaces the weight-gradient half of cudnn/ATen convolution_backward for the layers cited above. */
 int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db,
-                      void *workspace, size_t workspace_bytes, int engine, void *stream);
+                      void *workspace, size_t workspace_bytes, int engine, int accumulate, void *stream);
 /* Scratch bytes ctagan_conv_wgrad needs for this geometry/engine: the per-CTA / per-split partial sums of every engine's split
  * reduction (each CTA stores its partial result in its own row, a second kernel adds the rows in order: no floating-point atomics,
  * the same inputs give the same bits). */
@@ -131,6 +133,28 @@ typedef struct {
   int32_t O, I, KH, KW, mode;
 } ctagan_pack_item;
 int ctagan_pack_weights_multi(const ctagan_pack_item *items, int n_items, int dtype, void *stream);
+
+/* f3: the optimiser step of a whole parameter group in ONE launch -- torch.optim.Adam(betas=(0.5, 0.999)) of trainer/CycTrainer.py:67-73
+ * (RegTrainer.py:97-101, HdTrainer.py:101-105, p2pTrainer.py:62-63) with the arithmetic of PyTorch's fused Adam kernel, operation for
+ * operation -- that also emits both packed copies of every convolution weight (ctagan_pack_weights modes 0 and 1, `packed_dtype`) from
+ * the tile it has just updated.  An item is one parameter tensor viewed as [O][I][KH][KW] (1-D tensors: O = numel, I = KH = KW = 1);
+ * wp0 / wp1 may be NULL.  items_dev / tile_start_dev: the table in DEVICE memory (ctagan_adam_pack_tiles fills the host copy of
+ * tile_start[n_items + 1]; total_tiles = tile_start[n_items]); lr_dev: the learning rate; step_dev: the step counter as a float
+ * (incremented by the kernel, as torch's state['step']); ticket_dev: one zeroed uint32.  Capturable in CUDA graphs. */
+typedef struct {
+  float *p;
+  const float *g;
+  float *m;
+  float *v;
+  void *wp0;
+  void *wp1;
+  int32_t O, I, KH, KW;
+} ctagan_adam_item;
+size_t ctagan_adam_pack_smem_bytes(const ctagan_adam_item *items_host, int n_items);
+int ctagan_adam_pack_tiles(const ctagan_adam_item *items_host, int n_items, int *tile_start_host);
+int ctagan_adam_pack_multi(const ctagan_adam_item *items_dev, const int *tile_start_dev, int n_items, int total_tiles, size_t smem_bytes,
+                           const float *lr_dev, float *step_dev, uint32_t *ticket_dev, float beta1, float beta2, float eps, int packed_dtype,
+                           void *stream);
 
 /* InstanceNorm2d statistics (affine=False, eps=1e-5, biased variance; Model/CycleGan.py:12,16,29,37,52,82,86,90,
  * trainer/layers.py:14): x[N][HW][C] -> stats[N][C][2] = (mean, rstd) fp32.  acc: caller scratch of
