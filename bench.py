@@ -74,6 +74,8 @@ def workload_config(args):
             "n_epochs": 1, "batchSize": args.batch, "lr": 1e-4, "lrd": 1e-4, "decay_epoch": 1, "size": args.size, "input_nc": 1, "output_nc": 1,
             "cuda": True, "n_cpu": 1, "precision": args.precision, "synthetic": True, "save_checkpoints": False, "log_every": 10 ** 9}
     base["name"] = {"cyc": "CycleGan", "reg": "RegGan", "hd": "HdGan", "infer": "P2p"}[args.workload]
+    if os.environ.get("CTAGAN_FUSED_OPT") == "0":          # A/B switch: torch.optim.Adam + separate re-pack instead of the one-kernel optimiser
+        base["fused_optimizer"] = False
     return base
 
 
@@ -662,9 +664,16 @@ def run_ours(args):
 
 
 def _finish(world):
-    """Multi-rank runs end with os._exit: tearing down a NCCL communicator that captured CUDA graphs still reference can block."""
+    """Multi-rank runs end together (rank 0 still measures the kernel rooflines after the timed regions: the other ranks wait for it, a
+    worker that exits early makes the launcher tear the job down) and with os._exit: tearing down a NCCL communicator that captured CUDA
+    graphs still reference can block."""
     sys.stdout.flush(); sys.stderr.flush()
     if world > 1:
+        import torch.distributed as dist
+        try:
+            dist.barrier()
+        except Exception:                                # noqa: BLE001
+            pass
         os._exit(0)
 
 

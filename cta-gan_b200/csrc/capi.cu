@@ -45,12 +45,13 @@ int ctagan_num_sms() {
 }
 
 namespace {
-__global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restrict__ part, float *__restrict__ out, int parts, long long n,
-                                                          int accumulate) {
+template <bool ACC>
+__global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restrict__ part, float *__restrict__ out, int parts, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < parts; ++k) s += __ldcg(part + (long long)k * n + i);
-    out[i] = accumulate ? out[i] + s : s;
+    if (ACC) s += out[i];
+    out[i] = s;
   }
 }
 }  // namespace
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restric
 int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st, int accumulate) {
   long long blocks = (n + 255) / 256;
   if (blocks > 8LL * ctagan_num_sms()) blocks = 8LL * ctagan_num_sms();
-  ordered_sum_kernel<<<(int)blocks, 256, 0, st>>>(part, out, parts, n, accumulate);
+  if (accumulate) ordered_sum_kernel<true><<<(int)blocks, 256, 0, st>>>(part, out, parts, n);
+  else ordered_sum_kernel<false><<<(int)blocks, 256, 0, st>>>(part, out, parts, n);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }

@@ -358,7 +358,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
 }
 
 // dw[co][ci][tap] = sum_s ws[s][co][tap][ci]     (also the [co][tap][ci] -> PyTorch OIHW transpose)
-__global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci, int accumulate) {
+template <bool ACC>
+__global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci) {
   pdl_wait();
   const long long total = (long long)Co * ntaps * Ci;
   ws += (long long)blockIdx.y * splits * total;       // grouped launch: one weight gradient per group
@@ -371,7 +372,8 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restr
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += ws[(long long)k * total + idx];
     float *dst = dw + ((long long)co * Ci + ci) * ntaps + tap;
-    *dst = accumulate ? *dst + s : s;
+    if (ACC) s += *dst;             // (a template parameter: the plain store must not carry a speculative load of the strided destination)
+    *dst = s;
   }
 }
 
@@ -1103,7 +1105,8 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   const long long total = (long long)g->Co * p.ntaps * g->Ci;
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctagan_num_sms() * 8) blocks = ctagan_num_sms() * 8;
-  CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci, accumulate));
+  if (accumulate) CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel<true>, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
+  else CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel<false>, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
   CTAGAN_LAUNCH_OK();
   if (db) {
     const long long pixels = (long long)(g->N / n_groups) * g->Ho * g->Wo;

@@ -190,7 +190,7 @@ class ConvPrim:
         # gradient bucket: the first writer of the step overwrites and leaves an event, a later one (the other use of this network,
         # possibly on another stream) waits for it and accumulates
         acc = self.grad_writes > 0
-        if acc and self.grad_event is not None:
+        if acc and self.grad_event is not None and os.environ.get("CTAGAN_BUCKET_NOWAIT") != "1":
             torch.cuda.current_stream().wait_event(self.grad_event)
         out = ops.conv_wgrad(gy, gx, g, want_bias and self.grad_b is not None, _ENGINE["value"], out_w=self.grad_w,
                              out_b=self.grad_b if want_bias else None, accumulate=acc)

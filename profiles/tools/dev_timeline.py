@@ -1,6 +1,6 @@
 """Developer probe: CUPTI timeline (torch.profiler) of one graph-replayed Cyc iteration -> per-stream busy time, overlap, gaps."""
 import sys, os, random, json, collections
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "cta-gan_b200"))
 import torch
 import bench
@@ -8,8 +8,10 @@ from ctagan import trainers as TR
 from ctagan.graphs import GraphedTrainer
 import argparse
 wl = sys.argv[1] if len(sys.argv) > 1 else "cyc"
-args = argparse.Namespace(workload=wl, batch=None, size=256, precision="bf16")
+args = argparse.Namespace(workload=wl, batch=(1 if wl == "cyc" else 8), size=256, precision="bf16", hd_stage=2)
 cfg = bench.workload_config(args)
+if os.environ.get("CTAGAN_FUSED_OPT") == "0":
+    cfg["fused_optimizer"] = False
 random.seed(42); torch.manual_seed(42)
 tr = (TR.Cyc_Trainer if wl == "cyc" else TR.Reg_Trainer)(cfg)
 loader = TR.SyntheticSlices(cfg["batchSize"], 256, 4, 42, tr.data_keys, pool=2)
