@@ -141,8 +141,15 @@ extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, cons
   CTAGAN_REQUIRE(gy && gx && dw, "conv_wgrad: null pointer");
   CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_wgrad: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
+  CTAGAN_REQUIRE((accumulate & ~(CTAGAN_WGRAD_ACCUMULATE | CTAGAN_WGRAD_PACKED)) == 0, "conv_wgrad: bad flags");
   if (engine == 2) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st, 1, accumulate);
-  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, workspace, workspace_bytes, st, accumulate);
+  if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) {
+    if (accumulate & CTAGAN_WGRAD_PACKED) {
+      ctagan_set_error("conv_wgrad: the packed gradient layout is not available for 1-2 channel layers");
+      return CTAGAN_ERR_UNSUPPORTED;
+    }
+    return ctagan_conv_wgrad_thin(g, gy, gx, dw, db, workspace, workspace_bytes, st, accumulate);
+  }
   if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st, 1, accumulate);
   return ctagan_conv_wgrad_simt(g, gy, gx, dw, db, workspace, workspace_bytes, st, accumulate);
 }

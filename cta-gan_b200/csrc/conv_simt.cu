@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) conv_gather_simt_kernel(ctagan_conv_geom 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ctagan_conv_geom g, const T *__restrict__ gy,
                                                               const T *__restrict__ gx, float *__restrict__ dw,
-                                                              float *__restrict__ db, int pixels_per_split) {
+                                                              float *__restrict__ db, int pixels_per_split, int packed) {
   // split-K: split z stores its partial sums in row z of dw[gridDim.z][Co*Ci*taps] / db[gridDim.z][Co] (the host points dw / db at the
   // workspace and adds the rows in order with ctagan_ordered_sum when there is more than one split: no floating-point atomics)
   dw += (long long)blockIdx.z * g.Co * g.Ci * g.KH * g.KW;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ctagan_conv_geom g
       const int np = blockIdx.y * BN + tx * 4 + j;
       if (np >= NP) continue;
       const int tap = np / B, bb = np - tap * B;
-      float *dst = dw + ((long long)a * B + bb) * ntaps + tap;
+      float *dst = packed ? dw + (long long)a * NP + np : dw + ((long long)a * B + bb) * ntaps + tap;      // [A][taps][B] or [A][B][taps]
       *dst = acc[i][j];
     }
   }
@@ -368,6 +368,8 @@ int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void
   const int splits = simt_wgrad_splits(g, pps);
   const long long dw_elems = (long long)g->Co * g->Ci * ntaps;
   float *dw_dst = dw, *db_dst = db;
+  const int packed = (accumulate & CTAGAN_WGRAD_PACKED) ? 1 : 0;
+  accumulate &= CTAGAN_WGRAD_ACCUMULATE;
   const bool staged = splits > 1 || accumulate;
   if (staged) {
     const size_t need = ctagan_conv_wgrad_simt_workspace(g);
@@ -377,7 +379,7 @@ int ctagan_conv_wgrad_simt(const ctagan_conv_geom *g, const void *gy, const void
   }
   dim3 grid(gx_, gy_, splits);
   CTAGAN_DISPATCH_DTYPE(g->dtype, T, {
-    conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw_dst, db_dst, pps);
+    conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(*g, (const T *)gy, (const T *)gx, dw_dst, db_dst, pps, packed);
   });
   CTAGAN_LAUNCH_OK();
   if (staged) {

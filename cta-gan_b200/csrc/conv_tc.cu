@@ -13,11 +13,14 @@
 // warps 2..5 = epilogue (tcgen05.ld -> bias/activation -> bf16 -> global).  STAGES-deep mbarrier ring between producer
 // and MMA; tcgen05.commit releases stages and signals the epilogue.
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -217,8 +220,11 @@ struct WgParams {
   int bkh, bkw;               // chunk = bkh x bkw output pixels (= 64)
   int total_chunks, chunks_per_split;   // chunks of ONE group (grouped launch: blockIdx.z = group, its images follow each other)
   int ci_tiles;
-  int splits;
-  float *ws;                  // [groups][splits][Co][ntaps][Ci] fp32 partials
+  int splits;                 // K splits of a tile == CTAs of its thread-block cluster (1, 2, 4 or 8)
+  float *dw;                  // [groups][Co][Ci][KH][KW] fp32 (PyTorch OIHW) or, dw_packed, [groups][Co][KH][KW][Ci]: written (or added to)
+  int dw_packed;
+  float *ws;                  // split-K workspace [groups][tiles][splits][128][BNW] fp32 (splits > 1)
+  long long *prof;            // developer probe (CTAGAN_WG_PROF=1): clock64 phase accounting of CTA (0,0,0), else nullptr
 };
 
 constexpr int WG_M = 128;       // Co tile
@@ -231,12 +237,19 @@ struct WgConfig {
   static constexpr int B_BYTES = (BNW / 64) * WG_SLAB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BNW >= 256 ? 4 : 5;
+  static constexpr int ACC_PITCH = BNW + 4;                  // fp32 words per row of the accumulator dump (16-byte rows, conflict-free float4 stores)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = BNW < 32 ? 32 : BNW;
+  static_assert(WG_M * ACC_PITCH * 4 <= STAGES * STAGE_BYTES, "the accumulator dump reuses the operand ring");
 };
 
-// dW[co][tap][ci] partial over one K split:  D[co][ci] = sum_pix gy[pix][co] * gx[pix + tap][ci]   (both operands MN-major)
-template <int BNW>
+// dW[co][ci][tap] = sum_pix gy[pix][co] * gx[pix + tap][ci]   (both operands MN-major).
+// One CTA = one (tap, Co tile, Ci tile) and one K split (a range of 64-pixel chunks); the K splits of a tile form ONE THREAD-BLOCK
+// CLUSTER (grid.x = cluster size = splits).  Every CTA dumps its fp32 accumulator (TMEM) into its own shared memory -- the operand ring
+// is free by then -- and after a cluster barrier CTA r adds rows [r*128/S, (r+1)*128/S) of all S dumps through distributed shared
+// memory, IN RANK ORDER (deterministic), and stores the result straight into the OIHW gradient (optionally adding to what is
+// there: the second use of a network in the same iteration).  No split-K workspace in global memory, no reduce launch.
+template <int BNW, bool ACC>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_gx, const WgParams p) {
   using Cfg = WgConfig<BNW>;
@@ -248,15 +261,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.x;
+  int t = blockIdx.y;
   const int ci_t = t % p.ci_tiles; t /= p.ci_tiles;
   const int co_tiles = (p.Co + WG_M - 1) / WG_M;
   const int co_t = t % co_tiles; t /= co_tiles;
   const int tap = t;
   const int kh = tap / p.KW, kw = tap - kh * p.KW;
-  const int split = blockIdx.y, grp = blockIdx.z;
+  const int split = blockIdx.x, grp = blockIdx.z;          // split == rank of this CTA in its cluster
   const int chunk_lo = split * p.chunks_per_split;
-  const int n_iters = min(p.total_chunks, chunk_lo + p.chunks_per_split) - chunk_lo;
+  const int n_iters = max(0, min(p.total_chunks, chunk_lo + p.chunks_per_split) - chunk_lo);
   const int chunk0 = grp * p.total_chunks + chunk_lo;          // global chunk index: (image, row block, column block)
   const int co0 = co_t * WG_M, ci0 = ci_t * BNW;
 
@@ -277,12 +290,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
+  __shared__ long long prof_s[10];                            // developer probe: phase clocks of this CTA
   if (warp == 0) {
     // TMA producer: converged warp, one elected lane issues (see elect_one)
+    long long t_wait = 0, t_all = clock64();
     for (int it = 0; it < n_iters; ++it) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+      const long long tw = clock64();
       mbar_wait(&empty_bar[s], ph ^ 1u);
+      t_wait += clock64() - tw;
       int ch = chunk0 + it;
       const int cbi = ch % p.cb; ch /= p.cb;
       const int rbi = ch % p.rb;
@@ -300,12 +317,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
       }
       __syncwarp();
     }
+    if (lane == 0) { prof_s[0] = clock64() - t_all; prof_s[1] = t_wait; prof_s[8] = n_iters; }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16_mn(WG_M, BNW);
+    long long t_wait = 0, t_all = clock64();
     for (int it = 0; it < n_iters; ++it) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+      const long long tw = clock64();
       mbar_wait(&full_bar[s], ph);
+      t_wait += clock64() - tw;
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -322,58 +343,132 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
       }
       __syncwarp();
     }
+    if (lane == 0) { prof_s[2] = clock64() - t_all; prof_s[3] = t_wait; }
   } else {
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;          // co within the tile
-    float *dst = p.ws + ((((long long)grp * p.splits + split) * p.Co + co0 + row) * p.ntaps + tap) * p.Ci + ci0;
-    const bool row_ok = co0 + row < p.Co;
+    // epilogue warps: wait for the accumulator (the commit behind the last MMA also means every operand read of the ring is done)
+    const long long t_e0 = clock64();
     if (n_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    pdl_trigger();          // only the epilogue is left: let the split-K reduce be scheduled
+    if (threadIdx.x == 64) prof_s[4] = clock64() - t_e0;
+  }
+  // ---- split-K reduction.  The K splits of a tile are the CTAs of one cluster, so they are co-resident and a cluster barrier orders them
+  // (no grid-wide synchronisation, no second launch).  CTA r OWNS rows [r*128/S, (r+1)*128/S) of the tile:
+  //   1. the epilogue warps dump the accumulator (TMEM lane = co row) into this CTA's shared memory (the operand ring is free: the
+  //      commit behind the last MMA means every operand read is done), row pitch BNW+4 words: conflict-free 16-byte stores;
+  //   2. all warps copy the rows OTHER CTAs own to the split-K workspace in global memory (L2) with fully coalesced 16-byte stores;
+  //   3. cluster barrier (release / acquire at cluster scope);
+  //   4. every CTA adds the S partial sums of its own rows IN RANK ORDER (deterministic; its own from shared memory, the others from
+  //      L2) and writes the gradient: coalesced when the destination is the packed [co][tap][ci] layout, a 4-byte scatter for OIHW.
+  const int S = p.splits;
+  const int rows_per = WG_M / S;
+  constexpr int VPR = BNW / 4;                                // float4 per row
+  float *acc = reinterpret_cast<float *>(smem);               // [128][ACC_PITCH] fp32, over the ring
+  const long long t_s0 = clock64();
+  if (warp >= 2) {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    float4 *dst = reinterpret_cast<float4 *>(acc + row * Cfg::ACC_PITCH);
 #pragma unroll 1
     for (int c = 0; c < BNW; c += 32) {
       uint32_t r[32];
       if (n_iters > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
         tmem_ld_wait();
-      } else {
+      } else {                                    // a split without chunks (ragged division) contributes zeros
 #pragma unroll
         for (int e = 0; e < 32; ++e) r[e] = 0u;
       }
-      if (row_ok && ci0 + c < p.Ci) {           // Ci is a multiple of 32 here
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) d4[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-      }
+      for (int g = 0; g < 8; ++g)
+        dst[c / 4 + g] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
     }
   }
   tc_fence_before();
   __syncthreads();
+  const long long t_s1 = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
-}
-
-// dw[co][ci][tap] = sum_s ws[s][co][tap][ci]     (also the [co][tap][ci] -> PyTorch OIHW transpose)
-template <bool ACC>
-__global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ dw, int splits, int Co, int ntaps, int Ci) {
-  pdl_wait();
-  const long long total = (long long)Co * ntaps * Ci;
-  ws += (long long)blockIdx.y * splits * total;       // grouped launch: one weight gradient per group
-  dw += (long long)blockIdx.y * total;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(idx % Ci);
-    long long r = idx / Ci;
-    const int tap = (int)(r % ntaps);
-    const int co = (int)(r / ntaps);
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[(long long)k * total + idx];
-    float *dst = dw + ((long long)co * Ci + ci) * ntaps + tap;
-    if (ACC) s += *dst;             // (a template parameter: the plain store must not carry a speculative load of the strided destination)
-    *dst = s;
+  // workspace: [group][tile][split][128][BNW] fp32
+  float *ws_tile = p.ws + ((long long)grp * gridDim.y + blockIdx.y) * S * (WG_M * BNW);
+  if (S > 1) {
+    // rows other CTAs own: (S-1) * rows_per rows of VPR float4 each, skipping this CTA's own block of rows; four independent
+    // 16-byte copies per thread and iteration
+    float4 *mine = reinterpret_cast<float4 *>(ws_tile + (long long)split * (WG_M * BNW));
+    const int n_vec = (WG_M - rows_per) * VPR;
+    for (int v0 = threadIdx.x; v0 < n_vec; v0 += 4 * 192) {
+      float4 t[4];
+      int dst_v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * 192;
+        int row = v / VPR;
+        const int c4 = v - row * VPR;
+        if (row >= split * rows_per) row += rows_per;
+        dst_v[u] = row * VPR + c4;
+        if (v < n_vec) t[u] = *reinterpret_cast<const float4 *>(acc + row * Cfg::ACC_PITCH + c4 * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v0 + u * 192 < n_vec) mine[dst_v[u]] = t[u];
+    }
+    __threadfence();
+  }
+  const long long t_s2 = clock64();
+  cg::cluster_group cluster = cg::this_cluster();
+  if (S > 1) cluster.sync();
+  const long long t_s3 = clock64();
+  {
+    float *dw = p.dw + (long long)grp * p.Co * p.Ci * p.ntaps;
+    constexpr int UV = 2;                          // rows-of-4 per thread and iteration: UV * (S-1) independent L2 loads in flight
+    for (int v0 = threadIdx.x; v0 < rows_per * VPR; v0 += UV * 192) {
+      float4 u[UV][8];
+      int rowv[UV], cv[UV];
+      bool ok[UV];
+#pragma unroll
+      for (int q = 0; q < UV; ++q) {
+        const int v = v0 + q * 192;
+        const int lr = v / VPR;
+        rowv[q] = split * rows_per + lr;
+        cv[q] = (v - lr * VPR) * 4;
+        ok[q] = v < rows_per * VPR && co0 + rowv[q] < p.Co && ci0 + cv[q] < p.Ci;        // Ci is a multiple of 32 here
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < S && ok[q])
+            u[q][k] = k == split ? *reinterpret_cast<const float4 *>(acc + rowv[q] * Cfg::ACC_PITCH + cv[q])
+                                 : __ldcg(reinterpret_cast<const float4 *>(ws_tile + (long long)k * (WG_M * BNW) + rowv[q] * BNW + cv[q]));
+      }
+#pragma unroll
+      for (int q = 0; q < UV; ++q) {
+        if (!ok[q]) continue;
+        float4 sum = u[q][0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+          if (k < S) { sum.x += u[q][k].x; sum.y += u[q][k].y; sum.z += u[q][k].z; sum.w += u[q][k].w; }      // rank order: deterministic
+        const int row = rowv[q], c = cv[q];
+        if (p.dw_packed) {                          // [co][tap][ci]: ci contiguous
+          float4 *d = reinterpret_cast<float4 *>(dw + ((long long)(co0 + row) * p.ntaps + tap) * p.Ci + ci0 + c);
+          if (ACC) { const float4 o = *d; sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w; }
+          *d = sum;
+        } else {                                    // PyTorch OIHW: tap is the fastest index
+          float *d = dw + ((long long)(co0 + row) * p.Ci + ci0 + c) * p.ntaps + tap;
+          if (ACC) {                                // (a template parameter: the plain store must not carry a speculative load of the strided destination)
+            sum.x += d[0]; sum.y += d[p.ntaps]; sum.z += d[2 * p.ntaps]; sum.w += d[3 * p.ntaps];
+          }
+          d[0] = sum.x; d[p.ntaps] = sum.y; d[2 * p.ntaps] = sum.z; d[3 * p.ntaps] = sum.w;
+        }
+      }
+    }
+  }
+  if (p.prof && blockIdx.x + blockIdx.y + blockIdx.z == 0) {
+    __syncthreads();
+    if (threadIdx.x == 64) {
+      prof_s[5] = t_s1 - t_s0; prof_s[6] = t_s2 - t_s1; prof_s[7] = t_s3 - t_s2; prof_s[9] = clock64() - t_s3;
+      for (int k = 0; k < 10; ++k) p.prof[k] = prof_s[k];
+    }
   }
 }
 
@@ -1028,30 +1123,35 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl, int n_groups = 1) {
   pl.cb = (Wvld + pl.bkw - 1) / pl.bkw;
   pl.total_chunks = (g->N / n_groups) * pl.rb * pl.cb;        // per group
   pl.tiles = g->KH * g->KW * ((g->Co + WG_M - 1) / WG_M) * ((g->Ci + pl.bnw - 1) / pl.bnw);
-  static int split_div = 0;
-  if (!split_div) { const char *e = getenv("CTAGAN_WG_SPLIT_DIV"); split_div = e ? atoi(e) : 1; if (split_div < 1) split_div = 1; }
-  int splits = (ctagan_num_sms() / split_div + pl.tiles * n_groups - 1) / (pl.tiles * n_groups);
-  // at least 32 chunks (2048 pixels) per CTA: measured on the batch-1 Cyc step, where the wgrads run on a side stream next to the
-  // backward chain, 2 splits (36 CTAs) beat 8 (144 CTAs) by 8% of the step; large batches still reach one CTA per SM
+  // K splits = CTAs of the tile's cluster (1, 2, 4 or 8): enough of them to put a CTA on every SM, but at least `min_chunks` chunks
+  // (64 pixels each) of main loop per CTA
   static int min_chunks = 0;
-  if (!min_chunks) { const char *e = getenv("CTAGAN_WG_MIN_CHUNKS"); min_chunks = e ? atoi(e) : 32; if (min_chunks < 1) min_chunks = 32; }
-  const int max_splits = (pl.total_chunks + min_chunks - 1) / min_chunks;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  if (!min_chunks) { const char *e = getenv("CTAGAN_WG_MIN_CHUNKS"); min_chunks = e ? atoi(e) : 4; if (min_chunks < 1) min_chunks = 1; }
+  static int max_cluster = 0;
+  if (!max_cluster) { const char *e = getenv("CTAGAN_WG_MAX_CLUSTER"); max_cluster = e ? atoi(e) : 8; if (max_cluster < 1 || max_cluster > 8) max_cluster = 8; }
+  // a cluster of S CTAs (one per SM: the operand ring fills the shared memory) must fit into ONE GPC (~18 SMs): at most 16 clusters of
+  // 8, 32 of 4 or 72 of 2 are resident at a time -- more tiles than that would run as two waves
+  int splits = 1;
+  while (splits * 2 <= max_cluster && pl.total_chunks >= splits * 2 * min_chunks) {
+    const int s2 = splits * 2, clusters = pl.tiles * n_groups;
+    const int cap = s2 == 8 ? 16 : (s2 == 4 ? 32 : 72);
+    if (clusters > cap || clusters * s2 > ctagan_num_sms()) break;
+    splits = s2;
+  }
+  pl.splits = splits;
   pl.cps = (pl.total_chunks + splits - 1) / splits;
-  pl.splits = (pl.total_chunks + pl.cps - 1) / pl.cps;
   return true;
 }
 
-template <int BNW>
+template <int BNW, bool ACC>
 int launch_wg(const CUtensorMap &my, const CUtensorMap &mx, const WgParams &p, dim3 grid, cudaStream_t st) {
   using Cfg = WgConfig<BNW>;
   static bool configured = false;
   if (!configured) {
-    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BNW, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  CTAGAN_CUDA_OK(launch_pdl(conv_wgrad_tc_kernel<BNW>, grid, dim3(192), Cfg::SMEM_BYTES, st, my, mx, p));
+  CTAGAN_CUDA_OK(launch_cluster_pdl(conv_wgrad_tc_kernel<BNW, ACC>, grid, dim3(192), Cfg::SMEM_BYTES, st, (unsigned)p.splits, my, mx, p));
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
@@ -1063,16 +1163,17 @@ int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups) {
   return (n_groups >= 1 && g->N % n_groups == 0 && plan_wgrad(g, pl, n_groups)) ? 1 : 0;
 }
 
-// split-K partial sums [groups][splits][Co][taps][Ci] followed by the bias-gradient partial sums [groups][WG_DB_BLOCKS][Co]
-static size_t wg_split_bytes(const ctagan_conv_geom *g, const WgPlan &pl, int n_groups) {
-  return (size_t)n_groups * pl.splits * g->Co * g->KH * g->KW * g->Ci * sizeof(float);
+// workspace: split-K partial sums [groups][tiles][splits][128][BNW] fp32 (splits > 1), then the bias-gradient partial sums
+// [groups][WG_DB_BLOCKS][Co]
+static size_t wg_split_bytes(const WgPlan &pl, int n_groups) {
+  return pl.splits > 1 ? (size_t)n_groups * pl.tiles * pl.splits * WG_M * pl.bnw * sizeof(float) : 0;
 }
 static int wg_db_blocks() { return 2 * ctagan_num_sms(); }
 
 size_t ctagan_conv_wgrad_tc_workspace(const ctagan_conv_geom *g, int n_groups) {
   WgPlan pl;
   if (n_groups < 1 || g->N % n_groups || !plan_wgrad(g, pl, n_groups)) return 0;
-  return wg_split_bytes(g, pl, n_groups) + (size_t)n_groups * wg_db_blocks() * g->Co * sizeof(float);
+  return wg_split_bytes(pl, n_groups) + (size_t)n_groups * wg_db_blocks() * g->Co * sizeof(float);
 }
 
 // n_groups > 1: the batch is n_groups consecutive image groups and dw / db hold one gradient per group ([groups][Co][Ci][KH][KW])
@@ -1093,28 +1194,39 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
   WgParams p;
   p.ntaps = g->KH * g->KW; p.KW = g->KW; p.Co = g->Co; p.Ci = g->Ci; p.stride = g->stride; p.pad = g->pad_h;
   p.margin = g->gy_margin; p.rb = pl.rb; p.cb = pl.cb; p.bkh = pl.bkh; p.bkw = pl.bkw;
-  p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.ci_tiles = (g->Ci + pl.bnw - 1) / pl.bnw; p.ws = (float *)workspace;
+  p.total_chunks = pl.total_chunks; p.chunks_per_split = pl.cps; p.ci_tiles = (g->Ci + pl.bnw - 1) / pl.bnw; p.dw = dw;
   p.splits = pl.splits;
-  dim3 grid((unsigned)pl.tiles, (unsigned)pl.splits, (unsigned)n_groups);
+  p.dw_packed = (accumulate & CTAGAN_WGRAD_PACKED) ? 1 : 0;
+  accumulate &= CTAGAN_WGRAD_ACCUMULATE;
+  p.ws = (float *)workspace;
+  p.prof = nullptr;
+  static long long *prof_buf = nullptr;
+  static int prof_on = -1;
+  if (prof_on < 0) { const char *e = getenv("CTAGAN_WG_PROF"); prof_on = e ? atoi(e) : 0; }
+  if (prof_on) {
+    if (!prof_buf) cudaMallocManaged(&prof_buf, 16 * sizeof(long long));
+    p.prof = prof_buf;
+  }
+  dim3 grid((unsigned)pl.splits, (unsigned)pl.tiles, (unsigned)n_groups);        // x = K split = rank in the tile's cluster
   switch (pl.bnw) {
-    case 256: rc = launch_wg<256>(my, mx, p, grid, st); break;
-    case 128: rc = launch_wg<128>(my, mx, p, grid, st); break;
-    default: rc = launch_wg<64>(my, mx, p, grid, st); break;
+    case 256: rc = accumulate ? launch_wg<256, true>(my, mx, p, grid, st) : launch_wg<256, false>(my, mx, p, grid, st); break;
+    case 128: rc = accumulate ? launch_wg<128, true>(my, mx, p, grid, st) : launch_wg<128, false>(my, mx, p, grid, st); break;
+    default: rc = accumulate ? launch_wg<64, true>(my, mx, p, grid, st) : launch_wg<64, false>(my, mx, p, grid, st); break;
   }
   if (rc) return rc;
-  const long long total = (long long)g->Co * p.ntaps * g->Ci;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > ctagan_num_sms() * 8) blocks = ctagan_num_sms() * 8;
-  if (accumulate) CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel<true>, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
-  else CTAGAN_CUDA_OK(launch_pdl(wgrad_reduce_kernel<false>, dim3(blocks, n_groups), dim3(256), 0, st, (const float *)workspace, dw, pl.splits, g->Co, p.ntaps, g->Ci));
-  CTAGAN_LAUNCH_OK();
+  if (prof_on) {
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[wgrad prof] Co=%d Ci=%d K=%d N=%d grid=(%d,%d,%d) bnw=%d iters=%lld | producer total %lld wait_empty %lld | mma total %lld wait_full %lld | epi wait_acc %lld | "
+            "dump %lld to-L2 %lld sync %lld sum+store %lld (clk)\n", g->Co, g->Ci, g->KH, g->N, pl.splits, pl.tiles, n_groups, pl.bnw, prof_buf[8], prof_buf[0], prof_buf[1], prof_buf[2],
+            prof_buf[3], prof_buf[4], prof_buf[5], prof_buf[6], prof_buf[7], prof_buf[9]);
+  }
   if (db) {
     const long long pixels = (long long)(g->N / n_groups) * g->Ho * g->Wo;
     long long blocks = (pixels + 511) / 512;
     if (blocks > wg_db_blocks()) blocks = wg_db_blocks();
     const long long ppb = (pixels + blocks - 1) / blocks;
     const int nb = (int)((pixels + ppb - 1) / ppb);
-    float *part = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + wg_split_bytes(g, pl, n_groups));
+    float *part = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + wg_split_bytes(pl, n_groups));
     for (int k = 0; k < n_groups; ++k) {
       float *pk = part + (size_t)k * wg_db_blocks() * g->Co;
       colsum_kernel<<<nb, 256, 0, st>>>((const bf16 *)gy + (size_t)k * pixels * g->Co, pk, pixels, g->Co, ppb);

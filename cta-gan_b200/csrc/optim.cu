@@ -49,7 +49,14 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(const ctagan_adam_item *
     const int o = idx / row, r = idx - o * row;
     const long long gi = ((long long)(o0 + o) * I + i0) * taps + r;
     float p = it.p[gi], m = it.m[gi], v = it.v[gi];
-    adam_update(p, it.g[gi], m, v, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+    float g;
+    if (it.g_packed) {                    // gradient stored [O][taps][I] (128-byte runs of this tile: sector-complete, served by L1)
+      const int i = r / taps, tap = r - i * taps;
+      g = it.g[((long long)(o0 + o) * taps + tap) * I + i0 + i];
+    } else {
+      g = it.g[gi];
+    }
+    adam_update(p, g, m, v, lr, beta1, beta2, eps, bc1, bc2_sqrt);
     it.p[gi] = p; it.m[gi] = m; it.v[gi] = v;
     tile[o * pitch + r] = p;
   }

@@ -79,12 +79,21 @@ class ConvPrim:
         # persistent gradient buffers (slices of an optimiser's flat gradient bucket, ctagan.optim.FusedAdam): the weight-gradient
         # kernels write there directly; the first use of the layer in a step overwrites, a second use accumulates
         self.grad_w: Optional[torch.Tensor] = None
+        self.grad_w_raw: Optional[torch.Tensor] = None
+        self.grad_packed = False
         self.grad_b: Optional[torch.Tensor] = None
         self.grad_writes = 0
         self.grad_event = None
 
     def attach_grads(self, grad_w, grad_b):
+        """grad_w: the persistent gradient of the weight, logical shape [O][I][K][K]; either contiguous (PyTorch order) or a
+        channels-last view of contiguous [O][K][K][I] storage (what the tensor-core kernel writes as whole rows)."""
         self.grad_w, self.grad_b, self.grad_writes, self.grad_event = grad_w, grad_b, 0, None
+        self.grad_w_raw, self.grad_packed = grad_w, False
+        if grad_w is not None and not grad_w.is_contiguous():
+            raw = grad_w.permute(0, 2, 3, 1)
+            assert raw.is_contiguous(), "gradient buffers must be contiguous or channels-last"
+            self.grad_w_raw, self.grad_packed = raw, True
 
     def mark_packed(self, dtype: torch.dtype):
         """The optimiser kernel has just re-packed both copies of `dtype` from the updated master weights: every other cached copy is
@@ -192,8 +201,9 @@ class ConvPrim:
         acc = self.grad_writes > 0
         if acc and self.grad_event is not None and os.environ.get("CTAGAN_BUCKET_NOWAIT") != "1":
             torch.cuda.current_stream().wait_event(self.grad_event)
-        out = ops.conv_wgrad(gy, gx, g, want_bias and self.grad_b is not None, _ENGINE["value"], out_w=self.grad_w,
-                             out_b=self.grad_b if want_bias else None, accumulate=acc)
+        _, db = ops.conv_wgrad(gy, gx, g, want_bias and self.grad_b is not None, _ENGINE["value"], out_w=self.grad_w_raw,
+                               out_b=self.grad_b if want_bias else None, accumulate=acc, packed=self.grad_packed)
+        out = (self.grad_w, db)
         self.grad_writes += 1
         self.grad_event = torch.cuda.Event()
         self.grad_event.record()

@@ -38,7 +38,8 @@ class PackItem(ctypes.Structure):
 
 class AdamItem(ctypes.Structure):
     _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p), ("wp0", ctypes.c_void_p),
-                ("wp1", ctypes.c_void_p), ("O", ctypes.c_int32), ("I", ctypes.c_int32), ("KH", ctypes.c_int32), ("KW", ctypes.c_int32)]
+                ("wp1", ctypes.c_void_p), ("O", ctypes.c_int32), ("I", ctypes.c_int32), ("KH", ctypes.c_int32), ("KW", ctypes.c_int32),
+                ("g_packed", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 def _ctype_of(decl: str):

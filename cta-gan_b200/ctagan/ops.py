@@ -172,10 +172,10 @@ def conv_wgrad_grouped(gy, gx, g: L.ConvGeom, groups: int, want_bias: bool, ws_b
     return dw, db
 
 
-def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO, out_w=None, out_b=None, accumulate=False):
+def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO, out_w=None, out_b=None, accumulate=False, packed=False):
     """Weight (and bias) gradient.  out_w / out_b: persistent gradient buffers to write into (e.g. slices of an optimiser's flat
     gradient bucket) instead of fresh tensors; accumulate: add to them instead of overwriting (the second use of a network in one
-    backward pass)."""
+    backward pass); packed: out_w is the contiguous [Co][KH][KW][Ci] storage of a channels-last gradient."""
     _require_cuda(gy, gx)
     dw = out_w if out_w is not None else torch.empty((g.Co, g.Ci, g.KH, g.KW), dtype=torch.float32, device=gy.device)
     db = None
@@ -185,7 +185,7 @@ def conv_wgrad(gy, gx, g: L.ConvGeom, want_bias: bool, engine=L.ENGINE_AUTO, out
     ws_bytes = L.load().ctagan_conv_wgrad_workspace_bytes(ctypes.byref(g), engine)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device) if ws_bytes else None
     _count(3 if ws_bytes and want_bias else (2 if ws_bytes else 1))
-    L.check(L.load().ctagan_conv_wgrad(ctypes.byref(g), _p(gy), _p(gx), _p(dw), _p(db), _p(ws), ws_bytes, engine, int(bool(accumulate)), _stream()))
+    L.check(L.load().ctagan_conv_wgrad(ctypes.byref(g), _p(gy), _p(gx), _p(dw), _p(db), _p(ws), ws_bytes, engine, int(bool(accumulate)) | (2 if packed else 0), _stream()))
     return dw, db
 
 

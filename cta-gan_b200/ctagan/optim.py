@@ -62,7 +62,12 @@ class FusedAdam:
         self.grad_flat = torch.zeros((offs[-1],), dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.grad_flat)
         self.exp_avg_sq = torch.zeros_like(self.grad_flat)
-        self.views = [self.grad_flat[o:o + n].view_as(p) for p, o, n in zip(self.params, offs, sizes)]
+        # Weights of the layers the tensor-core engine serves keep their gradient in channels-last order ([O][KH][KW][I] storage behind a
+        # [O][I][KH][KW] view: what torch calls torch.channels_last): the weight-gradient kernel writes whole rows, the optimiser
+        # kernel reads the tile it needs either way.  Everything else (biases, the 1-2 channel layers) stays in PyTorch order.
+        self.packed = [self._wants_packed(p) for p in self.params]
+        self.views = [self.grad_flat[o:o + n].view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2) if pk
+                      else self.grad_flat[o:o + n].view_as(p) for p, o, n, pk in zip(self.params, offs, sizes, self.packed)]
         self._offs, self._sizes = offs, sizes
         for p, v in zip(self.params, self.views):
             p.grad = v
@@ -83,6 +88,10 @@ class FusedAdam:
                 prim.attach_grads(by_id[id(p)], by_id.get(id(prim.b)) if prim.b is not None else None)
                 self.prims.append(prim)
         self._prim_of = {id(prim.w): prim for prim in self.prims}
+
+    @staticmethod
+    def _wants_packed(p) -> bool:
+        return p.dim() == 4 and p.shape[0] % 32 == 0 and p.shape[1] % 32 == 0 and p.shape[2] * p.shape[3] > 1
 
     @staticmethod
     def _plans_of(net):
@@ -108,7 +117,7 @@ class FusedAdam:
         lib = L.load()
         n = len(self.params)
         items = (L.AdamItem * n)()
-        for k, (p, o, sz) in enumerate(zip(self.params, self._offs, self._sizes)):
+        for k, (p, o, sz, pk) in enumerate(zip(self.params, self._offs, self._sizes, self.packed)):
             prim = self._prim_of.get(id(p))
             wp0 = wp1 = None
             if prim is not None:
@@ -117,8 +126,10 @@ class FusedAdam:
                 O, I, KH, KW = p.shape
             else:
                 O, I, KH, KW = p.numel(), 1, 1, 1
+            if pk and prim is None:
+                O, I, KH, KW = p.shape            # a packed gradient without a ConvPrim (unused layer): the optimiser still needs the geometry
             items[k] = L.AdamItem(p.data_ptr(), self.grad_flat[o:].data_ptr(), self.exp_avg[o:].data_ptr(), self.exp_avg_sq[o:].data_ptr(),
-                                  wp0, wp1, O, I, KH, KW)
+                                  wp0, wp1, O, I, KH, KW, 1 if pk else 0, 0)
         tiles = (ctypes.c_int * (n + 1))()
         L.check(lib.ctagan_adam_pack_tiles(ctypes.cast(items, ctypes.c_void_p), n, tiles))
         self._smem = int(lib.ctagan_adam_pack_smem_bytes(ctypes.cast(items, ctypes.c_void_p), n))

@@ -113,7 +113,13 @@ int ctagan_conv_wgrad_grouped(const ctagan_conv_geom *g, int groups, const void 
  * PyTorch's [A][B][KH][KW] order and is OVERWRITTEN (db too, may be NULL) -- or, with accumulate != 0, ADDED TO (the second use of a
  * network inside one backward pass, e.g. the cycle pass of CycTrainer.py:153-157, lands in the same gradient buffer as the first:
  * what autograd's AccumulateGrad does, without a temporary and an add kernel).  Conv2d: gy=dy, gx=x.  ConvTranspose2d: gy=x, gx=dy.
+ * `accumulate` is a bit set: CTAGAN_WGRAD_ACCUMULATE (1) as above; CTAGAN_WGRAD_PACKED (2): dw is stored as [A][KH][KW][B] (the
+ * channels-last order of the same logical [A][B][KH][KW] tensor, i.e. what `p.grad` is when it is a torch.channels_last view): the
+ * tensor-core kernel then writes whole 16-byte rows instead of a 4-byte scatter with stride KH*KW.  Not available for the 1-2 channel
+ * layers (CTAGAN_ERR_UNSUPPORTED).
  * Replaces the weight-gradient half of cudnn/ATen convolution_backward for the layers cited above. */
+#define CTAGAN_WGRAD_ACCUMULATE 1
+#define CTAGAN_WGRAD_PACKED 2
 int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db,
                       void *workspace, size_t workspace_bytes, int engine, int accumulate, void *stream);
 /* Scratch bytes ctagan_conv_wgrad needs for this geometry/engine: the per-CTA / per-split partial sums of every engine's split
@@ -149,6 +155,8 @@ typedef struct {
   void *wp0;
   void *wp1;
   int32_t O, I, KH, KW;
+  int32_t g_packed; /* 0: g is [O][I][KH][KW] like p; 1: g is [O][KH][KW][I] (CTAGAN_WGRAD_PACKED) */
+  int32_t reserved;
 } ctagan_adam_item;
 size_t ctagan_adam_pack_smem_bytes(const ctagan_adam_item *items_host, int n_items);
 int ctagan_adam_pack_tiles(const ctagan_adam_item *items_host, int n_items, int *tile_start_host);
