@@ -230,25 +230,32 @@ class _WgradLane:
 
     def __init__(self):
         self.main = torch.cuda.current_stream()
-        self.side = None
-        self.used = False
+        self.sides = []
+        self.used = set()
+        self.turn = 0
         self.keep = []
         if _WGRAD_OVERLAP["value"]:
             key = self.main.cuda_stream
-            side = _WGRAD_STREAMS.get(key)
-            if side is None:
-                side = ops.named_stream(f"lane:{key}")
-                _WGRAD_STREAMS[key] = side
-            self.side = side
+            sides = _WGRAD_STREAMS.get(key)
+            if sides is None:
+                # several side streams per chain, used round-robin: weight gradients of different layers are independent of each other,
+                # and when a backward chain ends its leftover weight gradients then run side by side instead of one after the other
+                n = max(1, int(os.environ.get("CTAGAN_WG_LANES", "3")))
+                sides = [ops.named_stream(f"lane{k}:{key}") for k in range(n)]
+                _WGRAD_STREAMS[key] = sides
+            self.sides = sides
 
     def run(self, fn):
-        if self.side is None:
+        if not self.sides:
             return fn()
-        self.used = True
-        self.side.wait_stream(self.main)
+        k = self.turn % len(self.sides)
+        self.turn += 1
+        side = self.sides[k]
+        self.used.add(k)
+        side.wait_stream(self.main)
         prev, _ACTIVE_LANE["value"] = _ACTIVE_LANE["value"], self
         try:
-            with torch.cuda.stream(self.side):
+            with torch.cuda.stream(side):
                 return fn()
         finally:
             _ACTIVE_LANE["value"] = prev
@@ -257,14 +264,14 @@ class _WgradLane:
         # (only when something was forked: waiting on a stream that never joined a CUDA-graph capture would invalidate the capture)
         d = _DEFERRED["value"]
         if d is not None:                 # the caller collects the weight gradients after the whole backward: nobody waits here
-            if self.side is not None and self.used:
-                d.lanes[(self.main.cuda_stream, self.side.cuda_stream)] = (self.main, self.side)
-                d.keep += self.keep
-            self.keep = []
+            for k in self.used:
+                d.lanes[(self.main.cuda_stream, self.sides[k].cuda_stream)] = (self.main, self.sides[k])
+            d.keep += self.keep
+            self.keep, self.used = [], set()
             return
-        if self.side is not None and self.used:
-            self.main.wait_stream(self.side)
-        self.keep = []
+        for k in self.used:
+            self.main.wait_stream(self.sides[k])
+        self.keep, self.used = [], set()
 
 
 _DEFERRED = {"value": None}
