@@ -84,6 +84,10 @@ class ConvPrim:
         self.grad_b: Optional[torch.Tensor] = None
         self.grad_writes = 0
         self.grad_event = None
+        # data-parallel overlap: how many weight-gradient launches this layer receives per step (learnt from the previous step) and who
+        # wants to know that the last one has been enqueued (trainers.GradSync: the bucket chunk can go to the all-reduce)
+        self.expected_writes: Optional[int] = None
+        self.final_hook = None
 
     def attach_grads(self, grad_w, grad_b):
         """grad_w: the persistent gradient of the weight, logical shape [O][I][K][K]; either contiguous (PyTorch order) or a
@@ -207,6 +211,10 @@ class ConvPrim:
         self.grad_writes += 1
         self.grad_event = torch.cuda.Event()
         self.grad_event.record()
+        if self.expected_writes is not None:
+            assert self.grad_writes <= self.expected_writes, "a layer received more weight-gradient launches than in the previous step"
+            if self.final_hook is not None and self.grad_writes == self.expected_writes:
+                self.final_hook(self)
         return out
 
 

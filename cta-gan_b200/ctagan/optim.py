@@ -76,6 +76,7 @@ class FusedAdam:
         self._bind_prims()
         self._table_key = None
         self._dtype = None
+        self.grad_sync = None             # trainers.GradSync (data parallel): armed by zero_grad, fed by the layers' final-write hooks
 
     def _bind_prims(self):
         prims = _prims_of(self.nets)
@@ -111,7 +112,11 @@ class FusedAdam:
             self._bind_prims()            # a network rebuilt its plan (e.g. after .to()): attach the gradient slices to the new ConvPrims
             self._table_key = None
         for prim in self.prims:
+            if prim.grad_writes > 0:
+                prim.expected_writes = prim.grad_writes        # the schedule of a step is static: what the last step did, this one will
             prim.grad_writes, prim.grad_event = 0, None
+        if self.grad_sync is not None:
+            self.grad_sync.arm()
 
     def _build_table(self, dtype):
         lib = L.load()

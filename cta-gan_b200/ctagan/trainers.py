@@ -67,16 +67,88 @@ class SyntheticSlices:
 class GradSync:
     """Data-parallel gradient averaging (weak scaling over slices; every op on the path is per-sample, so N ranks x b slices ==
     1 rank x N*b slices up to reduction order).  With the fused optimiser the gradients already live in one flat bucket per optimiser
-    group, which IS the NCCL buffer: no flatten copy.  The bucket is reduced in chunks of ~`chunk_mb` on a communication stream, so
-    that a chunk's all-reduce runs under the next chunk's wait / the optimiser kernels of other groups, and the training stream only
-    waits for the last event."""
+    group, which IS the NCCL buffer: no flatten copy.  The bucket is cut into chunks of ~`chunk_mb` at parameter boundaries, and a
+    chunk goes to the all-reduce (on a communication stream) AS SOON AS the last weight-gradient launch of the step into it has been
+    enqueued: every ConvPrim knows how many launches it receives per step (learnt from the previous step: the schedule is static) and
+    calls `_final` after the last one; the chunk's all-reduce waits for those launches' events only, so it runs under the rest of
+    the backward pass (gradients complete in reverse layer order, the head layers' last).  `__call__` (right before the optimiser
+    step) reduces whatever is left -- everything, on the very first step -- and makes the training stream wait for the collectives.
+    All ranks enqueue the collectives in the same order because they run the same host code."""
 
-    def __init__(self, source, chunk_mb: float = 24.0):
+    def __init__(self, source, chunk_mb: float = None):
         self.opt = source if hasattr(source, "grad_flat") else None
         self.params = None if self.opt is not None else [p for p in source]
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if chunk_mb is None:
+            chunk_mb = float(os.environ.get("CTAGAN_DDP_CHUNK_MB", "128"))
         self.chunk = int(chunk_mb * (1 << 20) / 4)
         self._comm = None
+        # Measured on 2 B200s (Cyc step, batch 1 per GPU): one all-reduce per optimiser after the backward 5.42 ms/step; chunks of 8-24 MB
+        # sent while the backward is still running 5.48-5.54 ms (the NCCL kernels take SMs from a latency-bound backward and every
+        # collective pays its own launch latency); Reg step (batch 8): no difference (16.03-16.09 ms).  Early chunks are therefore opt-in.
+        self.early = os.environ.get("CTAGAN_DDP_EARLY", "0") != "0"
+        self.chunks = []              # [start, end, [prims]]
+        self._chunk_of = {}           # id(prim) -> chunk index
+        self._left, self._done = [], []
+        self.n_early = 0              # chunks that went to the all-reduce before the end of their backward pass (all steps)
+        if self.opt is not None and self.world > 1 and self.opt.grad_flat.is_cuda:
+            self.opt.grad_sync = self
+            self._build_chunks()
+
+    def _build_chunks(self):
+        opt = self.opt
+        self.chunks, self._chunk_of = [], {}
+        start, prims = 0, []
+        n = len(opt.params)
+        bias_ids = {id(q.b) for q in opt.prims if q.b is not None}
+        for k, p in enumerate(opt.params):
+            prim = opt._prim_of.get(id(p))
+            if prim is not None:
+                prims.append(prim)
+            end = opt._offs[k + 1]
+            # (a layer's bias gradient is written by the same launches as its weight gradient: never cut a chunk between the two)
+            if (end - start >= self.chunk and not (k + 1 < n and id(opt.params[k + 1]) in bias_ids)) or k == n - 1:
+                self.chunks.append([start, end, prims])
+                start, prims = end, []
+        for ci, (_, _, prims) in enumerate(self.chunks):
+            for prim in prims:
+                self._chunk_of[id(prim)] = ci
+                prim.final_hook = self._final
+        self._prims_key = tuple(id(q) for q in opt.prims)
+        self.arm()
+
+    def arm(self):
+        """Start of a backward pass (FusedAdam.zero_grad)."""
+        if self.opt is None or self.world == 1 or not self.chunks:
+            return
+        if tuple(id(q) for q in self.opt.prims) != self._prims_key:      # the optimiser re-bound its layers (a network rebuilt its plan)
+            self._build_chunks()
+            return
+        # a chunk is reduced early only when every layer in it announces its last launch (expected_writes known from the previous step)
+        self._left = [len(prims) if prims and all(q.expected_writes is not None for q in prims) else -1 for _, _, prims in self.chunks]
+        self._done = [False] * len(self.chunks)
+
+    def _comm_stream(self):
+        if self._comm is None:
+            self._comm = ops.named_stream("ddp.comm")
+        return self._comm
+
+    def _final(self, prim):
+        """The last weight-gradient launch of this step into `prim`'s slice has just been enqueued (its event is prim.grad_event)."""
+        ci = self._chunk_of.get(id(prim))
+        if ci is None or not self.early or not self._left or self._left[ci] < 0 or self._done[ci]:
+            return
+        self._left[ci] -= 1
+        if self._left[ci] > 0:
+            return
+        start, end, prims = self.chunks[ci]
+        comm = self._comm_stream()
+        for q in prims:
+            comm.wait_event(q.grad_event)
+        with torch.cuda.stream(comm):
+            self._all_reduce(self.opt.grad_flat[start:end])
+        self._done[ci] = True
+        self.n_early += 1
 
     def _all_reduce(self, flat):
         if dist.get_backend() == "nccl":
@@ -93,14 +165,19 @@ class GradSync:
             if not flat.is_cuda:
                 self._all_reduce(flat)
                 return
-            if self._comm is None:
-                self._comm = ops.named_stream("ddp.comm")
+            comm = self._comm_stream()
             cur = torch.cuda.current_stream()
-            self._comm.wait_stream(cur)
-            with torch.cuda.stream(self._comm):
-                for o in range(0, flat.numel(), self.chunk):
-                    self._all_reduce(flat[o:o + self.chunk])
-            cur.wait_stream(self._comm)
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                if self.chunks:
+                    for ci, (start, end, _) in enumerate(self.chunks):
+                        if not (self._done and self._done[ci]):
+                            self._all_reduce(flat[start:end])
+                    self._done = [True] * len(self.chunks)
+                else:
+                    for o in range(0, flat.numel(), self.chunk):
+                        self._all_reduce(flat[o:o + self.chunk])
+            cur.wait_stream(comm)
             return
         owners = [p for p in self.params if p.grad is not None]
         grads = [p.grad for p in owners]
@@ -587,6 +664,7 @@ class Reg_Trainer(_TrainerBase):
         self.target_real, self.target_fake = 1.0, 0.0
         if self._fused(self.optimizer_G):
             sr, sg = GradSync(self.optimizer_R_A), GradSync(self.optimizer_G)
+            self._sync_R, self._sync_G = sr, sg
             self._sync_GR = lambda: (sr(), sg())
             self._sync_D = GradSync(self.optimizer_D_B)
         else:

@@ -43,3 +43,23 @@ def test_two_ranks_equal_one_rank_with_twice_the_batch(kind, size, tmp_path):
     assert (num / den) ** 0.5 <= 1e-4, (num / den) ** 0.5
     for k, v in b["losses"].items():
         pass        # (the per-rank losses are over different slices: only the gradients are comparable)
+
+
+@pytest.mark.parametrize("kind,size", [("cyc", 64), ("reg", 256)])
+def test_overlapped_all_reduce_equals_all_reduce_after_backward(kind, size, tmp_path):
+    """The bucket chunks that go to the all-reduce while the backward pass is still running (GradSync._final, from the second step on)
+    must give exactly what one all-reduce after the whole backward gives: three bf16 training steps on two ranks, every weight of
+    every network bit for bit (the kernels are deterministic and an average of two ranks does not depend on the chunking)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = os.path.join(ROOT, "tests", "ddp_worker.py")
+    outs = {}
+    for early in ("1", "0"):
+        out = str(tmp_path / f"early{early}.pt")
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", CTAGAN_DDP_EARLY=early, CTAGAN_DDP_CHUNK_MB="2")
+        subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_free_port()), worker, kind, str(size), "1", "2", out, "3", "bf16"], check=True, env=env, timeout=600)
+        outs[early] = torch.load(out)
+    assert outs["1"]["early_chunks"] > 0 and len(outs["1"]["weights"]) == len(outs["0"]["weights"])
+    for k, (a, b) in enumerate(zip(outs["1"]["weights"], outs["0"]["weights"])):
+        assert torch.equal(a, b), (k, float((a - b).abs().max()))
