@@ -48,6 +48,7 @@ struct TcParams {
   int n_stages;                // pipeline depth actually used (<= TcConfig::STAGES)
   int dbg;                     // tuning/debug knobs (0 in production)
   long long *prof;             // optional per-phase clock64 stamps of CTA 0 (developer probe)
+  long long dbg_t0;
   const float *bias;
   bf16 *out;
   float *stat_part;            // optional [N][stat_parts][Co][2]: per-tile (sum, sum of squares) of the fp32 conv output over the tile's rows
@@ -702,17 +703,22 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                          // producer grid complete + flushed: nothing above touches global memory
+  __shared__ long long prof_s[12];     // developer probe (CTAGAN_TC_PROF=1): phase clocks of CTA (0,0)
+  const long long t_start = clock64();
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp walks the ring (coordinates stay warp-uniform), one elected lane issues =====
     int s = 0;
     uint32_t ph = 0;
+    long long t_wait = 0;
     for (int tap = 0; tap < p.n_taps; ++tap) {
       const int dh = p.tap_dh[tap], dw = p.tap_dw[tap], wcol = p.tap_w_col[tap];
       const int row2d = (int)(q0 + dh * p.Wv + dw);
       const int c1 = tile_j0 * p.stride + dw, c2 = tile_i0 * p.stride + dh;
       for (int gk = 0; gk < groups; ++gk) {
+        const long long tw = clock64();
         mbar_wait(&empty_bar[s], ph ^ 1u);
+        t_wait += clock64() - tw;
         if (elect_one()) {
           uint8_t *a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t *b_dst = a_dst + KCH * Cfg::A_BYTES;
@@ -729,14 +735,18 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
+    if (lane == 0) { prof_s[0] = clock64() - t_start; prof_s[1] = t_wait; }
   } else if (warp == 1) {
     // ===== MMA issuer: converged warp, one elected lane issues the tcgen05.mma / commit =====
     constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
     const int n_iters = p.n_taps * groups;
     int s = 0;
     uint32_t ph = 0;
+    long long t_wait = 0, t_first = 0;
     for (int it = 0; it < n_iters; ++it) {
+      const long long tw = clock64();
       mbar_wait(&full_bar[s], ph);
+      if (it == 0) t_first = clock64() - tw; else t_wait += clock64() - tw;
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -757,21 +767,28 @@ conv_tc_valid_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       __syncwarp();
       if (++s == NS) { s = 0; ph ^= 1u; }
     }
+    if (lane == 0) { prof_s[2] = clock64() - t_start; prof_s[3] = t_wait; prof_s[4] = t_first; prof_s[5] = n_iters; }
   } else {
     // ===== epilogue: warps 2..5 =====
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) prof_s[6] = clock64() - t_start;
     // accumulator complete: from here on only the epilogue is left, so let the consumer's CTAs be scheduled now (they run their
     // prologue and block in their own pdl_wait() until this grid has finished).  Triggering at kernel start instead made the
     // step SLOWER: early-resident consumers held shared memory that the other streams' kernels needed.
     pdl_trigger();
     tc_epilogue<BN>(p, tmem_base, warp, lane, img, tile, co0, wrow0, (int)blockIdx.y, epi);
+    if (threadIdx.x == 64) prof_s[7] = clock64() - t_start;
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+  if (p.prof && blockIdx.x + blockIdx.y == 0 && threadIdx.x == 64) {
+    for (int k = 0; k < 8; ++k) p.prof[k] = prof_s[k];
+    p.prof[8] = t_start - p.dbg_t0;
   }
 }
 
@@ -863,8 +880,23 @@ int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, d
     if (ns >= 1 && ns <= Cfg::STAGES) q.n_stages = ns;
   }
   const size_t smem_bytes = (size_t)q.n_stages * Cfg::STAGE_BYTES + 1024 + 256;
+  static long long *prof_buf = nullptr;
+  static int prof_on = -1;
+  if (prof_on < 0) { const char *e = getenv("CTAGAN_TC_PROF"); prof_on = e ? atoi(e) : 0; }
+  if (prof_on) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(long long));
+    q.prof = prof_buf;
+  }
   CTAGAN_CUDA_OK(launch_pdl(conv_tc_valid_kernel<BN, KCH>, grid, dim3(192), smem_bytes, st, mx, mw, q));
   CTAGAN_LAUNCH_OK();
+  if (prof_on) {
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[conv prof] BN=%d KCH=%d stages=%d grid=(%u,%u) Ci=%d Co=%d taps=%d stats=%d iters=%lld | producer done %lld (wait_empty %lld) | mma done %lld "
+            "(first full %lld, later waits %lld) | acc ready %lld | epilogue done %lld (clk from kernel start)\n", BN, KCH, q.n_stages, grid.x, grid.y, p.Ci, p.Co,
+            p.n_taps, p.stat_part ? 1 : 0, h[5], h[0], h[1], h[2], h[4], h[3], h[6], h[7]);
+  }
   return CTAGAN_OK;
 }
 

@@ -24,7 +24,7 @@ __device__ __forceinline__ void adam_update(float &param, float grad, float &exp
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) adam_pack_kernel(const ctagan_adam_item *__restrict__ items, const int *__restrict__ tile_start, int n_items,
+__global__ void __launch_bounds__(256, 5) adam_pack_kernel(const ctagan_adam_item *__restrict__ items, const int *__restrict__ tile_start, int n_items,
                                                         const float *__restrict__ lr_ptr, float *__restrict__ step_ptr, unsigned int *ticket,
                                                         float beta1, float beta2, float eps) {
   extern __shared__ float tile[];        // [no][ni * taps (+1 pad)]
@@ -45,41 +45,60 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(const ctagan_adam_item *
   const float lr = *lr_ptr;
   const float bc1 = 1.f - powf(beta1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
-  for (int idx = threadIdx.x; idx < no * row; idx += 256) {
-    const int o = idx / row, r = idx - o * row;
-    const long long gi = ((long long)(o0 + o) * I + i0) * taps + r;
-    float p = it.p[gi], m = it.m[gi], v = it.v[gi];
-    float g;
-    if (it.g_packed) {                    // gradient stored [O][taps][I] (128-byte runs of this tile: sector-complete, served by L1)
-      const int i = r / taps, tap = r - i * taps;
-      g = it.g[((long long)(o0 + o) * taps + tap) * I + i0 + i];
-    } else {
-      g = it.g[gi];
+  // The tile is no rows (output channels) of `row` = ni * taps contiguous master weights.  Threads walk it in row-major order, 256
+  // consecutive elements per pass (coalesced, whole DRAM bursts), and keep (o, i, tap) of their element up to date incrementally: no
+  // per-element integer division.  U passes are batched -- all 4 * U loads are issued before the first store -- because the compiler
+  // must assume that the weight / moment stores alias the next pass's loads and would otherwise serialise the passes on DRAM latency.
+  {
+    constexpr int U = 2;
+    const int di = 256 / taps, dt = 256 - di * taps;
+    int o = (int)threadIdx.x / row, r0 = (int)threadIdx.x - o * row;
+    int i = r0 / taps, tap = r0 - i * taps;
+    const int row_stride = I * taps;                        // (a tensor has < 2^31 elements: 32-bit offsets)
+    const int tile_base = (o0 * I + i0) * taps;             // + o * row_stride + (i * taps + tap)
+    const int gpk_base = o0 * taps * I + i0;                // packed gradient [O][taps][I]: + (o * taps + tap) * I + i
+    while (o < no) {
+      float pv[U], mv[U], vv[U], gv[U];
+      int gi[U], so[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = i * taps + tap;
+        so[u] = o < no ? o * pitch + r : -1;
+        gi[u] = tile_base + o * row_stride + r;
+        if (o < no) {
+          pv[u] = it.p[gi[u]]; mv[u] = it.m[gi[u]]; vv[u] = it.v[gi[u]];
+          gv[u] = it.g[it.g_packed ? gpk_base + (o * taps + tap) * I + i : gi[u]];
+        }
+        i += di; tap += dt;                          // 256 elements further in row-major order
+        if (tap >= taps) { tap -= taps; ++i; }
+        while (i >= ni) { i -= ni; ++o; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (so[u] < 0) continue;
+        adam_update(pv[u], gv[u], mv[u], vv[u], lr, beta1, beta2, eps, bc1, bc2_sqrt);
+        it.p[gi[u]] = pv[u]; it.m[gi[u]] = mv[u]; it.v[gi[u]] = vv[u];
+        tile[so[u]] = pv[u];
+      }
     }
-    adam_update(p, g, m, v, lr, beta1, beta2, eps, bc1, bc2_sqrt);
-    it.p[gi] = p; it.m[gi] = m; it.v[gi] = v;
-    tile[o * pitch + r] = p;
   }
   if (it.wp0 != nullptr || it.wp1 != nullptr) {
     __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (it.wp0 != nullptr) {
-      // wp[o][tap][i]: consecutive threads -> consecutive i
+      // wp[o][tap][i]: one warp per (o, tap) row, lanes along i (bank = (i * taps + tap) mod 32: conflict-free for odd taps)
       T *dst = reinterpret_cast<T *>(it.wp0);
-      for (int idx = threadIdx.x; idx < no * taps * ni; idx += 256) {
-        const int i = idx % ni;
-        const int r = idx / ni;
-        const int tap = r % taps, o = r / taps;
-        dst[((long long)(o0 + o) * taps + tap) * I + i0 + i] = from_f<T>(tile[o * pitch + i * taps + tap]);
+      for (int q = warp; q < no * taps; q += 8) {
+        const int o = q / taps, tap = q - o * taps;
+        if (lane < ni) dst[((long long)(o0 + o) * taps + tap) * I + i0 + lane] = from_f<T>(tile[o * pitch + lane * taps + tap]);
       }
     }
     if (it.wp1 != nullptr) {
-      // wp[i][taps-1-tap][o]: consecutive threads -> consecutive o
+      // wp[i][taps-1-tap][o]: one warp per (i, tap) row, lanes along o (pitch is odd: conflict-free)
       T *dst = reinterpret_cast<T *>(it.wp1);
-      for (int idx = threadIdx.x; idx < ni * taps * no; idx += 256) {
-        const int o = idx % no;
-        const int r = idx / no;
-        const int tap = r % taps, i = r / taps;
-        dst[((long long)(i0 + i) * taps + (taps - 1 - tap)) * O + o0 + o] = from_f<T>(tile[o * pitch + i * taps + tap]);
+      for (int q = warp; q < ni * taps; q += 8) {
+        const int i = q / taps, tap = q - i * taps;
+        if (lane < no) dst[((long long)(i0 + i) * taps + (taps - 1 - tap)) * O + o0 + lane] = from_f<T>(tile[lane * pitch + i * taps + tap]);
       }
     }
   }

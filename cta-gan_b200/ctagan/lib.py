@@ -11,7 +11,7 @@ import re
 from typing import Dict, List, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctagan.so")
+LIB_PATH = os.environ.get("CTAGAN_LIB") or os.path.join(_HERE, "libctagan.so")       # (CTAGAN_LIB: developer A/B of two builds)
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "ctagan.h")
 
 F32, BF16 = 0, 1
