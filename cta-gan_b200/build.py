@@ -10,6 +10,8 @@ SOURCES = ["capi.cu", "conv_simt.cu", "conv_small.cu", "conv_tc.cu", "data_eval.
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-diag-suppress", "20281", "-Xptxas", "-v" if os.environ.get("CTAGAN_PTXAS_V") else "-O3"]
+if os.environ.get("CTAGAN_PROBES") == "1":          # developer build: clock64 phase probes inside the tcgen05 kernels (see conv_tc.cu)
+    FLAGS.append("-DCTAGAN_PROBES=1")
 
 
 def needs_build():

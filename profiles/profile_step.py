@@ -16,11 +16,12 @@ import bench  # noqa: E402
 from ctagan import trainers as TR  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "cyc"
-args = bench.parse.__globals__["argparse"].Namespace(workload=workload, batch=int(sys.argv[2]) if len(sys.argv) > 2 else None,
-                                                     size=256, precision="bf16")
+default_batch = {"cyc": 1, "reg": 8, "hd": 4}[workload]
+args = bench.parse.__globals__["argparse"].Namespace(workload=workload, batch=int(sys.argv[2]) if len(sys.argv) > 2 else default_batch,
+                                                     size=512 if workload == "hd" else 256, precision="bf16", hd_stage=2)
 cfg = bench.workload_config(args)
 random.seed(42); torch.manual_seed(42)
-trainer = (TR.Cyc_Trainer if workload == "cyc" else TR.Reg_Trainer)(cfg)
+trainer = {"cyc": TR.Cyc_Trainer, "reg": TR.Reg_Trainer, "hd": TR.Hd_Trainer_x2}[workload](cfg)
 loader = TR.SyntheticSlices(cfg["batchSize"], cfg["size"], 4, 42, trainer.data_keys, pool=2)
 for b in loader.batches:
     trainer.step(b)
