@@ -24,6 +24,10 @@ int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void
                            size_t workspace_bytes, cudaStream_t st, int accumulate = 0);
 size_t ctagan_conv_wgrad_thin_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups = 1);
+int ctagan_conv_wgrad_thin_tc_eligible(const ctagan_conv_geom *g);
+size_t ctagan_conv_wgrad_thin_tc_workspace(const ctagan_conv_geom *g);
+int ctagan_conv_wgrad_thin_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                              size_t workspace_bytes, cudaStream_t st, int accumulate);
 
 static thread_local char g_err[512] = "";
 
@@ -46,23 +50,62 @@ int ctagan_num_sms() {
 
 namespace {
 template <bool ACC>
-__global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restrict__ part, float *__restrict__ out, int parts, long long n) {
+__global__ void __launch_bounds__(256) ordered_sum_kernel(const float *__restrict__ part, float *__restrict__ out, int parts, long long n,
+                                                          long long row_stride) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int k = 0; k < parts; ++k) s += __ldcg(part + (long long)k * n + i);
+    for (int k = 0; k < parts; ++k) s += __ldcg(part + (long long)k * row_stride + i);
     if (ACC) s += out[i];
     out[i] = s;
   }
 }
 }  // namespace
 
-int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st, int accumulate) {
-  long long blocks = (n + 255) / 256;
-  if (blocks > 8LL * ctagan_num_sms()) blocks = 8LL * ctagan_num_sms();
-  if (accumulate) ordered_sum_kernel<true><<<(int)blocks, 256, 0, st>>>(part, out, parts, n);
-  else ordered_sum_kernel<false><<<(int)blocks, 256, 0, st>>>(part, out, parts, n);
+// Many rows, few columns (the per-CTA partial rows of the thin-layer weight gradients: ~148 rows of a few thousand floats): one WARP per
+// output element -- lane l adds rows l, l + 32, ... in order, then the lanes are combined by a fixed shuffle tree -- so the row loop is 5
+// independent loads deep instead of 148 dependent-latency steps.  A fixed order again: the same inputs give the same bits.  The row may
+// hold two results ([dw | db]) that go to two destinations.
+template <bool ACC>
+__global__ void __launch_bounds__(256) ordered_sum_warp_kernel(const float *__restrict__ part, float *__restrict__ out1, long long n1,
+                                                               float *__restrict__ out2, long long n2, int parts, long long row_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = wid; i < n1 + n2; i += nw) {
+    float s = 0.f;
+    for (int k = lane; k < parts; k += 32) s += __ldcg(part + (long long)k * row_stride + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      float *dst = i < n1 ? out1 + i : out2 + (i - n1);
+      if (ACC) s += *dst;
+      *dst = s;
+    }
+  }
+}
+
+// rows [dw (n1) | db (n2)] `row_stride` floats apart -> out1[n1], out2[n2] (out2 may be NULL with n2 = 0)
+int ctagan_ordered_sum_rows2(const float *part, float *out1, long long n1, float *out2, long long n2, int parts, long long row_stride,
+                             cudaStream_t st, int accumulate) {
+  const long long warps = n1 + n2;
+  long long blocks = (warps + 7) / 8;
+  if (blocks > 16LL * ctagan_num_sms()) blocks = 16LL * ctagan_num_sms();
+  if (accumulate) ordered_sum_warp_kernel<true><<<(int)blocks, 256, 0, st>>>(part, out1, n1, out2, n2, parts, row_stride);
+  else ordered_sum_warp_kernel<false><<<(int)blocks, 256, 0, st>>>(part, out1, n1, out2, n2, parts, row_stride);
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
+}
+
+int ctagan_ordered_sum_strided(const float *part, float *out, int parts, long long n, long long row_stride, cudaStream_t st, int accumulate) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8LL * ctagan_num_sms()) blocks = 8LL * ctagan_num_sms();
+  if (accumulate) ordered_sum_kernel<true><<<(int)blocks, 256, 0, st>>>(part, out, parts, n, row_stride);
+  else ordered_sum_kernel<false><<<(int)blocks, 256, 0, st>>>(part, out, parts, n, row_stride);
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}
+
+int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st, int accumulate) {
+  return ctagan_ordered_sum_strided(part, out, parts, n, n, st, accumulate);
 }
 
 bool ctagan_pdl_enabled() {
@@ -129,6 +172,7 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
 extern "C" size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine) {
   if (!g) return 0;
   if (engine == 2) return ctagan_conv_wgrad_tc_workspace(g);
+  if ((engine == 0 || engine == 1) && ctagan_conv_wgrad_thin_tc_eligible(g)) return ctagan_conv_wgrad_thin_tc_workspace(g);
   if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) return ctagan_conv_wgrad_thin_workspace(g);
   if (engine == 0 && ctagan_conv_wgrad_tc_eligible(g)) return ctagan_conv_wgrad_tc_workspace(g);
   return ctagan_conv_wgrad_simt_workspace(g);
@@ -143,6 +187,9 @@ extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, cons
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_REQUIRE((accumulate & ~(CTAGAN_WGRAD_ACCUMULATE | CTAGAN_WGRAD_PACKED)) == 0, "conv_wgrad: bad flags");
   if (engine == 2) return ctagan_conv_wgrad_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st, 1, accumulate);
+  // 1-2 channel layers: the patch-matrix tensor-core kernel where it applies (bf16, large maps), else the CUDA-core kernels
+  if ((engine == 0 || engine == 1) && !(accumulate & CTAGAN_WGRAD_PACKED) && ctagan_conv_wgrad_thin_tc_eligible(g))
+    return ctagan_conv_wgrad_thin_tc(g, gy, gx, dw, db, workspace, workspace_bytes, st, accumulate);
   if (engine != 3 && ctagan_conv_wgrad_thin_eligible(g)) {
     if (accumulate & CTAGAN_WGRAD_PACKED) {
       ctagan_set_error("conv_wgrad: the packed gradient layout is not available for 1-2 channel layers");

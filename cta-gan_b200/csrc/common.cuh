@@ -171,3 +171,8 @@ int ctagan_num_sms();
 // out[i] = (accumulate ? out[i] : 0) + part[0][i] + part[1][i] + ... + part[parts-1][i]  (i < n), added in row order: the deterministic
 // second half of every split reduction of the library (each CTA stores its partial result in its own row; no floating-point atomics)
 int ctagan_ordered_sum(const float *part, float *out, int parts, long long n, cudaStream_t st, int accumulate = 0);
+// many rows of [out1 (n1) | out2 (n2)] -> out1, out2: one warp per element (fixed order: lane-strided rows, then a shuffle tree)
+int ctagan_ordered_sum_rows2(const float *part, float *out1, long long n1, float *out2, long long n2, int parts, long long row_stride,
+                             cudaStream_t st, int accumulate = 0);
+// the same with rows `row_stride` floats apart (partial rows that hold more than one result, e.g. [dw | db])
+int ctagan_ordered_sum_strided(const float *part, float *out, int parts, long long n, long long row_stride, cudaStream_t st, int accumulate = 0);

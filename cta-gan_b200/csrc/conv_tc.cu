@@ -80,6 +80,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -1279,4 +1282,351 @@ int ctagan_conv_wgrad_tc(const ctagan_conv_geom *g, const void *gy, const void *
     }
   }
   return CTAGAN_OK;
+}
+
+// =====================================================================================================================
+// Weight gradient of the layers with 1-2 channels on one side (7x7 head Cin = 1, 7x7 tail Cout = 1, the discriminator's first and
+// last layer, Reg's first conv) on the tensor cores.
+//
+// V = the wide tensor ([N][VH][VW][C], C <= 128), S = the thin one (SC <= 2 channels):
+//   gx thin (gy_thin = 0):  dw[c][sc][kh][kw] = sum_v V[v][c] * S[n, vh*s + kh - pad, vw*s + kw - pad, sc]       (V = gy, v = output position)
+//   gy thin (gy_thin = 1):  dw[sc][c][kh][kw] = sum_v V[v][c] * S[n, vh + pad - kh,  vw + pad - kw,  sc]        (V = gx, v = input position)
+// Both are D[c][col] = sum_v V[v][c] * P[v][col] with the PATCH MATRIX P[v][col = sc*taps + tap] of the thin tensor: a GEMM with
+// M = 128 (c, channels past C are TMA zero fill), N = 64 (sc*taps <= 64 columns, the rest zero), K = positions.  V tiles of 64
+// positions arrive by TMA ([64 px][128 B] slabs = MN-major A operand, as in conv_wgrad_tc_kernel); the matching P tile -- [64 px]
+// [64 cols] bf16 = the MN-major B operand -- is BUILT IN SHARED MEMORY by four builder warps from the few rows of the thin tensor the
+// chunk touches (staged in shared memory first), in the 128-byte-swizzled layout the MMA reads.  Column SC*taps of P is set to 1, so
+// the same GEMM also yields db[c] = sum_v gy[v][c] (gx thin).  Every CTA walks a contiguous range of chunks and stores its partial
+// D in its own row of the workspace; ctagan_ordered_sum adds the rows in CTA order (deterministic).
+// Against the CUDA-core kernels (conv_wgrad_thin_vec_kernel: FMA-issue bound): 7x7 head, batch 1, 256^2: ~100 us -> ~10 us.
+// =====================================================================================================================
+namespace {
+
+struct ThinTcParams {
+  int gy_thin;
+  int C, SC, KH, KW, stride, pad;
+  int VH, VW, SH, SW;
+  int ncols;                  // SC * taps (+ 1 ones column when the bias gradient rides along)
+  int ones_col;               // index of the ones column or -1
+  int chunks_w;               // 64-position chunks per row of V
+  int total_chunks, chunks_per_cta;
+  int win_w;                  // window columns (positions of S) a chunk touches
+  float *part;                // [ctas][part_elems]
+  int part_elems;             // Co*Ci*taps (+ Co for db)
+  int db_off;                 // offset of db inside a partial row, or -1
+  const bf16 *S;
+};
+
+constexpr int TT_STAGES = 4;
+constexpr int TT_V_BYTES = 2 * WG_SLAB;          // 128 channels x 64 positions
+constexpr int TT_P_BYTES = WG_SLAB;              // 64 columns x 64 positions
+constexpr int TT_STAGE_BYTES = TT_V_BYTES + TT_P_BYTES;
+constexpr int TT_WIN_MAX = 7 * 136 * 2;          // KH <= 7 rows x (63 * 2 + 7 + pad) columns x SC <= 2, bf16 elements
+constexpr int TT_SMEM_BYTES = TT_STAGES * TT_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_thin_tc_kernel(const __grid_constant__ CUtensorMap map_v, const ThinTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + TT_STAGES * TT_STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + TT_STAGES;
+  uint64_t *tmem_full_bar = empty_bar + TT_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+  __shared__ bf16 win[2][TT_WIN_MAX];             // double-buffered window of the thin tensor
+  __shared__ short lut[64];                       // column -> offset inside the window (-1: zero column, -2: ones column)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk_lo = blockIdx.x * p.chunks_per_cta;
+  const int n_iters = max(0, min(p.total_chunks, chunk_lo + p.chunks_per_cta) - chunk_lo);
+  const int taps = p.KH * p.KW;
+  const int win_pitch = p.win_w * p.SC;           // elements per window row
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_v);
+    for (int s = 0; s < TT_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1 + 4);             // the producer's expect_tx arrival + one arrival per builder warp
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 64) {
+    const int col = threadIdx.x;
+    int v = -1;
+    if (col < p.SC * taps) {
+      const int sc = col / taps, tap = col - sc * taps;
+      const int kh = tap / p.KW, kw = tap - kh * p.KW;
+      // window row / column of the sample that position r = 0 of the chunk needs for this tap
+      const int wr = p.gy_thin ? (p.KH - 1 - kh) : kh;
+      const int wc = p.gy_thin ? (p.KW - 1 - kw) : kw;
+      v = wr * win_pitch + wc * p.SC + sc;
+    } else if (col == p.ones_col) {
+      v = -2;
+    }
+    lut[col] = (short)v;
+  }
+  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer: V tiles =====
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % TT_STAGES;
+      const uint32_t ph = (uint32_t)(it / TT_STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      int ch = chunk_lo + it;
+      const int cw = ch % p.chunks_w; ch /= p.chunks_w;
+      const int vh = ch % p.VH;
+      const int n = ch / p.VH;
+      if (elect_one()) {
+        uint8_t *v_dst = smem + s * TT_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], TT_V_BYTES);
+        tma_load_4d(&map_v, &full_bar[s], v_dst, 0, cw * 64, vh, n);
+        tma_load_4d(&map_v, &full_bar[s], v_dst + WG_SLAB, 64, cw * 64, vh, n);       // channels >= C: zero fill
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16_mn(WG_M, 64);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % TT_STAGES;
+      const uint32_t ph = (uint32_t)(it / TT_STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * TT_STAGE_BYTES);
+        const uint32_t b_addr = a_addr + TT_V_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_KPIX / UMMA_K; ++k) {
+          const uint64_t adesc = make_mnmajor_sw128_desc(a_addr + k * 2048, WG_SLAB);
+          const uint64_t bdesc = make_mnmajor_sw128_desc(b_addr + k * 2048, WG_SLAB);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (it == n_iters - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== builders (warps 2..5, 128 threads): window of the thin tensor -> shared memory -> swizzled patch tile =====
+    const int bt = (int)threadIdx.x - 64;          // 0..127
+    const int c8 = bt & 7;                          // this thread's 16-byte piece (8 columns) of every row it builds
+    int off[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) off[e] = lut[c8 * 8 + e];
+    const int rstep = (p.gy_thin ? 1 : p.stride) * p.SC;       // window elements per position step
+    const int win_elems = p.KH * win_pitch;
+    constexpr int WE = (TT_WIN_MAX + 127) / 128;               // window elements per builder thread (at most)
+    // this thread's window elements e = bt, bt + 128, ...: (row, column * SC + sc) once, without per-chunk divisions
+    short e_wr[WE], e_rem[WE];
+#pragma unroll
+    for (int q = 0; q < WE; ++q) {
+      const int e = bt + q * 128;
+      e_wr[q] = (short)(e < win_elems ? e / win_pitch : -1);
+      e_rem[q] = (short)(e < win_elems ? e - (e / win_pitch) * win_pitch : 0);
+    }
+    unsigned short pre[WE];                                    // the NEXT chunk's window values, loaded while the current tile is built
+    auto prefetch = [&](int it) {
+      int ch = chunk_lo + it;
+      const int cw = ch % p.chunks_w; ch /= p.chunks_w;
+      const int vh = ch % p.VH;
+      const int n = ch / p.VH;
+      // window origin in S: row of window row 0, column * SC of window column 0
+      const int sh0 = p.gy_thin ? vh + p.pad - (p.KH - 1) : vh * p.stride - p.pad;
+      const int sw0 = p.gy_thin ? cw * 64 + p.pad - (p.KW - 1) : cw * 64 * p.stride - p.pad;
+      const unsigned short *S16 = reinterpret_cast<const unsigned short *>(p.S) + (long long)n * p.SH * p.SW * p.SC;
+#pragma unroll
+      for (int q = 0; q < WE; ++q) {
+        const int sh = sh0 + e_wr[q];
+        const int col = sw0 * p.SC + e_rem[q];                 // element index inside the row of S (column * SC + sc)
+        pre[q] = (e_wr[q] >= 0 && sh >= 0 && sh < p.SH && col >= 0 && col < p.SW * p.SC) ? __ldg(S16 + (long long)sh * p.SW * p.SC + col) : (unsigned short)0;
+      }
+    };
+    if (n_iters > 0) prefetch(0);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % TT_STAGES;
+      const uint32_t ph = (uint32_t)(it / TT_STAGES) & 1u;
+      bf16 *w = win[it & 1];
+#pragma unroll
+      for (int q = 0; q < WE; ++q)
+        if (e_wr[q] >= 0) w[bt + q * 128] = __ushort_as_bfloat16(pre[q]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");           // window complete (the other window buffer is still being read by nobody:
+                                                               // every builder passed the previous bar.sync after its last read of it)
+      if (it + 1 < n_iters) prefetch(it + 1);                  // in flight while this tile is built
+      mbar_wait(&empty_bar[s], ph ^ 1u);                       // the MMAs that read this stage's previous patch tile have retired
+      uint8_t *p_dst = smem + s * TT_STAGE_BYTES + TT_V_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = (bt >> 3) + 16 * k;                      // position inside the chunk
+        const int base = r * rstep;
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const unsigned short lo = off[e] >= 0 ? __bfloat16_as_ushort(w[off[e] + base]) : (off[e] == -2 ? (unsigned short)0x3F80 : (unsigned short)0);
+          const unsigned short hi = off[e + 1] >= 0 ? __bfloat16_as_ushort(w[off[e + 1] + base]) : (off[e + 1] == -2 ? (unsigned short)0x3F80 : (unsigned short)0);
+          pk[e / 2] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        *reinterpret_cast<uint4 *>(p_dst + r * 128 + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async();                                     // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ===== epilogue: this CTA's partial D -> its row of the workspace, in the final dw (and db) layout =====
+    const int quarter = warp & 3;
+    const int c = quarter * 32 + lane;               // channel of V == TMEM lane
+    float *row = p.part + (long long)blockIdx.x * p.part_elems;
+    if (n_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t r[32];
+      if (n_iters > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = 0u;
+      }
+      if (c < p.C) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = c0 + e;
+          if (col < p.SC * taps) {
+            const int sc = col / taps, tap = col - sc * taps;
+            const long long idx = p.gy_thin ? ((long long)sc * p.C + c) * taps + tap : ((long long)c * p.SC + sc) * taps + tap;
+            row[idx] = __uint_as_float(r[e]);
+          } else if (col == p.ones_col && p.db_off >= 0) {
+            row[p.db_off + c] = __uint_as_float(r[e]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+// sum of a thin (1-2 channel) tensor per channel: part[block][SC], fixed order inside the block (the bias gradient of a Cout <= 2 layer)
+__global__ void __launch_bounds__(256) thin_sum_kernel(const bf16 *__restrict__ x, float *__restrict__ part, long long pixels, int SC, int part_stride) {
+  __shared__ float wsum[8];
+  const long long per = (pixels + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = min(pixels, p0 + per);
+  for (int s = 0; s < SC; ++s) {
+    float t = 0.f;
+    for (long long q = p0 + threadIdx.x; q < p1; q += blockDim.x) t += __bfloat162float(x[q * SC + s]);
+    t = warp_sum(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += wsum[w];
+      part[(long long)blockIdx.x * part_stride + s] = a;
+    }
+  }
+}
+
+struct ThinTcPlan {
+  int gy_thin, C, SC, ctas, cpc, total_chunks, chunks_w, win_w;
+};
+
+bool plan_thin_tc(const ctagan_conv_geom *g, ThinTcPlan &pl) {
+  if (g->dtype != CTAGAN_BF16 || g->dil != 1 || g->gy_margin != 0) return false;
+  if (g->KH > 7 || g->KW > 7 || g->stride > 2) return false;
+  static int enabled = -1;
+  if (enabled < 0) { const char *e = getenv("CTAGAN_THIN_TC"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return false;
+  if (g->Ci <= 2 && g->Co >= 8) pl.gy_thin = 0;
+  else if (g->Co <= 2 && g->Ci >= 8 && g->stride == 1) pl.gy_thin = 1;
+  else return false;
+  pl.C = pl.gy_thin ? g->Ci : g->Co;
+  pl.SC = pl.gy_thin ? g->Co : g->Ci;
+  if (pl.C % 8 || pl.C > 128) return false;
+  if (pl.SC * g->KH * g->KW + 1 > 64) return false;
+  const int VH = pl.gy_thin ? g->Hi : g->Ho, VW = pl.gy_thin ? g->Wi : g->Wo;
+  if (VW < 64) return false;                                   // (a ragged last chunk of a row is TMA zero fill: it adds nothing)
+  if ((long long)g->N * VH * VW < 4096) return false;          // tiny maps: the CUDA-core kernels
+  pl.chunks_w = (VW + 63) / 64;
+  pl.total_chunks = g->N * VH * pl.chunks_w;
+  pl.win_w = pl.gy_thin ? 63 + g->KW : 63 * g->stride + g->KW;
+  if (g->KH * pl.win_w * pl.SC > TT_WIN_MAX) return false;
+  int ctas = ctagan_num_sms();
+  if (ctas > pl.total_chunks / 2) ctas = pl.total_chunks / 2 > 0 ? pl.total_chunks / 2 : 1;     // at least two chunks per CTA
+  pl.cpc = (pl.total_chunks + ctas - 1) / ctas;
+  pl.ctas = (pl.total_chunks + pl.cpc - 1) / pl.cpc;
+  return true;
+}
+
+}  // namespace
+
+int ctagan_conv_wgrad_thin_tc_eligible(const ctagan_conv_geom *g) {
+  ThinTcPlan pl;
+  return plan_thin_tc(g, pl) ? 1 : 0;
+}
+
+// partial sums [ctas][Co*Ci*taps + Co]
+size_t ctagan_conv_wgrad_thin_tc_workspace(const ctagan_conv_geom *g) {
+  ThinTcPlan pl;
+  if (!plan_thin_tc(g, pl)) return 0;
+  return (size_t)pl.ctas * ((size_t)g->Co * g->Ci * g->KH * g->KW + g->Co) * sizeof(float);
+}
+
+int ctagan_conv_wgrad_thin_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
+                              size_t workspace_bytes, cudaStream_t st, int accumulate) {
+  ThinTcPlan pl;
+  if (!plan_thin_tc(g, pl)) {
+    ctagan_set_error("conv_wgrad_thin_tc: geometry not supported");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  const size_t need = ctagan_conv_wgrad_thin_tc_workspace(g);
+  CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_wgrad(thin tc): workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+  const void *V = pl.gy_thin ? gx : gy;
+  const void *S = pl.gy_thin ? gy : gx;
+  CTAGAN_REQUIRE((reinterpret_cast<uintptr_t>(V) & 15) == 0, "conv_wgrad(thin tc): the wide tensor must be 16-byte aligned");
+  const int VH = pl.gy_thin ? g->Hi : g->Ho, VW = pl.gy_thin ? g->Wi : g->Wo;
+  CUtensorMap mv;
+  int rc = make_map_4d(&mv, V, g->N, VH, VW, pl.C, 64, 1, 1);
+  if (rc) return rc;
+  const long long dw_elems = (long long)g->Co * g->Ci * g->KH * g->KW;
+  ThinTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.gy_thin = pl.gy_thin; p.C = pl.C; p.SC = pl.SC; p.KH = g->KH; p.KW = g->KW; p.stride = g->stride; p.pad = g->pad_h;
+  p.VH = VH; p.VW = VW; p.SH = pl.gy_thin ? g->Ho : g->Hi; p.SW = pl.gy_thin ? g->Wo : g->Wi;
+  p.ncols = pl.SC * g->KH * g->KW;
+  const bool ones = db != nullptr && !pl.gy_thin;         // db[c] = sum of gy rides along as a column of ones
+  p.ones_col = ones ? p.ncols : -1;
+  p.chunks_w = pl.chunks_w; p.total_chunks = pl.total_chunks; p.chunks_per_cta = pl.cpc; p.win_w = pl.win_w;
+  p.part = (float *)workspace;
+  p.part_elems = (int)(dw_elems + g->Co);
+  p.db_off = ones ? (int)dw_elems : -1;
+  p.S = (const bf16 *)S;
+  static bool configured = false;
+  if (!configured) {
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_thin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_BYTES));
+    configured = true;
+  }
+  CTAGAN_CUDA_OK(launch_pdl(conv_wgrad_thin_tc_kernel, dim3((unsigned)pl.ctas), dim3(192), (size_t)TT_SMEM_BYTES, st, mv, p));
+  CTAGAN_LAUNCH_OK();
+  int parts = pl.ctas;
+  if (db != nullptr && pl.gy_thin) {                      // bias gradient of the thin output: a plain sum of gy
+    const long long pixels = (long long)g->N * g->Ho * g->Wo;
+    int blocks = pl.ctas;
+    thin_sum_kernel<<<blocks, 256, 0, st>>>((const bf16 *)gy, p.part + dw_elems, pixels, g->Co, p.part_elems);
+    CTAGAN_LAUNCH_OK();
+  }
+  // rows are [dw | db]: one launch adds the CTA rows (one warp per element) into the two destinations
+  return ctagan_ordered_sum_rows2(p.part, dw, dw_elems, db, db ? g->Co : 0, parts, p.part_elems, st, accumulate & CTAGAN_WGRAD_ACCUMULATE);
 }
