@@ -24,6 +24,10 @@ int ctagan_conv_wgrad_thin(const ctagan_conv_geom *g, const void *gy, const void
                            size_t workspace_bytes, cudaStream_t st, int accumulate = 0);
 size_t ctagan_conv_wgrad_thin_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_tc_eligible(const ctagan_conv_geom *g, int n_groups = 1);
+int ctagan_conv_fewin_tc_eligible(const ctagan_conv_geom *g);
+size_t ctagan_conv_fewin_tc_stat_bytes(const ctagan_conv_geom *g);
+int ctagan_conv_fewin_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, unsigned int *stat_ticket,
+                         void *stat_scratch, size_t stat_scratch_bytes, float *stat_out, cudaStream_t st);
 int ctagan_conv_wgrad_thin_tc_eligible(const ctagan_conv_geom *g);
 size_t ctagan_conv_wgrad_thin_tc_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_thin_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
@@ -164,6 +168,7 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
   CTAGAN_REQUIRE(engine >= 0 && engine <= 3, "conv_gather: bad engine");
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == 2) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, 0, nullptr, st);
+  if ((engine == 0 || engine == 1) && ctagan_conv_fewin_tc_eligible(g)) return ctagan_conv_fewin_tc(g, x, wp, bias, y, nullptr, nullptr, 0, nullptr, st);
   if (engine != 3 && ctagan_conv_small_kind(g)) return ctagan_conv_gather_small(g, x, wp, bias, y, st);
   if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, 0, nullptr, st);
   return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
@@ -205,6 +210,7 @@ extern "C" int ctagan_conv_wgrad(const ctagan_conv_geom *g, const void *gy, cons
 extern "C" int ctagan_conv_gather_engine(const ctagan_conv_geom *g, int engine) {
   if (!g) return 0;
   if (engine == 2) return 2;
+  if ((engine == 0 || engine == 1) && ctagan_conv_fewin_tc_eligible(g)) return 2;        // patch-matrix tensor-core kernel of the 1-2 input channel layers
   if (engine != 3 && ctagan_conv_small_kind(g)) return 4;
   if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return 2;
   return 1;
@@ -249,6 +255,7 @@ extern "C" int ctagan_conv_wgrad_grouped(const ctagan_conv_geom *g, int groups, 
 
 extern "C" size_t ctagan_conv_gather_stats_scratch_bytes(const ctagan_conv_geom *g, int engine) {
   if (!g || ctagan_conv_gather_engine(g, engine) != 2) return 0;
+  if (engine != 2 && ctagan_conv_fewin_tc_eligible(g)) return ctagan_conv_fewin_tc_stat_bytes(g);
   return ctagan_conv_gather_tc_stat_bytes(g);
 }
 
@@ -262,5 +269,7 @@ extern "C" int ctagan_conv_gather_stats(const ctagan_conv_geom *g, const void *x
     ctagan_set_error("conv_gather_stats: fused statistics need the tcgen05 engine (use ctagan_conv_gather + ctagan_instnorm_stats)");
     return CTAGAN_ERR_UNSUPPORTED;
   }
+  if (engine != 2 && ctagan_conv_fewin_tc_eligible(g))
+    return ctagan_conv_fewin_tc(g, x, wp, bias, y, stat_tickets, stat_scratch, stat_scratch_bytes, stats_out, (cudaStream_t)stream);
   return ctagan_conv_gather_tc(g, x, wp, bias, y, stat_tickets, stat_scratch, stat_scratch_bytes, stats_out, (cudaStream_t)stream);
 }

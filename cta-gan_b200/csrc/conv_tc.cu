@@ -547,7 +547,8 @@ struct EpiSmem {
 
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t tmem_acc, int warp, int lane, int img, int tile, int co0, int wrow0,
-                                            int co_tile, EpiSmem<BN> &es) {
+                                            int co_tile, EpiSmem<BN> &es, uint64_t *acc_drained = nullptr, int et_base = 64,
+                                            bool commit_stats = true) {
   const int quarter = warp & 3;
   const int row = quarter * 32 + lane;
   const int BW = 1 << p.bw_log2;
@@ -612,11 +613,16 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, uint32_t tmem_acc
       }
     }
   }
-  if (!stats) return;
+  if (acc_drained != nullptr) {          // the accumulator is in registers / stored: hand it back to the MMA issuer (persistent callers)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_drained);
+  }
+  if (!stats || !commit_stats) return;      // (!commit_stats: the caller accumulates es.part over its tiles and publishes one slot per image)
   // combine the four warps (in warp order) and store this tile's slot; then "last CTA finalises": once every CTA of this (image,
   // column tile) has stored its slot, the last one adds the slots in slot order and turns them into (mean, rstd); it also re-arms
   // the ticket (the buffer is zero again when the kernel ends)
-  const int et = (int)threadIdx.x - 64;      // 0..127
+  const int et = (int)threadIdx.x - et_base;      // 0..127
   asm volatile("bar.sync 1, 128;" ::: "memory");
   float2 *slot = reinterpret_cast<float2 *>(p.stat_part) + ((long long)img * p.stat_parts + p.stat_part0 + tile) * p.Co + co0;
 #pragma unroll
@@ -1629,4 +1635,319 @@ int ctagan_conv_wgrad_thin_tc(const ctagan_conv_geom *g, const void *gy, const v
   }
   // rows are [dw | db]: one launch adds the CTA rows (one warp per element) into the two destinations
   return ctagan_ordered_sum_rows2(p.part, dw, dw_elems, db, db ? g->Co : 0, parts, p.part_elems, st, accumulate & CTAGAN_WGRAD_ACCUMULATE);
+}
+
+// =====================================================================================================================
+// Forward convolution of the layers with 1-2 INPUT channels (7x7 head Cin = 1, the discriminator's first layer, Reg's first conv; also
+// the input gradient of a Cout <= 2 layer, which is the same operation on flipped weights) on the tensor cores:
+//   y[px][co] = act(bias[co] + sum_col P[px][col] * wp[co][col]),   col = (kh * KW + kw) * Ci + ci  (<= 64 columns)
+// i.e. a GEMM with M = 128 output positions, N = 64 (Co <= 64), K = 64: the A operand is the PATCH MATRIX of the thin input, built in
+// shared memory (128-byte-swizzled K-major rows) by four builder warps from a window of the input staged in shared memory; B = the packed
+// weights, padded to 64 columns, resident in shared memory for the whole kernel.  Persistent CTAs walk the tiles; the accumulator is
+// double-buffered in tensor memory so that the epilogue warps (bias / activation / bf16 stores / fused InstanceNorm statistics: the
+// shared tc_epilogue) work on tile i while the builders and the MMAs are on tile i+1.  No TMA: nothing here is a dense tile in memory.
+// Roles (288 threads): warp 0 = TMEM allocation + MMA issuer, warps 1-4 = builders, warps 5-8 = epilogue.
+// =====================================================================================================================
+namespace {
+
+struct FewinParams {
+  int SC, KH, KW, stride, pad;
+  int Hi, Wi;
+  int ncols;                   // KH * KW * SC
+  int win_w, win_h;            // window of input positions a tile touches
+  int n_tiles;                 // N * tiles_per_img
+  const bf16 *x;
+  const bf16 *wp;              // [Co][ncols]
+};
+
+constexpr int FI_STAGES = 3;
+constexpr int FI_P_BYTES = TILE_M * 128;          // 128 positions x 64 columns
+constexpr int FI_B_BYTES = 64 * 128;              // 64 output channels x 64 columns
+constexpr int FI_WIN_MAX = 2304;                  // bf16 elements of the input window (7 x 134 x 2, 4 x 258 x 2, ...)
+constexpr int FI_SMEM_BYTES = FI_STAGES * FI_P_BYTES + FI_B_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(288, 1)
+conv_fewin_tc_kernel(const TcParams p, const FewinParams f) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *b_smem = smem + FI_STAGES * FI_P_BYTES;
+  uint64_t *p_full = reinterpret_cast<uint64_t *>(b_smem + FI_B_BYTES);
+  uint64_t *p_empty = p_full + FI_STAGES;
+  uint64_t *tmem_full_bar = p_empty + FI_STAGES;       // [2]
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+  __shared__ bf16 win[2][FI_WIN_MAX];
+  __shared__ short lut[64];
+  __shared__ EpiSmem<64> epi;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int win_pitch = f.win_w * f.SC;
+  const int BW = 1 << p.bw_log2;
+  const int my_tiles = (int)blockIdx.x < f.n_tiles ? (f.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < FI_STAGES; ++s) {
+      mbar_init(&p_full[s], 4);                    // one arrival per builder warp
+      mbar_init(&p_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);            // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 64) {
+    const int col = threadIdx.x;
+    int v = -1;
+    if (col < f.ncols) {
+      const int tap = col / f.SC, sc = col - tap * f.SC;
+      const int kh = tap / f.KW, kw = tap - kh * f.KW;
+      v = kh * win_pitch + kw * f.SC + sc;
+    }
+    lut[col] = (short)v;
+  }
+  pdl_wait();
+  // resident B operand: wp[co][col] -> K-major rows of 128 bytes, 16-byte pieces XOR-swizzled by (row & 7); rows >= Co and columns >= ncols zero
+  for (int e = threadIdx.x; e < 64 * 8; e += blockDim.x) {
+    const int co = e >> 3, c8 = e & 7;
+    uint32_t pk[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      unsigned short v2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int col = c8 * 8 + h * 2 + u;
+        v2[u] = (co < p.Co && col < f.ncols) ? __bfloat16_as_ushort(f.wp[(long long)co * f.ncols + col]) : (unsigned short)0;
+      }
+      pk[h] = (uint32_t)v2[0] | ((uint32_t)v2[1] << 16);
+    }
+    *reinterpret_cast<uint4 *>(b_smem + co * 128 + ((c8 ^ (co & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, 64);
+    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_smem));
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int s = lt % FI_STAGES, a = lt & 1;
+      mbar_wait(&tmem_empty_bar[a], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      mbar_wait(&p_full[s], (uint32_t)(lt / FI_STAGES) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + s * FI_P_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < CHUNK_K / UMMA_K; ++kk)
+          umma_bf16(tmem_base + (uint32_t)(a * 64), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk > 0 ? 1u : 0u);
+        umma_commit(&p_empty[s]);
+        umma_commit(&tmem_full_bar[a]);
+      }
+      __syncwarp();
+    }
+  } else if (warp <= 4) {
+    // ===== builders =====
+    const int bt = (int)threadIdx.x - 32;            // 0..127
+    const int c8 = bt & 7;
+    int off[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) off[e] = lut[c8 * 8 + e];
+    const int win_elems = f.win_h * win_pitch;
+    constexpr int WE = FI_WIN_MAX / 128;             // 18
+    short e_wr[WE], e_rem[WE];
+#pragma unroll
+    for (int q = 0; q < WE; ++q) {
+      const int e = bt + q * 128;
+      e_wr[q] = (short)(e < win_elems ? e / win_pitch : -1);
+      e_rem[q] = (short)(e < win_elems ? e - (e / win_pitch) * win_pitch : 0);
+    }
+    unsigned short pre[WE];
+    auto prefetch = [&](int lt) {
+      const int t = (int)blockIdx.x + lt * (int)gridDim.x;
+      const int img = t / p.tiles_per_img, tile = t - img * p.tiles_per_img;
+      const int ti0 = (tile / p.tiles_w) * (TILE_M >> p.bw_log2), tj0 = (tile % p.tiles_w) * BW;
+      const int sh0 = ti0 * f.stride - f.pad, sc0 = (tj0 * f.stride - f.pad) * f.SC;
+      const unsigned short *X16 = reinterpret_cast<const unsigned short *>(f.x) + (long long)img * f.Hi * f.Wi * f.SC;
+#pragma unroll
+      for (int q = 0; q < WE; ++q) {
+        const int sh = sh0 + e_wr[q];
+        const int col = sc0 + e_rem[q];
+        pre[q] = (e_wr[q] >= 0 && sh >= 0 && sh < f.Hi && col >= 0 && col < f.Wi * f.SC) ? __ldg(X16 + (long long)sh * f.Wi * f.SC + col) : (unsigned short)0;
+      }
+    };
+    if (my_tiles > 0) prefetch(0);
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int s = lt % FI_STAGES;
+      bf16 *w = win[lt & 1];
+#pragma unroll
+      for (int q = 0; q < WE; ++q)
+        if (e_wr[q] >= 0) w[bt + q * 128] = __ushort_as_bfloat16(pre[q]);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (lt + 1 < my_tiles) prefetch(lt + 1);
+      mbar_wait(&p_empty[s], ((uint32_t)(lt / FI_STAGES) & 1u) ^ 1u);
+      uint8_t *p_dst = smem + s * FI_P_BYTES;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = (bt >> 3) + 16 * k;                          // position inside the tile
+        const int base = ((r >> p.bw_log2) * win_pitch + (r & (BW - 1)) * f.SC) * f.stride;
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const unsigned short lo = off[e] >= 0 ? __bfloat16_as_ushort(w[off[e] + base]) : (unsigned short)0;
+          const unsigned short hi = off[e + 1] >= 0 ? __bfloat16_as_ushort(w[off[e + 1] + base]) : (unsigned short)0;
+          pk[e / 2] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        *reinterpret_cast<uint4 *>(p_dst + r * 128 + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[s]);
+    }
+  } else {
+    // ===== epilogue (warps 5..8: TMEM lane quarters 1, 2, 3, 0) =====
+    // InstanceNorm statistics: a layer of this kind has hundreds of tiles per image, so the per-tile slot + ticket of the dense kernel
+    // would put one __threadfence per tile on this warpgroup and ~30 dependent rounds of slot reads on the last CTA.  Instead every
+    // CTA keeps the column sums of ITS tiles of an image (tile order) and publishes ONE slot per image -- also for images it has no
+    // tile of (zeros) -- so an image has exactly gridDim.x slots; the last CTA to arrive adds them in CTA order (deterministic).
+    const int et = (int)threadIdx.x - 160;          // 0..127; thread et < 64 owns column et
+    const bool stats = p.stat_part != nullptr;
+    const int n_imgs = f.n_tiles / p.tiles_per_img;
+    float acc_s = 0.f, acc_q = 0.f;
+    int cur_img = 0;
+    auto flush = [&](int img) {
+      float2 *slots = reinterpret_cast<float2 *>(p.stat_part) + (long long)img * gridDim.x * p.Co;
+      if (et < p.Co && et < 64) slots[(long long)blockIdx.x * p.Co + et] = make_float2(acc_s, acc_q);
+      acc_s = acc_q = 0.f;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      unsigned int *ticket = p.stat_ticket + (long long)img * p.stat_tpi;
+      if (et == 0) epi.ticket = atomicAdd(ticket, 1u);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (epi.ticket == gridDim.x - 1u) {
+        __threadfence();
+        if (et < p.Co && et < 64) {
+          double s1 = 0.0, s2 = 0.0;
+          for (unsigned k0 = 0; k0 < gridDim.x; k0 += 16) {
+            float2 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = k0 + u < gridDim.x ? __ldcg(slots + (long long)(k0 + u) * p.Co + et) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { s1 += (double)v[u].x; s2 += (double)v[u].y; }
+          }
+          const double inv = 1.0 / (double)p.stat_hw;
+          const double m = s1 * inv;
+          double var = s2 * inv - m * m;
+          if (var < 0) var = 0;
+          *reinterpret_cast<float2 *>(p.stat_out + ((long long)img * p.Co + et) * 2) = make_float2((float)m, (float)(1.0 / sqrt(var + 1e-5)));
+        }
+        if (et == 0) *ticket = 0u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // epi.ticket is free again
+    };
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int a = lt & 1;
+      const int t = (int)blockIdx.x + lt * (int)gridDim.x;
+      const int img = t / p.tiles_per_img, tile = t - img * p.tiles_per_img;
+      if (stats)
+        for (; cur_img < img; ++cur_img) flush(cur_img);
+      mbar_wait(&tmem_full_bar[a], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      tc_epilogue<64>(p, tmem_base + (uint32_t)(a * 64), warp, lane, img, tile, 0, 0, 0, epi, &tmem_empty_bar[a], 160, false);
+      if (stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // the four warps' column sums of this tile are in epi.part
+        if (et < 64) {
+          acc_s += (epi.part[0][et][0] + epi.part[1][et][0]) + (epi.part[2][et][0] + epi.part[3][et][0]);
+          acc_q += (epi.part[0][et][1] + epi.part[1][et][1]) + (epi.part[2][et][1] + epi.part[3][et][1]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // ... and may be overwritten by the next tile
+      }
+    }
+    if (stats)
+      for (; cur_img < n_imgs; ++cur_img) flush(cur_img);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+bool plan_fewin_tc(const ctagan_conv_geom *g, int &bw_log2, int &win_w, int &win_h) {
+  if (g->dtype != CTAGAN_BF16 || g->dil != 1 || g->stride > 2) return false;
+  static int enabled = -1;
+  if (enabled < 0) { const char *e = getenv("CTAGAN_THIN_TC"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return false;
+  if (g->Ci > 2 || g->Co > 64 || g->Co <= 32 || g->Co % 8) return false;
+  if (g->KH * g->KW * g->Ci > 64 || g->KH > 7 || g->KW > 7) return false;
+  // measured against the CUDA-core kernels (conv_fewin_tiled): a clear win for the 7x7 head (49 columns: 24 -> 14 us at batch 1, 145 ->
+  // 61 us at batch 8) and for 4x4 on 2 channels (26 -> 19 us); slower for 3x3 / 4x4 on one channel and for 32 output channels
+  if (g->KH * g->KW * g->Ci < 32) return false;
+  if ((long long)g->N * g->Ho * g->Wo < 4096 || g->Wo < 16) return false;       // tiny maps: the CUDA-core kernels
+  bw_log2 = ceil_log2(g->Wo < 128 ? g->Wo : 128);
+  const int BW = 1 << bw_log2, BH = TILE_M >> bw_log2;
+  win_w = (BW - 1) * g->stride + g->KW;
+  win_h = (BH - 1) * g->stride + g->KH;
+  return win_w * win_h * g->Ci <= FI_WIN_MAX;
+}
+
+}  // namespace
+
+int ctagan_conv_fewin_tc_eligible(const ctagan_conv_geom *g) {
+  int a, b, c;
+  return plan_fewin_tc(g, a, b, c) ? 1 : 0;
+}
+
+size_t ctagan_conv_fewin_tc_stat_bytes(const ctagan_conv_geom *g) {
+  int bwl, ww, wh;
+  if (!plan_fewin_tc(g, bwl, ww, wh)) return 0;
+  const int BW = 1 << bwl, BH = TILE_M >> bwl;
+  const long long tiles = (long long)g->N * ((g->Wo + BW - 1) / BW) * ((g->Ho + BH - 1) / BH);
+  const long long ctas = tiles < ctagan_num_sms() ? tiles : ctagan_num_sms();
+  return (size_t)g->N * ctas * g->Co * 2 * sizeof(float);          // one slot per (image, CTA)
+}
+
+int ctagan_conv_fewin_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, unsigned int *stat_ticket,
+                         void *stat_scratch, size_t stat_scratch_bytes, float *stat_out, cudaStream_t st) {
+  int bwl, ww, wh;
+  if (!plan_fewin_tc(g, bwl, ww, wh)) {
+    ctagan_set_error("conv_fewin_tc: geometry not supported");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  CTAGAN_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv_fewin_tc: the output must be 16-byte aligned");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = 1; p.Ci = g->Ci; p.Co = g->Co; p.stride = g->stride;
+  p.out_H = g->Ho; p.out_W = g->Wo; p.sy = p.sx = 1; p.ay = p.ax = 0;
+  p.Hov = g->Ho; p.Wov = g->Wo;
+  p.act = g->act; p.bias = bias; p.out = (bf16 *)y;
+  p.bw_log2 = bwl;
+  const int BW = 1 << bwl, BH = TILE_M >> bwl;
+  p.tiles_w = (g->Wo + BW - 1) / BW;
+  p.tiles_per_img = p.tiles_w * ((g->Ho + BH - 1) / BH);
+  p.imgs_per_group = g->N;
+  if (stat_out) {
+    CTAGAN_REQUIRE(stat_ticket && stat_scratch && stat_scratch_bytes >= ctagan_conv_fewin_tc_stat_bytes(g),
+                   "conv_fewin_tc: ticket buffer and %zu bytes of scratch required", ctagan_conv_fewin_tc_stat_bytes(g));
+    p.stat_part = (float *)stat_scratch; p.stat_ticket = stat_ticket; p.stat_out = stat_out;
+    p.stat_hw = g->Ho * g->Wo; p.stat_parts = p.tiles_per_img; p.stat_part0 = 0;
+    p.stat_tpi = (g->Co + 31) / 32;
+  }
+  FewinParams f;
+  f.SC = g->Ci; f.KH = g->KH; f.KW = g->KW; f.stride = g->stride; f.pad = g->pad_h; f.Hi = g->Hi; f.Wi = g->Wi;
+  f.ncols = g->KH * g->KW * g->Ci; f.win_w = ww; f.win_h = wh; f.n_tiles = g->N * p.tiles_per_img;
+  f.x = (const bf16 *)x; f.wp = (const bf16 *)wp;
+  static bool configured = false;
+  if (!configured) {
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_fewin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FI_SMEM_BYTES));
+    configured = true;
+  }
+  const int ctas = f.n_tiles < ctagan_num_sms() ? f.n_tiles : ctagan_num_sms();
+  CTAGAN_CUDA_OK(launch_pdl(conv_fewin_tc_kernel, dim3((unsigned)ctas), dim3(288), (size_t)FI_SMEM_BYTES, st, p, f));
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
 }

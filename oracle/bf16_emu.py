@@ -67,6 +67,12 @@ def _on_tc(n, ci, co, ho, wo, strided) -> bool:
     return wo >= 2 if strided else True
 
 
+def _on_fewin_tc(n, ci, co, k, ho, wo) -> bool:
+    """Does this 1-2 input channel conv run on the patch-matrix tensor-core kernel (statistics from the fp32 accumulator)?
+    (conv_tc.cu: plan_fewin_tc)"""
+    return ci <= 2 and 32 < co <= 64 and co % 8 == 0 and 32 <= k * k * ci <= 64 and k <= 7 and n * ho * wo >= 4096 and wo >= 16
+
+
 def _norm_act(c: Tensor, act, tc: bool, res: Tensor = None) -> Tensor:
     """c: fp32 conv accumulator.  Returns the stored bf16 activation act((r - mean) * rstd) (+ res)."""
     r = q(c)
@@ -105,7 +111,8 @@ def generator_forward(sd, x: Tensor, n_blocks: int = 9) -> Tensor:
     n = x.shape[0]
     x = q(x)
     c = F.conv2d(R._rpad(x, 3), w("model_head.1"), _bias(b("model_head.1")))
-    x = _norm_act(c, "relu", tc=False)                                                     # Cin = 1: CUDA-core kernel + instnorm_stats
+    # Cin = 1: patch-matrix tensor-core kernel with fused statistics on large maps, else CUDA-core kernel + instnorm_stats
+    x = _norm_act(c, "relu", tc=_on_fewin_tc(n, x.shape[1], c.shape[1], 7, c.shape[2], c.shape[3]))
     for k in ("model_head.4", "model_head.7"):
         c = F.conv2d(x, w(k), _bias(b(k)), stride=2, padding=1)
         x = _norm_act(c, "relu", _on_tc(n, x.shape[1], c.shape[1], c.shape[2], c.shape[3], True))

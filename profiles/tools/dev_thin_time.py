@@ -45,7 +45,7 @@ CASES = [
     ("Reg out 3x3 32->2 b8", 8, 32, 2, 256, 256, 3, 1, 1),
     ("G head 7x7 1->64 512 b4", 4, 1, 64, 518, 518, 7, 1, 0),
 ]
-for name, N, Ci, Co, H, W, K, s, p in CASES:
+for name, N, Ci, Co, H, W, K, s, p in (CASES if __name__ == "__main__" else []):
     x = torch.randn(N, H, W, Ci, device="cuda").bfloat16()
     w = torch.randn(Co, Ci, K, K, device="cuda") / (Ci * K * K) ** 0.5
     b = torch.zeros(Co, device="cuda")
