@@ -28,6 +28,10 @@ int ctagan_conv_fewin_tc_eligible(const ctagan_conv_geom *g);
 size_t ctagan_conv_fewin_tc_stat_bytes(const ctagan_conv_geom *g);
 int ctagan_conv_fewin_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, unsigned int *stat_ticket,
                          void *stat_scratch, size_t stat_scratch_bytes, float *stat_out, cudaStream_t st);
+int ctagan_conv_fewout_tc_eligible(const ctagan_conv_geom *g);
+size_t ctagan_conv_fewout_tc_workspace(const ctagan_conv_geom *g);
+int ctagan_conv_fewout_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, void *workspace,
+                          size_t workspace_bytes, cudaStream_t st);
 int ctagan_conv_wgrad_thin_tc_eligible(const ctagan_conv_geom *g);
 size_t ctagan_conv_wgrad_thin_tc_workspace(const ctagan_conv_geom *g);
 int ctagan_conv_wgrad_thin_tc(const ctagan_conv_geom *g, const void *gy, const void *gx, float *dw, float *db, void *workspace,
@@ -172,6 +176,22 @@ extern "C" int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, cons
   if (engine != 3 && ctagan_conv_small_kind(g)) return ctagan_conv_gather_small(g, x, wp, bias, y, st);
   if (engine == 0 && ctagan_conv_gather_tc_eligible(g)) return ctagan_conv_gather_tc(g, x, wp, bias, y, nullptr, nullptr, 0, nullptr, st);
   return ctagan_conv_gather_simt(g, x, wp, bias, y, st);
+}
+
+extern "C" size_t ctagan_conv_gather_workspace_bytes(const ctagan_conv_geom *g, int engine) {
+  if (!g || !(engine == 0 || engine == 1)) return 0;
+  return ctagan_conv_fewout_tc_eligible(g) ? ctagan_conv_fewout_tc_workspace(g) : 0;
+}
+
+extern "C" int ctagan_conv_gather_ws(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, void *workspace,
+                                     size_t workspace_bytes, int engine, void *stream) {
+  if (g && workspace && (engine == 0 || engine == 1) && ctagan_conv_fewout_tc_eligible(g)) {
+    int rc = check_geom(g, "conv_gather_ws");
+    if (rc) return rc;
+    CTAGAN_REQUIRE(x && wp && y, "conv_gather_ws: null pointer");
+    return ctagan_conv_fewout_tc(g, x, wp, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  return ctagan_conv_gather(g, x, wp, bias, y, engine, stream);
 }
 
 extern "C" size_t ctagan_conv_wgrad_workspace_bytes(const ctagan_conv_geom *g, int engine) {

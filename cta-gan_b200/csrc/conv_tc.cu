@@ -1951,3 +1951,221 @@ int ctagan_conv_fewin_tc(const ctagan_conv_geom *g, const void *x, const void *w
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
 }
+
+// =====================================================================================================================
+// Forward convolution of the layers with 1-2 OUTPUT channels and stride 1 (7x7 tail Cout = 1 + tanh, Reg's 2-channel flow head; also the
+// input gradient of a Cin <= 2 layer = the same operation on flipped weights) on the tensor cores, in two steps:
+//   1. Z^T[col][q] = sum_ci x[q][ci] * wp[col][ci],   col = co * taps + tap (<= 64 columns), q = every INPUT position:
+//      ONE small GEMM per 128 positions (M = 128, N = 64, K = Ci <= 64) -- x is read exactly once, as plain 2-D TMA boxes;
+//   2. y[n,i,j,co] = act(bias[co] + sum_tap Z^T[co * taps + tap][n, i + kh - pad, j + kw - pad]): a gather of taps fp32 values per
+//      output, coalesced along j because Z is stored column-major (one plane per filter tap).
+// Against the direct form (taps x 64 FMAs per output on CUDA cores, FMA-issue bound: 48 us at batch 1, 297 us at batch 8 for the 7x7
+// tail) the arithmetic moves to the tensor pipe and what is left is bandwidth: x once, Z (taps x 4 bytes per position) written and read
+// once (L2-resident at batch 1).
+// =====================================================================================================================
+namespace {
+
+struct FewoutZParams {
+  int Ci, ncols;               // ncols = Co * taps
+  long long n_rows;            // N * Hi * Wi input positions
+  int n_tiles;
+  const bf16 *wp;              // [ncols][Ci]
+  float *zt;                   // [ncols][n_rows]
+};
+
+constexpr int FO_STAGES = 4;
+constexpr int FO_A_BYTES = TILE_M * 128;
+constexpr int FO_SMEM_BYTES = FO_STAGES * FO_A_BYTES + FI_B_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(192, 1)
+conv_fewout_z_kernel(const __grid_constant__ CUtensorMap map_x, const FewoutZParams f) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *b_smem = smem + FO_STAGES * FO_A_BYTES;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(b_smem + FI_B_BYTES);
+  uint64_t *empty_bar = full_bar + FO_STAGES;
+  uint64_t *tmem_full_bar = empty_bar + FO_STAGES;     // [2]
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (int)blockIdx.x < f.n_tiles ? (f.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < FO_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  pdl_wait();
+  // resident B operand: wp[col][ci] -> K-major rows of 128 bytes (swizzled); rows >= ncols and channels >= Ci zero
+  for (int e = threadIdx.x; e < 64 * 8; e += blockDim.x) {
+    const int col = e >> 3, c8 = e & 7;
+    uint32_t pk[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      unsigned short v2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ci = c8 * 8 + h * 2 + u;
+        v2[u] = (col < f.ncols && ci < f.Ci) ? __bfloat16_as_ushort(f.wp[(long long)col * f.Ci + ci]) : (unsigned short)0;
+      }
+      pk[h] = (uint32_t)v2[0] | ((uint32_t)v2[1] << 16);
+    }
+    *reinterpret_cast<uint4 *>(b_smem + col * 128 + ((c8 ^ (col & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int s = lt % FO_STAGES;
+      mbar_wait(&empty_bar[s], ((uint32_t)(lt / FO_STAGES) & 1u) ^ 1u);
+      if (elect_one()) {
+        const int t = (int)blockIdx.x + lt * (int)gridDim.x;
+        mbar_expect_tx(&full_bar[s], FO_A_BYTES);
+        tma_load_2d(&map_x, &full_bar[s], smem + s * FO_A_BYTES, 0, t * TILE_M);        // rows past the end: zero fill
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, 64);
+    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_smem));
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int s = lt % FO_STAGES, a = lt & 1;
+      mbar_wait(&tmem_empty_bar[a], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      mbar_wait(&full_bar[s], (uint32_t)(lt / FO_STAGES) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + s * FO_A_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < CHUNK_K / UMMA_K; ++kk)
+          umma_bf16(tmem_base + (uint32_t)(a * 64), adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk > 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        umma_commit(&tmem_full_bar[a]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int a = lt & 1;
+      const int t = (int)blockIdx.x + lt * (int)gridDim.x;
+      const long long q = (long long)t * TILE_M + quarter * 32 + lane;
+      mbar_wait(&tmem_full_bar[a], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        if (c0 >= f.ncols) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t)(a * 64) + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (q < f.n_rows) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < f.ncols) f.zt[(long long)(c0 + e) * f.n_rows + q] = __uint_as_float(r[e]);      // a warp stores 32 consecutive positions
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+// step 2: one thread per output position (all Co <= 2 channels)
+__global__ void __launch_bounds__(256) conv_fewout_gather_kernel(ctagan_conv_geom g, const float *__restrict__ zt, const float *__restrict__ bias,
+                                                                 bf16 *__restrict__ y, long long n_rows) {
+  const long long total = (long long)g.N * g.Ho * g.Wo;
+  const int taps = g.KH * g.KW;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(o % g.Wo);
+    const long long r = o / g.Wo;
+    const int i = (int)(r % g.Ho), n = (int)(r / g.Ho);
+    const float *zn = zt + (long long)n * g.Hi * g.Wi;
+    for (int co = 0; co < g.Co; ++co) {
+      float acc = bias ? bias[co] : 0.f;
+      const float *zc = zn + (long long)co * taps * n_rows;
+      for (int kh = 0; kh < g.KH; ++kh) {
+        const int ih = i + kh - g.pad_h;
+        if (ih < 0 || ih >= g.Hi) continue;
+        const float *zr = zc + (long long)kh * g.KW * n_rows + (long long)ih * g.Wi + (j - g.pad_w);
+#pragma unroll 7
+        for (int kw = 0; kw < g.KW; ++kw) {
+          const int iw = j + kw - g.pad_w;
+          if (iw >= 0 && iw < g.Wi) acc += __ldg(zr + (long long)kw * n_rows + kw);
+        }
+      }
+      y[o * g.Co + co] = __float2bfloat16_rn(apply_act(acc, g.act));
+    }
+  }
+}
+
+bool plan_fewout_tc(const ctagan_conv_geom *g) {
+  if (g->dtype != CTAGAN_BF16 || g->dil != 1 || g->stride != 1) return false;
+  static int enabled = -1;
+  if (enabled < 0) { const char *e = getenv("CTAGAN_THIN_TC"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return false;
+  if (g->Co > 2 || g->Ci % 8 || g->Ci < 16 || g->Ci > 64) return false;
+  if (g->Co * g->KH * g->KW > 64) return false;
+  if ((long long)g->N * g->Ho * g->Wo < 32768) return false;     // small maps (the discriminator's patch head): the CUDA-core kernels are faster
+  return true;
+}
+
+}  // namespace
+
+int ctagan_conv_fewout_tc_eligible(const ctagan_conv_geom *g) { return plan_fewout_tc(g) ? 1 : 0; }
+
+// scratch: Z^T [Co * taps][N * Hi * Wi] fp32
+size_t ctagan_conv_fewout_tc_workspace(const ctagan_conv_geom *g) {
+  if (!plan_fewout_tc(g)) return 0;
+  return (size_t)g->Co * g->KH * g->KW * g->N * g->Hi * g->Wi * sizeof(float);
+}
+
+int ctagan_conv_fewout_tc(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, void *workspace,
+                          size_t workspace_bytes, cudaStream_t st) {
+  if (!plan_fewout_tc(g)) {
+    ctagan_set_error("conv_fewout_tc: geometry not supported");
+    return CTAGAN_ERR_UNSUPPORTED;
+  }
+  const size_t need = ctagan_conv_fewout_tc_workspace(g);
+  CTAGAN_REQUIRE(workspace && workspace_bytes >= need, "conv_fewout_tc: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+  CTAGAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "conv_fewout_tc: the input must be 16-byte aligned");
+  FewoutZParams f;
+  f.Ci = g->Ci; f.ncols = g->Co * g->KH * g->KW;
+  f.n_rows = (long long)g->N * g->Hi * g->Wi;
+  f.n_tiles = (int)((f.n_rows + TILE_M - 1) / TILE_M);
+  f.wp = (const bf16 *)wp; f.zt = (float *)workspace;
+  CUtensorMap mx;
+  int rc = make_map_2d(&mx, x, (uint64_t)f.n_rows, (uint64_t)g->Ci, TILE_M);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    CTAGAN_CUDA_OK(cudaFuncSetAttribute(conv_fewout_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FO_SMEM_BYTES));
+    configured = true;
+  }
+  const int ctas = f.n_tiles < ctagan_num_sms() ? f.n_tiles : ctagan_num_sms();
+  CTAGAN_CUDA_OK(launch_pdl(conv_fewout_z_kernel, dim3((unsigned)ctas), dim3(192), (size_t)FO_SMEM_BYTES, st, mx, f));
+  CTAGAN_LAUNCH_OK();
+  const long long total = (long long)g->N * g->Ho * g->Wo;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * ctagan_num_sms()) blocks = 16LL * ctagan_num_sms();
+  conv_fewout_gather_kernel<<<(int)blocks, 256, 0, st>>>(*g, (const float *)workspace, bias, (bf16 *)y, f.n_rows);
+  CTAGAN_LAUNCH_OK();
+  return CTAGAN_OK;
+}

@@ -76,8 +76,15 @@ def conv_gather(x, wp, bias, g: L.ConvGeom, engine=L.ENGINE_AUTO):
     _require_cuda(x, wp)
     ensure_device()
     y = torch.empty((g.N, g.Ho, g.Wo, g.Co), dtype=x.dtype, device=x.device)
+    lib = L.load()
+    ws_bytes = int(lib.ctagan_conv_gather_workspace_bytes(ctypes.byref(g), engine))
+    if ws_bytes:            # 1-2 output channels on the tensor cores: per-tap planes Z^T in caller-owned scratch, then a gather
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+        _count(2)
+        L.check(lib.ctagan_conv_gather_ws(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(ws), ws_bytes, engine, _stream()))
+        return y
     _count(1)
-    L.check(L.load().ctagan_conv_gather(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), engine, _stream()))
+    L.check(lib.ctagan_conv_gather(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), engine, _stream()))
     return y
 
 

@@ -73,6 +73,13 @@ typedef struct {
  * tcgen05 kernel (error if ineligible), 3 = generic CUDA-core implicit-GEMM kernel only (cross-check). */
 int ctagan_conv_gather(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y,
                        int engine, void *stream);
+/* The same with caller-provided scratch: the layers with 1-2 OUTPUT channels (7x7 tail of Model/CycleGan.py:58-60, the 2-channel flow
+ * head of trainer/reg.py) then run on the tensor cores in two steps (one GEMM per 128 input positions into per-tap planes, then a
+ * gather of taps values per output), which needs ctagan_conv_gather_workspace_bytes bytes (0 for every other geometry: the call is
+ * then identical to ctagan_conv_gather and workspace may be NULL). */
+size_t ctagan_conv_gather_workspace_bytes(const ctagan_conv_geom *g, int engine);
+int ctagan_conv_gather_ws(const ctagan_conv_geom *g, const void *x, const void *wp, const float *bias, void *y, void *workspace,
+                          size_t workspace_bytes, int engine, void *stream);
 
 /* ctagan_conv_gather with the InstanceNorm statistics fused into the epilogue (tcgen05 engine only; CTAGAN_ERR_UNSUPPORTED
  * otherwise -- query with ctagan_conv_gather_engine).  stats_out[N][Co][2] receives (mean, rstd) of the fp32 convolution output.
