@@ -1178,7 +1178,7 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl, int n_groups = 1) {
   // K splits = CTAs of the tile's cluster (1, 2, 4 or 8): enough of them to put a CTA on every SM, but at least `min_chunks` chunks
   // (64 pixels each) of main loop per CTA
   static int min_chunks = 0;
-  if (!min_chunks) { const char *e = getenv("CTAGAN_WG_MIN_CHUNKS"); min_chunks = e ? atoi(e) : 4; if (min_chunks < 1) min_chunks = 1; }
+  if (!min_chunks) { const char *e = getenv("CTAGAN_WG_MIN_CHUNKS"); min_chunks = e ? atoi(e) : 32; if (min_chunks < 1) min_chunks = 1; }     // (measured: Cyc 4.67 -> 4.60 ms against 4)
   static int max_cluster = 0;
   if (!max_cluster) { const char *e = getenv("CTAGAN_WG_MAX_CLUSTER"); max_cluster = e ? atoi(e) : 8; if (max_cluster < 1 || max_cluster > 8) max_cluster = 8; }
   // a cluster of S CTAs (one per SM: the operand ring fills the shared memory) must fit into ONE GPC (~18 SMs): at most 16 clusters of

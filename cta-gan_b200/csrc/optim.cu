@@ -26,7 +26,7 @@ __device__ __forceinline__ void adam_update(float &param, float grad, float &exp
 template <typename T>
 __global__ void __launch_bounds__(256, 5) adam_pack_kernel(const ctagan_adam_item *__restrict__ items, const int *__restrict__ tile_start, int n_items,
                                                         const float *__restrict__ lr_ptr, float *__restrict__ step_ptr, unsigned int *ticket,
-                                                        float beta1, float beta2, float eps) {
+                                                        float beta1, float beta2, float eps, int advance) {
   extern __shared__ float tile[];        // [no][ni * taps (+1 pad)]
   int lo = 0, hi = n_items - 1;
   while (lo < hi) {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256, 5) adam_pack_kernel(const ctagan_adam_ite
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
-    *step_ptr = step;
+    if (advance) *step_ptr = step;         // (an early launch over part of the group leaves the counter to the launch that completes the step)
     *ticket = 0u;
   }
 }
@@ -144,13 +144,13 @@ extern "C" int ctagan_adam_pack_tiles(const ctagan_adam_item *items_host, int n_
 
 extern "C" int ctagan_adam_pack_multi(const ctagan_adam_item *items_dev, const int *tile_start_dev, int n_items, int total_tiles, size_t smem_bytes,
                                       const float *lr_dev, float *step_dev, uint32_t *ticket_dev, float beta1, float beta2, float eps,
-                                      int packed_dtype, void *stream) {
+                                      int packed_dtype, int advance_step, void *stream) {
   CTAGAN_REQUIRE(items_dev && tile_start_dev && n_items > 0 && total_tiles > 0 && lr_dev && step_dev && ticket_dev, "adam_pack_multi: bad arguments");
   CTAGAN_REQUIRE(smem_bytes <= 200 * 1024, "adam_pack_multi: filter window too large for one tile");
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(packed_dtype, T, {
     if (smem_bytes > 48 * 1024) CTAGAN_CUDA_OK(cudaFuncSetAttribute(adam_pack_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    adam_pack_kernel<T><<<total_tiles, 256, smem_bytes, st>>>(items_dev, tile_start_dev, n_items, lr_dev, step_dev, ticket_dev, beta1, beta2, eps);
+    adam_pack_kernel<T><<<total_tiles, 256, smem_bytes, st>>>(items_dev, tile_start_dev, n_items, lr_dev, step_dev, ticket_dev, beta1, beta2, eps, advance_step);
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;

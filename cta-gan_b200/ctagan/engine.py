@@ -248,7 +248,7 @@ class _WgradLane:
             if sides is None:
                 # several side streams per chain, used round-robin: weight gradients of different layers are independent of each other,
                 # and when a backward chain ends its leftover weight gradients then run side by side instead of one after the other
-                n = max(1, int(os.environ.get("CTAGAN_WG_LANES", "3")))
+                n = max(1, int(os.environ.get("CTAGAN_WG_LANES", "4")))
                 sides = [ops.named_stream(f"lane{k}:{key}") for k in range(n)]
                 _WGRAD_STREAMS[key] = sides
             self.sides = sides
@@ -498,6 +498,16 @@ class GeneratorPlan:
         w, b = nxt(); self.tail7 = ConvPrim(w, b, 1, 0)
         self.n_blocks = n_blocks
         self.params = list(params)
+        # called (with need_dw) by generator_backward once the input-gradient chain has passed every residual block: from here on only
+        # the three head layers still read packed weights / receive weight gradients (ctagan.optim.FusedAdam: early optimiser launch)
+        self.body_done_hook = None
+
+    def early_prims(self):
+        """The layers whose weights are neither read nor differentiated after `body_done_hook`: the residual blocks and the tail."""
+        out = []
+        for c1, c2 in self.blocks:
+            out += [c1, c2]
+        return out + [self.tail0, self.tail3, self.tail7]
 
     def prims(self):
         out = [self.head1, self.head4, self.head7]
@@ -599,6 +609,8 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
         dr3 = ops.norm_act_pad_bwd(G, r3, s3, L.ACT_RELU, 0, pool=bpool)
     else:
         dr3 = ops.norm_act_pad_bwd(dXp, r3, s3, L.ACT_RELU, 1, addend=G, pool=bpool)
+    if need_dw and plan.body_done_hook is not None:
+        plan.body_done_hook(plan)        # every kernel that reads a residual-block / tail weight in this pass is enqueued (this stream or a lane)
     dWh7, _ = wg(plan.head7, dr3, A2)
     dA2 = plan.head7.bprop(dr3, (A2.shape[1], A2.shape[2]))
     dr2 = ops.norm_act_pad_bwd(dA2, r2, s2, L.ACT_RELU, 0, pool=bpool)

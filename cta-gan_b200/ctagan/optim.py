@@ -15,6 +15,7 @@ gradient slice: Adam leaves them untouched, exactly like torch.optim.Adam skippi
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Iterable, List, Sequence
 
 import torch
@@ -54,7 +55,7 @@ class FusedAdam:
         self.lr = torch.tensor(float(lr), dtype=torch.float32, device=dev)
         self.param_groups = [{"params": self.params, "lr": self.lr, "betas": betas, "eps": eps}]      # torch.optim surface the trainers use
         self.step_count = torch.zeros((), dtype=torch.float32, device=dev)
-        self.ticket = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.ticket = torch.zeros((2,), dtype=torch.int32, device=dev)      # [0]: the (late / only) launch, [1]: the early launch
         sizes = [p.numel() for p in self.params]
         offs = [0]
         for n in sizes:
@@ -73,10 +74,25 @@ class FusedAdam:
             p.grad = v
         # attach the gradient slices to the ConvPrims (weight + its bias)
         self.nets = list(nets)
+        self._early_plans = []            # GeneratorPlans of this optimiser (set by _bind_prims)
+        self._early_seen = {}             # id(plan) -> body_done calls so far in this step
         self._bind_prims()
         self._table_key = None
         self._dtype = None
         self.grad_sync = None             # trainers.GradSync (data parallel): armed by zero_grad, fed by the layers' final-write hooks
+        # Early launch (single GPU): the residual blocks and the tail of a generator hold 97 % of its parameters, and nothing reads
+        # their packed weights or adds to their gradients once the backward pass of the generator's LAST use in the step has passed
+        # the blocks.  From then on their optimiser kernel can run under the rest of the backward (the head layers, the lagging
+        # weight-gradient lanes); step() only launches the remainder.  How many passes a generator sees per step is learnt from the
+        # previous step (the schedule is static); data-parallel runs keep the single launch (the gradients must be averaged first).
+        # MEASURED (B200, same box): Cyc 4.626 ms with the early launch against 4.591 ms without, Hd 26.26 against 26.02 ms -- the
+        # optimiser kernel takes SMs and HBM from the tail of the backward it was meant to hide under.  Opt-in (CTAGAN_EARLY_ADAM=1).
+        self.early_enabled = os.environ.get("CTAGAN_EARLY_ADAM", "0") != "0"
+        self._early_expected = {}         # id(plan) -> body_done calls per step (from the previous step)
+        self._early_events = []
+        self._early_launched = False
+        self._early_stream = None
+        self._tables = {}
 
     def _bind_prims(self):
         prims = _prims_of(self.nets)
@@ -89,6 +105,13 @@ class FusedAdam:
                 prim.attach_grads(by_id[id(p)], by_id.get(id(prim.b)) if prim.b is not None else None)
                 self.prims.append(prim)
         self._prim_of = {id(prim.w): prim for prim in self.prims}
+        self._early_plans = []
+        for plans in self._plans:
+            for plan in plans:
+                if isinstance(plan, E.GeneratorPlan):
+                    plan.body_done_hook = self._body_done
+                    self._early_plans.append(plan)
+        self._early_seen = {id(pl): 0 for pl in self._early_plans}
 
     @staticmethod
     def _wants_packed(p) -> bool:
@@ -117,12 +140,59 @@ class FusedAdam:
             prim.grad_writes, prim.grad_event = 0, None
         if self.grad_sync is not None:
             self.grad_sync.arm()
+        for pl in self._early_plans:
+            if self._early_seen.get(id(pl), 0) > 0:
+                self._early_expected[id(pl)] = self._early_seen[id(pl)]
+            self._early_seen[id(pl)] = 0
+        self._early_events, self._early_launched = [], False
+
+    # ---- early launch ----------------------------------------------------------------------------------------------------------
+    def _body_done(self, plan):
+        """generator_backward of `plan` has enqueued everything that touches its residual blocks / tail (on the current stream or on
+        lanes whose events the ConvPrims hold)."""
+        k = id(plan)
+        self._early_seen[k] = self._early_seen.get(k, 0) + 1
+        if (not self.early_enabled or self._early_launched or self.grad_sync is not None or self._table_key is None
+                or "early" not in self._tables or self._early_expected.get(k) != self._early_seen[k]
+                or self._table_key[0] != E.get_precision() or self._table_key[1][0] != self.params[0].data_ptr()):
+            return
+        ev = torch.cuda.Event()
+        ev.record()                                   # covers the input-gradient kernels of this pass (they read the packed weights)
+        self._early_events.append(ev)
+        if any(self._early_expected.get(id(pl)) != self._early_seen.get(id(pl)) for pl in self._early_plans):
+            return                                    # another generator of this optimiser still has a pass to go
+        early = [q for pl in self._early_plans for q in pl.early_prims()]
+        if any(q.grad_event is None or q.expected_writes is None or q.grad_writes != q.expected_writes for q in early):
+            return                                    # (a layer without its final gradient: leave everything to step())
+        if self._early_stream is None:
+            self._early_stream = ops.named_stream("opt.early")
+        st = self._early_stream
+        for ev in self._early_events:
+            st.wait_event(ev)
+        for q in early:
+            st.wait_event(q.grad_event)               # the last weight-gradient launch into every early layer (on its lane)
+        with torch.cuda.stream(st):
+            self._launch("early", 0)
+        self._early_launched = True
 
     def _build_table(self, dtype):
+        """Three item tables: every parameter ("all"), the early set (weights of the residual blocks / tails of the generators and their
+        biases) and the rest ("late")."""
+        early_w = {id(q.w) for pl in self._early_plans for q in pl.early_prims()}
+        early_b = {id(q.b) for pl in self._early_plans for q in pl.early_prims() if q.b is not None}
+        is_early = [id(p) in early_w or id(p) in early_b for p in self.params]
+        self._tables = {"all": self._build_one(dtype, [True] * len(self.params))}
+        if any(is_early) and not all(is_early):
+            self._tables["early"] = self._build_one(dtype, is_early)
+            self._tables["late"] = self._build_one(dtype, [not e for e in is_early])
+        self._dtype = dtype
+
+    def _build_one(self, dtype, select):
         lib = L.load()
-        n = len(self.params)
+        chosen = [(p, o, sz, pk) for (p, o, sz, pk), s_ in zip(zip(self.params, self._offs, self._sizes, self.packed), select) if s_]
+        n = len(chosen)
         items = (L.AdamItem * n)()
-        for k, (p, o, sz, pk) in enumerate(zip(self.params, self._offs, self._sizes, self.packed)):
+        for k, (p, o, sz, pk) in enumerate(chosen):
             prim = self._prim_of.get(id(p))
             wp0 = wp1 = None
             if prim is not None:
@@ -137,12 +207,21 @@ class FusedAdam:
                                   wp0, wp1, O, I, KH, KW, 1 if pk else 0, 0)
         tiles = (ctypes.c_int * (n + 1))()
         L.check(lib.ctagan_adam_pack_tiles(ctypes.cast(items, ctypes.c_void_p), n, tiles))
-        self._smem = int(lib.ctagan_adam_pack_smem_bytes(ctypes.cast(items, ctypes.c_void_p), n))
+        smem = int(lib.ctagan_adam_pack_smem_bytes(ctypes.cast(items, ctypes.c_void_p), n))
         raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
-        self._items_dev = raw.to(self.device)
-        self._tiles_dev = torch.tensor(list(tiles), dtype=torch.int32).to(self.device)
-        self._n, self._total = n, int(tiles[n])
-        self._dtype = dtype
+        return {"items": raw.to(self.device), "tiles": torch.tensor(list(tiles), dtype=torch.int32).to(self.device), "n": n,
+                "total": int(tiles[n]), "smem": smem}
+
+    def _launch(self, which: str, advance: int):
+        """One optimiser kernel over table `which` on the current stream; advance: 1 = this launch moves the step counter on."""
+        t = self._tables[which]
+        ops._count(1)
+        L.check(L.load().ctagan_adam_pack_multi(ctypes.c_void_p(t["items"].data_ptr()), ctypes.c_void_p(t["tiles"].data_ptr()), t["n"],
+                                                t["total"], t["smem"], ctypes.c_void_p(self.lr.data_ptr()),
+                                                ctypes.c_void_p(self.step_count.data_ptr()),
+                                                ctypes.c_void_p(self.ticket[0 if advance else 1:].data_ptr()),
+                                                float(self.betas[0]), float(self.betas[1]), float(self.eps), _DT[self._dtype], int(advance),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def step(self):
         dtype = E.get_precision()
@@ -151,11 +230,10 @@ class FusedAdam:
             self._build_table(dtype)
             self._table_key = key
         ops.ensure_device()
-        ops._count(1)
-        L.check(L.load().ctagan_adam_pack_multi(ctypes.c_void_p(self._items_dev.data_ptr()), ctypes.c_void_p(self._tiles_dev.data_ptr()), self._n,
-                                                self._total, self._smem, ctypes.c_void_p(self.lr.data_ptr()),
-                                                ctypes.c_void_p(self.step_count.data_ptr()), ctypes.c_void_p(self.ticket.data_ptr()),
-                                                float(self.betas[0]), float(self.betas[1]), float(self.eps), _DT[dtype],
-                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        if self._early_launched and "late" in self._tables:
+            torch.cuda.current_stream().wait_stream(self._early_stream)      # also orders the step counter: the early launch read it first
+            self._launch("late", 1)
+        else:
+            self._launch("all", 1)
         for prim in self.prims:
             prim.mark_packed(dtype)

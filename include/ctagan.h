@@ -153,7 +153,10 @@ int ctagan_pack_weights_multi(const ctagan_pack_item *items, int n_items, int dt
  * the tile it has just updated.  An item is one parameter tensor viewed as [O][I][KH][KW] (1-D tensors: O = numel, I = KH = KW = 1);
  * wp0 / wp1 may be NULL.  items_dev / tile_start_dev: the table in DEVICE memory (ctagan_adam_pack_tiles fills the host copy of
  * tile_start[n_items + 1]; total_tiles = tile_start[n_items]); lr_dev: the learning rate; step_dev: the step counter as a float
- * (incremented by the kernel, as torch's state['step']); ticket_dev: one zeroed uint32.  Capturable in CUDA graphs. */
+ * (as torch's state['step']; incremented by the kernel when advance_step != 0 -- a step may be split into several launches over disjoint
+ * parts of the group, e.g. an early one for the layers whose gradients are final before the backward pass ends: only the last one
+ * advances the counter, and it must be ordered after the others); ticket_dev: one zeroed uint32 per launch in flight.  Capturable in
+ * CUDA graphs. */
 typedef struct {
   float *p;
   const float *g;
@@ -169,7 +172,7 @@ size_t ctagan_adam_pack_smem_bytes(const ctagan_adam_item *items_host, int n_ite
 int ctagan_adam_pack_tiles(const ctagan_adam_item *items_host, int n_items, int *tile_start_host);
 int ctagan_adam_pack_multi(const ctagan_adam_item *items_dev, const int *tile_start_dev, int n_items, int total_tiles, size_t smem_bytes,
                            const float *lr_dev, float *step_dev, uint32_t *ticket_dev, float beta1, float beta2, float eps, int packed_dtype,
-                           void *stream);
+                           int advance_step, void *stream);
 
 /* InstanceNorm2d statistics (affine=False, eps=1e-5, biased variance; Model/CycleGan.py:12,16,29,37,52,82,86,90,
  * trainer/layers.py:14): x[N][HW][C] -> stats[N][C][2] = (mean, rstd) fp32.  acc: caller scratch of
