@@ -609,7 +609,7 @@ def generator_backward(plan: GeneratorPlan, saved, dout: torch.Tensor, need_dx: 
         dr3 = ops.norm_act_pad_bwd(G, r3, s3, L.ACT_RELU, 0, pool=bpool)
     else:
         dr3 = ops.norm_act_pad_bwd(dXp, r3, s3, L.ACT_RELU, 1, addend=G, pool=bpool)
-    if need_dw and plan.body_done_hook is not None:
+    if need_dw and getattr(plan, "body_done_hook", None) is not None:
         plan.body_done_hook(plan)        # every kernel that reads a residual-block / tail weight in this pass is enqueued (this stream or a lane)
     dWh7, _ = wg(plan.head7, dr3, A2)
     dA2 = plan.head7.bprop(dr3, (A2.shape[1], A2.shape[2]))
