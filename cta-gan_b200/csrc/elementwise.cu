@@ -130,42 +130,57 @@ __global__ void instnorm_finalize_kernel(const T *__restrict__ x, const double *
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// out[n,hp,wp,c] = act((x-mean)*rstd) + res ; gather form (one thread per output vector), reflect indices.
+// out[n,hp,wp,c] = act((x-mean)*rstd) + res ; gather form, reflect indices.
+// grid (pixel chunks, N); block = CV channel vectors x (256 / CV) pixel lanes: a thread keeps its channel vector, so (mean, rstd) are
+// loaded once per thread instead of once per 16-byte output and the pixel walk needs one division per pixel.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_act_pad_kernel(const T *__restrict__ x, const float *__restrict__ stats,
                                                            const T *__restrict__ res, int res_pad, T *__restrict__ out, int N, int H,
-                                                           int W, int C, int pad, int act) {
+                                                           int W, int C, int pad, int act, int pix_per_block) {
   pdl_wait();
   const int CV = C / V;
+  const int n = blockIdx.y;
+  const int lanes = 256 / CV > 0 ? 256 / CV : 1;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  if (pl >= lanes) return;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-  const idx_t total = (idx_t)N * Hp * Wp * CV;
-  for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % CV);
-    idx_t r = idx / CV;
-    const int wp = (int)(r % Wp);
-    r /= Wp;
-    const int hp = (int)(r % Hp);
-    const int n = (int)(r / Hp);
-    const int h = reflect_idx(hp - pad, H), w = reflect_idx(wp - pad, W);
-    float v[V];
-    load_vec<T, V>(x + (((idx_t)n * H + h) * W + w) * C + cv * V, v);
-    if (stats) {
-      float mean[V], rstd[V];
-      load_stats<V>(stats + ((idx_t)n * C + cv * V) * 2, mean, rstd);
+  float mean[V], rstd[V];
+  if (stats) load_stats<V>(stats + ((idx_t)n * C + cv * V) * 2, mean, rstd);
+  const int q0 = blockIdx.x * pix_per_block, q1 = min(Hp * Wp, q0 + pix_per_block);
+  const T *xn = x + (idx_t)n * H * W * C + cv * V;
+  T *on = out + (idx_t)n * Hp * Wp * C + cv * V;
+  const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
+  const T *rn = res ? res + (idx_t)n * Hr * Wr * C + cv * V : nullptr;
+  constexpr int U = 4;                          // independent pixels in flight per thread
+  for (int q = q0 + pl; q < q1; q += lanes * U) {
+    float v[U][V], rv[U][V];
+    bool ok[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = (v[i] - mean[i]) * rstd[i];
+    for (int u = 0; u < U; ++u) {
+      const int qq = q + u * lanes;
+      ok[u] = qq < q1;
+      const int qc = ok[u] ? qq : q;
+      const int hp = qc / Wp, wp = qc - hp * Wp;
+      const int h = reflect_idx(hp - pad, H), w = reflect_idx(wp - pad, W);
+      load_vec<T, V>(xn + ((idx_t)h * W + w) * C, v[u]);
+      if (rn) load_vec<T, V>(rn + ((idx_t)(h + res_pad) * Wr + w + res_pad) * C, rv[u]);
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) v[i] = apply_act(v[i], act);
-    if (res) {
-      float rv[V];
-      const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
-      load_vec<T, V>(res + (((idx_t)n * Hr + h + res_pad) * Wr + w + res_pad) * C + cv * V, rv);
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      if (stats) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) v[i] += rv[i];
+        for (int i = 0; i < V; ++i) v[u][i] = (v[u][i] - mean[i]) * rstd[i];
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[u][i] = apply_act(v[u][i], act);
+      if (rn) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[u][i] += rv[u][i];
+      }
+      store_vec<T, V>(on + (idx_t)(q + u * lanes) * C, v[u]);
     }
-    store_vec<T, V>(out + idx * V, v);
   }
 }
 
@@ -873,8 +888,16 @@ extern "C" int ctagan_norm_act_pad(const void *x, const float *stats, const void
   cudaStream_t st = (cudaStream_t)stream;
   CTAGAN_DISPATCH_DTYPE(dtype, T, {
     const int v = pick_vec<T>(C);
-    const idx_t total = (idx_t)N * (H + 2 * pad) * (W + 2 * pad) * (C / v);
-    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_act_pad_kernel<T, V>, dim3(ew_blocks(total)), dim3(256), 0, st, (const T *)x, stats, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act)));
+    CTAGAN_REQUIRE(C / v <= 256, "norm_act_pad: at most 256 channel vectors per pixel");
+    const int out_px = (H + 2 * pad) * (W + 2 * pad);
+    const int lanes = 256 / (C / v) > 0 ? 256 / (C / v) : 1;
+    int chunks = (16 * ctagan_num_sms() + N - 1) / N;             // ~16 blocks per SM (two waves of full occupancy), at least 4 pixels per lane
+    const int max_chunks = (out_px + 4 * lanes - 1) / (4 * lanes);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    const int ppb = (out_px + chunks - 1) / chunks;
+    chunks = (out_px + ppb - 1) / ppb;
+    VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_act_pad_kernel<T, V>, dim3(chunks, N), dim3(256), 0, st, (const T *)x, stats, (const T *)res, res_pad, (T *)out, N, H, W, C, pad, act, ppb)));
   });
   CTAGAN_LAUNCH_OK();
   return CTAGAN_OK;
@@ -937,12 +960,12 @@ extern "C" int ctagan_norm_act_pad_bwd(const void *gout, const void *x, const fl
       VEC_SWITCH(T, v, V, CTAGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<T, V>, grid, dim3(256), 0, st, (const T *)gout, (const T *)x, stats, (const T *)addend, acc, scratch, N, H, W, C, pad, act, ppb)));
     }
     {
-      // pixel chunks x images: ~4 blocks per SM, at least 8 pixels per lane
+      // pixel chunks x images: ~16 blocks per SM, at least 4 pixels per lane
       CTAGAN_REQUIRE(C / v <= 256, "norm_act_pad_bwd: at most 256 channel vectors per pixel");
       const int out_px = (H + 2 * out_pad) * (W + 2 * out_pad);
       const int lanes = 256 / (C / v) > 0 ? 256 / (C / v) : 1;
-      int chunks = (4 * ctagan_num_sms() + N - 1) / N;
-      const int max_chunks = (out_px + 8 * lanes - 1) / (8 * lanes);
+      int chunks = (16 * ctagan_num_sms() + N - 1) / N;
+      const int max_chunks = (out_px + 4 * lanes - 1) / (4 * lanes);
       if (chunks > max_chunks) chunks = max_chunks;
       if (chunks < 1) chunks = 1;
       const int ppb = (out_px + chunks - 1) / chunks;
