@@ -373,7 +373,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   //   4. every CTA adds the S partial sums of its own rows IN RANK ORDER (deterministic; its own from shared memory, the others from
   //      L2) and writes the gradient: coalesced when the destination is the packed [co][tap][ci] layout, a 4-byte scatter for OIHW.
   const int S = p.splits;
-  const int rows_per = WG_M / S;
+  const int rows_per = (WG_M + S - 1) / S;                    // (S need not divide 128: the last CTA then owns fewer rows)
+  const int my_row0 = split * rows_per;
+  const int my_rows = max(0, min(WG_M, my_row0 + rows_per) - my_row0);
   constexpr int VPR = BNW / 4;                                // float4 per row
   float *acc = reinterpret_cast<float *>(smem);               // [128][ACC_PITCH] fp32, over the ring
   const long long t_s0 = probe_clock();
@@ -409,7 +411,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
     // rows other CTAs own: (S-1) * rows_per rows of VPR float4 each, skipping this CTA's own block of rows; four independent
     // 16-byte copies per thread and iteration
     float4 *mine = reinterpret_cast<float4 *>(ws_tile + (long long)split * (WG_M * BNW));
-    const int n_vec = (WG_M - rows_per) * VPR;
+    const int n_vec = (WG_M - my_rows) * VPR;
     for (int v0 = threadIdx.x; v0 < n_vec; v0 += 4 * 192) {
       float4 t[4];
       int dst_v[4];
@@ -418,7 +420,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
         const int v = v0 + u * 192;
         int row = v / VPR;
         const int c4 = v - row * VPR;
-        if (row >= split * rows_per) row += rows_per;
+        if (row >= my_row0) row += my_rows;
         dst_v[u] = row * VPR + c4;
         if (v < n_vec) t[u] = *reinterpret_cast<const float4 *>(acc + row * Cfg::ACC_PITCH + c4 * 4);
       }
@@ -435,7 +437,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
   {
     float *dw = p.dw + (long long)grp * p.Co * p.Ci * p.ntaps;
     constexpr int UV = 2;                          // rows-of-4 per thread and iteration: UV * (S-1) independent L2 loads in flight
-    for (int v0 = threadIdx.x; v0 < rows_per * VPR; v0 += UV * 192) {
+    for (int v0 = threadIdx.x; v0 < my_rows * VPR; v0 += UV * 192) {
       float4 u[UV][8];
       int rowv[UV], cv[UV];
       bool ok[UV];
@@ -443,9 +445,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_co
       for (int q = 0; q < UV; ++q) {
         const int v = v0 + q * 192;
         const int lr = v / VPR;
-        rowv[q] = split * rows_per + lr;
+        rowv[q] = my_row0 + lr;
         cv[q] = (v - lr * VPR) * 4;
-        ok[q] = v < rows_per * VPR && co0 + rowv[q] < p.Co && ci0 + cv[q] < p.Ci;        // Ci is a multiple of 32 here
+        ok[q] = v < my_rows * VPR && co0 + rowv[q] < p.Co && ci0 + cv[q] < p.Ci;        // Ci is a multiple of 32 here
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if (k < S && ok[q])
@@ -1181,14 +1183,16 @@ bool plan_wgrad(const ctagan_conv_geom *g, WgPlan &pl, int n_groups = 1) {
   if (!min_chunks) { const char *e = getenv("CTAGAN_WG_MIN_CHUNKS"); min_chunks = e ? atoi(e) : 32; if (min_chunks < 1) min_chunks = 1; }     // (measured: Cyc 4.67 -> 4.60 ms against 4)
   static int max_cluster = 0;
   if (!max_cluster) { const char *e = getenv("CTAGAN_WG_MAX_CLUSTER"); max_cluster = e ? atoi(e) : 8; if (max_cluster < 1 || max_cluster > 8) max_cluster = 8; }
-  // a cluster of S CTAs (one per SM: the operand ring fills the shared memory) must fit into ONE GPC (~18 SMs): at most 16 clusters of
-  // 8, 32 of 4 or 72 of 2 are resident at a time -- more tiles than that would run as two waves
-  int splits = 1;
-  while (splits * 2 <= max_cluster && pl.total_chunks >= splits * 2 * min_chunks) {
-    const int s2 = splits * 2, clusters = pl.tiles * n_groups;
-    const int cap = s2 == 8 ? 16 : (s2 == 4 ? 32 : 72);
-    if (clusters > cap || clusters * s2 > ctagan_num_sms()) break;
-    splits = s2;
+  // a cluster of S CTAs (one per SM: the operand ring fills the shared memory) must fit into ONE GPC (~18 SMs), so at most
+  // 8 * floor(18 / S) clusters are resident at a time (16 of 8, 24 of 6, 32 of 4, 48 of 3, 72 of 2) -- more tiles than that would run as
+  // two waves.  Pick the S <= max_cluster that puts the most CTAs on the chip in ONE wave (18 tiles of a res-block layer: 6 x 18 = 108
+  // CTAs, not 4 x 18 = 72), subject to >= min_chunks chunks of main loop per CTA.
+  int splits = 1, best = pl.tiles * n_groups < ctagan_num_sms() ? pl.tiles * n_groups : ctagan_num_sms();
+  for (int s2 = 2; s2 <= max_cluster; ++s2) {
+    if (pl.total_chunks < s2 * min_chunks) break;
+    const int clusters = pl.tiles * n_groups, cap = 8 * (18 / s2);
+    if (clusters > cap || clusters * s2 > ctagan_num_sms()) continue;
+    if (clusters * s2 > best) { best = clusters * s2; splits = s2; }
   }
   pl.splits = splits;
   pl.cps = (pl.total_chunks + splits - 1) / splits;
