@@ -23,7 +23,7 @@ def golden():
     return g
 
 
-_ORDER = ["test_abi_and_host", "test_oracle", "test_ddp", "test_gpu_ops", "test_gpu_tc", "test_gpu_data_eval", "test_gpu_optim", "test_gpu_determinism", "test_gpu_modules",
+_ORDER = ["test_abi_and_host", "test_oracle", "test_ddp", "test_gpu_ops", "test_gpu_tc", "test_gpu_thin_tc", "test_gpu_data_eval", "test_gpu_optim", "test_gpu_determinism", "test_gpu_modules",
           "test_gpu_bf16", "test_gpu_steps", "test_gpu_curves", "test_gpu_ddp"]
 
 
