@@ -211,10 +211,8 @@ class ConvPrim:
         self.grad_writes += 1
         self.grad_event = torch.cuda.Event()
         self.grad_event.record()
-        if self.expected_writes is not None:
-            assert self.grad_writes <= self.expected_writes, "a layer received more weight-gradient launches than in the previous step"
-            if self.final_hook is not None and self.grad_writes == self.expected_writes:
-                self.final_hook(self)
+        if self.final_hook is not None and self.expected_writes is not None and self.grad_writes >= self.expected_writes:
+            self.final_hook(self)          # (>: one launch more than in the previous step -- the hook's owner decides what that means)
         return out
 
 

@@ -136,7 +136,16 @@ class GradSync:
     def _final(self, prim):
         """The last weight-gradient launch of this step into `prim`'s slice has just been enqueued (its event is prim.grad_event)."""
         ci = self._chunk_of.get(id(prim))
-        if ci is None or not self.early or not self._left or self._left[ci] < 0 or self._done[ci]:
+        if ci is None or not self.early or not self._left:
+            return
+        if prim.grad_writes > prim.expected_writes:
+            # this step launches more weight gradients into the layer than the previous one did: the chunk must not go early any more
+            if self._done[ci]:
+                raise RuntimeError("GradSync: a gradient chunk was all-reduced early and then written again (the step's schedule changed); "
+                                   "run one step with CTAGAN_DDP_EARLY=0 semantics first or keep the schedule static")
+            self._left[ci] = -1
+            return
+        if self._left[ci] < 0 or self._done[ci]:
             return
         self._left[ci] -= 1
         if self._left[ci] > 0:
