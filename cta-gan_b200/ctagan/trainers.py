@@ -11,9 +11,11 @@ Each trainer exposes `step(batch)` = one iteration body, which is what bench.py 
 """
 from __future__ import annotations
 
+import contextlib
 import itertools
 import os
-from typing import Dict, Iterable
+import threading
+from typing import Dict, Iterable, List
 
 import torch
 import torch.distributed as dist
@@ -62,6 +64,16 @@ class SyntheticSlices:
     def __iter__(self):
         for i in range(self.n_batches):
             yield self.batches[i % len(self.batches)]
+
+
+# ---- f4: checkpoints are written by a background thread ---------------------------------------------------------------
+_PENDING_SAVES: List[threading.Thread] = []
+
+
+def wait_checkpoints():
+    """Block until every checkpoint handed to a writer thread is on disk (called before a checkpoint is read and at the end of train())."""
+    while _PENDING_SAVES:
+        _PENDING_SAVES.pop().join()
 
 
 class GradSync:
@@ -277,6 +289,7 @@ class _TrainerBase:
 
     def load_checkpoint(self, net, fname, required=True):
         """load_state_dict(torch.load(save_root + fname)) (CycTrainer.py:239 etc.); a missing file is an error unless required=False."""
+        wait_checkpoints()
         path = os.path.join(self.config.get("save_root") or "", fname)
         if not os.path.exists(path):
             if required:
@@ -292,17 +305,86 @@ class _TrainerBase:
         return [self.inputs[k] for k in self.data_keys]
 
     def _log(self, epoch, i, n):
-        if self.rank == 0 and self.step_count % self.config["log_every"] == 0:
-            msg = " | ".join(f"{k}: {float(v):.4f}" for k, v in self.last_losses.items())
-            print(f"[{self.name}] epoch {epoch} batch {i + 1}/{n} -- {msg}", flush=True)
+        """Every `log_every` steps the losses of the step are copied to a pinned host buffer (asynchronously, behind an event) and
+        printed once the copy has landed -- at the latest at the next log point -- so the hot loop never waits for the device
+        (the reference's Logger.log reads every loss on every iteration: trainer/utils.py:76,92)."""
+        if self.rank != 0:
+            return
+        self._flush_log(block=False)
+        if self.step_count % self.config["log_every"] != 0 or not self.last_losses:
+            return
+        self._flush_log(block=True)                     # (a previous read-back that is still pending: print it first, in order)
+        keys = list(self.last_losses)
+        vals = torch.stack([v.detach().float().reshape(()) for v in self.last_losses.values()])      # the graph overwrites its outputs: copy now
+        ev = None
+        if vals.is_cuda:
+            host = torch.empty(vals.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(vals, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        else:
+            host = vals
+        self._log_pending = (epoch, i, n, keys, host, ev)
 
-    def _save(self, epoch, nets: Dict[str, torch.nn.Module]):
+    def _flush_log(self, block: bool):
+        pend = getattr(self, "_log_pending", None)
+        if pend is None:
+            return
+        epoch, i, n, keys, host, ev = pend
+        if ev is not None:
+            if not block and not ev.query():
+                return
+            ev.synchronize()
+        msg = " | ".join(f"{k}: {float(v):.4f}" for k, v in zip(keys, host.tolist()))
+        print(f"[{self.name}] epoch {epoch} batch {i + 1}/{n} -- {msg}", flush=True)
+        self._log_pending = None
+
+    def _save(self, epoch, nets: Dict[str, torch.nn.Module], wait: bool = False):
+        """Rank 0 writes `state_dict`s under the reference's file names (RegTrainer.py:225-240, HdTrainer.py:275-280) WITHOUT stalling the
+        training loop: the parameters are copied to pinned host memory on a copy stream (the training stream only waits for that copy,
+        so the next optimiser step cannot overwrite weights that are still being read), and a writer thread pickles them and renames
+        the file into place when it is complete.  The files are what `torch.save(net.state_dict())` writes, with CPU tensors."""
         c = self.config
         if self.rank != 0 or not c.get("save_checkpoints") or not c.get("save_root"):
             return
         os.makedirs(c["save_root"], exist_ok=True)
-        for fname, net in nets.items():
-            torch.save(net.state_dict(), os.path.join(c["save_root"], fname.format(st=str(epoch))))
+        on_gpu = any(p.is_cuda for net in nets.values() for p in net.parameters())
+        copy_stream = ops.named_stream("ckpt.copy") if on_gpu else None
+        if on_gpu:
+            copy_stream.wait_stream(torch.cuda.current_stream())
+        jobs = []
+        with (torch.cuda.stream(copy_stream) if on_gpu else contextlib.nullcontext()):
+            for fname, net in nets.items():
+                state = net.state_dict()
+                host = type(state)()
+                for k, v in state.items():
+                    if v.is_cuda:
+                        h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                        h.copy_(v.detach(), non_blocking=True)
+                    else:
+                        h = v.detach().clone()
+                    host[k] = h
+                if hasattr(state, "_metadata"):
+                    host._metadata = state._metadata
+                jobs.append((os.path.join(c["save_root"], fname.format(st=str(epoch))), host))
+        ev = None
+        if on_gpu:
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            torch.cuda.current_stream().wait_event(ev)
+
+        def work():
+            if ev is not None:
+                ev.synchronize()
+            for path, host in jobs:
+                torch.save(host, path + ".tmp")
+                os.replace(path + ".tmp", path)
+
+        t = threading.Thread(target=work, name="ctagan-checkpoint-writer")
+        t.start()
+        _PENDING_SAVES.append(t)
+        if wait:
+            wait_checkpoints()
 
     def train(self):
         """The reference's epoch loop (CycTrainer.py:128-236 etc.).  Every iteration is a CUDA-graph replay (config `cuda_graphs`, default
@@ -318,6 +400,8 @@ class _TrainerBase:
                 runner.step_host(batch)
                 self._log(epoch, i, len(loader))
             self._save(epoch, self.checkpoint_nets())
+        self._flush_log(block=True)
+        wait_checkpoints()
 
     test_checkpoint = "aa.pth"          # CycTrainer.py:239 / RegTrainer.py:245: `save_root + 'aa.pth'`
 

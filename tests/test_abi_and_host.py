@@ -178,3 +178,63 @@ def test_packed_weight_cache_is_invalidated_per_optimizer_and_keeps_its_buffers(
     assert p1._cache[(0, torch.float32)][1].data_ptr() == buf[ga.slots[0]].data_ptr()
     assert p2._cache[(0, torch.float32)][1].data_ptr() == buf[ga.slots[1]].data_ptr()
     assert len(p1.stale_entries(torch.float32, modes=(0,))) == 1             # re-homed copies are stale until re-packed
+
+
+def test_checkpoints_are_written_by_a_background_thread(tmp_path):
+    """f4: _save hands the state_dicts to a writer thread (atomic rename into the reference's file names) and returns; load_checkpoint /
+    wait_checkpoints join it.  Host logic only (CPU tensors take the same path minus the pinned copies)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cta-gan_b200"))
+    import torch
+    from ctagan import trainers as TR
+
+    class Stub:
+        rank = 0
+        device = torch.device("cpu")
+        config = {"save_checkpoints": True, "save_root": str(tmp_path) + "/"}
+        _save = TR._TrainerBase._save
+        load_checkpoint = TR._TrainerBase.load_checkpoint
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3), torch.nn.Conv2d(4, 1, 3))
+    st = Stub()
+    st._save(7, {"netG_A2B_{st}.pth": net, "R_A_x_{st}.pth": net})
+    TR.wait_checkpoints()
+    assert sorted(os.listdir(tmp_path)) == ["R_A_x_7.pth", "netG_A2B_7.pth"]
+    sd = torch.load(tmp_path / "netG_A2B_7.pth", weights_only=True)
+    assert list(sd) == list(net.state_dict()) and all(torch.equal(sd[k], v) for k, v in net.state_dict().items())
+    other = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3), torch.nn.Conv2d(4, 1, 3))
+    st._save(8, {"netG_A2B_{st}.pth": net})
+    assert st.load_checkpoint(other, "netG_A2B_8.pth")            # joins the writer first
+    assert all(torch.equal(a, b) for a, b in zip(other.state_dict().values(), net.state_dict().values()))
+    st.rank = 1
+    st._save(9, {"netG_A2B_{st}.pth": net})                       # only rank 0 writes
+    TR.wait_checkpoints()
+    assert "netG_A2B_9.pth" not in os.listdir(tmp_path)
+
+
+def test_loss_log_is_deferred_not_synchronous(capsys):
+    """f4: _log copies the losses of a log step and prints them when the copy has landed (immediately for CPU tensors, at the next call or
+    at the end of train() for device tensors) -- in order, once each."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cta-gan_b200"))
+    import torch
+    from ctagan import trainers as TR
+
+    class Stub:
+        rank, name = 0, "Stub"
+        config = {"log_every": 2}
+        step_count = 0
+        last_losses = {}
+        _log = TR._TrainerBase._log
+        _flush_log = TR._TrainerBase._flush_log
+
+    st = Stub()
+    for step in range(1, 7):
+        st.step_count = step
+        st.last_losses = {"loss_G": torch.tensor(float(step)), "loss_D": torch.tensor(0.5)}
+        st._log(1, step - 1, 6)
+    st._flush_log(block=True)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("[Stub]")]
+    assert [l.split("loss_G: ")[1].split(" ")[0] for l in lines] == ["2.0000", "4.0000", "6.0000"]
+    assert all("loss_D: 0.5000" in l for l in lines)

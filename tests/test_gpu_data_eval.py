@@ -103,8 +103,11 @@ def test_slice_list_loader_and_trainer_test(tmp_path):
     assert out["slices"] == 5 and all(np.isfinite(out[k]) for k in ("MAE", "PSNR", "SSIM", "UQI", "MAEw", "PSNRw", "SSIMw", "UQIw"))
     # the Hd stage hand-off: stage 1 writes the _x_ names stage 2 loads
     tr1 = Hd_Trainer_x1(_cfg("HdGan", 256, precision="bf16", save_root=str(tmp_path) + "/", save_checkpoints=True))
-    tr1._save(45, tr1.checkpoint_nets())
+    tr1._save(45, tr1.checkpoint_nets())                                               # pinned copies + a writer thread: the call does not wait
+    from ctagan.trainers import wait_checkpoints
+    wait_checkpoints()
     assert all(os.path.exists(tmp_path / n) for n in ("netG_A2B_x_45.pth", "R_A_x_45.pth", "netD_B_x_45.pth"))
+    assert not any(n.endswith(".tmp") for n in os.listdir(tmp_path))
     from trainer import Hd_Trainer_x2
     random.seed(9); torch.manual_seed(9)
     tr2 = Hd_Trainer_x2(_cfg("HdGan", 256, precision="bf16", save_root=str(tmp_path) + "/"))
